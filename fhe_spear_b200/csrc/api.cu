@@ -1,0 +1,763 @@
+// api.cu -- extern "C" surface declared in include/spear_b200.h.
+// Thin: argument checks, object allocation, and calls into the engine (bsgs.cu / ops.cu / ...).
+#include <cstring>
+#include <exception>
+#include <string>
+
+#include "../../include/spear_b200.h"
+#include "engine.h"
+#include "ops.h"
+
+unsigned long long g_spear_launches = 0;
+
+int create_coeff_modulus(u64 N, const int* bits, int n, u64* out);
+Ctx* ctx_create(u64 N, const u64* moduli, int K, int P, int device);
+void ctx_destroy(Ctx* c);
+namespace eng {
+void keyswitch(const Ctx* c, const u64* cin, int l, const u64* key, const u64* add0, u64* out, cudaStream_t s);
+void apply_galois(const Ctx* c, const u64* ct, int l, u32 elt, const u64* key, u64* out, cudaStream_t s);
+void relinearize(const Ctx* c, const u64* ct3, int l, const u64* rlk, u64* out, cudaStream_t s);
+void rescale(const Ctx* c, const u64* in, int polys, int l, u64* out, cudaStream_t s);
+void bsgs_exact(const Ctx* c, const u64* const* baby, const u64* const* pts, int G, int B, int D, int l,
+                const u32* gelt, const u64* const* gkey, u64* out, cudaStream_t s);
+void bsgs_hoisted(const Ctx* c, const u64* ct, int l, const u64* diag, int rshift, int G, int B, int D,
+                  const u32* belt, const u64* const* bkey, const u32* gelt, const u64* const* gkey, u64* out,
+                  cudaStream_t s);
+}  // namespace eng
+
+namespace {
+
+thread_local std::string g_err;
+
+#define API_BEGIN try {
+#define API_END                                  \
+    }                                            \
+    catch (const spear_error& e) {               \
+        g_err = e.msg;                           \
+        return e.code ? e.code : SPEAR_ERR_INVALID; \
+    }                                            \
+    catch (const std::exception& e) {            \
+        g_err = e.what();                        \
+        return SPEAR_ERR_INVALID;                \
+    }                                            \
+    return SPEAR_OK;
+
+inline Ctx* C_(spear_context* c) { return reinterpret_cast<Ctx*>(c); }
+inline const Obj* O_(const spear_obj* o) { return reinterpret_cast<const Obj*>(o); }
+inline spear_obj* H_(Obj* o) { return reinterpret_cast<spear_obj*>(o); }
+
+Obj* new_obj(Ctx* c, int size, int l, bool ext, int n, double scale) {
+    std::unique_ptr<Obj> o(new Obj);
+    o->ctx = c, o->size = size, o->l = l, o->ext = ext, o->n = n, o->scale = scale;
+    o->d = c->alloc(o->words());
+    return o.release();
+}
+void use(Ctx* c) { CUDA_CHECK(cudaSetDevice(c->device)); }
+
+void check_ct(const Obj* o, const char* what) {
+    REQUIRE(o && o->size >= 2 && !o->ext && o->n == o->ctx->N, "%s: expected a ciphertext", what);
+}
+void check_pt(const Obj* o, const char* what) {
+    REQUIRE(o && o->size == 1 && o->n == o->ctx->N, "%s: expected a plaintext", what);
+}
+RowMap data_rows(const Ctx* c, int l) { return RowMap{l, l, c->L, 0}; }
+
+u64 elt_from_step(int step, u64 N) {
+    u64 m = 2 * N, half = N / 2;
+    if (step == 0) return m - 1;
+    u64 e = step > 0 ? (u64)step % half : (half - ((u64)(-(long long)step) % half)) % half;
+    u64 r = 1, g = 5;
+    for (; e; e >>= 1, g = g * g & (m - 1))
+        if (e & 1) r = r * g & (m - 1);
+    return r;
+}
+
+// one switching key from `snew` (the key being switched away from), streams tagged by `tag`
+KSKey* gen_switch_key(Ctx* c, const SecretKey* sk, u64 tag, const u64* snew) {
+    const size_t N = c->N, K = c->K;
+    std::unique_ptr<KSKey> key(new KSKey);
+    key->ctx = c;
+    key->d = c->alloc((size_t)c->beta * 2 * K * N);
+    u64* e = c->alloc(K * N);
+    RowMap all{c->K, c->L, c->L, 0};
+    for (int j = 0; j < c->beta; j++) {
+        u64 id = (tag << 8) | (u64)j;
+        u64* k0 = key->d + ((size_t)j * 2 + 0) * K * N;
+        u64* k1 = key->d + ((size_t)j * 2 + 1) * K * N;
+        sampler::uniform(c, sk->seed, stream_id(DOM_KSK_A, id), k1, c->K, all, c->stream);
+        sampler::cbd(c, sk->seed, stream_id(DOM_KSK_E, id), e, c->K, all, c->stream);
+        ntt_forward(c, e, c->K, all, c->N, c->stream);
+        sampler::ksk_combine(c, k1, e, sk->d, snew, j, k0, c->stream);
+    }
+    c->free(e);
+    return key.release();
+}
+
+KSKey* gen_galois_key(Ctx* c, const SecretKey* sk, u32 elt) {
+    REQUIRE((elt & 1) && elt < 2u * c->N, "invalid Galois element %u", elt);
+    u64* sn = c->alloc((size_t)c->K * c->N);
+    ops::galois(c, sk->d, sn, c->K, elt, c->stream);
+    KSKey* k = gen_switch_key(c, sk, elt, sn);
+    c->free(sn);
+    return k;
+}
+
+const KSKey* find_key(const GaloisKeys* gk, u32 elt) {
+    auto it = gk->keys.find(elt);
+    if (it == gk->keys.end()) spear_throw(SPEAR_ERR_NOKEY, "no Galois key for element %u", elt);
+    return it->second.get();
+}
+
+// vals_full[v][j] = vals[v][j % D]  (replicate a period-D vector over all slots, as reference :371-378)
+__global__ void k_tile(const double2* __restrict__ in, double2* __restrict__ out, int count, int D, int slots) {
+    size_t total = (size_t)count * slots;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x)
+        out[e] = in[(e / slots) * D + (e % slots) % D];
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* spear_last_error(void) { return g_err.c_str(); }
+const char* spear_version(void) { return "spear-b200 0.1 (sm_100a)"; }
+uint64_t spear_launch_count(void) { return g_spear_launches; }
+
+int spear_create_coeff_modulus(uint64_t N, const int* bits, int count, uint64_t* out) {
+    API_BEGIN
+    REQUIRE(N >= 8 && (N & (N - 1)) == 0 && count > 0, "create_coeff_modulus: bad arguments");
+    create_coeff_modulus(N, bits, count, out);
+    API_END
+}
+uint64_t spear_get_elt_from_step(int step, uint64_t N) { return elt_from_step(step, N); }
+
+int spear_context_create(uint64_t N, const uint64_t* moduli, int count, int special, int device, spear_context** out) {
+    API_BEGIN
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        spear_throw(SPEAR_ERR_CUDA, "CUDA device required (no CPU fallback): %s", cudaGetErrorString(e));
+    REQUIRE(device >= 0 && device < ndev, "device %d out of range", device);
+    *out = reinterpret_cast<spear_context*>(ctx_create(N, moduli, count, special, device));
+    API_END
+}
+void spear_context_destroy(spear_context* ctx) { ctx_destroy(C_(ctx)); }
+int spear_context_sync(spear_context* ctx) {
+    API_BEGIN
+    use(C_(ctx));
+    CUDA_CHECK(cudaStreamSynchronize(C_(ctx)->stream));
+    API_END
+}
+void* spear_context_stream(spear_context* ctx) { return (void*)C_(ctx)->stream; }
+
+static thread_local cudaEvent_t t_ev0 = nullptr, t_ev1 = nullptr;
+int spear_timer_start(spear_context* ctx) {
+    API_BEGIN
+    use(C_(ctx));
+    if (!t_ev0) {
+        CUDA_CHECK(cudaEventCreate(&t_ev0));
+        CUDA_CHECK(cudaEventCreate(&t_ev1));
+    }
+    CUDA_CHECK(cudaEventRecord(t_ev0, C_(ctx)->stream));
+    API_END
+}
+int spear_timer_stop(spear_context* ctx, float* ms) {
+    API_BEGIN
+    use(C_(ctx));
+    REQUIRE(t_ev0, "timer not started");
+    CUDA_CHECK(cudaEventRecord(t_ev1, C_(ctx)->stream));
+    CUDA_CHECK(cudaEventSynchronize(t_ev1));
+    CUDA_CHECK(cudaEventElapsedTime(ms, t_ev0, t_ev1));
+    API_END
+}
+int spear_pinned_alloc(size_t bytes, void** out) {
+    API_BEGIN
+    CUDA_CHECK(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    API_END
+}
+void spear_pinned_free(void* p) { cudaFreeHost(p); }
+int spear_mem_info(spear_context* ctx, uint64_t* used, uint64_t* reserved) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    unsigned long long u = 0, r = 0;
+    CUDA_CHECK(cudaMemPoolGetAttribute(c->pool, cudaMemPoolAttrUsedMemCurrent, &u));
+    CUDA_CHECK(cudaMemPoolGetAttribute(c->pool, cudaMemPoolAttrReservedMemCurrent, &r));
+    *used = u, *reserved = r;
+    API_END
+}
+
+// ---- keys -------------------------------------------------------------------------------------
+int spear_secret_key_create(spear_context* ctx, const uint8_t seed[32], spear_secret_key** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    std::unique_ptr<SecretKey> sk(new SecretKey);
+    sk->ctx = c;
+    memcpy(sk->seed, seed, 32);
+    sk->d = c->alloc((size_t)c->K * c->N);
+    RowMap all{c->K, c->L, c->L, 0};
+    sampler::ternary(c, sk->seed, stream_id(DOM_SK, 0), sk->d, c->K, all, c->stream);
+    ntt_forward(c, sk->d, c->K, all, c->N, c->stream);
+    *out = reinterpret_cast<spear_secret_key*>(sk.release());
+    API_END
+}
+void spear_secret_key_destroy(spear_secret_key* sk) { delete reinterpret_cast<SecretKey*>(sk); }
+
+int spear_gen_public_key(spear_context* ctx, const spear_secret_key* sk_, spear_public_key** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const SecretKey* sk = reinterpret_cast<const SecretKey*>(sk_);
+    const size_t KN = (size_t)c->K * c->N;
+    std::unique_ptr<PublicKey> pk(new PublicKey);
+    pk->ctx = c;
+    memcpy(pk->seed, sk->seed, 32);
+    pk->d = c->alloc(2 * KN);
+    u64* e = c->alloc(KN);
+    RowMap all{c->K, c->L, c->L, 0};
+    sampler::uniform(c, sk->seed, stream_id(DOM_PK_A, 0), pk->d + KN, c->K, all, c->stream);
+    sampler::cbd(c, sk->seed, stream_id(DOM_PK_E, 0), e, c->K, all, c->stream);
+    ntt_forward(c, e, c->K, all, c->N, c->stream);
+    // pk0 = e - a*s  (same combine as a switching key digit that owns no limb)
+    sampler::ksk_combine(c, pk->d + KN, e, sk->d, sk->d, -1, pk->d, c->stream);
+    c->free(e);
+    *out = reinterpret_cast<spear_public_key*>(pk.release());
+    API_END
+}
+void spear_public_key_destroy(spear_public_key* pk) { delete reinterpret_cast<PublicKey*>(pk); }
+
+int spear_gen_relin_key(spear_context* ctx, const spear_secret_key* sk_, spear_kswitch_key** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const SecretKey* sk = reinterpret_cast<const SecretKey*>(sk_);
+    u64* s2 = c->alloc((size_t)c->K * c->N);
+    RowMap all{c->K, c->L, c->L, 0};
+    ops::mul(c, sk->d, sk->d, s2, 1, c->K, c->N, all, 1, c->stream);
+    KSKey* k = gen_switch_key(c, sk, 0, s2);
+    c->free(s2);
+    *out = reinterpret_cast<spear_kswitch_key*>(k);
+    API_END
+}
+void spear_kswitch_key_destroy(spear_kswitch_key* k) { delete reinterpret_cast<KSKey*>(k); }
+
+int spear_galois_keys_add(spear_context* ctx, const spear_secret_key* sk_, spear_galois_keys* gk_, const uint32_t* elts,
+                          int count) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    GaloisKeys* gk = reinterpret_cast<GaloisKeys*>(gk_);
+    const SecretKey* sk = reinterpret_cast<const SecretKey*>(sk_);
+    for (int i = 0; i < count; i++)
+        if (!gk->keys.count(elts[i])) gk->keys[elts[i]].reset(gen_galois_key(c, sk, elts[i]));
+    API_END
+}
+int spear_gen_galois_keys(spear_context* ctx, const spear_secret_key* sk, const uint32_t* elts, int count,
+                          spear_galois_keys** out) {
+    GaloisKeys* gk = new GaloisKeys;
+    gk->ctx = C_(ctx);
+    int rc = spear_galois_keys_add(ctx, sk, reinterpret_cast<spear_galois_keys*>(gk), elts, count);
+    if (rc) {
+        delete gk;
+        return rc;
+    }
+    *out = reinterpret_cast<spear_galois_keys*>(gk);
+    return SPEAR_OK;
+}
+int spear_galois_keys_has(const spear_galois_keys* gk, uint32_t elt) {
+    return (int)reinterpret_cast<const GaloisKeys*>(gk)->keys.count(elt);
+}
+void spear_galois_keys_destroy(spear_galois_keys* gk) { delete reinterpret_cast<GaloisKeys*>(gk); }
+
+// ---- objects ------------------------------------------------------------------------------------
+void spear_obj_destroy(spear_obj* o) { delete reinterpret_cast<Obj*>(o); }
+int spear_obj_info(const spear_obj* o_, int* size, int* limbs, int* ext, int* ring_n, double* scale, int* chain_index) {
+    API_BEGIN
+    const Obj* o = O_(o_);
+    REQUIRE(o, "null object");
+    if (size) *size = o->size;
+    if (limbs) *limbs = o->l;
+    if (ext) *ext = o->ext;
+    if (ring_n) *ring_n = o->n;
+    if (scale) *scale = o->scale;
+    if (chain_index) *chain_index = o->ctx->L - o->l + 1;
+    API_END
+}
+int spear_obj_set_scale(spear_obj* o, double scale) {
+    API_BEGIN
+    REQUIRE(o && scale > 0, "set_scale: bad arguments");
+    reinterpret_cast<Obj*>(o)->scale = scale;
+    API_END
+}
+static int export_words(const Ctx* c, const u64* d, size_t have, uint64_t* host, size_t words) {
+    API_BEGIN
+    REQUIRE(words == have, "export: buffer holds %zu words, object has %zu", words, have);
+    CUDA_CHECK(cudaSetDevice(c->device));
+    CUDA_CHECK(cudaMemcpyAsync(host, d, sizeof(u64) * words, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    API_END
+}
+int spear_obj_export(const spear_obj* o, uint64_t* host, size_t words) {
+    return export_words(O_(o)->ctx, O_(o)->d, O_(o)->words(), host, words);
+}
+int spear_obj_import(spear_context* ctx, const uint64_t* host, int size, int limbs, int ext, int ring_n, double scale,
+                     spear_obj** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    REQUIRE(size >= 1 && size <= 3 && limbs >= 1 && limbs <= c->L && ring_n >= 2 && ring_n <= c->N,
+            "import: bad shape");
+    std::unique_ptr<Obj> o(new_obj(c, size, limbs, ext != 0, ring_n, scale));
+    CUDA_CHECK(cudaMemcpyAsync(o->d, host, sizeof(u64) * o->words(), cudaMemcpyHostToDevice, c->stream));
+    *out = H_(o.release());
+    API_END
+}
+int spear_secret_key_export(const spear_secret_key* sk_, uint64_t* host, size_t words) {
+    const SecretKey* sk = reinterpret_cast<const SecretKey*>(sk_);
+    return export_words(sk->ctx, sk->d, (size_t)sk->ctx->K * sk->ctx->N, host, words);
+}
+int spear_kswitch_key_export(const spear_kswitch_key* k_, uint64_t* host, size_t words) {
+    const KSKey* k = reinterpret_cast<const KSKey*>(k_);
+    return export_words(k->ctx, k->d, (size_t)k->ctx->beta * 2 * k->ctx->K * k->ctx->N, host, words);
+}
+int spear_galois_key_export(const spear_galois_keys* gk_, uint32_t elt, uint64_t* host, size_t words) {
+    API_BEGIN
+    const GaloisKeys* gk = reinterpret_cast<const GaloisKeys*>(gk_);
+    const KSKey* k = find_key(gk, elt);
+    return export_words(k->ctx, k->d, (size_t)k->ctx->beta * 2 * k->ctx->K * k->ctx->N, host, words);
+    API_END
+}
+int spear_public_key_export(const spear_public_key* pk_, uint64_t* host, size_t words) {
+    const PublicKey* pk = reinterpret_cast<const PublicKey*>(pk_);
+    return export_words(pk->ctx, pk->d, (size_t)2 * pk->ctx->K * pk->ctx->N, host, words);
+}
+
+// ---- encoder ------------------------------------------------------------------------------------
+int spear_encode(spear_context* ctx, const double* values, int count, int ring_n, double scale, int chain_index,
+                 int ext, spear_obj** outs) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    REQUIRE(count >= 1 && chain_index >= 1 && chain_index <= c->L, "encode: chain_index %d out of range", chain_index);
+    REQUIRE(scale > 0, "encode: scale must be positive");
+    const int l = c->limbs_at(chain_index), rows = l + (ext ? c->P : 0);
+    const int chunk = std::max(1, std::min(count, (int)((64u << 20) / ((size_t)rows * ring_n))));
+    double2* dv = (double2*)c->alloc((size_t)chunk * ring_n);   // chunk * ring_n/2 double2 = chunk*ring_n words
+    u64* buf = c->alloc((size_t)chunk * rows * ring_n);
+    std::vector<std::unique_ptr<Obj>> made;
+    for (int v0 = 0; v0 < count; v0 += chunk) {
+        int nv = std::min(chunk, count - v0);
+        CUDA_CHECK(cudaMemcpyAsync(dv, values + (size_t)v0 * ring_n, sizeof(double) * nv * ring_n,
+                                   cudaMemcpyHostToDevice, c->stream));
+        encoder::encode(c, dv, nv, ring_n, scale, l, ext != 0, buf, c->stream);
+        for (int v = 0; v < nv; v++) {
+            made.emplace_back(new_obj(c, 1, l, ext != 0, ring_n, scale));
+            CUDA_CHECK(cudaMemcpyAsync(made.back()->d, buf + (size_t)v * rows * ring_n, sizeof(u64) * rows * ring_n,
+                                       cudaMemcpyDeviceToDevice, c->stream));
+        }
+    }
+    c->free(dv);
+    c->free(buf);
+    for (int v = 0; v < count; v++) outs[v] = H_(made[v].release());
+    API_END
+}
+int spear_decode(spear_context* ctx, const spear_obj* pt_, double* out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const Obj* pt = O_(pt_);
+    check_pt(pt, "decode");
+    double2* dv = (double2*)c->alloc((size_t)c->N);
+    encoder::decode(c, pt->d, pt->l, pt->scale, dv, c->stream);
+    CUDA_CHECK(cudaMemcpyAsync(out, dv, sizeof(double2) * (c->N / 2), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->free(dv);
+    API_END
+}
+
+// ---- encryption ---------------------------------------------------------------------------------
+int spear_encrypt_symmetric(spear_context* ctx, const spear_secret_key* sk_, const spear_obj* pt_, uint64_t enc_id,
+                            spear_obj** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const SecretKey* sk = reinterpret_cast<const SecretKey*>(sk_);
+    const Obj* pt = O_(pt_);
+    check_pt(pt, "encrypt_symmetric");
+    REQUIRE(!pt->ext, "encrypt_symmetric: plaintext carries special limbs");
+    const int l = pt->l;
+    const size_t N = c->N;
+    std::unique_ptr<Obj> ct(new_obj(c, 2, l, false, c->N, pt->scale));
+    u64* e = c->alloc(l * N);
+    RowMap rm = data_rows(c, l);
+    sampler::uniform(c, sk->seed, stream_id(DOM_ENC_A, enc_id), ct->poly(1), l, rm, c->stream);
+    sampler::cbd(c, sk->seed, stream_id(DOM_ENC_E, enc_id), e, l, rm, c->stream);
+    ntt_forward(c, e, l, rm, c->N, c->stream);
+    sampler::enc_combine(c, ct->poly(1), e, sk->d, pt->d, ct->poly(0), l, c->stream);
+    c->free(e);
+    *out = H_(ct.release());
+    API_END
+}
+int spear_encrypt_asymmetric(spear_context* ctx, const spear_public_key* pk_, const spear_obj* pt_, uint64_t enc_id,
+                             spear_obj** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const PublicKey* pk = reinterpret_cast<const PublicKey*>(pk_);
+    const Obj* pt = O_(pt_);
+    check_pt(pt, "encrypt_asymmetric");
+    REQUIRE(!pt->ext, "encrypt_asymmetric: plaintext carries special limbs");
+    const int l = pt->l, rows = l + c->P;
+    const size_t N = c->N, pw = (size_t)rows * N;
+    std::unique_ptr<Obj> ct(new_obj(c, 2, l, false, c->N, pt->scale));
+    u64* u = c->alloc(3 * pw);
+    u64 *e0 = u + pw, *e1 = u + 2 * pw;
+    u64* t = c->alloc(2 * pw);
+    u64* tmp = c->alloc(2 * l * N);
+    RowMap rm{rows, l, c->L, 0};
+    sampler::ternary(c, pk->seed, stream_id(DOM_ASYM_U, enc_id), u, rows, rm, c->stream);
+    sampler::cbd(c, pk->seed, stream_id(DOM_ASYM_E0, enc_id), e0, rows, rm, c->stream);
+    sampler::cbd(c, pk->seed, stream_id(DOM_ASYM_E1, enc_id), e1, rows, rm, c->stream);
+    ntt_forward(c, u, 3 * rows, rm, c->N, c->stream);
+    sampler::asym_combine(c, pk->d, u, e0, e1, t, l, c->stream);
+    ops::moddown(c, t, pw, 2, l, tmp, nullptr, ct->d, c->stream);
+    ops::add(c, ct->d, pt->d, ct->d, 1, l, c->N, data_rows(c, l), 1, c->stream);
+    c->free(u);
+    c->free(t);
+    c->free(tmp);
+    *out = H_(ct.release());
+    API_END
+}
+int spear_decrypt(spear_context* ctx, const spear_secret_key* sk_, const spear_obj* ct_, spear_obj** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const SecretKey* sk = reinterpret_cast<const SecretKey*>(sk_);
+    const Obj* ct = O_(ct_);
+    check_ct(ct, "decrypt");
+    std::unique_ptr<Obj> pt(new_obj(c, 1, ct->l, false, c->N, ct->scale));
+    sampler::dec_combine(c, ct->d, ct->size, ct->l, sk->d, pt->d, c->stream);
+    *out = H_(pt.release());
+    API_END
+}
+
+// ---- evaluator ------------------------------------------------------------------------------------
+int spear_negate(spear_context* ctx, const spear_obj* a_, spear_obj** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const Obj* a = O_(a_);
+    check_ct(a, "negate");
+    std::unique_ptr<Obj> o(new_obj(c, a->size, a->l, false, c->N, a->scale));
+    ops::neg(c, a->d, o->d, a->size, a->l, c->N, data_rows(c, a->l), c->stream);
+    *out = H_(o.release());
+    API_END
+}
+static int addsub(spear_context* ctx, const spear_obj* a_, const spear_obj* b_, spear_obj** out, bool is_sub) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const Obj *a = O_(a_), *b = O_(b_);
+    check_ct(a, "add/sub");
+    check_ct(b, "add/sub");
+    REQUIRE(a->l == b->l, "add/sub: chain_index mismatch (%d vs %d limbs)", a->l, b->l);
+    // a is the larger one
+    const bool swap = b->size > a->size;
+    const Obj *big = swap ? b : a, *small = swap ? a : b;
+    std::unique_ptr<Obj> o(new_obj(c, big->size, a->l, false, c->N, a->scale));
+    const size_t pw = (size_t)a->l * c->N;
+    RowMap rm = data_rows(c, a->l);
+    if (!is_sub) {
+        ops::add(c, big->d, small->d, o->d, small->size, a->l, c->N, rm, small->size, c->stream);
+        if (big->size > small->size)
+            CUDA_CHECK(cudaMemcpyAsync(o->d + small->size * pw, big->d + small->size * pw,
+                                       sizeof(u64) * (big->size - small->size) * pw, cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        ops::sub(c, a->d, b->d, o->d, small->size, a->l, c->N, rm, small->size, c->stream);
+        if (a->size > b->size)
+            CUDA_CHECK(cudaMemcpyAsync(o->d + small->size * pw, a->d + small->size * pw,
+                                       sizeof(u64) * (a->size - b->size) * pw, cudaMemcpyDeviceToDevice, c->stream));
+        else if (b->size > a->size)
+            ops::neg(c, b->d + small->size * pw, o->d + small->size * pw, b->size - a->size, a->l, c->N, rm, c->stream);
+    }
+    *out = H_(o.release());
+    API_END
+}
+int spear_add(spear_context* ctx, const spear_obj* a, const spear_obj* b, spear_obj** out) { return addsub(ctx, a, b, out, false); }
+int spear_sub(spear_context* ctx, const spear_obj* a, const spear_obj* b, spear_obj** out) { return addsub(ctx, a, b, out, true); }
+
+static int addsub_plain(spear_context* ctx, const spear_obj* ct_, const spear_obj* pt_, spear_obj** out, bool is_sub) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const Obj *ct = O_(ct_), *pt = O_(pt_);
+    check_ct(ct, "add_plain");
+    check_pt(pt, "add_plain");
+    REQUIRE(pt->l >= ct->l && !pt->ext, "add_plain: plaintext has fewer limbs than the ciphertext");
+    std::unique_ptr<Obj> o(new_obj(c, ct->size, ct->l, false, c->N, ct->scale));
+    CUDA_CHECK(cudaMemcpyAsync(o->d, ct->d, sizeof(u64) * ct->words(), cudaMemcpyDeviceToDevice, c->stream));
+    RowMap rm = data_rows(c, ct->l);
+    if (is_sub) ops::sub(c, ct->d, pt->d, o->d, 1, ct->l, c->N, rm, 1, c->stream);
+    else ops::add(c, ct->d, pt->d, o->d, 1, ct->l, c->N, rm, 1, c->stream);
+    *out = H_(o.release());
+    API_END
+}
+int spear_add_plain(spear_context* ctx, const spear_obj* ct, const spear_obj* pt, spear_obj** out) { return addsub_plain(ctx, ct, pt, out, false); }
+int spear_sub_plain(spear_context* ctx, const spear_obj* ct, const spear_obj* pt, spear_obj** out) { return addsub_plain(ctx, ct, pt, out, true); }
+
+int spear_multiply(spear_context* ctx, const spear_obj* a_, const spear_obj* b_, spear_obj** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const Obj *a = O_(a_), *b = O_(b_);
+    check_ct(a, "multiply");
+    check_ct(b, "multiply");
+    REQUIRE(a->size == 2 && b->size == 2, "multiply: operands must be size-2 ciphertexts (relinearize first)");
+    REQUIRE(a->l == b->l, "multiply: chain_index mismatch");
+    std::unique_ptr<Obj> o(new_obj(c, 3, a->l, false, c->N, a->scale * b->scale));
+    ops::tensor(c, a->d, b->d, o->d, a->l, c->stream);
+    *out = H_(o.release());
+    API_END
+}
+int spear_multiply_plain(spear_context* ctx, const spear_obj* ct_, const spear_obj* pt_, spear_obj** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const Obj *ct = O_(ct_), *pt = O_(pt_);
+    check_ct(ct, "multiply_plain");
+    check_pt(pt, "multiply_plain");
+    REQUIRE(pt->l >= ct->l && !pt->ext, "multiply_plain: plaintext has fewer limbs than the ciphertext");
+    std::unique_ptr<Obj> o(new_obj(c, ct->size, ct->l, false, c->N, ct->scale * pt->scale));
+    ops::mul(c, ct->d, pt->d, o->d, ct->size, ct->l, c->N, data_rows(c, ct->l), 1, c->stream);
+    *out = H_(o.release());
+    API_END
+}
+int spear_relinearize(spear_context* ctx, const spear_obj* ct_, const spear_kswitch_key* rlk_, spear_obj** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const Obj* ct = O_(ct_);
+    check_ct(ct, "relinearize");
+    const KSKey* rlk = reinterpret_cast<const KSKey*>(rlk_);
+    std::unique_ptr<Obj> o(new_obj(c, 2, ct->l, false, c->N, ct->scale));
+    if (ct->size == 2) CUDA_CHECK(cudaMemcpyAsync(o->d, ct->d, sizeof(u64) * ct->words(), cudaMemcpyDeviceToDevice, c->stream));
+    else eng::relinearize(c, ct->d, ct->l, rlk->d, o->d, c->stream);
+    *out = H_(o.release());
+    API_END
+}
+int spear_rescale_to_next(spear_context* ctx, const spear_obj* ct_, spear_obj** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const Obj* ct = O_(ct_);
+    check_ct(ct, "rescale_to_next");
+    REQUIRE(ct->l >= 2, "rescale_to_next: already at the last level");
+    std::unique_ptr<Obj> o(new_obj(c, ct->size, ct->l - 1, false, c->N, ct->scale / (double)c->q[ct->l - 1]));
+    eng::rescale(c, ct->d, ct->size, ct->l, o->d, c->stream);
+    *out = H_(o.release());
+    API_END
+}
+int spear_mod_switch_to_next(spear_context* ctx, const spear_obj* a_, spear_obj** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const Obj* a = O_(a_);
+    REQUIRE(a && !a->ext && a->n == c->N, "mod_switch_to_next: bad operand");
+    REQUIRE(a->l >= 2, "mod_switch_to_next: already at the last level");
+    std::unique_ptr<Obj> o(new_obj(c, a->size, a->l - 1, false, c->N, a->scale));
+    const size_t N = c->N;
+    CUDA_CHECK(cudaMemcpy2DAsync(o->d, sizeof(u64) * (a->l - 1) * N, a->d, sizeof(u64) * a->l * N,
+                                 sizeof(u64) * (a->l - 1) * N, a->size, cudaMemcpyDeviceToDevice, c->stream));
+    *out = H_(o.release());
+    API_END
+}
+int spear_apply_galois(spear_context* ctx, const spear_obj* ct_, uint32_t elt, const spear_galois_keys* gk_,
+                       spear_obj** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const Obj* ct = O_(ct_);
+    check_ct(ct, "apply_galois");
+    REQUIRE(ct->size == 2, "apply_galois: relinearize first");
+    const KSKey* key = find_key(reinterpret_cast<const GaloisKeys*>(gk_), elt);
+    std::unique_ptr<Obj> o(new_obj(c, 2, ct->l, false, c->N, ct->scale));
+    eng::apply_galois(c, ct->d, ct->l, elt, key->d, o->d, c->stream);
+    *out = H_(o.release());
+    API_END
+}
+int spear_hoisted_rotations(spear_context* ctx, const spear_obj* ct_, const uint32_t* elts, int count,
+                            const spear_galois_keys* gk_, spear_obj** outs) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const Obj* ct = O_(ct_);
+    check_ct(ct, "hoisting");
+    REQUIRE(ct->size == 2, "hoisting: relinearize first");
+    const GaloisKeys* gk = reinterpret_cast<const GaloisKeys*>(gk_);
+    const int l = ct->l, rows = l + c->P;
+    const size_t N = c->N, pw = (size_t)rows * N;
+    for (int i = 0; i < count; i++) find_key(gk, elts[i]);
+    u64* x = c->alloc(l * N);
+    u64* E = c->alloc((size_t)c->digits(l) * pw);
+    u64* acc = c->alloc(2 * pw);
+    u64* tmp = c->alloc(2 * l * N);
+    ops::decompose(c, ct->poly(1), l, x, E, c->stream);
+    std::vector<std::unique_ptr<Obj>> made;
+    for (int i = 0; i < count; i++) {
+        made.emplace_back(new_obj(c, 2, l, false, c->N, ct->scale));
+        // (P*pi(c0) + <pi(E), k0>, <pi(E), k1>) then ModDown
+        ops::ks_inner(c, E, find_key(gk, elts[i])->d, acc, l, elts[i], ct->poly(0), l, 1, 0, c->stream);
+        ops::moddown(c, acc, pw, 2, l, tmp, nullptr, made.back()->d, c->stream);
+    }
+    c->free(x), c->free(E), c->free(acc), c->free(tmp);
+    for (int i = 0; i < count; i++) outs[i] = H_(made[i].release());
+    API_END
+}
+
+// ---- BSGS ---------------------------------------------------------------------------------------
+int spear_bsgs_multiply_accumulate(spear_context* ctx, spear_obj* const* ct_baby, int n_baby, spear_obj* const* pts,
+                                   int n_pts, int G, int B, int D, const spear_galois_keys* gk_, spear_obj** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    REQUIRE(G >= 1 && B >= 1 && D >= 1 && n_baby >= std::min(G, D) && n_pts >= D && (size_t)G * B >= (size_t)D,
+            "bsgs: need G baby ciphertexts, D plaintexts and G*B >= D");
+    const GaloisKeys* gk = reinterpret_cast<const GaloisKeys*>(gk_);
+    const Obj* b0 = O_(ct_baby[0]);
+    check_ct(b0, "bsgs");
+    const int l = b0->l;
+    std::vector<const u64*> baby(G, nullptr), pt(D);
+    for (int b = 0; b < std::min(G, n_baby); b++) {
+        const Obj* o = O_(ct_baby[b]);
+        check_ct(o, "bsgs");
+        REQUIRE(o->size == 2 && o->l == l, "bsgs: baby ciphertext %d has a different level", b);
+        baby[b] = o->d;
+    }
+    for (int k = 0; k < D; k++) {
+        const Obj* o = O_(pts[k]);
+        check_pt(o, "bsgs");
+        REQUIRE(o->l >= l && !o->ext, "bsgs: diagonal %d has fewer limbs than the ciphertext", k);
+        pt[k] = o->d;
+    }
+    std::vector<u32> gelt(B, 0);
+    std::vector<const u64*> gkey(B, nullptr);
+    for (int g = 1; g < B && g * G < D; g++) {
+        gelt[g] = (u32)elt_from_step(g * G, c->N);
+        gkey[g] = find_key(gk, gelt[g])->d;
+    }
+    double scale = b0->scale * O_(pts[0])->scale / (double)c->q[l - 1];
+    REQUIRE(l >= 2, "bsgs: no level left for the final rescale");
+    std::unique_ptr<Obj> o(new_obj(c, 2, l - 1, false, c->N, scale));
+    eng::bsgs_exact(c, baby.data(), pt.data(), G, B, D, l, gelt.data(), gkey.data(), o->d, c->stream);
+    *out = H_(o.release());
+    API_END
+}
+
+int spear_diagset_encode(spear_context* ctx, const double* diags, int D, int G, int B, double scale, int chain_index,
+                         int compress, spear_diagset** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    REQUIRE(D >= 1 && G >= 1 && B >= 1 && (size_t)G * B >= (size_t)D && D <= c->N / 2, "diagset: bad D/G/B");
+    REQUIRE(chain_index >= 1 && chain_index <= c->L, "diagset: chain_index out of range");
+    const int slots = c->N / 2, l = c->limbs_at(chain_index), rows = l + c->P;
+    const bool pow2 = (D & (D - 1)) == 0;
+    REQUIRE(!compress || pow2, "diagset: sub-ring compression needs D to be a power of two");
+    const int n = (compress && pow2 && D >= 2) ? 2 * D : c->N;
+    std::unique_ptr<DiagSet> ds(new DiagSet);
+    ds->ctx = c, ds->D = D, ds->G = G, ds->B = B, ds->l = l, ds->n = n, ds->scale = scale;
+    ds->rshift = 0;
+    while ((n << ds->rshift) < c->N) ds->rshift++;
+    ds->d = c->alloc((size_t)D * rows * n);
+    double2* dv = (double2*)c->alloc((size_t)D * D * 2);
+    CUDA_CHECK(cudaMemcpyAsync(dv, diags, sizeof(double2) * D * D, cudaMemcpyHostToDevice, c->stream));
+    if (n == 2 * D) {
+        const int chunk = std::max(1, std::min(D, (int)((32u << 20) / ((size_t)n))));
+        for (int v0 = 0; v0 < D; v0 += chunk) {
+            int nv = std::min(chunk, D - v0);
+            encoder::encode(c, dv + (size_t)v0 * D, nv, n, scale, l, true, ds->d + (size_t)v0 * rows * n, c->stream);
+        }
+    } else {
+        const int chunk = std::max(1, std::min(D, (int)((32u << 20) / ((size_t)n))));
+        double2* full = (double2*)c->alloc((size_t)chunk * slots * 2);
+        for (int v0 = 0; v0 < D; v0 += chunk) {
+            int nv = std::min(chunk, D - v0);
+            LAUNCH(k_tile, c->sm_count * 8, 256, 0, c->stream)(dv + (size_t)v0 * D, full, nv, D, slots);
+            encoder::encode(c, full, nv, n, scale, l, true, ds->d + (size_t)v0 * rows * n, c->stream);
+        }
+        c->free(full);
+    }
+    c->free(dv);
+    *out = reinterpret_cast<spear_diagset*>(ds.release());
+    API_END
+}
+void spear_diagset_destroy(spear_diagset* d) { delete reinterpret_cast<DiagSet*>(d); }
+int spear_diagset_info(const spear_diagset* d_, int* D, int* G, int* B, int* limbs, int* ring_n, double* scale,
+                       uint64_t* bytes) {
+    API_BEGIN
+    const DiagSet* d = reinterpret_cast<const DiagSet*>(d_);
+    REQUIRE(d, "null diagset");
+    if (D) *D = d->D;
+    if (G) *G = d->G;
+    if (B) *B = d->B;
+    if (limbs) *limbs = d->l;
+    if (ring_n) *ring_n = d->n;
+    if (scale) *scale = d->scale;
+    if (bytes) *bytes = sizeof(u64) * (size_t)d->D * (d->l + d->ctx->P) * d->n;
+    API_END
+}
+int spear_diagset_export(const spear_diagset* d_, uint64_t* host, size_t words) {
+    const DiagSet* d = reinterpret_cast<const DiagSet*>(d_);
+    return export_words(d->ctx, d->d, (size_t)d->D * (d->l + d->ctx->P) * d->n, host, words);
+}
+
+int spear_bsgs_hoisted(spear_context* ctx, const spear_obj* ct_, const spear_diagset* ds_, const spear_galois_keys* gk_,
+                       spear_obj** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const Obj* ct = O_(ct_);
+    const DiagSet* ds = reinterpret_cast<const DiagSet*>(ds_);
+    const GaloisKeys* gk = reinterpret_cast<const GaloisKeys*>(gk_);
+    check_ct(ct, "bsgs_hoisted");
+    REQUIRE(ct->size == 2, "bsgs_hoisted: relinearize first");
+    REQUIRE(ds->l == ct->l, "bsgs_hoisted: diagonals encoded for %d limbs, ciphertext has %d", ds->l, ct->l);
+    REQUIRE(ct->l >= 2, "bsgs_hoisted: no level left for the final rescale");
+    const int G = ds->G, B = ds->B, D = ds->D, l = ct->l;
+    std::vector<u32> belt(G, 0), gelt(B, 0);
+    std::vector<const u64*> bkey(G, nullptr), gkey(B, nullptr);
+    for (int b = 1; b < G && b < D; b++) {
+        belt[b] = (u32)elt_from_step(b, c->N);
+        bkey[b] = find_key(gk, belt[b])->d;
+    }
+    for (int g = 1; g < B && g * G < D; g++) {
+        gelt[g] = (u32)elt_from_step(g * G, c->N);
+        gkey[g] = find_key(gk, gelt[g])->d;
+    }
+    std::unique_ptr<Obj> o(new_obj(c, 2, l - 1, false, c->N, ct->scale * ds->scale / (double)c->q[l - 1]));
+    eng::bsgs_hoisted(c, ct->d, l, ds->d, ds->rshift, std::min(G, D), B, D, belt.data(), bkey.data(), gelt.data(),
+                      gkey.data(), o->d, c->stream);
+    *out = H_(o.release());
+    API_END
+}
+
+int spear_ntt_host(spear_context* ctx, uint64_t* data, int rows, const int* limb_ids, int ring_n, int inverse) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    u64* d = c->alloc((size_t)rows * ring_n);
+    CUDA_CHECK(cudaMemcpyAsync(d, data, sizeof(u64) * rows * ring_n, cudaMemcpyHostToDevice, c->stream));
+    for (int r = 0; r < rows; r++) {
+        REQUIRE(limb_ids[r] >= 0 && limb_ids[r] < c->K, "ntt: limb id out of range");
+        RowMap rm{1, 0, limb_ids[r], 0};
+        if (inverse) ntt_inverse(c, d + (size_t)r * ring_n, 1, rm, ring_n, c->stream);
+        else ntt_forward(c, d + (size_t)r * ring_n, 1, rm, ring_n, c->stream);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(data, d, sizeof(u64) * rows * ring_n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->free(d);
+    API_END
+}
+
+}  // extern "C"

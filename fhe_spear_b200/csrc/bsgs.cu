@@ -1,0 +1,131 @@
+// bsgs.cu -- key switching, rotation and the two BSGS diagonal mat-vec drivers.
+//
+//  * bsgs_exact   : the reference's op order (scripts/bootstrap_generation.py:464-484): per giant
+//                   group a plaintext-diagonal MAC over the caller's baby ciphertexts, a full
+//                   rotate (permute -> decompose -> key inner product -> ModDown), sum, one rescale.
+//  * bsgs_hoisted : this build's fast path (DESIGN.md "hoisted mode"): one decomposition of c1 shared
+//                   by all baby steps, baby rotations kept in basis Q_l*P without ModDown, diagonal MAC in
+//                   that basis, one ModDown of the c1 part per giant step, giant key switches accumulated
+//                   in basis Q_l*P, one final ModDown, one rescale.
+// Both are restated step for step by the oracle (orc_bsgs_exact / orc_bsgs_hoisted).
+#include "engine.h"
+#include "ops.h"
+
+namespace eng {
+
+struct Scratch {   // stream-ordered temporaries, released on scope exit
+    const Ctx* c;
+    std::vector<void*> ptrs;
+    explicit Scratch(const Ctx* c_) : c(c_) {}
+    u64* get(size_t words) {
+        u64* p = c->alloc(words);
+        ptrs.push_back(p);
+        return p;
+    }
+    ~Scratch() {
+        for (void* p : ptrs) c->free(p);
+    }
+};
+
+// out[2][l][N] = ModDown(<decompose(cin), key>)  (+ add0[l][N] into polynomial 0)
+void keyswitch(const Ctx* c, const u64* cin, int l, const u64* key, const u64* add0, u64* out, cudaStream_t s) {
+    const size_t N = c->N, rows = l + c->P;
+    Scratch sc(c);
+    u64* x = sc.get(l * N);
+    u64* E = sc.get(c->digits(l) * rows * N);
+    u64* acc = sc.get(2 * rows * N);
+    u64* tmp = sc.get(2 * l * N);
+    ops::decompose(c, cin, l, x, E, s);
+    ops::ks_inner(c, E, key, acc, l, 0, nullptr, 0, 0, 0, s);
+    ops::moddown(c, acc, rows * N, 2, l, tmp, nullptr, out, s);
+    if (add0) ops::add(c, out, add0, out, 1, l, (int)N, RowMap{l, l, c->L, 0}, 1, s);
+}
+
+// reference op order: permute both polynomials, key-switch the permuted c1, add the permuted c0
+void apply_galois(const Ctx* c, const u64* ct, int l, u32 elt, const u64* key, u64* out, cudaStream_t s) {
+    const size_t N = c->N;
+    Scratch sc(c);
+    u64* perm = sc.get(2 * l * N);
+    ops::galois(c, ct, perm, 2 * l, elt, s);
+    keyswitch(c, perm + l * N, l, key, perm, out, s);
+}
+
+// ct3 [3][l][N] -> out [2][l][N]
+void relinearize(const Ctx* c, const u64* ct3, int l, const u64* rlk, u64* out, cudaStream_t s) {
+    const size_t N = c->N;
+    keyswitch(c, ct3 + 2 * l * N, l, rlk, nullptr, out, s);
+    ops::add(c, out, ct3, out, 2, l, (int)N, RowMap{l, l, c->L, 0}, 2, s);
+}
+
+void rescale(const Ctx* c, const u64* in, int polys, int l, u64* out, cudaStream_t s) {
+    const size_t N = c->N;
+    Scratch sc(c);
+    u64* last = sc.get(polys * N);
+    u64* tmp = sc.get((size_t)polys * (l - 1) * N);
+    ops::rescale(c, in, polys, l, last, tmp, out, s);
+}
+
+// baby[b]: [2][l][N] (b < G); pts[k]: [l][N] (k < D); gkey[g]: giant keys (g >= 1); out [2][l-1][N]
+void bsgs_exact(const Ctx* c, const u64* const* baby, const u64* const* pts, int G, int B, int D, int l,
+                const u32* gelt, const u64* const* gkey, u64* out, cudaStream_t s) {
+    const size_t N = c->N, ctw = 2 * l * N;
+    Scratch sc(c);
+    u64* inner = sc.get(ctw);
+    u64* rot = sc.get(ctw);
+    u64* res = sc.get(ctw);
+    bool have = false;
+    for (int g = 0; g < B; g++) {
+        int nb = std::min(G, D - g * G);
+        if (nb <= 0) break;
+        u64* dst = (g == 0) ? res : inner;
+        ops::pmac_list(c, baby, pts + (size_t)g * G, nb, dst, l, s);
+        if (g == 0) {
+            have = true;
+            continue;
+        }
+        apply_galois(c, inner, l, gelt[g], gkey[g], rot, s);
+        ops::add(c, res, rot, res, 2, l, (int)N, RowMap{l, l, c->L, 0}, 2, s);
+    }
+    REQUIRE(have, "bsgs: empty diagonal set");
+    rescale(c, res, 2, l, out, s);
+}
+
+// ct [2][l][N]; diag [D][l+P][N >> rshift]; bkey[b] (1 <= b < G), gkey[g] (1 <= g < B); out [2][l-1][N]
+void bsgs_hoisted(const Ctx* c, const u64* ct, int l, const u64* diag, int rshift, int G, int B, int D,
+                  const u32* belt, const u64* const* bkey, const u32* gelt, const u64* const* gkey, u64* out,
+                  cudaStream_t s) {
+    const size_t N = c->N, rows = l + c->P, pw = rows * N;
+    const int beta = c->digits(l);
+    Scratch sc(c);
+    u64* x = sc.get(l * N);
+    u64* E = sc.get(beta * pw);
+    u64* Y = sc.get((size_t)G * 2 * pw);
+    const int Beff = (D + G - 1) / G;
+    REQUIRE(Beff <= B, "bsgs: D=%d needs more than B=%d giant steps of G=%d", D, B, G);
+    u64* A = sc.get((size_t)Beff * 2 * pw);
+    const u64 *c0 = ct, *c1 = ct + l * N;
+
+    // 1-2. hoisted baby steps, kept in basis Q_l * P
+    ops::decompose(c, c1, l, x, E, s);
+    ops::pscale(c, ct, Y, l, s);
+    for (int b = 1; b < G; b++)
+        ops::ks_inner(c, E, bkey[b], Y + (size_t)b * 2 * pw, l, belt[b], c0, l, 1, 0, s);
+    // 3. diagonal multiply-accumulate for every giant group
+    ops::pmac_hoisted(c, Y, diag, A, G, Beff, D, l, rshift, s);
+    // 4. giant steps: R (= A[0], in place) += (pi_g(A_g.0) + <pi_g(F), k0>, <pi_g(F), k1>)
+    u64* R = A;
+    u64* t = sc.get(l * N);
+    u64* tmp = sc.get(2 * l * N);
+    for (int g = 1; g < Beff; g++) {
+        u64* Ag = A + (size_t)g * 2 * pw;
+        ops::moddown(c, Ag + pw, pw, 1, l, tmp, nullptr, t, s);
+        ops::decompose(c, t, l, x, E, s);
+        ops::ks_inner(c, E, gkey[g], R, l, gelt[g], Ag, (int)rows, 0, 1, s);
+    }
+    // 5. one ModDown, one rescale
+    u64* full = sc.get(2 * l * N);
+    ops::moddown(c, R, pw, 2, l, tmp, nullptr, full, s);
+    rescale(c, full, 2, l, out, s);
+}
+
+}  // namespace eng

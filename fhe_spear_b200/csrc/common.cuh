@@ -1,0 +1,157 @@
+// common.cuh -- shared types and 64-bit modular arithmetic for the sm_100a CKKS engine.
+//
+// All residues are uint64 < q < 2^61.  Three multiplication flavours:
+//   * Shoup (constant operand with precomputed floor(w*2^64/q))  -> NTT butterflies, scalar tables
+//   * 128-bit lazy accumulate + one Barrett-128 reduction        -> key-switch inner product, PMAC, base conversion
+//   * Barrett-64 for reducing a residue of one prime modulo another
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+
+#define SPEAR_MAX_LIMBS 64
+
+// ---------------------------------------------------------------------------------------------
+// error handling: every C-ABI entry point catches spear_error and returns a status code
+// ---------------------------------------------------------------------------------------------
+struct spear_error {
+    int code;
+    char msg[512];
+};
+void spear_throw(int code, const char* fmt, ...);
+
+#define SPEAR_OK 0
+#define SPEAR_ERR_INVALID 1
+#define SPEAR_ERR_CUDA 2
+#define SPEAR_ERR_OOM 3
+#define SPEAR_ERR_NOKEY 4
+
+#define CUDA_CHECK(expr)                                                                          \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            int code__ = (e__ == cudaErrorMemoryAllocation) ? SPEAR_ERR_OOM : SPEAR_ERR_CUDA;     \
+            spear_throw(code__, "CUDA error: %s%s at %s:%d", cudaGetErrorString(e__),             \
+                        code__ == SPEAR_ERR_OOM ? " (CUDA out of memory)" : "", __FILE__, __LINE__); \
+        }                                                                                         \
+    } while (0)
+
+// every kernel launch goes through LAUNCH so spear_launch_count() reports real launches
+extern unsigned long long g_spear_launches;
+#define LAUNCH(kernel, ...) g_spear_launches++, kernel<<<__VA_ARGS__>>>
+
+#define REQUIRE(cond, ...)                                   \
+    do {                                                     \
+        if (!(cond)) spear_throw(SPEAR_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device tables handed to kernels by value
+// ---------------------------------------------------------------------------------------------
+struct ModTab {
+    const u64* q;          // [K]
+    const u64* ratio0;     // [K] low  word of floor(2^128/q)
+    const u64* ratio1;     // [K] high word of floor(2^128/q)
+};
+
+struct NttTab {
+    const ulonglong2* psi;   // [K][N]  (w, shoup(w)), w = psi^{bitrev(i)}
+    const ulonglong2* ipsi;  // [K][N]  (w, shoup(w)), w = psi^{-bitrev(i)}
+    const ulonglong2* invn;  // [K][17] (n^{-1}, shoup) for transform size 2^k, k = 0..16
+    const u64* q;            // [K]
+};
+
+// Row r of a batch belongs to polynomial r / rpp; within the polynomial, rows < l are data limbs
+// base+idx, rows >= l are the special limbs L + (idx - l).
+struct RowMap {
+    int rpp;   // rows per polynomial
+    int l;     // data rows per polynomial
+    int L;     // index of the first special limb
+    int base;  // limb id of data row 0
+    __host__ __device__ __forceinline__ int limb(int row) const {
+        int idx = row % rpp;
+        return idx < l ? base + idx : L + (idx - l);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// arithmetic
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 add_mod(u64 a, u64 b, u64 q) {
+    u64 s = a + b;
+    return s >= q ? s - q : s;
+}
+__device__ __forceinline__ u64 sub_mod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
+__device__ __forceinline__ u64 neg_mod(u64 a, u64 q) { return a ? q - a : 0; }
+
+// a*w mod q in [0, 2q), wp = floor(w * 2^64 / q), any a < 2^64
+__device__ __forceinline__ u64 mul_shoup_lazy(u64 a, u64 w, u64 wp, u64 q) {
+    u64 h = __umul64hi(a, wp);
+    return a * w - h * q;
+}
+__device__ __forceinline__ u64 mul_shoup(u64 a, u64 w, u64 wp, u64 q) {
+    u64 r = mul_shoup_lazy(a, w, wp, q);
+    return r >= q ? r - q : r;
+}
+// x mod q for any x < 2^64; r1 = floor(2^64 / q)
+__device__ __forceinline__ u64 barrett64(u64 x, u64 q, u64 r1) {
+    u64 h = __umul64hi(x, r1);
+    u64 r = x - h * q;
+    return r >= q ? r - q : r;
+}
+// (hi:lo) mod q, (r1:r0) = floor(2^128 / q)
+__device__ __forceinline__ u64 barrett128(u64 lo, u64 hi, u64 q, u64 r0, u64 r1) {
+    u64 carry = __umul64hi(lo, r0);
+    u64 t2lo = lo * r1, t2hi = __umul64hi(lo, r1);
+    u64 tmp1 = t2lo + carry;
+    u64 tmp3 = t2hi + (tmp1 < t2lo);
+    t2lo = hi * r0;
+    t2hi = __umul64hi(hi, r0);
+    tmp1 += t2lo;
+    carry = t2hi + (tmp1 < t2lo);
+    tmp1 = hi * r1 + tmp3 + carry;
+    u64 r = lo - tmp1 * q;
+    return r >= q ? r - q : r;
+}
+__device__ __forceinline__ u64 mul_mod(u64 a, u64 b, u64 q, u64 r0, u64 r1) {
+    return barrett128(a * b, __umul64hi(a, b), q, r0, r1);
+}
+// (hi:lo) += a*b
+__device__ __forceinline__ void mac128(u64& lo, u64& hi, u64 a, u64 b) {
+    asm("mad.lo.cc.u64 %0, %2, %3, %0;\n\t"
+        "madc.hi.u64 %1, %2, %3, %1;"
+        : "+l"(lo), "+l"(hi)
+        : "l"(a), "l"(b));
+}
+// (hi:lo) += x
+__device__ __forceinline__ void add128(u64& lo, u64& hi, u64 x) {
+    asm("add.cc.u64 %0, %0, %2;\n\t"
+        "addc.u64 %1, %1, 0;"
+        : "+l"(lo), "+l"(hi)
+        : "l"(x));
+}
+
+// Galois automorphism x -> x^elt in the bit-reversed NTT domain:
+// out[i] = in[ bitrev( ((elt * (2*bitrev(i)+1) mod 2N) - 1) / 2 ) ].  Aligned blocks of 2^s
+// consecutive indices map onto aligned blocks, so a warp's gather stays inside one 256-byte line pair.
+__device__ __forceinline__ u32 galois_src(u32 i, u32 elt, int logn) {
+    u32 br = __brev(i) >> (32 - logn);
+    u32 k = (elt * (2u * br + 1u)) & ((2u << logn) - 1u);
+    return __brev((k - 1u) >> 1) >> (32 - logn);
+}
+
+// streaming (read-once) loads: bypass L1 and mark the line evict-first in L2 so that rotation keys
+// and diagonals flowing through do not displace the reused digits / baby ciphertexts
+__device__ __forceinline__ u64 evict_first_policy() {
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ u64 ld_stream(const u64* p, u64 pol) {
+    u64 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    return v;
+}

@@ -1,0 +1,124 @@
+// engine.h -- host-side object model of the sm_100a CKKS engine (internal; the public surface
+// is include/spear_b200.h).
+#pragma once
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "common.cuh"
+
+struct Ctx {
+    int N = 0, logn = 0;
+    int K = 0, P = 0, L = 0;   // K = L + P limbs, the P special primes last
+    int beta = 0;              // digits at the key level: ceil(L / P)
+    int device = 0;
+    std::vector<u64> q;
+
+    cudaStream_t stream = nullptr;
+    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_main = nullptr;
+    cudaEvent_t ev_aux[3] = {nullptr, nullptr, nullptr};
+    cudaMemPool_t pool = nullptr;
+    int sm_count = 148;
+
+    // device tables
+    u64 *d_q = nullptr, *d_ratio0 = nullptr, *d_ratio1 = nullptr;
+    ulonglong2 *d_psi = nullptr, *d_ipsi = nullptr, *d_invn = nullptr;
+    // per data limb i: P mod q_i, P^-1 mod q_i (with Shoup companions)
+    ulonglong2 *d_pmod = nullptr, *d_pinv = nullptr;
+    // ModUp tables, for level l (1..L) and digit j: hatinv[(l*beta + j)*P + a] (value, shoup),
+    // hat[((l*beta + j)*P + a)*K + t] = (Q_j / q_a) mod q_t
+    ulonglong2* d_up_hatinv = nullptr;
+    u64* d_up_hat = nullptr;
+    // ModDown tables: special prime k: (hatinv, shoup), half mod p_k ; data limb i: hat[k*K+i], half mod q_i
+    ulonglong2* d_dn_hatinv = nullptr;
+    u64 *d_dn_half = nullptr, *d_dn_hat = nullptr;
+    // rescale tables for dropping limb `last`: inv[last*K + i] = q_last^-1 mod q_i (value, shoup)
+    ulonglong2* d_rs_inv = nullptr;
+    // decode (Garner) tables: inv[i*3+j] = q_j^-1 mod q_i, i<3
+    ulonglong2* d_garner = nullptr;
+    // encoder: complex roots zeta^{bitrev(i)}, slot index maps are computed in-kernel
+    double2* d_zeta = nullptr;
+
+    ModTab modtab() const { return ModTab{d_q, d_ratio0, d_ratio1}; }
+    NttTab ntttab() const { return NttTab{d_psi, d_ipsi, d_invn, d_q}; }
+    int digits(int l) const { return (l + P - 1) / P; }
+    int limbs_at(int chain_index) const { return chain_index == 0 ? K : L - (chain_index - 1); }
+    int chain_of(int l, bool key_level) const { return key_level ? 0 : L - l + 1; }
+
+    u64* alloc(size_t n_u64) const;   // stream-ordered
+    void free(void* p) const;
+};
+
+// plaintext (size 1) or ciphertext (size 2 or 3); rows per polynomial = l (+ P if ext)
+struct Obj {
+    Ctx* ctx = nullptr;
+    int size = 0;      // polynomials
+    int l = 0;         // data limbs
+    bool ext = false;  // carries the P special limbs as well (basis Q_l * P)
+    int n = 0;         // coefficients per row (N, or 2*D for a sub-ring diagonal)
+    double scale = 1.0;
+    u64* d = nullptr;
+
+    int rows() const { return l + (ext ? ctx->P : 0); }
+    size_t words() const { return (size_t)size * rows() * n; }
+    u64* poly(int p) const { return d + (size_t)p * rows() * n; }
+    ~Obj() {
+        if (d && ctx) ctx->free(d);
+    }
+};
+
+struct KSKey {
+    Ctx* ctx = nullptr;
+    u64* d = nullptr;  // [beta][2][K][N]
+    ~KSKey() {
+        if (d && ctx) ctx->free(d);
+    }
+};
+
+struct GaloisKeys {
+    Ctx* ctx = nullptr;
+    std::map<u32, std::unique_ptr<KSKey>> keys;
+};
+
+struct SecretKey {
+    Ctx* ctx = nullptr;
+    u32 seed[8];
+    u64* d = nullptr;  // [K][N] NTT form
+    ~SecretKey() {
+        if (d && ctx) ctx->free(d);
+    }
+};
+
+struct PublicKey {
+    Ctx* ctx = nullptr;
+    u32 seed[8];
+    u64* d = nullptr;  // [2][K][N]
+    ~PublicKey() {
+        if (d && ctx) ctx->free(d);
+    }
+};
+
+// pre-encoded, pre-rotated BSGS diagonals in basis Q_l * P (hoisted path)
+struct DiagSet {
+    Ctx* ctx = nullptr;
+    int D = 0, G = 0, B = 0;
+    int l = 0;       // data limbs
+    int n = 0;       // coefficients stored per row (N >> rshift)
+    int rshift = 0;
+    double scale = 1.0;
+    u64* d = nullptr;  // [D][l+P][n]
+    ~DiagSet() {
+        if (d && ctx) ctx->free(d);
+    }
+};
+
+// ---- launchers (ntt.cu) --------------------------------------------------------------------
+// rows x n in-place transforms; `n` may be a power-of-two prefix size (sub-ring) <= N
+void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s, int skip_digit_alpha = 0);
+void ntt_inverse(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s);
+
+// ---- stream ids shared with the oracle ------------------------------------------------------
+enum { DOM_SK = 1, DOM_PK_A = 2, DOM_PK_E = 3, DOM_KSK_A = 4, DOM_KSK_E = 5,
+       DOM_ENC_A = 6, DOM_ENC_E = 7, DOM_ASYM_U = 8, DOM_ASYM_E0 = 9, DOM_ASYM_E1 = 10 };
+static inline u64 stream_id(int dom, u64 id) { return ((u64)dom << 56) | (id & 0x00FFFFFFFFFFFFFFull); }

@@ -1,0 +1,417 @@
+// ops.cu -- RNS kernels of the key-switch / BSGS path: element-wise ops, Galois permutation,
+// ModUp, key inner product, ModDown, rescale, plaintext-diagonal MAC.
+//
+// Every kernel is HBM/L2-bound integer work: one thread per coefficient (or coefficient pair),
+// consecutive threads on consecutive coefficients (coalesced), read-once operands (rotation keys,
+// diagonals) loaded with L1::no_allocate/L2::evict_first so the reused operands (decomposed digits,
+// baby ciphertexts) stay L2-resident.  Sums of products are accumulated lazily in 128 bits and
+// reduced once (Barrett-128).
+#include "engine.h"
+#include "ops.h"
+
+namespace {
+
+constexpr int TPB = 256;
+constexpr int MAX_ALPHA = 8;
+
+
+// ---- element-wise -------------------------------------------------------------------------
+enum { EW_ADD = 0, EW_SUB = 1, EW_NEG = 2, EW_MUL = 3 };
+
+// out[p][r][i] = a[p][r][i] (op) b[(bcast ? 0 : p)][r][i % bn]
+template <int OP>
+__global__ void k_ew(const u64* __restrict__ a, const u64* __restrict__ b, u64* __restrict__ out, int polys, int rows,
+                     int n, RowMap rm, ModTab mt, int b_polys) {
+    size_t total = (size_t)polys * rows * n;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        int i = (int)(e % n);
+        size_t pr = e / n;
+        int r = (int)(pr % rows), p = (int)(pr / rows);
+        int limb = rm.limb(r);
+        u64 q = mt.q[limb];
+        u64 x = a[e], v;
+        if (OP == EW_NEG) {
+            v = neg_mod(x, q);
+        } else {
+            u64 y = b[((size_t)(p < b_polys ? p : 0) * rows + r) * n + i];
+            if (OP == EW_ADD) v = add_mod(x, y, q);
+            else if (OP == EW_SUB) v = sub_mod(x, y, q);
+            else v = mul_mod(x, y, q, mt.ratio0[limb], mt.ratio1[limb]);
+        }
+        out[e] = v;
+    }
+}
+
+// tensor product of two size-2 ciphertexts -> size 3
+__global__ void k_tensor(const u64* __restrict__ a, const u64* __restrict__ b, u64* __restrict__ out, int l, int n,
+                         ModTab mt) {
+    size_t total = (size_t)l * n, pw = total;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        int limb = (int)(e / n);
+        u64 q = mt.q[limb], r0 = mt.ratio0[limb], r1 = mt.ratio1[limb];
+        u64 a0 = a[e], a1 = a[pw + e], b0 = b[e], b1 = b[pw + e];
+        out[e] = mul_mod(a0, b0, q, r0, r1);
+        u64 lo = 0, hi = 0;
+        mac128(lo, hi, a0, b1);
+        mac128(lo, hi, a1, b0);
+        out[pw + e] = barrett128(lo, hi, q, r0, r1);
+        out[2 * pw + e] = mul_mod(a1, b1, q, r0, r1);
+    }
+}
+
+// out[row][i] = in[row][galois_src(i)]
+__global__ void k_galois(const u64* __restrict__ in, u64* __restrict__ out, int rows, int N, int logn, u32 elt) {
+    size_t total = (size_t)rows * N;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        u32 i = (u32)(e & (N - 1));
+        out[e] = in[e - i + galois_src(i, elt, logn)];
+    }
+}
+
+// ---- ModUp --------------------------------------------------------------------------------
+// x: [l][N] coefficient form; cin: [l][N] the same polynomial in NTT form (copied into own-digit rows)
+// E: [beta][rows][N]; rows != own are left in coefficient form for the batched NTT that follows.
+__global__ void __launch_bounds__(TPB) k_modup(const u64* __restrict__ x, const u64* __restrict__ cin,
+                                                u64* __restrict__ E, int l, int N, int L, int P, int K, ModTab mt,
+                                                const ulonglong2* __restrict__ hatinv, const u64* __restrict__ hat) {
+    const int j = blockIdx.y, n = blockIdx.x * TPB + threadIdx.x;
+    const int rows = l + P, lo = j * P, hi = min(lo + P, l), a = hi - lo;
+    hatinv += (size_t)j * P;
+    hat += (size_t)j * P * K;
+    u64 y[MAX_ALPHA];
+#pragma unroll
+    for (int i = 0; i < MAX_ALPHA; i++)
+        if (i < a) {
+            ulonglong2 h = hatinv[i];
+            y[i] = mul_shoup(x[(size_t)(lo + i) * N + n], h.x, h.y, mt.q[lo + i]);
+        }
+    u64* Ej = E + (size_t)j * rows * N + n;
+    for (int r = 0; r < rows; r++) {
+        int t = r < l ? r : L + (r - l);
+        if (t >= lo && t < hi) {
+            Ej[(size_t)r * N] = cin[(size_t)t * N + n];
+            continue;
+        }
+        u64 alo = 0, ahi = 0;
+#pragma unroll
+        for (int i = 0; i < MAX_ALPHA; i++)
+            if (i < a) mac128(alo, ahi, y[i], hat[(size_t)i * K + t]);
+        Ej[(size_t)r * N] = barrett128(alo, ahi, mt.q[t], mt.ratio0[t], mt.ratio1[t]);
+    }
+}
+
+// ---- key-switch inner product -----------------------------------------------------------------
+// out[p][r][n] (+)= sum_j E[j][r][src(n)] * key[j][p][limb(r)][n]  (+ addp[r][src(n)] (* P) into p = 0)
+struct KsArgs {
+    const u64* E;      // [beta][rows][N]
+    const u64* key;    // [beta_key][2][K][N]
+    u64* out;          // [2][rows][N]
+    const u64* addp;   // optional polynomial added (after the same permutation) to out poly 0
+    int add_rows;      // rows of addp (l: data limbs only; rows: extended)
+    int add_pscale;    // multiply addp by P mod q first
+    int accumulate;    // out += instead of out =
+    int beta, l, rows, N, logn, L, K;
+    u32 elt;           // 0: identity
+};
+__global__ void __launch_bounds__(TPB) k_ks_inner(KsArgs a, ModTab mt, const ulonglong2* __restrict__ pmod) {
+    const int r = blockIdx.y, n = blockIdx.x * TPB + threadIdx.x;
+    const int t = r < a.l ? r : a.L + (r - a.l);
+    const u32 src = a.elt ? galois_src((u32)n, a.elt, a.logn) : (u32)n;
+    const u64 q = mt.q[t], r0 = mt.ratio0[t], r1 = mt.ratio1[t];
+    const u64* e = a.E + (size_t)r * a.N + src;
+    const u64* k = a.key + (size_t)t * a.N + n;
+    const size_t es = (size_t)a.rows * a.N, ks = (size_t)a.K * a.N;
+    u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+    const u64 pol = evict_first_policy();
+#pragma unroll 4
+    for (int j = 0; j < a.beta; j++) {
+        u64 d = e[j * es];
+        u64 k0 = ld_stream(k + (size_t)(2 * j) * ks, pol), k1 = ld_stream(k + (size_t)(2 * j + 1) * ks, pol);
+        mac128(lo0, hi0, d, k0);
+        mac128(lo1, hi1, d, k1);
+    }
+    u64 v0 = barrett128(lo0, hi0, q, r0, r1), v1 = barrett128(lo1, hi1, q, r0, r1);
+    if (a.addp && r < a.add_rows) {
+        u64 c = a.addp[(size_t)r * a.N + src];
+        if (a.add_pscale) {
+            ulonglong2 pm = pmod[t];
+            c = mul_shoup(c, pm.x, pm.y, q);
+        }
+        v0 = add_mod(v0, c, q);
+    }
+    u64* o0 = a.out + (size_t)r * a.N + n;
+    u64* o1 = o0 + es;
+    if (a.accumulate) {
+        v0 = add_mod(v0, *o0, q);
+        v1 = add_mod(v1, *o1, q);
+    }
+    *o0 = v0;
+    *o1 = v1;
+}
+
+// y[p][r][n] = x[p][r][n] * (P mod q_r)  on data rows, 0 on special rows (the b = 0 baby "rotation")
+__global__ void k_pscale(const u64* __restrict__ x, u64* __restrict__ y, int l, int rows, int N, ModTab mt,
+                         const ulonglong2* __restrict__ pmod) {
+    size_t total = (size_t)2 * rows * N;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        int n = (int)(e % N);
+        size_t pr = e / N;
+        int r = (int)(pr % rows), p = (int)(pr / rows);
+        u64 v = 0;
+        if (r < l) {
+            ulonglong2 pm = pmod[r];
+            v = mul_shoup(x[((size_t)p * l + r) * N + n], pm.x, pm.y, mt.q[r]);
+        }
+        y[e] = v;
+    }
+}
+
+// ---- ModDown --------------------------------------------------------------------------------
+// in: [polys][rows][N] with the P special rows already in coefficient form.
+// tmp[p][i][n] = sum_k [ (sp_k + half_k) * hatinv_k ]_{p_k} * hat[k][i]  - half_i   (mod q_i), coefficient form
+__global__ void __launch_bounds__(TPB) k_moddown_conv(const u64* __restrict__ in, u64* __restrict__ tmp, int l,
+                                                       int N, int L, int P, int K, size_t in_pstride, ModTab mt,
+                                                       const ulonglong2* __restrict__ hatinv,
+                                                       const u64* __restrict__ half, const u64* __restrict__ hat) {
+    const int p = blockIdx.y, n = blockIdx.x * TPB + threadIdx.x;
+    const u64* sp = in + (size_t)p * in_pstride + (size_t)l * N + n;
+    u64 y[MAX_ALPHA];
+#pragma unroll
+    for (int k = 0; k < MAX_ALPHA; k++)
+        if (k < P) {
+            u64 pk = mt.q[L + k];
+            ulonglong2 h = hatinv[k];
+            y[k] = mul_shoup(add_mod(sp[(size_t)k * N], half[L + k], pk), h.x, h.y, pk);
+        }
+    u64* o = tmp + (size_t)p * l * N + n;
+    for (int i = 0; i < l; i++) {
+        u64 alo = 0, ahi = 0;
+#pragma unroll
+        for (int k = 0; k < MAX_ALPHA; k++)
+            if (k < P) mac128(alo, ahi, y[k], hat[(size_t)k * K + i]);
+        u64 q = mt.q[i];
+        o[(size_t)i * N] = sub_mod(barrett128(alo, ahi, q, mt.ratio0[i], mt.ratio1[i]), half[i], q);
+    }
+}
+// out[p][i][n] = (in[p][i][n] - tmp[p][i][n]) * P^-1  (+ add[p][i][n])
+__global__ void k_moddown_final(const u64* __restrict__ in, const u64* __restrict__ tmp, const u64* __restrict__ add,
+                                u64* __restrict__ out, int polys, int l, int N, size_t in_pstride, ModTab mt,
+                                const ulonglong2* __restrict__ pinv) {
+    size_t total = (size_t)polys * l * N;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        int n = (int)(e % N);
+        size_t pr = e / N;
+        int i = (int)(pr % l), p = (int)(pr / l);
+        u64 q = mt.q[i];
+        ulonglong2 pi = pinv[i];
+        u64 v = mul_shoup(sub_mod(in[(size_t)p * in_pstride + (size_t)i * N + n], tmp[e], q), pi.x, pi.y, q);
+        if (add) v = add_mod(v, add[e], q);
+        out[e] = v;
+    }
+}
+
+// ---- rescale ---------------------------------------------------------------------------------
+// last: [polys][N] coefficient form of the dropped limb; tmp[p][i][n] = [(x + half)]_{q_i} - [half]_{q_i}
+__global__ void __launch_bounds__(TPB) k_rescale_conv(const u64* __restrict__ last, u64* __restrict__ tmp, int l,
+                                                       int N, ModTab mt) {
+    const int p = blockIdx.y, n = blockIdx.x * TPB + threadIdx.x;
+    const u64 ql = mt.q[l - 1], half = ql >> 1;
+    u64 x = add_mod(last[(size_t)p * N + n], half, ql);
+    u64* o = tmp + (size_t)p * (l - 1) * N + n;
+    for (int i = 0; i < l - 1; i++) {
+        u64 q = mt.q[i], r1 = mt.ratio1[i];
+        o[(size_t)i * N] = sub_mod(barrett64(x, q, r1), barrett64(half, q, r1), q);
+    }
+}
+__global__ void k_rescale_final(const u64* __restrict__ in, const u64* __restrict__ tmp, u64* __restrict__ out,
+                                int polys, int l, int N, ModTab mt, const ulonglong2* __restrict__ inv) {
+    size_t total = (size_t)polys * (l - 1) * N;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        int n = (int)(e % N);
+        size_t pr = e / N;
+        int i = (int)(pr % (l - 1)), p = (int)(pr / (l - 1));
+        u64 q = mt.q[i];
+        ulonglong2 w = inv[i];
+        out[e] = mul_shoup(sub_mod(in[((size_t)p * l + i) * N + n], tmp[e], q), w.x, w.y, q);
+    }
+}
+
+// ---- plaintext-diagonal multiply-accumulate (exact path) ------------------------------------------
+// inner[p][i][n] = sum_{b < nb} baby[b][p][i][n] * pt[b][i][n]      (pt pointers: consecutive plaintexts)
+struct PmacPtrs {
+    const u64* baby[128];
+    const u64* pt[128];
+};
+__global__ void __launch_bounds__(TPB) k_pmac_list(PmacPtrs ptrs, int nb, u64* __restrict__ out, int l, int N,
+                                                    ModTab mt) {
+    const int i = blockIdx.y, n = blockIdx.x * TPB + threadIdx.x;
+    const size_t off = (size_t)i * N + n, pw = (size_t)l * N;
+    u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+    const u64 pol = evict_first_policy();
+    for (int b = 0; b < nb; b++) {
+        u64 d = ld_stream(ptrs.pt[b] + off, pol);
+        mac128(lo0, hi0, ptrs.baby[b][off], d);
+        mac128(lo1, hi1, ptrs.baby[b][pw + off], d);
+    }
+    u64 q = mt.q[i], r0 = mt.ratio0[i], r1 = mt.ratio1[i];
+    out[off] = barrett128(lo0, hi0, q, r0, r1);
+    out[pw + off] = barrett128(lo1, hi1, q, r0, r1);
+}
+
+// ---- plaintext-diagonal multiply-accumulate (hoisted path) ----------------------------------------
+// A[g][p][r][n] = sum_{b : gG+b < D} Y[b][p][r][n] * diag[gG+b][r][n >> rshift]
+// One CTA owns (row r, TILE coefficients): the G baby tiles (both polynomials) are staged once in
+// shared memory and reused for all B giant groups, so Y is read from L2/HBM once and every diagonal
+// element is read once.
+constexpr int PM_TILE = 128;
+__global__ void __launch_bounds__(PM_TILE) k_pmac_hoisted(const u64* __restrict__ Y, const u64* __restrict__ diag,
+                                                           u64* __restrict__ A, int G, int B, int D, int l, int rows,
+                                                           int N, int L, int rshift, ModTab mt) {
+    extern __shared__ u64 sm[];   // [G][2][PM_TILE]
+    const int r = blockIdx.y, n = blockIdx.x * PM_TILE + threadIdx.x;
+    const int t = r < l ? r : L + (r - l);
+    const size_t pw = (size_t)rows * N, off = (size_t)r * N + n;
+    for (int b = 0; b < G; b++) {
+        sm[(b * 2 + 0) * PM_TILE + threadIdx.x] = Y[(size_t)b * 2 * pw + off];
+        sm[(b * 2 + 1) * PM_TILE + threadIdx.x] = Y[(size_t)b * 2 * pw + pw + off];
+    }
+    // each thread only re-reads its own column: no barrier needed
+    const u64 q = mt.q[t], r0 = mt.ratio0[t], r1 = mt.ratio1[t];
+    const int dn = N >> rshift;
+    const u64* dg = diag + (size_t)r * dn + (n >> rshift);
+    const size_t dstride = (size_t)rows * dn;
+    const u64 pol = evict_first_policy();
+    for (int g = 0; g < B; g++) {
+        int nb = min(G, D - g * G);
+        if (nb <= 0) break;
+        u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+        const u64* dgg = dg + (size_t)g * G * dstride;
+#pragma unroll 4
+        for (int b = 0; b < nb; b++) {
+            u64 d = ld_stream(dgg + (size_t)b * dstride, pol);
+            mac128(lo0, hi0, sm[(b * 2 + 0) * PM_TILE + threadIdx.x], d);
+            mac128(lo1, hi1, sm[(b * 2 + 1) * PM_TILE + threadIdx.x], d);
+        }
+        A[(size_t)g * 2 * pw + off] = barrett128(lo0, hi0, q, r0, r1);
+        A[(size_t)g * 2 * pw + pw + off] = barrett128(lo1, hi1, q, r0, r1);
+    }
+}
+
+}  // namespace
+
+// ===============================================================================================
+// host launchers
+// ===============================================================================================
+namespace ops {
+
+static int grid_for(const Ctx* c, size_t total) {
+    size_t blocks = (total + TPB - 1) / TPB;
+    size_t cap = (size_t)c->sm_count * 16;
+    return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
+}
+
+void add(const Ctx* c, const u64* a, const u64* b, u64* out, int polys, int rows, int n, RowMap rm, int b_polys,
+         cudaStream_t s) {
+    LAUNCH(k_ew<EW_ADD>, grid_for(c, (size_t)polys * rows * n), TPB, 0, s)(a, b, out, polys, rows, n, rm, c->modtab(), b_polys);
+}
+void sub(const Ctx* c, const u64* a, const u64* b, u64* out, int polys, int rows, int n, RowMap rm, int b_polys,
+         cudaStream_t s) {
+    LAUNCH(k_ew<EW_SUB>, grid_for(c, (size_t)polys * rows * n), TPB, 0, s)(a, b, out, polys, rows, n, rm, c->modtab(), b_polys);
+}
+void neg(const Ctx* c, const u64* a, u64* out, int polys, int rows, int n, RowMap rm, cudaStream_t s) {
+    LAUNCH(k_ew<EW_NEG>, grid_for(c, (size_t)polys * rows * n), TPB, 0, s)(a, nullptr, out, polys, rows, n, rm, c->modtab(), 0);
+}
+void mul(const Ctx* c, const u64* a, const u64* b, u64* out, int polys, int rows, int n, RowMap rm, int b_polys,
+         cudaStream_t s) {
+    LAUNCH(k_ew<EW_MUL>, grid_for(c, (size_t)polys * rows * n), TPB, 0, s)(a, b, out, polys, rows, n, rm, c->modtab(), b_polys);
+}
+void tensor(const Ctx* c, const u64* a, const u64* b, u64* out, int l, cudaStream_t s) {
+    LAUNCH(k_tensor, grid_for(c, (size_t)l * c->N), TPB, 0, s)(a, b, out, l, c->N, c->modtab());
+}
+void galois(const Ctx* c, const u64* in, u64* out, int rows, u32 elt, cudaStream_t s) {
+    LAUNCH(k_galois, grid_for(c, (size_t)rows * c->N), TPB, 0, s)(in, out, rows, c->N, c->logn, elt);
+}
+
+// cin [l][N] NTT form -> E [digits(l)][l+P][N] NTT form (scratch x: [l][N])
+void decompose(const Ctx* c, const u64* cin, int l, u64* x, u64* E, cudaStream_t s) {
+    const int N = c->N, P = c->P, rows = l + P, beta = c->digits(l);
+    REQUIRE(P <= MAX_ALPHA, "special_modulus_size > %d not supported", MAX_ALPHA);
+    REQUIRE(N % TPB == 0, "N must be a multiple of %d", TPB);
+    CUDA_CHECK(cudaMemcpyAsync(x, cin, sizeof(u64) * l * N, cudaMemcpyDeviceToDevice, s));
+    ntt_inverse(c, x, l, RowMap{l, l, c->L, 0}, N, s);
+    LAUNCH(k_modup, dim3(N / TPB, beta), TPB, 0, s)(x, cin, E, l, N, c->L, P, c->K, c->modtab(),
+                                                 c->d_up_hatinv + (size_t)l * c->beta * P,
+                                                 c->d_up_hat + (size_t)l * c->beta * P * c->K);
+    ntt_forward(c, E, beta * rows, RowMap{rows, l, c->L, 0}, N, s, P);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void ks_inner(const Ctx* c, const u64* E, const u64* key, u64* out, int l, u32 elt, const u64* addp, int add_rows,
+              int add_pscale, int accumulate, cudaStream_t s) {
+    KsArgs a;
+    a.E = E, a.key = key, a.out = out, a.addp = addp, a.add_rows = add_rows, a.add_pscale = add_pscale;
+    a.accumulate = accumulate, a.beta = c->digits(l), a.l = l, a.rows = l + c->P, a.N = c->N, a.logn = c->logn;
+    a.L = c->L, a.K = c->K, a.elt = elt;
+    LAUNCH(k_ks_inner, dim3(c->N / TPB, a.rows), TPB, 0, s)(a, c->modtab(), c->d_pmod);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void pscale(const Ctx* c, const u64* x, u64* y, int l, cudaStream_t s) {
+    int rows = l + c->P;
+    LAUNCH(k_pscale, grid_for(c, (size_t)2 * rows * c->N), TPB, 0, s)(x, y, l, rows, c->N, c->modtab(), c->d_pmod);
+}
+
+// in: [polys] polynomials of (l+P) rows, polynomial stride in_pstride words; destroys the special rows of `in`.
+// out[p][i] = ModDown(in[p])[i] (+ add[p][i]);  tmp: scratch [polys][l][N]
+void moddown(const Ctx* c, u64* in, size_t in_pstride, int polys, int l, u64* tmp, const u64* add, u64* out,
+             cudaStream_t s) {
+    const int N = c->N, P = c->P;
+    for (int p = 0; p < polys; p++)
+        ntt_inverse(c, in + (size_t)p * in_pstride + (size_t)l * N, P, RowMap{P, 0, c->L, 0}, N, s);
+    LAUNCH(k_moddown_conv, dim3(N / TPB, polys), TPB, 0, s)(in, tmp, l, N, c->L, P, c->K, in_pstride, c->modtab(),
+                                                         c->d_dn_hatinv, c->d_dn_half, c->d_dn_hat);
+    ntt_forward(c, tmp, polys * l, RowMap{l, l, c->L, 0}, N, s);
+    LAUNCH(k_moddown_final, grid_for(c, (size_t)polys * l * N), TPB, 0, s)(in, tmp, add, out, polys, l, N, in_pstride,
+                                                                       c->modtab(), c->d_pinv);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// in [polys][l][N] -> out [polys][l-1][N]; scratch last [polys][N], tmp [polys][l-1][N]
+void rescale(const Ctx* c, const u64* in, int polys, int l, u64* last, u64* tmp, u64* out, cudaStream_t s) {
+    const int N = c->N;
+    REQUIRE(l >= 2, "cannot rescale below one limb");
+    CUDA_CHECK(cudaMemcpy2DAsync(last, sizeof(u64) * N, in + (size_t)(l - 1) * N, sizeof(u64) * l * N, sizeof(u64) * N,
+                                 polys, cudaMemcpyDeviceToDevice, s));
+    ntt_inverse(c, last, polys, RowMap{1, 1, c->L, l - 1}, N, s);
+    LAUNCH(k_rescale_conv, dim3(N / TPB, polys), TPB, 0, s)(last, tmp, l, N, c->modtab());
+    ntt_forward(c, tmp, polys * (l - 1), RowMap{l - 1, l - 1, c->L, 0}, N, s);
+    LAUNCH(k_rescale_final, grid_for(c, (size_t)polys * (l - 1) * N), TPB, 0, s)(in, tmp, out, polys, l, N, c->modtab(),
+                                                                             c->d_rs_inv + (size_t)(l - 1) * c->K);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void pmac_list(const Ctx* c, const u64* const* baby, const u64* const* pt, int nb, u64* out, int l, cudaStream_t s) {
+    REQUIRE(nb <= 128, "at most 128 baby steps per giant group");
+    PmacPtrs p;
+    for (int b = 0; b < nb; b++) p.baby[b] = baby[b], p.pt[b] = pt[b];
+    LAUNCH(k_pmac_list, dim3(c->N / TPB, l), TPB, 0, s)(p, nb, out, l, c->N, c->modtab());
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void pmac_hoisted(const Ctx* c, const u64* Y, const u64* diag, u64* A, int G, int B, int D, int l, int rshift,
+                  cudaStream_t s) {
+    const int rows = l + c->P;
+    size_t smem = sizeof(u64) * (size_t)G * 2 * PM_TILE;
+    REQUIRE(smem <= 227 * 1024, "too many baby steps (%d) for the shared-memory tile", G);
+    REQUIRE(c->N % PM_TILE == 0, "N must be a multiple of %d", PM_TILE);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_pmac_hoisted, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    LAUNCH(k_pmac_hoisted, dim3(c->N / PM_TILE, rows), PM_TILE, smem, s)(Y, diag, A, G, B, D, l, rows, c->N, c->L, rshift,
+                                                                     c->modtab());
+    CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace ops

@@ -1,0 +1,43 @@
+// ops.h -- launchers of the RNS kernels in ops.cu / sampler.cu / encoder.cu (internal).
+#pragma once
+#include "engine.h"
+
+namespace ops {
+void add(const Ctx* c, const u64* a, const u64* b, u64* out, int polys, int rows, int n, RowMap rm, int b_polys, cudaStream_t s);
+void sub(const Ctx* c, const u64* a, const u64* b, u64* out, int polys, int rows, int n, RowMap rm, int b_polys, cudaStream_t s);
+void neg(const Ctx* c, const u64* a, u64* out, int polys, int rows, int n, RowMap rm, cudaStream_t s);
+void mul(const Ctx* c, const u64* a, const u64* b, u64* out, int polys, int rows, int n, RowMap rm, int b_polys, cudaStream_t s);
+void tensor(const Ctx* c, const u64* a, const u64* b, u64* out, int l, cudaStream_t s);
+void galois(const Ctx* c, const u64* in, u64* out, int rows, u32 elt, cudaStream_t s);
+void decompose(const Ctx* c, const u64* cin, int l, u64* x, u64* E, cudaStream_t s);
+void ks_inner(const Ctx* c, const u64* E, const u64* key, u64* out, int l, u32 elt, const u64* addp, int add_rows,
+              int add_pscale, int accumulate, cudaStream_t s);
+void pscale(const Ctx* c, const u64* x, u64* y, int l, cudaStream_t s);
+void moddown(const Ctx* c, u64* in, size_t in_pstride, int polys, int l, u64* tmp, const u64* add, u64* out, cudaStream_t s);
+void rescale(const Ctx* c, const u64* in, int polys, int l, u64* last, u64* tmp, u64* out, cudaStream_t s);
+void pmac_list(const Ctx* c, const u64* const* baby, const u64* const* pt, int nb, u64* out, int l, cudaStream_t s);
+void pmac_hoisted(const Ctx* c, const u64* Y, const u64* diag, u64* A, int G, int B, int D, int l, int rshift, cudaStream_t s);
+}  // namespace ops
+
+namespace sampler {
+// rows: `nrows` rows whose limb ids follow rm; uniform residues, NTT domain by definition
+void uniform(const Ctx* c, const u32* seed, u64 nonce, u64* out, int nrows, RowMap rm, cudaStream_t s);
+// small polynomial (ternary or centred binomial) written to every row in coefficient form (caller runs the NTT)
+void ternary(const Ctx* c, const u32* seed, u64 nonce, u64* out, int nrows, RowMap rm, cudaStream_t s);
+void cbd(const Ctx* c, const u32* seed, u64 nonce, u64* out, int nrows, RowMap rm, cudaStream_t s);
+// k0 = e - a*s (+ pmod * snew on the rows of digit j), one digit of a switching key; all [K][N]
+void ksk_combine(const Ctx* c, const u64* a, const u64* e, const u64* sk, const u64* snew, int digit, u64* k0, cudaStream_t s);
+// c0 = m + e - a*s on l data rows
+void enc_combine(const Ctx* c, const u64* a, const u64* e, const u64* sk, const u64* m, u64* c0, int l, cudaStream_t s);
+// pt = c0 + c1 s (+ c2 s^2)
+void dec_combine(const Ctx* c, const u64* ct, int size, int l, const u64* sk, u64* pt, cudaStream_t s);
+// out[p][r] = pk[p][limb(r)] * u[r] + e_p[r] on l+P rows
+void asym_combine(const Ctx* c, const u64* pk, const u64* u, const u64* e0, const u64* e1, u64* out, int l, cudaStream_t s);
+}  // namespace sampler
+
+namespace encoder {
+// values: host-resident doubles already on device as (re, im) pairs: [count][n/2]; out: [count][rows][n]
+void encode(const Ctx* c, const double2* vals, int count, int n, double scale, int l, bool ext, u64* out, cudaStream_t s);
+// pt [l][N] -> vals [N/2] (re, im)
+void decode(const Ctx* c, const u64* pt, int l, double scale, double2* vals, cudaStream_t s);
+}  // namespace encoder

@@ -1,0 +1,633 @@
+"""pyPhantom -- drop-in for the module the reference builds from gpu/phantom_binding.cu.
+
+Same names, argument order and error behaviour as the pybind11 module the reference scripts
+import (`import pyPhantom as ph`, scripts/bootstrap_generation.py:14, test_fully_enc_bsgs.py:14,
+fhe_rwkv_inference.py:9, fhe_common.py:14), including the fork-only symbols those scripts call
+(SURVEY.md section 8b).  Every call goes straight to libspear_b200.so (sm_100a CUDA); there is no
+CPU path.  Put the parent directory of this package on sys.path ahead of PHANTOM_PATH.
+
+Extras that the reference does not have (parity hooks, fast path): `secret_key(ctx, seed=...)`,
+`ciphertext.to_numpy()/from_numpy()`, `diagonal_set`, `bsgs_hoisted`.
+"""
+import ctypes as C
+import enum
+import os
+
+import numpy as np
+
+try:
+    from .. import _native as _n
+except ImportError:   # imported as top-level `pyPhantom` (sys.path points at fhe_spear_b200/), as the reference does
+    import sys as _sys
+    _sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from fhe_spear_b200 import _native as _n
+
+_lib = _n.lib
+_check = _n.check
+
+__version__ = _lib.spear_version().decode()
+
+
+# ---- enums  [ref: phantom_binding.cu:56-76] -------------------------------------------------------
+class scheme_type(enum.IntEnum):
+    none = 0
+    bgv = 1
+    bfv = 2
+    ckks = 3
+
+
+class mul_tech_type(enum.IntEnum):
+    none = 0
+    behz = 1
+    hps = 2
+    hps_overq = 3
+    hps_overq_leveled = 4
+
+
+class sec_level_type(enum.IntEnum):
+    none = 0
+    tc128 = 128
+    tc192 = 192
+    tc256 = 256
+
+
+for _e in (scheme_type, mul_tech_type, sec_level_type):   # pybind11 .export_values()
+    for _m in _e:
+        globals().setdefault(_m.name, _m)
+
+
+# ---- parameters  [ref: phantom_binding.cu:78-92] ---------------------------------------------------
+class modulus:
+    def __init__(self, value):
+        self._value = int(value)
+
+    def value(self):
+        return self._value
+
+    def __int__(self):
+        return self._value
+
+    def __repr__(self):
+        return f"modulus({self._value})"
+
+
+def create_coeff_modulus(poly_modulus_degree, bit_sizes):
+    bits = [int(b) for b in bit_sizes]
+    out = (C.c_uint64 * len(bits))()
+    _check(_lib.spear_create_coeff_modulus(int(poly_modulus_degree), (C.c_int * len(bits))(*bits), len(bits), out))
+    return [modulus(v) for v in out]
+
+
+def get_elt_from_step(step, poly_modulus_degree):
+    return int(_lib.spear_get_elt_from_step(int(step), int(poly_modulus_degree)))
+
+
+def get_elts_from_steps(steps, poly_modulus_degree):
+    return [get_elt_from_step(s, poly_modulus_degree) for s in steps]
+
+
+class params:
+    def __init__(self, scheme):
+        if scheme != scheme_type.ckks:
+            raise RuntimeError("only scheme_type.ckks is implemented")
+        self.scheme = scheme
+        self.poly_modulus_degree = 0
+        self.coeff_modulus = []
+        self.special_modulus_size = 1
+        self.galois_elts = None
+        self.mul_tech = mul_tech_type.none
+
+    def set_mul_tech(self, t):
+        self.mul_tech = t
+
+    def set_poly_modulus_degree(self, n):
+        self.poly_modulus_degree = int(n)
+
+    def set_special_modulus_size(self, p):
+        self.special_modulus_size = int(p)
+
+    def set_galois_elts(self, elts):
+        self.galois_elts = [int(e) for e in elts]
+
+    def set_coeff_modulus(self, mods):
+        self.coeff_modulus = [int(m) for m in mods]
+
+    def set_plain_modulus(self, m):
+        raise RuntimeError("plain modulus is a BFV/BGV parameter; only CKKS is implemented")
+
+
+class cuda_stream:   # [ref: phantom_binding.cu:94] exported by the reference, never passed by any script
+    pass
+
+
+# ---- context  [ref: phantom_binding.cu:97-98] ------------------------------------------------------
+class context:
+    def __init__(self, parms, device=None):
+        n = parms.poly_modulus_degree
+        mods = parms.coeff_modulus
+        if not mods:
+            raise RuntimeError("coeff_modulus is not set")
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", os.environ.get("SPEAR_DEVICE", "0")))
+        arr = (C.c_uint64 * len(mods))(*mods)
+        h = C.c_void_p()
+        _check(_lib.spear_context_create(n, arr, len(mods), parms.special_modulus_size, int(device), C.byref(h)))
+        self._h = h
+        self.N = n
+        self.moduli = list(mods)
+        self.P = parms.special_modulus_size
+        self.L = len(mods) - self.P
+        self.device = int(device)
+        if parms.galois_elts is None:   # library default: all power-of-two steps, both directions, and conjugation
+            elts = {2 * n - 1}
+            s = 1
+            while s < n // 2:
+                elts.add(get_elt_from_step(s, n))
+                elts.add(get_elt_from_step(-s, n))
+                s *= 2
+            self.galois_elts = sorted(elts)
+        else:
+            self.galois_elts = list(parms.galois_elts)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib.spear_context_destroy(h)
+
+    def synchronize(self):
+        _check(_lib.spear_context_sync(self._h))
+
+    def timer_start(self):
+        _check(_lib.spear_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        _check(_lib.spear_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def mem_info(self):
+        u, r = C.c_uint64(), C.c_uint64()
+        _check(_lib.spear_mem_info(self._h, C.byref(u), C.byref(r)))
+        return u.value, r.value
+
+
+# ---- plaintext / ciphertext  [ref: phantom_binding.cu:158-163 + fork-only accessors] -----------------
+class _obj:
+    def __init__(self, ctx=None, handle=None):
+        self._ctx = ctx
+        self._h = handle
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib.spear_obj_destroy(h)
+
+    def _info(self):
+        if not self._h:
+            raise RuntimeError("empty object")
+        size, limbs, ext, ring, ci = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        scale = C.c_double()
+        _check(_lib.spear_obj_info(self._h, C.byref(size), C.byref(limbs), C.byref(ext), C.byref(ring),
+                                   C.byref(scale), C.byref(ci)))
+        return size.value, limbs.value, ext.value, ring.value, scale.value, ci.value
+
+    def chain_index(self):
+        return self._info()[5]
+
+    def scale(self):
+        return self._info()[4]
+
+    def coeff_modulus_size(self):
+        return self._info()[1]
+
+    def set_scale(self, s):
+        _check(_lib.spear_obj_set_scale(self._h, float(s)))
+
+    def size(self):
+        return self._info()[0]
+
+    # parity hooks: raw limbs [size][limbs(+P)][ring_n]
+    def to_numpy(self, out=None):
+        size, limbs, ext, ring, _, _ = self._info()
+        rows = limbs + (self._ctx.P if ext else 0)
+        if out is None:
+            out = np.empty((size, rows, ring), dtype=np.uint64)
+        _check(_lib.spear_obj_export(self._h, out.ctypes.data_as(C.c_void_p), out.size))
+        return out
+
+    @classmethod
+    def from_numpy(cls, ctx, arr, scale, ext=False):
+        arr = np.ascontiguousarray(arr, dtype=np.uint64)
+        size, rows, ring = arr.shape
+        limbs = rows - (ctx.P if ext else 0)
+        h = C.c_void_p()
+        _check(_lib.spear_obj_import(ctx._h, arr.ctypes.data_as(C.c_void_p), size, limbs, int(ext), ring,
+                                     float(scale), C.byref(h)))
+        ctx.synchronize()   # arr may be pageable and freed by the caller
+        return cls(ctx, h)
+
+
+class plaintext(_obj):
+    pass
+
+
+class ciphertext(_obj):
+    pass
+
+
+def _new(cls, ctx, fn, *args):
+    h = C.c_void_p()
+    _check(fn(ctx._h, *args, C.byref(h)))
+    return cls(ctx, h)
+
+
+# ---- keys  [ref: phantom_binding.cu:100-122] -------------------------------------------------------
+class relin_key:
+    def __init__(self, ctx=None, handle=None):
+        self._ctx, self._h = ctx, handle
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib.spear_kswitch_key_destroy(h)
+
+    def to_numpy(self):
+        c = self._ctx
+        beta = (c.L + c.P - 1) // c.P
+        out = np.empty((beta, 2, c.L + c.P, c.N), dtype=np.uint64)
+        _check(_lib.spear_kswitch_key_export(self._h, out.ctypes.data_as(C.c_void_p), out.size))
+        return out
+
+
+class galois_key:
+    def __init__(self, ctx=None, handle=None):
+        self._ctx, self._h = ctx, handle
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib.spear_galois_keys_destroy(h)
+
+    def has(self, elt):
+        return bool(_lib.spear_galois_keys_has(self._h, int(elt)))
+
+    def to_numpy(self, elt):
+        c = self._ctx
+        beta = (c.L + c.P - 1) // c.P
+        out = np.empty((beta, 2, c.L + c.P, c.N), dtype=np.uint64)
+        _check(_lib.spear_galois_key_export(self._h, int(elt), out.ctypes.data_as(C.c_void_p), out.size))
+        return out
+
+
+class public_key:
+    def __init__(self, ctx=None, handle=None):
+        self._ctx, self._h = ctx, handle
+        self._enc = 0
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib.spear_public_key_destroy(h)
+
+    def encrypt_asymmetric(self, ctx, pt, enc_id=None):
+        if enc_id is None:
+            enc_id, self._enc = self._enc, self._enc + 1
+        return _new(ciphertext, ctx, _lib.spear_encrypt_asymmetric, self._h, pt._h, int(enc_id))
+
+    def to_numpy(self):
+        c = self._ctx
+        out = np.empty((2, c.L + c.P, c.N), dtype=np.uint64)
+        _check(_lib.spear_public_key_export(self._h, out.ctypes.data_as(C.c_void_p), out.size))
+        return out
+
+
+class secret_key:
+    def __init__(self, ctx, seed=None):
+        if seed is None:
+            env = os.environ.get("SPEAR_SEED")
+            seed = bytes.fromhex(env).ljust(32, b"\0")[:32] if env else os.urandom(32)
+        if isinstance(seed, int):
+            seed = seed.to_bytes(32, "little")
+        if len(seed) != 32:
+            raise RuntimeError("seed must be 32 bytes")
+        self._ctx = ctx
+        self.seed = bytes(seed)
+        self._enc = 0
+        h = C.c_void_p()
+        _check(_lib.spear_secret_key_create(ctx._h, self.seed, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib.spear_secret_key_destroy(h)
+
+    def gen_publickey(self, ctx):
+        return _new(public_key, ctx, _lib.spear_gen_public_key, self._h)
+
+    def gen_relinkey(self, ctx):
+        return _new(relin_key, ctx, _lib.spear_gen_relin_key, self._h)
+
+    def create_galois_keys(self, ctx, elts=None):
+        elts = list(ctx.galois_elts if elts is None else elts)
+        arr = (C.c_uint32 * len(elts))(*elts)
+        h = C.c_void_p()
+        _check(_lib.spear_gen_galois_keys(ctx._h, self._h, arr, len(elts), C.byref(h)))
+        return galois_key(ctx, h)
+
+    def add_galois_keys(self, ctx, gk, elts):
+        elts = list(elts)
+        arr = (C.c_uint32 * len(elts))(*elts)
+        _check(_lib.spear_galois_keys_add(ctx._h, self._h, gk._h, arr, len(elts)))
+
+    def encrypt_symmetric(self, ctx, pt, enc_id=None):
+        if enc_id is None:
+            enc_id, self._enc = self._enc, self._enc + 1
+        return _new(ciphertext, ctx, _lib.spear_encrypt_symmetric, self._h, pt._h, int(enc_id))
+
+    def decrypt(self, ctx, ct):
+        return _new(plaintext, ctx, _lib.spear_decrypt, self._h, ct._h)
+
+    def to_numpy(self):
+        c = self._ctx
+        out = np.empty((c.L + c.P, c.N), dtype=np.uint64)
+        _check(_lib.spear_secret_key_export(self._h, out.ctypes.data_as(C.c_void_p), out.size))
+        return out
+
+
+# ---- encoder  [ref: phantom_binding.cu:138-156; fork-only batch forms] --------------------------------
+def _as_complex_rows(values, slots):
+    v = np.asarray(values)
+    if v.ndim == 1:
+        v = v[None, :]
+    if v.shape[1] > slots:
+        raise RuntimeError(f"too many values: {v.shape[1]} > {slots} slots")
+    buf = np.zeros((v.shape[0], slots), dtype=np.complex128)
+    buf[:, :v.shape[1]] = v
+    return buf
+
+
+class ckks_encoder:
+    def __init__(self, ctx):
+        self._ctx = ctx
+
+    def slot_count(self):
+        return self._ctx.N // 2
+
+    def _encode(self, ctx, values, scale, chain_index, ext=False, ring_n=None):
+        ring_n = ctx.N if ring_n is None else ring_n
+        buf = _as_complex_rows(values, ring_n // 2)
+        count = buf.shape[0]
+        outs = (C.c_void_p * count)()
+        _check(_lib.spear_encode(ctx._h, buf.view(np.float64).ctypes.data_as(_n.f64p), count, ring_n, float(scale),
+                                 int(chain_index), int(ext), outs))
+        return [plaintext(ctx, C.c_void_p(h)) for h in outs]
+
+    def encode_double_vector(self, ctx, values, scale, chain_index=1):
+        return self._encode(ctx, np.asarray(values, dtype=np.float64), scale, chain_index)[0]
+
+    def encode_complex_vector(self, ctx, values, scale, chain_index=1):
+        return self._encode(ctx, np.asarray(values, dtype=np.complex128), scale, chain_index)[0]
+
+    def encode_double_vector_batch(self, ctx, values, scale, chain_index=1):
+        return self._encode(ctx, np.asarray(values, dtype=np.float64), scale, chain_index)
+
+    def encode_complex_vector_batch(self, ctx, values, scale, chain_index=1):
+        return self._encode(ctx, np.asarray(values, dtype=np.complex128), scale, chain_index)
+
+    def _decode(self, ctx, pt):
+        out = np.empty(ctx.N // 2, dtype=np.complex128)
+        _check(_lib.spear_decode(ctx._h, pt._h, out.view(np.float64).ctypes.data_as(_n.f64p)))
+        return out
+
+    def decode_double_vector(self, ctx, pt):
+        return self._decode(ctx, pt).real.tolist()
+
+    def decode_complex_vector(self, ctx, pt):
+        return self._decode(ctx, pt).tolist()
+
+
+class batch_encoder:   # [ref: phantom_binding.cu:128-136] BFV/BGV only
+    def __init__(self, ctx):
+        raise RuntimeError("batch_encoder is a BFV/BGV feature; only CKKS is implemented")
+
+
+# ---- evaluator  [ref: phantom_binding.cu:165-205] ----------------------------------------------------
+def negate(ctx, ct):
+    return _new(ciphertext, ctx, _lib.spear_negate, ct._h)
+
+
+def add(ctx, a, b):
+    return _new(ciphertext, ctx, _lib.spear_add, a._h, b._h)
+
+
+def sub(ctx, a, b, negate=False):
+    if negate:
+        a, b = b, a
+    return _new(ciphertext, ctx, _lib.spear_sub, a._h, b._h)
+
+
+def add_plain(ctx, ct, pt):
+    return _new(ciphertext, ctx, _lib.spear_add_plain, ct._h, pt._h)
+
+
+def sub_plain(ctx, ct, pt):
+    return _new(ciphertext, ctx, _lib.spear_sub_plain, ct._h, pt._h)
+
+
+def add_many(ctx, cts, dst=None):
+    acc = cts[0]
+    for ct in cts[1:]:
+        acc = add(ctx, acc, ct)
+    return acc
+
+
+def multiply(ctx, a, b):
+    return _new(ciphertext, ctx, _lib.spear_multiply, a._h, b._h)
+
+
+def multiply_plain(ctx, ct, pt):
+    return _new(ciphertext, ctx, _lib.spear_multiply_plain, ct._h, pt._h)
+
+
+def relinearize(ctx, ct, rlk):
+    return _new(ciphertext, ctx, _lib.spear_relinearize, ct._h, rlk._h)
+
+
+def multiply_and_relin(ctx, a, b, rlk):
+    return relinearize(ctx, multiply(ctx, a, b), rlk)
+
+
+def rescale_to_next(ctx, ct):
+    return _new(ciphertext, ctx, _lib.spear_rescale_to_next, ct._h)
+
+
+def mod_switch_to_next(ctx, obj):
+    return _new(type(obj), ctx, _lib.spear_mod_switch_to_next, obj._h)
+
+
+def mod_switch_to(ctx, obj, chain_index):
+    cur = obj.chain_index()
+    if chain_index < cur:
+        raise RuntimeError(f"cannot mod-switch from chain_index {cur} back to {chain_index}")
+    if chain_index == cur:   # functional style: still hand back a fresh object
+        return type(obj).from_numpy(ctx, obj.to_numpy(), obj.scale())
+    while obj.chain_index() < chain_index:
+        obj = mod_switch_to_next(ctx, obj)
+    return obj
+
+
+def apply_galois(ctx, ct, elt, gk):
+    return _new(ciphertext, ctx, _lib.spear_apply_galois, ct._h, int(elt), gk._h)
+
+
+def _naf(x):
+    out, i = [], 0
+    while x:
+        if x & 1:
+            d = 2 - (x & 3)
+            out.append(d * (1 << i))
+            x -= d
+        x >>= 1
+        i += 1
+    return out
+
+
+def rotate(ctx, ct, step, gk):
+    slots = ctx.N // 2
+    step = int(step)
+    if step % slots == 0:
+        return mod_switch_to(ctx, ct, ct.chain_index())
+    elt = get_elt_from_step(step, ctx.N)
+    if gk.has(elt):
+        return apply_galois(ctx, ct, elt, gk)
+    # no key for this step: compose power-of-two rotations (non-adjacent form), as SEAL's rotate_internal
+    s = step % slots
+    if s > slots // 2:
+        s -= slots
+    for part in _naf(abs(s)):
+        part = part if s > 0 else -part
+        e = get_elt_from_step(part, ctx.N)
+        if not gk.has(e):
+            raise RuntimeError(f"no Galois key for step {step} (element {elt}) nor for its power-of-two parts")
+        ct = apply_galois(ctx, ct, e, gk)
+    return ct
+
+
+def hoisting(ctx, ct, gk, steps):
+    """Rotations of one ciphertext by several steps sharing one decomposition (hoisted)."""
+    elts = [get_elt_from_step(int(s), ctx.N) for s in steps]
+    outs = (C.c_void_p * len(elts))()
+    _check(_lib.spear_hoisted_rotations(ctx._h, ct._h, (C.c_uint32 * len(elts))(*elts), len(elts), gk._h, outs))
+    return [ciphertext(ctx, C.c_void_p(h)) for h in outs]
+
+
+# ---- fork-only fused ops  [ref: scripts/bootstrap_generation.py:242, 339-357, 449, 459] -----------------
+def bsgs_multiply_accumulate(ctx, ct_baby, pts, G, B, D, gk):
+    nb, npt = len(ct_baby), len(pts)
+    cb = (C.c_void_p * nb)(*[c._h for c in ct_baby])
+    pp = (C.c_void_p * npt)(*[p._h for p in pts])
+    return _new(ciphertext, ctx, _lib.spear_bsgs_multiply_accumulate, cb, nb, pp, npt, int(G), int(B), int(D), gk._h)
+
+
+def offload_plaintexts(pts):
+    """list[plaintext] -> (data, chain_index, scale, coeff_modulus_size, poly_modulus_degree)."""
+    size, limbs, ext, ring, scale, ci = pts[0]._info()
+    data = np.empty((len(pts), limbs, ring), dtype=np.uint64)
+    for k, p in enumerate(pts):
+        p.to_numpy(out=data[k:k + 1])
+    return data, ci, scale, limbs, ring
+
+
+def upload_plaintexts(data, chain_index, scale, coeff_modulus_size, poly_modulus_degree, ctx=None):
+    ctx = ctx or _default_ctx()
+    data = np.asarray(data, dtype=np.uint64).reshape(-1, coeff_modulus_size, poly_modulus_degree)
+    return [plaintext.from_numpy(ctx, data[k:k + 1], scale) for k in range(data.shape[0])]
+
+
+def bsgs_from_cpu(ctx, ct_baby, data, ci, sc, cms, pmd, G, B, D, gk):
+    pts = upload_plaintexts(data, ci, sc, cms, pmd, ctx=ctx)
+    return bsgs_multiply_accumulate(ctx, ct_baby, pts, G, B, D, gk)
+
+
+def bsgs_complete_from_cpu(ctx, ct_x, data, ci, sc, cms, pmd, G, B, D, gk):
+    ct_baby = [ct_x] + [rotate(ctx, ct_x, b, gk) for b in range(1, G)]
+    return bsgs_from_cpu(ctx, ct_baby, data, ci, sc, cms, pmd, G, B, D, gk)
+
+
+_last_ctx = None
+
+
+def _default_ctx():
+    if _last_ctx is None:
+        raise RuntimeError("upload_plaintexts needs a context (none created yet)")
+    return _last_ctx
+
+
+_ctx_init = context.__init__
+
+
+def _ctx_init_track(self, *a, **k):
+    global _last_ctx
+    _ctx_init(self, *a, **k)
+    import weakref
+    _last_ctx = weakref.proxy(self)
+
+
+context.__init__ = _ctx_init_track
+
+
+# ---- fast path (not in the reference): pre-encoded diagonal sets + hoisted BSGS -------------------------
+class diagonal_set:
+    """D pre-rotated period-D diagonals encoded in basis Q_l*P, sub-ring compressed when D is a power of two."""
+
+    def __init__(self, ctx, diags, G, B, scale, chain_index=1, compress=True):
+        d = np.ascontiguousarray(np.asarray(diags, dtype=np.complex128))
+        D = d.shape[0]
+        if d.shape != (D, D):
+            raise RuntimeError("diagonal_set expects a (D, D) array of pre-rotated diagonals")
+        compress = bool(compress) and (D & (D - 1)) == 0 and D >= 2
+        h = C.c_void_p()
+        _check(_lib.spear_diagset_encode(ctx._h, d.view(np.float64).ctypes.data_as(_n.f64p), D, int(G), int(B),
+                                         float(scale), int(chain_index), int(compress), C.byref(h)))
+        self._ctx, self._h = ctx, h
+        self.D, self.G, self.B = D, int(G), int(B)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib.spear_diagset_destroy(h)
+
+    def info(self):
+        D, G, B, limbs, ring = (C.c_int() for _ in range(5))
+        scale, nbytes = C.c_double(), C.c_uint64()
+        _check(_lib.spear_diagset_info(self._h, C.byref(D), C.byref(G), C.byref(B), C.byref(limbs), C.byref(ring),
+                                       C.byref(scale), C.byref(nbytes)))
+        return dict(D=D.value, G=G.value, B=B.value, limbs=limbs.value, ring_n=ring.value, scale=scale.value,
+                    bytes=nbytes.value)
+
+    def to_numpy(self):
+        i = self.info()
+        out = np.empty((i["D"], i["limbs"] + self._ctx.P, i["ring_n"]), dtype=np.uint64)
+        _check(_lib.spear_diagset_export(self._h, out.ctypes.data_as(C.c_void_p), out.size))
+        return out
+
+
+def bsgs_hoisted(ctx, ct, diags, gk):
+    return _new(ciphertext, ctx, _lib.spear_bsgs_hoisted, ct._h, diags._h, gk._h)
+
+
+# ---- bootstrapping  [ref: fork-only ckks_bootstrapper, scripts/bootstrap_generation.py:72-75,110-116] ---
+class ckks_bootstrapper:
+    """Not built in this round; callers must pass skip_bootstrap=True."""
+
+    def __init__(self, encoder):
+        raise RuntimeError("ckks_bootstrapper is not implemented in this build (use skip_bootstrap=True / --no-bootstrap)")
+
+    @staticmethod
+    def get_galois_elements(poly_degree, flag, level_budget):
+        raise RuntimeError("ckks_bootstrapper is not implemented in this build (use skip_bootstrap=True / --no-bootstrap)")
+
+    @staticmethod
+    def get_bootstrap_depth(level_budget):
+        raise RuntimeError("ckks_bootstrapper is not implemented in this build (use skip_bootstrap=True / --no-bootstrap)")

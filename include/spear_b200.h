@@ -1,0 +1,163 @@
+/*
+ * spear_b200.h -- C ABI of libspear_b200.so, the sm_100a CKKS BSGS diagonal mat-vec engine.
+ *
+ * This is the drop-in boundary for the hot path of mozendr/FHE-SPEAR: it replaces what the
+ * reference binds through pybind11 in gpu/phantom_binding.cu (module `pyPhantom`) plus the
+ * fork-only symbols its scripts call.  Each entry point cites the reference
+ * interface it stands in for as  [ref: file:line].  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every function returning int returns 0 on success, non-zero on failure; the message is
+ *     available from spear_last_error() (thread-local).  Out-of-memory messages contain both
+ *     "CUDA" and "out of memory" (the reference string-matches them, scripts/bootstrap_generation.py:1164).
+ *   - handles are opaque; each *_create / operation result is owned by the caller and released
+ *     with the matching *_destroy.  Operations never mutate their inputs (reference style:
+ *     every evaluator call returns a new object) except spear_obj_set_scale.
+ *   - all work is queued on the context's CUDA stream; calls that return host data synchronise it.
+ *   - chain_index: 0 = key level (all L+P limbs), 1 = fresh ciphertext (L limbs), +1 per rescale /
+ *     mod-switch  [ref: fhe_rwkv_inference.py:218, scripts/bootstrap_generation.py:272].
+ *   - polynomials are uint64 residues, layout [poly][limb][coefficient], NTT (bit-reversed) form.
+ *   - there is no CPU fallback: without a CUDA device spear_context_create fails.
+ */
+#ifndef SPEAR_B200_H
+#define SPEAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct spear_context spear_context;         /* [ref: phantom_binding.cu:97  PhantomContext]     */
+typedef struct spear_secret_key spear_secret_key;   /* [ref: phantom_binding.cu:100 PhantomSecretKey]   */
+typedef struct spear_public_key spear_public_key;   /* [ref: phantom_binding.cu:112 PhantomPublicKey]   */
+typedef struct spear_kswitch_key spear_kswitch_key; /* [ref: phantom_binding.cu:118 PhantomRelinKey]    */
+typedef struct spear_galois_keys spear_galois_keys; /* [ref: phantom_binding.cu:121 PhantomGaloisKey]   */
+typedef struct spear_obj spear_obj;                 /* [ref: phantom_binding.cu:158-163 plaintext / ciphertext] */
+typedef struct spear_diagset spear_diagset;         /* pre-encoded BSGS diagonals [ref: bootstrap_generation.py:252-262] */
+
+const char* spear_last_error(void);
+const char* spear_version(void);
+uint64_t spear_launch_count(void);   /* kernels launched by this library so far (bench.py gpu_launches) */
+
+/* ---- parameters ------------------------------------------------------------------------------- */
+/* [ref: phantom_binding.cu:81 create_coeff_modulus] NTT-friendly primes for the requested bit sizes */
+int spear_create_coeff_modulus(uint64_t poly_degree, const int* bit_sizes, int count, uint64_t* out);
+/* [ref: phantom_binding.cu:124-126 get_elt_from_step / get_elts_from_steps] generator 5, step 0 = conjugation */
+uint64_t spear_get_elt_from_step(int step, uint64_t poly_degree);
+
+/* ---- context ---------------------------------------------------------------------------------- */
+/* [ref: phantom_binding.cu:85-98 params + context] special primes are the last `special` moduli */
+int spear_context_create(uint64_t poly_degree, const uint64_t* moduli, int count, int special, int device,
+                         spear_context** out);
+void spear_context_destroy(spear_context* ctx);
+int spear_context_sync(spear_context* ctx);
+void* spear_context_stream(spear_context* ctx);   /* cudaStream_t */
+/* device-side timing on the context stream (CUDA events) */
+int spear_timer_start(spear_context* ctx);
+int spear_timer_stop(spear_context* ctx, float* elapsed_ms);
+/* pinned host buffers for the host<->device legs of the end-to-end path */
+int spear_pinned_alloc(size_t bytes, void** out);
+void spear_pinned_free(void* p);
+/* device memory currently held by the stream-ordered pool (bytes) */
+int spear_mem_info(spear_context* ctx, uint64_t* used, uint64_t* reserved);
+
+/* ---- keys ------------------------------------------------------------------------------------- */
+/* [ref: phantom_binding.cu:100-101 secret_key(ctx)] ternary secret from a 32-byte seed (ChaCha20 streams) */
+int spear_secret_key_create(spear_context* ctx, const uint8_t seed[32], spear_secret_key** out);
+void spear_secret_key_destroy(spear_secret_key* sk);
+/* [ref: phantom_binding.cu:102 gen_publickey] */
+int spear_gen_public_key(spear_context* ctx, const spear_secret_key* sk, spear_public_key** out);
+void spear_public_key_destroy(spear_public_key* pk);
+/* [ref: phantom_binding.cu:103 gen_relinkey] */
+int spear_gen_relin_key(spear_context* ctx, const spear_secret_key* sk, spear_kswitch_key** out);
+void spear_kswitch_key_destroy(spear_kswitch_key* k);
+/* [ref: phantom_binding.cu:104 create_galois_keys; :91 set_galois_elts] one hybrid switching key per element */
+int spear_gen_galois_keys(spear_context* ctx, const spear_secret_key* sk, const uint32_t* elts, int count,
+                          spear_galois_keys** out);
+int spear_galois_keys_add(spear_context* ctx, const spear_secret_key* sk, spear_galois_keys* gk, const uint32_t* elts,
+                          int count);
+int spear_galois_keys_has(const spear_galois_keys* gk, uint32_t elt);
+void spear_galois_keys_destroy(spear_galois_keys* gk);
+
+/* ---- plaintext / ciphertext objects -------------------------------------------------------------- */
+void spear_obj_destroy(spear_obj* o);
+/* [ref: fork-only ct.chain_index() / ct.scale() / ct.coeff_modulus_size(), bootstrap_generation.py:152,178,272] */
+int spear_obj_info(const spear_obj* o, int* size, int* limbs, int* ext, int* ring_n, double* scale, int* chain_index);
+/* [ref: phantom_binding.cu:163 ciphertext.set_scale] */
+int spear_obj_set_scale(spear_obj* o, double scale);
+/* parity hooks and the host-buffer path: raw limbs [size][limbs(+P)][ring_n] */
+int spear_obj_export(const spear_obj* o, uint64_t* host, size_t words);
+int spear_obj_import(spear_context* ctx, const uint64_t* host, int size, int limbs, int ext, int ring_n, double scale,
+                     spear_obj** out);
+int spear_secret_key_export(const spear_secret_key* sk, uint64_t* host, size_t words);             /* [K][N] */
+int spear_kswitch_key_export(const spear_kswitch_key* k, uint64_t* host, size_t words);            /* [beta][2][K][N] */
+int spear_galois_key_export(const spear_galois_keys* gk, uint32_t elt, uint64_t* host, size_t words);
+int spear_public_key_export(const spear_public_key* pk, uint64_t* host, size_t words);             /* [2][K][N] */
+
+/* ---- encoder ------------------------------------------------------------------------------------ */
+/* [ref: phantom_binding.cu:138-156 ckks_encoder.encode_*; fork-only encode_*_vector_batch,
+ *  bootstrap_generation.py:382,423]  values: `count` vectors of ring_n/2 complex slots, interleaved
+ *  (re, im) doubles on the host.  ring_n = poly_degree for ordinary plaintexts.  ext != 0 also emits
+ *  the special limbs (basis Q_l * P).  outs receives `count` handles. */
+int spear_encode(spear_context* ctx, const double* values, int count, int ring_n, double scale, int chain_index,
+                 int ext, spear_obj** outs);
+/* [ref: phantom_binding.cu:149-156 decode_*] out: poly_degree/2 complex slots, interleaved (re, im) */
+int spear_decode(spear_context* ctx, const spear_obj* pt, double* out);
+
+/* ---- encryption --------------------------------------------------------------------------------- */
+/* [ref: phantom_binding.cu:105-107 encrypt_symmetric] enc_id selects the randomness streams (parity hook) */
+int spear_encrypt_symmetric(spear_context* ctx, const spear_secret_key* sk, const spear_obj* pt, uint64_t enc_id,
+                            spear_obj** out);
+/* [ref: phantom_binding.cu:113-116 encrypt_asymmetric] */
+int spear_encrypt_asymmetric(spear_context* ctx, const spear_public_key* pk, const spear_obj* pt, uint64_t enc_id,
+                             spear_obj** out);
+/* [ref: phantom_binding.cu:108-110 decrypt] */
+int spear_decrypt(spear_context* ctx, const spear_secret_key* sk, const spear_obj* ct, spear_obj** out);
+
+/* ---- evaluator  [ref: phantom_binding.cu:165-205] ----------------------------------------------------- */
+int spear_negate(spear_context* ctx, const spear_obj* a, spear_obj** out);
+int spear_add(spear_context* ctx, const spear_obj* a, const spear_obj* b, spear_obj** out);
+int spear_sub(spear_context* ctx, const spear_obj* a, const spear_obj* b, spear_obj** out);
+int spear_add_plain(spear_context* ctx, const spear_obj* ct, const spear_obj* pt, spear_obj** out);
+int spear_sub_plain(spear_context* ctx, const spear_obj* ct, const spear_obj* pt, spear_obj** out);
+int spear_multiply(spear_context* ctx, const spear_obj* a, const spear_obj* b, spear_obj** out);
+int spear_multiply_plain(spear_context* ctx, const spear_obj* ct, const spear_obj* pt, spear_obj** out);
+int spear_relinearize(spear_context* ctx, const spear_obj* ct3, const spear_kswitch_key* rlk, spear_obj** out);
+int spear_rescale_to_next(spear_context* ctx, const spear_obj* ct, spear_obj** out);
+int spear_mod_switch_to_next(spear_context* ctx, const spear_obj* o, spear_obj** out);   /* ct or pt */
+int spear_apply_galois(spear_context* ctx, const spear_obj* ct, uint32_t elt, const spear_galois_keys* gk,
+                       spear_obj** out);
+/* [ref: phantom_binding.cu:205 hoisting] rotations of one ciphertext by several elements sharing one
+ * decomposition; outs receives `count` ciphertexts */
+int spear_hoisted_rotations(spear_context* ctx, const spear_obj* ct, const uint32_t* elts, int count,
+                            const spear_galois_keys* gk, spear_obj** outs);
+
+/* ---- BSGS diagonal mat-vec ------------------------------------------------------------------------ */
+/* [ref: fork-only ph.bsgs_multiply_accumulate(ctx, ct_baby, pts, G, B, D, gk), bootstrap_generation.py:459;
+ *  executable spec = the Python loop :464-484]  exact mode: reference op order, result rescaled. */
+int spear_bsgs_multiply_accumulate(spear_context* ctx, spear_obj* const* ct_baby, int n_baby, spear_obj* const* pts,
+                                   int n_pts, int G, int B, int D, const spear_galois_keys* gk, spear_obj** out);
+/* [ref: pre_encode_real_diags / pre_encode_complex_diags, bootstrap_generation.py:252-262, 361-432]
+ *  diags: D period-D complex vectors (already pre-rotated by +gG per giant group, :365-369), interleaved
+ *  (re, im).  compress != 0 stores the sub-ring form (ring 2D, N/(2D)-fold smaller). */
+int spear_diagset_encode(spear_context* ctx, const double* diags, int D, int G, int B, double scale, int chain_index,
+                         int compress, spear_diagset** out);
+void spear_diagset_destroy(spear_diagset* d);
+int spear_diagset_info(const spear_diagset* d, int* D, int* G, int* B, int* limbs, int* ring_n, double* scale,
+                       uint64_t* bytes);
+int spear_diagset_export(const spear_diagset* d, uint64_t* host, size_t words);   /* [D][limbs+P][ring_n] */
+/* hoisted mode (this build's fast path): baby steps, diagonal MAC and giant steps in one call
+ * [ref: fork-only ph.bsgs_complete_from_cpu(ctx, ct_x, ...), bootstrap_generation.py:242] */
+int spear_bsgs_hoisted(spear_context* ctx, const spear_obj* ct, const spear_diagset* diags,
+                       const spear_galois_keys* gk, spear_obj** out);
+
+/* ---- raw transforms (tests / profiling) ------------------------------------------------------------- */
+/* in-place on a host buffer of `rows` x ring_n residues whose row r uses modulus limb_ids[r] */
+int spear_ntt_host(spear_context* ctx, uint64_t* data, int rows, const int* limb_ids, int ring_n, int inverse);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

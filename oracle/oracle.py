@@ -251,6 +251,12 @@ class Oracle:
         self.lib.orc_apply_galois(self.ctx, int(l), _p(ct), C.c_uint32(elt), _p(key), _p(o))
         return o
 
+    def hoisted_rotation(self, ct, elt, key):
+        ct = _u64(ct)
+        o = np.empty_like(ct)
+        self.lib.orc_hoisted_rotation(self.ctx, int(ct.shape[1]), _p(ct), C.c_uint32(elt), _p(key), _p(o))
+        return o
+
     def rotate(self, ct, step, keys):
         elt = self.elt_from_step(step)
         return self.apply_galois(ct, elt, keys[elt])

@@ -699,6 +699,43 @@ void orc_apply_galois(const orc_ctx *c, int l, const u64 *ct, u32 elt, const u64
         out[(u64)i * N + n] = addmod(out[(u64)i * N + n], p0[(u64)i * N + n], c->q[i]);
     free(p0); free(p1);
 }
+/* hoisted rotation (ph.hoisting): decompose c1 once, permute the digits, ModDown:
+ * out = ModDown( P*pi(c0) + <pi(E),k0> , <pi(E),k1> ) */
+void orc_hoisted_rotation(const orc_ctx *c, int l, const u64 *ct, u32 elt, const u64 *key, u64 *out) {
+    u64 N = c->N; int rows = l + c->P, beta = n_digits(c, l);
+    u64 *E = (u64 *)malloc(sizeof(u64) * N * rows * beta);
+    u64 *acc = (u64 *)malloc(sizeof(u64) * N * rows * 2);
+    orc_decompose(c, l, ct + (u64)l * N, E);
+    ks_inner(c, l, E, elt, key, acc, 0);
+    for (int i = 0; i < l; i++) { u64 q = c->q[i], pm = pmod(c, i);
+        for (u64 n = 0; n < N; n++)
+            acc[(u64)i * N + n] = addmod(acc[(u64)i * N + n], mulmod(pm, ct[(u64)i * N + galois_src(c, elt, (u32)n)], q), q); }
+    moddown_poly(c, l, acc, out);
+    moddown_poly(c, l, acc + (u64)rows * N, out + (u64)l * N);
+    free(E); free(acc);
+}
+/* asymmetric encryption: (pk0*u + e0, pk1*u + e1) on Q_l*P, ModDown, + m */
+void orc_encrypt_asymmetric(const orc_ctx *c, const u32 *seed, u64 enc_id, const u64 *pk /*[2][K][N]*/,
+                            const u64 *pt, int l, u64 *ct) {
+    u64 N = c->N; int rows = l + c->P, K = c->K;
+    int *v = (int *)malloc(sizeof(int) * N);
+    u64 *u = (u64 *)malloc(sizeof(u64) * N * rows), *e = (u64 *)malloc(sizeof(u64) * N * rows);
+    u64 *t = (u64 *)malloc(sizeof(u64) * N * rows);
+    for (u64 n = 0; n < N; n++) v[n] = sample_ternary(seed, stream_id(DOM_ASYM_U, enc_id), n);
+    small_poly_rows(c, v, l, 1, u);
+    for (int p = 0; p < 2; p++) {
+        u64 ne = stream_id(p ? DOM_ASYM_E1 : DOM_ASYM_E0, enc_id);
+        for (u64 n = 0; n < N; n++) v[n] = sample_cbd(seed, ne, n);
+        small_poly_rows(c, v, l, 1, e);
+        for (int r = 0; r < rows; r++) { int tl = row_limb(c, l, r); u64 q = c->q[tl];
+            for (u64 n = 0; n < N; n++)
+                t[(u64)r * N + n] = addmod(mulmod(pk[((u64)p * K + tl) * N + n], u[(u64)r * N + n], q), e[(u64)r * N + n], q); }
+        moddown_poly(c, l, t, ct + (u64)p * l * N);
+    }
+    for (int i = 0; i < l; i++) for (u64 n = 0; n < N; n++)
+        ct[(u64)i * N + n] = addmod(ct[(u64)i * N + n], pt[(u64)i * N + n], c->q[i]);
+    free(v); free(u); free(e); free(t);
+}
 /* relinearize a size-3 ciphertext */
 void orc_relinearize(const orc_ctx *c, int l, const u64 *ct3, const u64 *rlk, u64 *out) {
     u64 N = c->N;
