@@ -12,7 +12,6 @@ unsigned long long g_spear_launches = 0;
 
 int create_coeff_modulus(u64 N, const int* bits, int n, u64* out);
 Ctx* ctx_create(u64 N, const u64* moduli, int K, int P, int device);
-void ctx_destroy(Ctx* c);
 namespace eng {
 void keyswitch(const Ctx* c, const u64* cin, int l, const u64* key, const u64* add0, u64* out, cudaStream_t s);
 void apply_galois(const Ctx* c, const u64* ct, int l, u32 elt, const u64* key, u64* out, cudaStream_t s);
@@ -48,7 +47,7 @@ inline spear_obj* H_(Obj* o) { return reinterpret_cast<spear_obj*>(o); }
 
 Obj* new_obj(Ctx* c, int size, int l, bool ext, int n, double scale) {
     std::unique_ptr<Obj> o(new Obj);
-    o->ctx = c, o->size = size, o->l = l, o->ext = ext, o->n = n, o->scale = scale;
+    o->bind(c), o->size = size, o->l = l, o->ext = ext, o->n = n, o->scale = scale;
     o->d = c->alloc(o->words());
     return o.release();
 }
@@ -76,7 +75,7 @@ u64 elt_from_step(int step, u64 N) {
 KSKey* gen_switch_key(Ctx* c, const SecretKey* sk, u64 tag, const u64* snew) {
     const size_t N = c->N, K = c->K;
     std::unique_ptr<KSKey> key(new KSKey);
-    key->ctx = c;
+    key->bind(c);
     key->d = c->alloc((size_t)c->beta * 2 * K * N);
     u64* e = c->alloc(K * N);
     RowMap all{c->K, c->L, c->L, 0};
@@ -141,7 +140,7 @@ int spear_context_create(uint64_t N, const uint64_t* moduli, int count, int spec
     *out = reinterpret_cast<spear_context*>(ctx_create(N, moduli, count, special, device));
     API_END
 }
-void spear_context_destroy(spear_context* ctx) { ctx_destroy(C_(ctx)); }
+void spear_context_destroy(spear_context* ctx) { ctx_release(C_(ctx)); }
 int spear_context_sync(spear_context* ctx) {
     API_BEGIN
     use(C_(ctx));
@@ -193,7 +192,7 @@ int spear_secret_key_create(spear_context* ctx, const uint8_t seed[32], spear_se
     Ctx* c = C_(ctx);
     use(c);
     std::unique_ptr<SecretKey> sk(new SecretKey);
-    sk->ctx = c;
+    sk->bind(c);
     memcpy(sk->seed, seed, 32);
     sk->d = c->alloc((size_t)c->K * c->N);
     RowMap all{c->K, c->L, c->L, 0};
@@ -211,7 +210,7 @@ int spear_gen_public_key(spear_context* ctx, const spear_secret_key* sk_, spear_
     const SecretKey* sk = reinterpret_cast<const SecretKey*>(sk_);
     const size_t KN = (size_t)c->K * c->N;
     std::unique_ptr<PublicKey> pk(new PublicKey);
-    pk->ctx = c;
+    pk->bind(c);
     memcpy(pk->seed, sk->seed, 32);
     pk->d = c->alloc(2 * KN);
     u64* e = c->alloc(KN);
@@ -256,7 +255,7 @@ int spear_galois_keys_add(spear_context* ctx, const spear_secret_key* sk_, spear
 int spear_gen_galois_keys(spear_context* ctx, const spear_secret_key* sk, const uint32_t* elts, int count,
                           spear_galois_keys** out) {
     GaloisKeys* gk = new GaloisKeys;
-    gk->ctx = C_(ctx);
+    gk->bind(C_(ctx));
     int rc = spear_galois_keys_add(ctx, sk, reinterpret_cast<spear_galois_keys*>(gk), elts, count);
     if (rc) {
         delete gk;
@@ -666,7 +665,7 @@ int spear_diagset_encode(spear_context* ctx, const double* diags, int D, int G, 
     REQUIRE(!compress || pow2, "diagset: sub-ring compression needs D to be a power of two");
     const int n = (compress && pow2 && D >= 2) ? 2 * D : c->N;
     std::unique_ptr<DiagSet> ds(new DiagSet);
-    ds->ctx = c, ds->D = D, ds->G = G, ds->B = B, ds->l = l, ds->n = n, ds->scale = scale;
+    ds->bind(c), ds->D = D, ds->G = G, ds->B = B, ds->l = l, ds->n = n, ds->scale = scale;
     ds->rshift = 0;
     while ((n << ds->rshift) < c->N) ds->rshift++;
     ds->d = c->alloc((size_t)D * rows * n);

@@ -246,6 +246,12 @@ Ctx* ctx_create(u64 N, const u64* moduli, int K, int P, int device) {
     return c.release();
 }
 
+void ctx_retain(Ctx* c) { c->refs.fetch_add(1); }
+void ctx_destroy(Ctx* c);
+void ctx_release(Ctx* c) {
+    if (c && c->refs.fetch_sub(1) == 1) ctx_destroy(c);
+}
+
 void ctx_destroy(Ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);

@@ -1,6 +1,7 @@
 // engine.h -- host-side object model of the sm_100a CKKS engine (internal; the public surface
 // is include/spear_b200.h).
 #pragma once
+#include <atomic>
 #include <map>
 #include <memory>
 #include <vector>
@@ -8,6 +9,7 @@
 #include "common.cuh"
 
 struct Ctx {
+    std::atomic<int> refs{1};   // the user's handle + one per live object (keys, plaintexts, ciphertexts, ...)
     int N = 0, logn = 0;
     int K = 0, P = 0, L = 0;   // K = L + P limbs, the P special primes last
     int beta = 0;              // digits at the key level: ceil(L / P)
@@ -50,9 +52,23 @@ struct Ctx {
     void free(void* p) const;
 };
 
-// plaintext (size 1) or ciphertext (size 2 or 3); rows per polynomial = l (+ P if ext)
-struct Obj {
+// Objects keep their context alive: destroying the context handle first (Python GC order is arbitrary)
+// only drops the user's reference.
+void ctx_retain(Ctx* c);
+void ctx_release(Ctx* c);
+struct CtxRef {
     Ctx* ctx = nullptr;
+    void bind(Ctx* c) {
+        ctx = c;
+        ctx_retain(c);
+    }
+    ~CtxRef() {
+        if (ctx) ctx_release(ctx);
+    }
+};
+
+// plaintext (size 1) or ciphertext (size 2 or 3); rows per polynomial = l (+ P if ext)
+struct Obj : CtxRef {
     int size = 0;      // polynomials
     int l = 0;         // data limbs
     bool ext = false;  // carries the P special limbs as well (basis Q_l * P)
@@ -68,21 +84,18 @@ struct Obj {
     }
 };
 
-struct KSKey {
-    Ctx* ctx = nullptr;
+struct KSKey : CtxRef {
     u64* d = nullptr;  // [beta][2][K][N]
     ~KSKey() {
         if (d && ctx) ctx->free(d);
     }
 };
 
-struct GaloisKeys {
-    Ctx* ctx = nullptr;
+struct GaloisKeys : CtxRef {
     std::map<u32, std::unique_ptr<KSKey>> keys;
 };
 
-struct SecretKey {
-    Ctx* ctx = nullptr;
+struct SecretKey : CtxRef {
     u32 seed[8];
     u64* d = nullptr;  // [K][N] NTT form
     ~SecretKey() {
@@ -90,8 +103,7 @@ struct SecretKey {
     }
 };
 
-struct PublicKey {
-    Ctx* ctx = nullptr;
+struct PublicKey : CtxRef {
     u32 seed[8];
     u64* d = nullptr;  // [2][K][N]
     ~PublicKey() {
@@ -100,8 +112,7 @@ struct PublicKey {
 };
 
 // pre-encoded, pre-rotated BSGS diagonals in basis Q_l * P (hoisted path)
-struct DiagSet {
-    Ctx* ctx = nullptr;
+struct DiagSet : CtxRef {
     int D = 0, G = 0, B = 0;
     int l = 0;       // data limbs
     int n = 0;       // coefficients stored per row (N >> rshift)

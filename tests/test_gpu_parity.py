@@ -108,7 +108,7 @@ def test_encode_decode_match_oracle(S, G_):
     for k in range(3):
         assert np.array_equal(pts[k].to_numpy()[0], S.o.encode(big[k], S.scale, S.L - 1))
     with pytest.raises(RuntimeError):
-        enc.encode_double_vector(ctx, [2.0 ** 70], S.scale)
+        enc.encode_double_vector(ctx, [2.0 ** 80], S.scale)
 
 
 def test_encrypt_decrypt_match_oracle(S, G_):
