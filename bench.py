@@ -1,0 +1,330 @@
+#!/usr/bin/env python3
+"""bench.py -- d=2048 BSGS CKKS mat-vecs/s on B200 (BASELINE.json metric, config C3).
+
+  python bench.py --gpus N --steps K --warmup W            this build (CUDA, hoisted BSGS)
+  python bench.py --impl reference --gpus N ...            CPU arm: the oracle port of the reference's
+                                                           op order on the host cores (PhantomFHE itself is
+                                                           not available: SURVEY.md section 8c)
+
+A step is one 2048x2048 encrypted mat-vec (CKKS N=32768, L0=24 x 59-bit, P=3, G=46, B=45: 89 rotations)
+over pre-encoded diagonals; rotation keys (10.1 GB) and diagonals are far larger than L2, so no explicit
+flush is needed between iterations.  `value` is timed with CUDA events on the engine's stream with the
+input ciphertext already in HBM; `e2e` goes through the pyPhantom call surface with pinned host buffers
+(H2D of the input ciphertext and D2H of the result inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "d=2048 BSGS CKKS matvecs/s"
+UNIT = "matvecs/s"
+CONFIGS = {
+    # name: (N, L0, P, D)
+    "c3": (32768, 24, 3, 2048),
+    "c2": (16384, 24, 3, 1024),
+    "small": (4096, 6, 3, 64),
+}
+MATVECS_PER_TOKEN = 8 * 24   # RWKV-7 1.5B: 8 BSGS calls per block, 24 blocks (reference bootstrap_generation.py:756-899)
+
+
+def workload_name(cfg):
+    N, L0, P, D = CONFIGS[cfg]
+    G = int(np.ceil(np.sqrt(D)))
+    B = int(np.ceil(D / G))
+    return (f"{cfg.upper()}: {D}x{D} BSGS projection, CKKS N={N}, L0={L0}x59-bit, P={P}, G={G} B={B} "
+            f"({G + B - 2} rotations), pre-encoded diagonals")
+
+
+# ---- clocks -----------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---- CPU arm: oracle port of the reference's op order -----------------------------------------------------
+def cpu_matvec_rate(cfg, reps, seed=0):
+    """Time the oracle's restatement of the reference BSGS loop (un-hoisted rotations, multiply_plain + add
+    per diagonal, one rescale: scripts/bootstrap_generation.py:215-220, 464-484) on the host cores.
+    A full C3 mat-vec is 89 rotations + 2048 plaintext MACs; each rep times a bounded sample (one
+    rotation, 8 diagonal MACs, one rescale) and the mat-vec time is composed from the per-op times."""
+    from oracle.oracle import Oracle
+    N, L0, P, D = CONFIGS[cfg]
+    G = int(np.ceil(np.sqrt(D)))
+    B = int(np.ceil(D / G))
+    q = Oracle.create_coeff_modulus(N, [59] * (L0 + P))
+    o = Oracle(N, q, P)
+    rng = np.random.default_rng(seed)
+    K = L0 + P
+    # timing does not depend on the values: random residues stand in for a ciphertext, a rotation key and diagonals
+    ct = np.stack([rng.integers(0, int(q[i]), N, dtype=np.uint64) for i in range(L0)] * 2).reshape(2, L0, N)
+    beta = o.num_digits(L0)
+    key = np.empty((beta, 2, K, N), dtype=np.uint64)
+    for i in range(K):
+        key[:, :, i, :] = rng.integers(0, int(q[i]), (beta, 2, N), dtype=np.uint64)
+    pt = ct[0].copy()
+    elt = o.elt_from_step(1)
+    n_mac = 8
+    t_rot = t_mac = t_rs = 0.0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        r = o.apply_galois(ct, elt, key)
+        t1 = time.perf_counter()
+        acc = r
+        for _k in range(n_mac):
+            acc = o.add(acc, o.multiply_plain(ct, pt))
+        t2 = time.perf_counter()
+        o.rescale(acc)
+        t3 = time.perf_counter()
+        t_rot += t1 - t0
+        t_mac += (t2 - t1) / n_mac
+        t_rs += t3 - t2
+    t_rot, t_mac, t_rs = t_rot / reps, t_mac / reps, t_rs / reps
+    t_matvec = (G + B - 2) * t_rot + D * t_mac + t_rs
+    cores = os.cpu_count() or 1
+    return {
+        "value": 1.0 / t_matvec, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": (f"{reps} x (1 rotation = {t_rot * 1e3:.1f} ms, 1 plaintext MAC = {t_mac * 1e3:.2f} ms, "
+                   f"1 rescale = {t_rs * 1e3:.1f} ms) at full {cfg.upper()} size; mat-vec = {G + B - 2} rot + {D} MAC + "
+                   f"1 rescale = {t_matvec:.2f} s; oracle C port, OpenMP over limbs"),
+        "s_per_matvec": t_matvec,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    res = cpu_matvec_rate(args.config, max(1, args.steps + args.warmup))
+    wall = time.perf_counter() - t0
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["s_per_matvec"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(args.config), "mode": "reference op order on CPU (un-hoisted)",
+                   "note": "PhantomFHE (the reference's GPU library) is absent and unpinned; this arm is the oracle port"},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": wall,
+    }
+    print(json.dumps(line))
+
+
+# ---- this build ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from fhe_spear_b200 import _native
+    from fhe_spear_b200 import bsgs as hb
+    from fhe_spear_b200 import pyPhantom as ph
+
+    N, L0, P, D = CONFIGS[args.config]
+    G, B = hb.compute_bsgs_params(D)
+    t_setup = time.perf_counter()
+    ckks = hb.CKKSBootstrapContext(poly_degree=N, L0=L0, prime_bits=59, special_mod_size=P, max_rot_dim=1,
+                                   bsgs_dim=[D], skip_bootstrap=True, seed=bytes(range(32)), device=local,
+                                   verbose=(rank == 0 and args.verbose))
+    ctx = ckks.ctx
+    # every rank serves its own projection (weak scaling: the 8 projections of a block are independent)
+    rng = np.random.default_rng(1000 + rank)
+    W = rng.standard_normal((D, D)) * 0.02
+    x = rng.standard_normal(D) * 0.1
+    diags = hb.pre_encode_real_diags(ckks, W, D, G, B, level=1, compress=not args.full_diagonals)
+    ct_x = ckks.encrypt_replicated(x)
+    info = diags.info()
+    ctx.synchronize()
+    t_setup = time.perf_counter() - t_setup
+
+    # correctness of exactly what is timed (decrypt error vs float64 W.x)
+    y = ph.bsgs_hoisted(ctx, ct_x, diags, ckks.gk)
+    err = float(np.abs(ckks.decrypt_vec(y, D) - W @ x).max())
+    if not err < 1e-6:
+        raise SystemExit(f"bench: decrypted result is wrong (max abs err {err})")
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def step():
+        return ph.bsgs_hoisted(ctx, ct_x, diags, ckks.gk)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    clocks = ClockSampler(local)
+    launches0 = _native.launch_count()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms = ctx.timer_stop()
+    launches = _native.launch_count() - launches0
+    barrier()
+    clk = clocks.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * args.steps / (ms_max * 1e-3)
+
+    # per-kernel-class times of the same steps (event pair around each launch), for the roofline line
+    ctx.profile(True)
+    for _ in range(args.steps):
+        step()
+    prof = ctx.profile_read()
+    ctx.profile(False)
+
+    # end to end through the public call surface with pinned host buffers
+    l = ct_x.coeff_modulus_size()
+    h_in = ph.pinned_empty((2, l, N))
+    h_out = ph.pinned_empty((2, l - 1, N))
+    ct_x.to_numpy(out=h_in)
+    scale = ct_x.scale()
+    for _ in range(2):
+        ph.bsgs_hoisted(ctx, ph.ciphertext.from_numpy(ctx, h_in, scale), diags, ckks.gk).to_numpy(out=h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ct_in = ph.ciphertext.from_numpy(ctx, h_in, scale)          # H2D
+        ph.bsgs_hoisted(ctx, ct_in, diags, ckks.gk).to_numpy(out=h_out)   # compute + D2H (synchronises)
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps / float(te.item())
+    assert np.array_equal(h_out, y.to_numpy()), "e2e result differs from the resident-input result"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant HBM kernel: the key-switch inner product streams one rotation key per launch
+    beta = (l + P - 1) // P
+    key_bytes = beta * 2 * (l + P) * N * 8
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    ks = prof["ks_inner"]
+    ks_ms = ks["ms"] / max(1, ks["launches"])
+    achieved = key_bytes / (ks_ms * 1e-3) / 1e9 if ks_ms > 0 else 0.0
+    step_ms = ms_max / args.steps
+    keys_total = (G + B - 2) * key_bytes
+    roofline = {
+        "bound": "hbm", "kernel": "k_ks_inner (rotation-key inner product)", "achieved": achieved, "peak": peak,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "algorithmic_bytes_per_launch": key_bytes, "avg_launch_ms": ks_ms, "launches_per_step": ks["launches"] // args.steps,
+        "peak_source": peak_src,
+        "matvec": {"algorithmic_bytes": keys_total + info["bytes"] + (4 * l - 2) * N * 8,
+                   "achieved_gbs": (keys_total + info["bytes"] + (4 * l - 2) * N * 8) / (step_ms * 1e-3) / 1e9,
+                   "diagonal_bytes": info["bytes"], "key_bytes": keys_total},
+        "share_of_step": {k: v["ms"] / args.steps / step_ms for k, v in prof.items()},
+    }
+    roofline["matvec"]["frac"] = roofline["matvec"]["achieved_gbs"] / peak
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_matvec_rate(args.config, args.cpu_reps)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(args.config), "mode": "hoisted BSGS (spear_bsgs_hoisted)",
+                   "diagonals": f"pre-encoded, basis Q_l*P, ring {info['ring_n']} ({'sub-ring compressed' if info['ring_n'] < N else 'full ring'}), {info['bytes'] / 1e9:.2f} GB",
+                   "l2": "inputs larger than L2 (rotation keys + diagonals >> 126 MB); no flush",
+                   "parallelism": f"{world} independent projections, one per GPU" if world > 1 else "1 GPU",
+                   "max_abs_err_vs_float64": err},
+        "server_ms_per_token": MATVECS_PER_TOKEN / value * 1e3,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_in.nbytes), "d2h_bytes_per_step": int(h_out.nbytes)},
+        "gpu_launches": int(launches),
+        "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "setup_s": t_setup,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    ap.add_argument("--full-diagonals", action="store_true", help="store diagonals on the full ring (12.9+ GB at C3)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-reps", type=int, default=3)
+    ap.add_argument("--verbose", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

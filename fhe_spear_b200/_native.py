@@ -35,6 +35,8 @@ _SIG = {
     "spear_context_stream": (vp, [vp]),
     "spear_timer_start": (C.c_int, [vp]),
     "spear_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
+    "spear_profile_enable": (C.c_int, [vp, C.c_int]),
+    "spear_profile_read": (C.c_int, [vp, f64p, u64p, C.c_int]),
     "spear_pinned_alloc": (C.c_int, [C.c_size_t, vpp]),
     "spear_pinned_free": (None, [vp]),
     "spear_mem_info": (C.c_int, [vp, u64p, u64p]),

@@ -186,6 +186,33 @@ int spear_mem_info(spear_context* ctx, uint64_t* used, uint64_t* reserved) {
     API_END
 }
 
+int spear_profile_enable(spear_context* ctx, int on) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    for (auto& r : c->prof) cudaEventDestroy(r.a), cudaEventDestroy(r.b);
+    c->prof.clear();
+    c->profiling = on != 0;
+    API_END
+}
+int spear_profile_read(spear_context* ctx, double* ms, uint64_t* launches, int classes) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    REQUIRE(classes >= PROF_CLASSES, "profile_read: need room for %d classes", PROF_CLASSES);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < classes; i++) ms[i] = 0, launches[i] = 0;
+    for (auto& r : c->prof) {
+        float t = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&t, r.a, r.b));
+        ms[r.cls] += t, launches[r.cls]++;
+        cudaEventDestroy(r.a), cudaEventDestroy(r.b);
+    }
+    c->prof.clear();
+    API_END
+}
+
 // ---- keys -------------------------------------------------------------------------------------
 int spear_secret_key_create(spear_context* ctx, const uint8_t seed[32], spear_secret_key** out) {
     API_BEGIN

@@ -48,6 +48,14 @@ struct Ctx {
     int limbs_at(int chain_index) const { return chain_index == 0 ? K : L - (chain_index - 1); }
     int chain_of(int l, bool key_level) const { return key_level ? 0 : L - l + 1; }
 
+    // optional per-kernel-class timing (CUDA events on the launching stream), used by bench.py
+    struct ProfRec {
+        int cls;
+        cudaEvent_t a, b;
+    };
+    mutable bool profiling = false;
+    mutable std::vector<ProfRec> prof;
+
     u64* alloc(size_t n_u64) const;   // stream-ordered
     void free(void* p) const;
 };
@@ -121,6 +129,25 @@ struct DiagSet : CtxRef {
     u64* d = nullptr;  // [D][l+P][n]
     ~DiagSet() {
         if (d && ctx) ctx->free(d);
+    }
+};
+
+enum { PROF_KS_INNER = 0, PROF_PMAC = 1, PROF_NTT = 2, PROF_MODUP = 3, PROF_MODDOWN = 4, PROF_RESCALE = 5,
+       PROF_OTHER = 6, PROF_CLASSES = 7 };
+struct ProfScope {   // brackets the launches of one kernel class with an event pair when profiling is on
+    const Ctx* c;
+    cudaStream_t s;
+    cudaEvent_t b = nullptr;
+    ProfScope(const Ctx* c_, int cls, cudaStream_t s_) : c(c_), s(s_) {
+        if (!c->profiling) return;
+        cudaEvent_t a;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, s);
+        c->prof.push_back({cls, a, b});
+    }
+    ~ProfScope() {
+        if (b) cudaEventRecord(b, s);
     }
 };
 

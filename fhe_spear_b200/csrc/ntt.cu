@@ -180,6 +180,7 @@ void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream
     int sA, sB;
     split(logn, sA, sB);
     NttTab tb = c->ntttab();
+    ProfScope ps(c, PROF_NTT, s);
     if (sA > 0) {
         dim3 grid((n >> sA) / COLS, rows);
         LAUNCH(ntt_fwd_a, grid, TPB, sizeof(u64) * COLS << sA, s)(data, rm, tb, c->N, n, sA, skip_alpha);
@@ -198,6 +199,7 @@ void ntt_inverse(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream
     int sA, sB;
     split(logn, sA, sB);
     NttTab tb = c->ntttab();
+    ProfScope ps(c, PROF_NTT, s);
     int elems = n < B_ELEMS ? n : B_ELEMS;
     dim3 grid(n / elems, rows);
     LAUNCH(ntt_inv_b, grid, TPB, sizeof(u64) * elems, s)(data, rm, tb, c->N, n, sA, sB, logn);

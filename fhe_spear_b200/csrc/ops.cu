@@ -339,9 +339,12 @@ void decompose(const Ctx* c, const u64* cin, int l, u64* x, u64* E, cudaStream_t
     REQUIRE(N % TPB == 0, "N must be a multiple of %d", TPB);
     CUDA_CHECK(cudaMemcpyAsync(x, cin, sizeof(u64) * l * N, cudaMemcpyDeviceToDevice, s));
     ntt_inverse(c, x, l, RowMap{l, l, c->L, 0}, N, s);
-    LAUNCH(k_modup, dim3(N / TPB, beta), TPB, 0, s)(x, cin, E, l, N, c->L, P, c->K, c->modtab(),
+    {
+        ProfScope ps(c, PROF_MODUP, s);
+        LAUNCH(k_modup, dim3(N / TPB, beta), TPB, 0, s)(x, cin, E, l, N, c->L, P, c->K, c->modtab(),
                                                  c->d_up_hatinv + (size_t)l * c->beta * P,
                                                  c->d_up_hat + (size_t)l * c->beta * P * c->K);
+    }
     ntt_forward(c, E, beta * rows, RowMap{rows, l, c->L, 0}, N, s, P);
     CUDA_CHECK(cudaGetLastError());
 }
@@ -352,6 +355,7 @@ void ks_inner(const Ctx* c, const u64* E, const u64* key, u64* out, int l, u32 e
     a.E = E, a.key = key, a.out = out, a.addp = addp, a.add_rows = add_rows, a.add_pscale = add_pscale;
     a.accumulate = accumulate, a.beta = c->digits(l), a.l = l, a.rows = l + c->P, a.N = c->N, a.logn = c->logn;
     a.L = c->L, a.K = c->K, a.elt = elt;
+    ProfScope ps(c, PROF_KS_INNER, s);
     LAUNCH(k_ks_inner, dim3(c->N / TPB, a.rows), TPB, 0, s)(a, c->modtab(), c->d_pmod);
     CUDA_CHECK(cudaGetLastError());
 }
@@ -368,9 +372,13 @@ void moddown(const Ctx* c, u64* in, size_t in_pstride, int polys, int l, u64* tm
     const int N = c->N, P = c->P;
     for (int p = 0; p < polys; p++)
         ntt_inverse(c, in + (size_t)p * in_pstride + (size_t)l * N, P, RowMap{P, 0, c->L, 0}, N, s);
-    LAUNCH(k_moddown_conv, dim3(N / TPB, polys), TPB, 0, s)(in, tmp, l, N, c->L, P, c->K, in_pstride, c->modtab(),
+    {
+        ProfScope ps(c, PROF_MODDOWN, s);
+        LAUNCH(k_moddown_conv, dim3(N / TPB, polys), TPB, 0, s)(in, tmp, l, N, c->L, P, c->K, in_pstride, c->modtab(),
                                                          c->d_dn_hatinv, c->d_dn_half, c->d_dn_hat);
+    }
     ntt_forward(c, tmp, polys * l, RowMap{l, l, c->L, 0}, N, s);
+    ProfScope ps(c, PROF_MODDOWN, s);
     LAUNCH(k_moddown_final, grid_for(c, (size_t)polys * l * N), TPB, 0, s)(in, tmp, add, out, polys, l, N, in_pstride,
                                                                        c->modtab(), c->d_pinv);
     CUDA_CHECK(cudaGetLastError());
@@ -394,6 +402,7 @@ void pmac_list(const Ctx* c, const u64* const* baby, const u64* const* pt, int n
     REQUIRE(nb <= 128, "at most 128 baby steps per giant group");
     PmacPtrs p;
     for (int b = 0; b < nb; b++) p.baby[b] = baby[b], p.pt[b] = pt[b];
+    ProfScope ps(c, PROF_PMAC, s);
     LAUNCH(k_pmac_list, dim3(c->N / TPB, l), TPB, 0, s)(p, nb, out, l, c->N, c->modtab());
     CUDA_CHECK(cudaGetLastError());
 }
@@ -404,6 +413,7 @@ void pmac_hoisted(const Ctx* c, const u64* Y, const u64* diag, u64* A, int G, in
     size_t smem = sizeof(u64) * (size_t)G * 2 * PM_TILE;
     REQUIRE(smem <= 227 * 1024, "too many baby steps (%d) for the shared-memory tile", G);
     REQUIRE(c->N % PM_TILE == 0, "N must be a multiple of %d", PM_TILE);
+    ProfScope ps(c, PROF_PMAC, s);
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_CHECK(cudaFuncSetAttribute(k_pmac_hoisted, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

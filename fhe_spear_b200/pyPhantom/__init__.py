@@ -165,6 +165,18 @@ class context:
         _check(_lib.spear_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
+    PROFILE_CLASSES = ("ks_inner", "pmac", "ntt", "modup", "moddown", "rescale", "other")
+
+    def profile(self, on=True):
+        """Bracket every launch of each kernel class with a CUDA event pair (bench.py roofline line)."""
+        _check(_lib.spear_profile_enable(self._h, int(bool(on))))
+
+    def profile_read(self):
+        n = len(self.PROFILE_CLASSES)
+        ms, cnt = (C.c_double * n)(), (C.c_uint64 * n)()
+        _check(_lib.spear_profile_read(self._h, ms, cnt, n))
+        return {k: {"ms": ms[i], "launches": int(cnt[i])} for i, k in enumerate(self.PROFILE_CLASSES)}
+
     def mem_info(self):
         u, r = C.c_uint64(), C.c_uint64()
         _check(_lib.spear_mem_info(self._h, C.byref(u), C.byref(r)))
@@ -225,6 +237,20 @@ class _obj:
                                      float(scale), C.byref(h)))
         ctx.synchronize()   # arr may be pageable and freed by the caller
         return cls(ctx, h)
+
+
+def pinned_empty(shape, dtype=np.uint64):
+    """numpy array over page-locked host memory (host legs of the end-to-end path)."""
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    _check(_lib.spear_pinned_alloc(nbytes, C.byref(p)))
+    buf = (C.c_char * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    _pinned_keepalive.append((p, buf))
+    return arr
+
+
+_pinned_keepalive = []
 
 
 class plaintext(_obj):

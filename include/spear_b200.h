@@ -57,6 +57,10 @@ void* spear_context_stream(spear_context* ctx);   /* cudaStream_t */
 /* device-side timing on the context stream (CUDA events) */
 int spear_timer_start(spear_context* ctx);
 int spear_timer_stop(spear_context* ctx, float* elapsed_ms);
+/* per-kernel-class device timing (event pair around every launch of the class) for the roofline line:
+ * classes 0 key-switch inner product, 1 diagonal MAC, 2 NTT/INTT, 3 ModUp, 4 ModDown, 5 rescale, 6 other */
+int spear_profile_enable(spear_context* ctx, int on);
+int spear_profile_read(spear_context* ctx, double* ms, uint64_t* launches, int classes);
 /* pinned host buffers for the host<->device legs of the end-to-end path */
 int spear_pinned_alloc(size_t bytes, void** out);
 void spear_pinned_free(void* p);

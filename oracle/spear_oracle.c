@@ -639,6 +639,7 @@ static void moddown_poly(const orc_ctx *c, int l, const u64 *in, u64 *out) {
         for (int k2 = 0; k2 < P; k2++) if (k2 != k) h = mulmod(h, c->q[L + k2] % pk, pk);
         hatinv[k] = invmod(h, pk);
     }
+    #pragma omp parallel for schedule(static)
     for (int k = 0; k < P; k++) {
         u64 pk = c->q[L + k];
         memcpy(sp + (u64)k * N, in + (u64)(l + k) * N, sizeof(u64) * N);
@@ -690,6 +691,7 @@ void orc_keyswitch(const orc_ctx *c, int l, const u64 *cin, const u64 *key, u64 
 void orc_apply_galois(const orc_ctx *c, int l, const u64 *ct, u32 elt, const u64 *key, u64 *out) {
     u64 N = c->N;
     u64 *p0 = (u64 *)malloc(sizeof(u64) * N * l), *p1 = (u64 *)malloc(sizeof(u64) * N * l);
+    #pragma omp parallel for schedule(static)
     for (int i = 0; i < l; i++) {
         orc_apply_galois_ntt(c, elt, ct + (u64)i * N, p0 + (u64)i * N);
         orc_apply_galois_ntt(c, elt, ct + ((u64)l + i) * N, p1 + (u64)i * N);
@@ -780,14 +782,17 @@ void orc_rescale(const orc_ctx *c, int l, int size, const u64 *ct, u64 *out) {
 }
 /* element-wise helpers on [rows][N] blocks whose row r has limb id r (data limbs) */
 void orc_add(const orc_ctx *c, int rows_per_poly, int polys, const u64 *a, const u64 *b, u64 *o) {
+    #pragma omp parallel for schedule(static) collapse(2)
     for (int p = 0; p < polys; p++) for (int i = 0; i < rows_per_poly; i++) for (u64 n = 0; n < c->N; n++) {
         u64 k = ((u64)p * rows_per_poly + i) * c->N + n; o[k] = addmod(a[k], b[k], c->q[i]); }
 }
 void orc_sub(const orc_ctx *c, int rows_per_poly, int polys, const u64 *a, const u64 *b, u64 *o) {
+    #pragma omp parallel for schedule(static) collapse(2)
     for (int p = 0; p < polys; p++) for (int i = 0; i < rows_per_poly; i++) for (u64 n = 0; n < c->N; n++) {
         u64 k = ((u64)p * rows_per_poly + i) * c->N + n; o[k] = submod(a[k], b[k], c->q[i]); }
 }
 void orc_multiply_plain(const orc_ctx *c, int l, int polys, const u64 *ct, const u64 *pt, u64 *o) {
+    #pragma omp parallel for schedule(static) collapse(2)
     for (int p = 0; p < polys; p++) for (int i = 0; i < l; i++) for (u64 n = 0; n < c->N; n++) {
         u64 k = ((u64)p * l + i) * c->N + n; o[k] = mulmod(ct[k], pt[(u64)i * c->N + n], c->q[i]); }
 }
