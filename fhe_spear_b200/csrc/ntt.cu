@@ -165,6 +165,287 @@ __global__ void __launch_bounds__(TPB) ntt_inv_a(u64* __restrict__ data, RowMap 
         base[(size_t)(e / COLS) * S + c0 + (e % COLS)] = mul_shoup(sm[e], ninv.x, ninv.y, q);
 }
 
+
+// =============================================================================================
+// v2 kernels (n >= 2048): every thread keeps 8 coefficients in registers and runs up to three
+// butterfly stages per shared-memory exchange.
+//   pass B: one warp owns one 256-coefficient chunk (8 stages = 3 + 2 + 3), all exchanges are
+//           intra-warp (__syncwarp only) through an XOR-swizzled, bank-conflict-free layout;
+//           global loads and stores are fully coalesced (lane j touches j + 32k).
+//   pass A: a CTA owns a [2^SA rows][16 columns] tile; lanes run along the columns so every
+//           shared/global access is a contiguous 128-byte row segment.
+// =============================================================================================
+constexpr int WB = 4;   // warps (= chunks) per pass-B CTA
+
+__device__ __forceinline__ int swz(int x) { return x ^ (((x >> 4) & 7) | ((x >> 2) & 8)); }
+
+__global__ void __launch_bounds__(WB * 32) ntt_fwd_b2(u64* __restrict__ data, RowMap rm, NttTab tb, int N, int n,
+                                                       int sA, int skip_alpha) {
+    __shared__ u64 smem[WB][256];
+    const int row = blockIdx.y;
+    const int limb = rm.limb(row);
+    if (skip_alpha && limb < rm.L && limb / skip_alpha == row / rm.rpp) return;
+    const u64 q = tb.q[limb], q2 = q << 1;
+    const ulonglong2* __restrict__ tw = tb.psi + (size_t)limb * N;
+    const int warp = threadIdx.x >> 5, j = threadIdx.x & 31;
+    const int gc = blockIdx.x * WB + warp;
+    u64* base = data + (size_t)row * n + (size_t)gc * 256;
+    u64* s = smem[warp];
+    u64 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = base[j + 32 * k];
+    int m = 1 << sA;
+    {   // x = j + 32k ; t = 128, 64, 32
+        ulonglong2 w = tw[m + gc];
+#pragma unroll
+        for (int k = 0; k < 4; k++) ct_butterfly(v[k], v[k + 4], w, q, q2);
+        m <<= 1;
+        ulonglong2 w0 = tw[m + 2 * gc], w1 = tw[m + 2 * gc + 1];
+        ct_butterfly(v[0], v[2], w0, q, q2), ct_butterfly(v[1], v[3], w0, q, q2);
+        ct_butterfly(v[4], v[6], w1, q, q2), ct_butterfly(v[5], v[7], w1, q, q2);
+        m <<= 1;
+#pragma unroll
+        for (int k = 0; k < 4; k++) ct_butterfly(v[2 * k], v[2 * k + 1], tw[m + 4 * gc + k], q, q2);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[swz(j + 32 * k)] = v[k];
+    __syncwarp();
+    {   // x = 32*blk + b + 8i ; t = 16, 8
+        const int bh = j >> 3, b = j & 7;
+        m <<= 1;
+#pragma unroll
+        for (int qd = 0; qd < 2; qd++) {
+            const int blk = bh + 4 * qd;
+            u64* e = v + 4 * qd;
+#pragma unroll
+            for (int i = 0; i < 4; i++) e[i] = s[swz(32 * blk + b + 8 * i)];
+            ulonglong2 w = tw[m + 8 * gc + blk];
+            ct_butterfly(e[0], e[2], w, q, q2), ct_butterfly(e[1], e[3], w, q, q2);
+            ulonglong2 wa = tw[2 * m + 16 * gc + 2 * blk], wb = tw[2 * m + 16 * gc + 2 * blk + 1];
+            ct_butterfly(e[0], e[1], wa, q, q2), ct_butterfly(e[2], e[3], wb, q, q2);
+#pragma unroll
+            for (int i = 0; i < 4; i++) s[swz(32 * blk + b + 8 * i)] = e[i];
+        }
+        m <<= 1;
+    }
+    __syncwarp();
+    {   // x = 8j + i ; t = 4, 2, 1
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = s[swz(8 * j + i)];
+        m <<= 1;
+        ulonglong2 w = tw[m + 32 * gc + j];
+#pragma unroll
+        for (int k = 0; k < 4; k++) ct_butterfly(v[k], v[k + 4], w, q, q2);
+        m <<= 1;
+        ulonglong2 w0 = tw[m + 64 * gc + 2 * j], w1 = tw[m + 64 * gc + 2 * j + 1];
+        ct_butterfly(v[0], v[2], w0, q, q2), ct_butterfly(v[1], v[3], w0, q, q2);
+        ct_butterfly(v[4], v[6], w1, q, q2), ct_butterfly(v[5], v[7], w1, q, q2);
+        m <<= 1;
+#pragma unroll
+        for (int k = 0; k < 4; k++) ct_butterfly(v[2 * k], v[2 * k + 1], tw[m + 128 * gc + 4 * j + k], q, q2);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            u64 x = v[i];
+            x = x >= q2 ? x - q2 : x;
+            s[swz(8 * j + i)] = x >= q ? x - q : x;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; k++) base[j + 32 * k] = s[swz(j + 32 * k)];
+}
+
+__global__ void __launch_bounds__(WB * 32) ntt_inv_b2(u64* __restrict__ data, RowMap rm, NttTab tb, int N, int n,
+                                                       int sA, int logn) {
+    __shared__ u64 smem[WB][256];
+    const int row = blockIdx.y;
+    const int limb = rm.limb(row);
+    const u64 q = tb.q[limb], q2 = q << 1;
+    const ulonglong2* __restrict__ tw = tb.ipsi + (size_t)limb * N;
+    const int warp = threadIdx.x >> 5, j = threadIdx.x & 31;
+    const int gc = blockIdx.x * WB + warp;
+    u64* base = data + (size_t)row * n + (size_t)gc * 256;
+    u64* s = smem[warp];
+    u64 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[swz(j + 32 * k)] = base[j + 32 * k];
+    __syncwarp();
+    {   // x = 8j + i ; t = 1, 2, 4
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = s[swz(8 * j + i)];
+        int h = n >> 1;
+#pragma unroll
+        for (int k = 0; k < 4; k++) gs_butterfly(v[2 * k], v[2 * k + 1], tw[h + 128 * gc + 4 * j + k], q, q2);
+        h >>= 1;
+        ulonglong2 w0 = tw[h + 64 * gc + 2 * j], w1 = tw[h + 64 * gc + 2 * j + 1];
+        gs_butterfly(v[0], v[2], w0, q, q2), gs_butterfly(v[1], v[3], w0, q, q2);
+        gs_butterfly(v[4], v[6], w1, q, q2), gs_butterfly(v[5], v[7], w1, q, q2);
+        h >>= 1;
+        ulonglong2 w = tw[h + 32 * gc + j];
+#pragma unroll
+        for (int k = 0; k < 4; k++) gs_butterfly(v[k], v[k + 4], w, q, q2);
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[swz(8 * j + i)] = v[i];
+    }
+    __syncwarp();
+    {   // x = 32*blk + b + 8i ; t = 8, 16
+        const int bh = j >> 3, b = j & 7;
+        const int h8 = n >> 4, h16 = n >> 5;
+#pragma unroll
+        for (int qd = 0; qd < 2; qd++) {
+            const int blk = bh + 4 * qd;
+            u64* e = v + 4 * qd;
+#pragma unroll
+            for (int i = 0; i < 4; i++) e[i] = s[swz(32 * blk + b + 8 * i)];
+            ulonglong2 wa = tw[h8 + 16 * gc + 2 * blk], wb = tw[h8 + 16 * gc + 2 * blk + 1];
+            gs_butterfly(e[0], e[1], wa, q, q2), gs_butterfly(e[2], e[3], wb, q, q2);
+            ulonglong2 w = tw[h16 + 8 * gc + blk];
+            gs_butterfly(e[0], e[2], w, q, q2), gs_butterfly(e[1], e[3], w, q, q2);
+#pragma unroll
+            for (int i = 0; i < 4; i++) s[swz(32 * blk + b + 8 * i)] = e[i];
+        }
+    }
+    __syncwarp();
+    {   // x = j + 32k ; t = 32, 64, 128
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = s[swz(j + 32 * k)];
+        int h = n >> 6;
+#pragma unroll
+        for (int k = 0; k < 4; k++) gs_butterfly(v[2 * k], v[2 * k + 1], tw[h + 4 * gc + k], q, q2);
+        h >>= 1;
+        ulonglong2 w0 = tw[h + 2 * gc], w1 = tw[h + 2 * gc + 1];
+        gs_butterfly(v[0], v[2], w0, q, q2), gs_butterfly(v[1], v[3], w0, q, q2);
+        gs_butterfly(v[4], v[6], w1, q, q2), gs_butterfly(v[5], v[7], w1, q, q2);
+        h >>= 1;
+        ulonglong2 w = tw[h + gc];
+#pragma unroll
+        for (int k = 0; k < 4; k++) gs_butterfly(v[k], v[k + 4], w, q, q2);
+    }
+    if (sA == 0) {
+        ulonglong2 ninv = tb.invn[limb * 17 + logn];
+#pragma unroll
+        for (int k = 0; k < 8; k++) base[j + 32 * k] = mul_shoup(v[k], ninv.x, ninv.y, q);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) base[j + 32 * k] = v[k];
+    }
+}
+
+// pass A, forward: SA stages on a [R = 2^SA][16] tile, 2R threads, thread = (column c, row group g)
+template <int SA>
+__global__ void __launch_bounds__(2 << SA) ntt_fwd_a2(u64* __restrict__ data, RowMap rm, NttTab tb, int N, int n,
+                                                       int skip_alpha) {
+    constexpr int R = 1 << SA;
+    __shared__ u64 sm[R * COLS];
+    const int row = blockIdx.y;
+    const int limb = rm.limb(row);
+    if (skip_alpha && limb < rm.L && limb / skip_alpha == row / rm.rpp) return;
+    const u64 q = tb.q[limb], q2 = q << 1;
+    const ulonglong2* __restrict__ tw = tb.psi + (size_t)limb * N;
+    const int c = threadIdx.x & (COLS - 1), g = threadIdx.x >> 4;
+    const int S = n >> SA;
+    u64* base = data + (size_t)row * n + blockIdx.x * COLS + c;
+    u64 v[8];
+#pragma unroll
+    for (int s0 = 0; s0 < SA; s0 += 3) {
+        const int ns = (SA - s0) < 3 ? (SA - s0) : 3;
+        const int gbot = R >> (s0 + ns);                 // smallest row gap of this round
+        const int rowbase = (g / gbot) * (8 * gbot) + (g % gbot);
+        if (s0 == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = base[(size_t)(rowbase + k * gbot) * S];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = sm[(rowbase + k * gbot) * COLS + c];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            if (i < ns) {
+                const int st = s0 + i, kgap = 1 << (ns - 1 - i);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (!(k & kgap)) {
+                        const int r = rowbase + k * gbot;
+                        ct_butterfly(v[k], v[k + kgap], tw[(1 << st) + (r >> (SA - st))], q, q2);
+                    }
+                }
+            }
+        }
+        if (s0 + 3 >= SA) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) base[(size_t)(rowbase + k * gbot) * S] = v[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) sm[(rowbase + k * gbot) * COLS + c] = v[k];
+            __syncthreads();
+        }
+    }
+}
+
+// pass A, inverse: row gaps 1, 2, ..., R/2, then n^-1
+template <int SA>
+__global__ void __launch_bounds__(2 << SA) ntt_inv_a2(u64* __restrict__ data, RowMap rm, NttTab tb, int N, int n,
+                                                       int logn) {
+    constexpr int R = 1 << SA;
+    __shared__ u64 sm[R * COLS];
+    const int row = blockIdx.y;
+    const int limb = rm.limb(row);
+    const u64 q = tb.q[limb], q2 = q << 1;
+    const ulonglong2* __restrict__ tw = tb.ipsi + (size_t)limb * N;
+    const int c = threadIdx.x & (COLS - 1), g = threadIdx.x >> 4;
+    const int S = n >> SA;
+    u64* base = data + (size_t)row * n + blockIdx.x * COLS + c;
+    const ulonglong2 ninv = tb.invn[limb * 17 + logn];
+    u64 v[8];
+    // a partial round (SA % 3 stages) comes first, where the 8 rows of a thread are contiguous
+    constexpr int NS0 = (SA % 3) ? (SA % 3) : 3;
+#pragma unroll
+    for (int u0 = 0; u0 < SA; u0 += (u0 == 0 ? NS0 : 3)) {
+        const int ns = u0 == 0 ? NS0 : 3;
+        const int gs = 1 << u0;                           // smallest row gap of this round
+        const int rowbase = (g / gs) * (8 * gs) + (g % gs);
+        if (u0 == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = base[(size_t)(rowbase + k * gs) * S];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = sm[(rowbase + k * gs) * COLS + c];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            if (i < ns) {
+                const int u = u0 + i, kgap = 1 << i;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (!(k & kgap)) {
+                        const int r = rowbase + k * gs;
+                        gs_butterfly(v[k], v[k + kgap], tw[(R >> (u + 1)) + (r >> (u + 1))], q, q2);
+                    }
+                }
+            }
+        }
+        if (u0 + ns >= SA) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) base[(size_t)(rowbase + k * gs) * S] = mul_shoup(v[k], ninv.x, ninv.y, q);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) sm[(rowbase + k * gs) * COLS + c] = v[k];
+            __syncthreads();
+        }
+    }
+}
+
+template <int SA>
+void launch_fwd_a2(u64* data, int rows, RowMap rm, NttTab tb, int N, int n, int skip_alpha, cudaStream_t s) {
+    dim3 grid((n >> SA) / COLS, rows);
+    LAUNCH(ntt_fwd_a2<SA>, grid, 2 << SA, 0, s)(data, rm, tb, N, n, skip_alpha);
+}
+template <int SA>
+void launch_inv_a2(u64* data, int rows, RowMap rm, NttTab tb, int N, int n, int logn, cudaStream_t s) {
+    dim3 grid((n >> SA) / COLS, rows);
+    LAUNCH(ntt_inv_a2<SA>, grid, 2 << SA, 0, s)(data, rm, tb, N, n, logn);
+}
+
 inline void split(int logn, int& sA, int& sB) {
     sB = logn < 8 ? logn : 8;
     sA = logn - sB;
@@ -181,6 +462,19 @@ void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream
     split(logn, sA, sB);
     NttTab tb = c->ntttab();
     ProfScope ps(c, PROF_NTT, s);
+    if (sA >= 3) {   // n >= 2048: register-tiled kernels
+        switch (sA) {
+            case 3: launch_fwd_a2<3>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
+            case 4: launch_fwd_a2<4>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
+            case 5: launch_fwd_a2<5>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
+            case 6: launch_fwd_a2<6>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
+            case 7: launch_fwd_a2<7>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
+            default: launch_fwd_a2<8>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
+        }
+        LAUNCH(ntt_fwd_b2, dim3(n / (256 * WB), rows), WB * 32, 0, s)(data, rm, tb, c->N, n, sA, skip_alpha);
+        CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     if (sA > 0) {
         dim3 grid((n >> sA) / COLS, rows);
         LAUNCH(ntt_fwd_a, grid, TPB, sizeof(u64) * COLS << sA, s)(data, rm, tb, c->N, n, sA, skip_alpha);
@@ -200,6 +494,19 @@ void ntt_inverse(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream
     split(logn, sA, sB);
     NttTab tb = c->ntttab();
     ProfScope ps(c, PROF_NTT, s);
+    if (sA >= 3) {
+        LAUNCH(ntt_inv_b2, dim3(n / (256 * WB), rows), WB * 32, 0, s)(data, rm, tb, c->N, n, sA, logn);
+        switch (sA) {
+            case 3: launch_inv_a2<3>(data, rows, rm, tb, c->N, n, logn, s); break;
+            case 4: launch_inv_a2<4>(data, rows, rm, tb, c->N, n, logn, s); break;
+            case 5: launch_inv_a2<5>(data, rows, rm, tb, c->N, n, logn, s); break;
+            case 6: launch_inv_a2<6>(data, rows, rm, tb, c->N, n, logn, s); break;
+            case 7: launch_inv_a2<7>(data, rows, rm, tb, c->N, n, logn, s); break;
+            default: launch_inv_a2<8>(data, rows, rm, tb, c->N, n, logn, s); break;
+        }
+        CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     int elems = n < B_ELEMS ? n : B_ELEMS;
     dim3 grid(n / elems, rows);
     LAUNCH(ntt_inv_b, grid, TPB, sizeof(u64) * elems, s)(data, rm, tb, c->N, n, sA, sB, logn);

@@ -44,7 +44,7 @@ def test_ntt_matches_oracle(S, G_):
         assert np.array_equal(back, a)
 
 
-@pytest.mark.parametrize("N", [4096, 32768, 65536])
+@pytest.mark.parametrize("N", [4096, 8192, 16384, 32768, 65536])
 def test_ntt_large_sizes(N):
     import ctypes as C
     from fhe_spear_b200 import _native as n
