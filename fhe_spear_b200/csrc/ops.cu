@@ -6,6 +6,8 @@
 // diagonals) loaded with L1::no_allocate/L2::evict_first so the reused operands (decomposed digits,
 // baby ciphertexts) stay L2-resident.  Sums of products are accumulated lazily in 128 bits and
 // reduced once (Barrett-128).
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "engine.h"
 #include "ops.h"
 
@@ -297,6 +299,82 @@ __global__ void __launch_bounds__(PM_TILE) k_pmac_hoisted(const u64* __restrict_
     }
 }
 
+
+// ---- plaintext-diagonal multiply-accumulate, TMA-staged (sub-ring compressed diagonals) -------------
+// Same contraction as k_pmac_hoisted.  A CTA owns (row r, 128 coefficients); thread = (polynomial p,
+// coefficient i).  The G baby tiles sit in shared memory for the whole kernel; for every giant group g
+// one TMA box [G diagonals][1 row][128 >> rshift values] (UTMALDG, 3-stage mbarrier ring) brings the
+// diagonal values, so each diagonal byte crosses HBM->SM once and the MAC loop only touches shared memory.
+constexpr int PM_STAGES = 3;
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(bar)),
+                 "r"(bytes));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, u32 parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"((u32)__cvta_generic_to_shared(bar)),
+        "r"(parity));
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            (u32)__cvta_generic_to_shared(dst)),
+        "l"(map), "r"((u32)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(2 * PM_TILE) k_pmac_tma(const __grid_constant__ CUtensorMap tmap,
+                                                           const u64* __restrict__ Y, u64* __restrict__ A, int G,
+                                                           int Beff, int l, int rows, int N, int L, int rshift, ModTab mt) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const int W = PM_TILE >> rshift;                      // diagonal values per tile row
+    u64* dsm = reinterpret_cast<u64*>(smraw);             // [PM_STAGES][G][W]
+    u64* ysm = dsm + (size_t)PM_STAGES * G * W;           // [G][2][PM_TILE]
+    uint64_t* full = reinterpret_cast<uint64_t*>(ysm + (size_t)G * 2 * PM_TILE);
+    const int tid = threadIdx.x, p = tid / PM_TILE, i = tid % PM_TILE;
+    const int r = blockIdx.y, n0 = blockIdx.x * PM_TILE;
+    const int t = r < l ? r : L + (r - l);
+    const u32 stage_bytes = (u32)G * W * sizeof(u64);
+    if (tid == 0) {
+        for (int s = 0; s < PM_STAGES; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < PM_STAGES && s < Beff; s++) {
+            mbar_expect_tx(&full[s], stage_bytes);
+            tma_load_3d(dsm + (size_t)s * G * W, &tmap, n0 >> rshift, r, s * G, &full[s]);
+        }
+    }
+    const size_t pw = (size_t)rows * N, off = (size_t)r * N + n0 + i;
+    for (int b = 0; b < G; b++) ysm[(b * 2 + p) * PM_TILE + i] = Y[(size_t)(b * 2 + p) * pw + off];
+    const u64 q = mt.q[t], r0 = mt.ratio0[t], r1 = mt.ratio1[t];
+    const u64* ycol = ysm + p * PM_TILE + i;
+    for (int g = 0; g < Beff; g++) {
+        const int s = g % PM_STAGES;
+        mbar_wait(&full[s], (g / PM_STAGES) & 1);
+        const u64* dg = dsm + (size_t)s * G * W + (i >> rshift);
+        u64 lo = 0, hi = 0;
+#pragma unroll 2
+        for (int b = 0; b < G; b++) mac128(lo, hi, ycol[b * 2 * PM_TILE], dg[b * W]);
+        A[(size_t)(g * 2 + p) * pw + off] = barrett128(lo, hi, q, r0, r1);
+        __syncthreads();   // every thread is done with stage s
+        if (tid == 0 && g + PM_STAGES < Beff) {
+            mbar_expect_tx(&full[s], stage_bytes);
+            tma_load_3d(dsm + (size_t)s * G * W, &tmap, n0 >> rshift, r, (g + PM_STAGES) * G, &full[s]);
+        }
+    }
+}
+
 }  // namespace
 
 // ===============================================================================================
@@ -407,14 +485,53 @@ void pmac_list(const Ctx* c, const u64* const* baby, const u64* const* pt, int n
     CUDA_CHECK(cudaGetLastError());
 }
 
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st));
+        REQUIRE(p && st == cudaDriverEntryPointSuccess, "CUDA driver does not provide cuTensorMapEncodeTiled");
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
 void pmac_hoisted(const Ctx* c, const u64* Y, const u64* diag, u64* A, int G, int B, int D, int l, int rshift,
                   cudaStream_t s) {
-    const int rows = l + c->P;
+    const int rows = l + c->P, dn = c->N >> rshift, W = PM_TILE >> rshift;
+    REQUIRE(c->N % PM_TILE == 0, "N must be a multiple of %d", PM_TILE);
+    const size_t tma_smem = sizeof(u64) * ((size_t)PM_STAGES * G * W + (size_t)G * 2 * PM_TILE) + 64;
+    ProfScope ps(c, PROF_PMAC, s);
+    if (rshift >= 1 && W * sizeof(u64) >= 16 && ((size_t)G * W * sizeof(u64)) % 128 == 0 && G <= 256 &&
+        tma_smem <= 227 * 1024) {
+        CUtensorMap tmap;
+        cuuint64_t dims[3] = {(cuuint64_t)dn, (cuuint64_t)rows, (cuuint64_t)D};
+        cuuint64_t strides[2] = {(cuuint64_t)dn * sizeof(u64), (cuuint64_t)rows * dn * sizeof(u64)};
+        cuuint32_t box[3] = {(cuuint32_t)W, 1, (cuuint32_t)G};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult rc = encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, (void*)diag, dims, strides, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
+        static bool attr = false;
+        if (!attr) {
+            CUDA_CHECK(cudaFuncSetAttribute(k_pmac_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr = true;
+        }
+        LAUNCH(k_pmac_tma, dim3(c->N / PM_TILE, rows), 2 * PM_TILE, tma_smem, s)(tmap, Y, A, G, B, l, rows, c->N, c->L,
+                                                                                 rshift, c->modtab());
+        CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     size_t smem = sizeof(u64) * (size_t)G * 2 * PM_TILE;
     REQUIRE(smem <= 227 * 1024, "too many baby steps (%d) for the shared-memory tile", G);
-    REQUIRE(c->N % PM_TILE == 0, "N must be a multiple of %d", PM_TILE);
-    ProfScope ps(c, PROF_PMAC, s);
     static bool attr_set = false;
+
     if (!attr_set) {
         CUDA_CHECK(cudaFuncSetAttribute(k_pmac_hoisted, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
