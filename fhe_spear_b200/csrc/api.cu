@@ -715,6 +715,8 @@ int spear_diagset_encode(spear_context* ctx, const double* diags, int D, int G, 
         c->free(full);
     }
     c->free(dv);
+    // the diagonal MAC kernels consume the split-30 storage form (common.cuh)
+    ops::split30_inplace(c, ds->d, (size_t)D * rows * n, false, c->stream);
     *out = reinterpret_cast<spear_diagset*>(ds.release());
     API_END
 }
@@ -734,8 +736,19 @@ int spear_diagset_info(const spear_diagset* d_, int* D, int* G, int* B, int* lim
     API_END
 }
 int spear_diagset_export(const spear_diagset* d_, uint64_t* host, size_t words) {
+    API_BEGIN
     const DiagSet* d = reinterpret_cast<const DiagSet*>(d_);
-    return export_words(d->ctx, d->d, (size_t)d->D * (d->l + d->ctx->P) * d->n, host, words);
+    Ctx* c = d->ctx;
+    use(c);
+    const size_t have = (size_t)d->D * (d->l + c->P) * d->n;
+    REQUIRE(words == have, "export: buffer holds %zu words, diagonal set has %zu", words, have);
+    u64* tmp = c->alloc(have);   // canonical residues for the caller; the resident copy stays split-30
+    CUDA_CHECK(cudaMemcpyAsync(tmp, d->d, sizeof(u64) * have, cudaMemcpyDeviceToDevice, c->stream));
+    ops::split30_inplace(c, tmp, have, true, c->stream);
+    int rc = export_words(c, tmp, have, host, words);
+    c->free(tmp);
+    return rc;
+    API_END
 }
 
 int spear_bsgs_hoisted(spear_context* ctx, const spear_obj* ct_, const spear_diagset* ds_, const spear_galois_keys* gk_,

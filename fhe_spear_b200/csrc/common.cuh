@@ -134,6 +134,35 @@ __device__ __forceinline__ void add128(u64& lo, u64& hi, u64 x) {
         : "l"(x));
 }
 
+// ---- split-30 operands: x = x1 * 2^30 + x0 stored as (x1 << 32) | x0, x0 < 2^30, x1 < 2^30 (q < 2^60) ----
+// Products of 30-bit halves are < 2^60, so IMAD.WIDE can accumulate them in plain 64-bit registers
+// with no carry handling: S0 += a0*b0, S1 += a0*b1 + a1*b0, S2 += a1*b1; the three sums are folded
+// into a 128-bit accumulator every FOLD terms (8 for q < 2^60, 16 for q < 2^59).
+__device__ __forceinline__ u64 split30(u64 x) { return ((x >> 30) << 32) | (x & 0x3FFFFFFFull); }
+__device__ __forceinline__ u64 unsplit30(u64 s) { return ((s >> 32) << 30) | (s & 0xFFFFFFFFull); }
+struct Acc3 {
+    u64 s0, s1, s2;
+};
+__device__ __forceinline__ void mac_split(Acc3& a, u64 xs, u64 ys) {
+    const u32 x0 = (u32)xs, x1 = (u32)(xs >> 32), y0 = (u32)ys, y1 = (u32)(ys >> 32);
+    a.s0 = (u64)x0 * y0 + a.s0;
+    a.s1 = (u64)x0 * y1 + a.s1;
+    a.s1 = (u64)x1 * y0 + a.s1;
+    a.s2 = (u64)x1 * y1 + a.s2;
+}
+// (hi:lo) += s0 + s1 * 2^30 + s2 * 2^60 ; clears the partial sums
+__device__ __forceinline__ void fold_split(u64& lo, u64& hi, Acc3& a) {
+    asm("add.cc.u64 %0, %0, %2;\n\t"
+        "addc.u64 %1, %1, 0;\n\t"
+        "add.cc.u64 %0, %0, %3;\n\t"
+        "addc.u64 %1, %1, %4;\n\t"
+        "add.cc.u64 %0, %0, %5;\n\t"
+        "addc.u64 %1, %1, %6;"
+        : "+l"(lo), "+l"(hi)
+        : "l"(a.s0), "l"(a.s1 << 30), "l"(a.s1 >> 34), "l"(a.s2 << 60), "l"(a.s2 >> 4));
+    a.s0 = a.s1 = a.s2 = 0;
+}
+
 // Galois automorphism x -> x^elt in the bit-reversed NTT domain:
 // out[i] = in[ bitrev( ((elt * (2*bitrev(i)+1) mod 2N) - 1) / 2 ) ].  Aligned blocks of 2^s
 // consecutive indices map onto aligned blocks, so a warp's gather stays inside one 256-byte line pair.

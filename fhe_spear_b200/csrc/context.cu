@@ -133,8 +133,8 @@ Ctx* ctx_create(u64 N, const u64* moduli, int K, int P, int device) {
     c->device = device;
     c->q.assign(moduli, moduli + K);
     for (int i = 0; i < K; i++) {
-        REQUIRE(c->q[i] < (1ull << 61) && (c->q[i] - 1) % (2 * N) == 0 && is_prime(c->q[i]),
-                "modulus %d is not an NTT-friendly prime below 2^61", i);
+        REQUIRE(c->q[i] < (1ull << 60) && (c->q[i] - 1) % (2 * N) == 0 && is_prime(c->q[i]),
+                "modulus %d is not an NTT-friendly prime below 2^60", i);
         for (int j = 0; j < i; j++) REQUIRE(c->q[i] != c->q[j], "duplicate modulus");
     }
     CUDA_CHECK(cudaSetDevice(device));

@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(PM_TILE) k_pmac_hoisted(const u64* __restrict_
         const u64* dgg = dg + (size_t)g * G * dstride;
 #pragma unroll 4
         for (int b = 0; b < nb; b++) {
-            u64 d = ld_stream(dgg + (size_t)b * dstride, pol);
+            u64 d = unsplit30(ld_stream(dgg + (size_t)b * dstride, pol));
             mac128(lo0, hi0, sm[(b * 2 + 0) * PM_TILE + threadIdx.x], d);
             mac128(lo1, hi1, sm[(b * 2 + 1) * PM_TILE + threadIdx.x], d);
         }
@@ -305,7 +305,9 @@ __global__ void __launch_bounds__(PM_TILE) k_pmac_hoisted(const u64* __restrict_
 // coefficient i).  The G baby tiles sit in shared memory for the whole kernel; for every giant group g
 // one TMA box [G diagonals][1 row][128 >> rshift values] (UTMALDG, 3-stage mbarrier ring) brings the
 // diagonal values, so each diagonal byte crosses HBM->SM once and the MAC loop only touches shared memory.
-constexpr int PM_STAGES = 3;
+constexpr int PM_STAGES = 2;
+constexpr int PM_GT = 4;        // giant groups per pipeline stage (register tile over g)
+constexpr int PM_T2 = 64;       // coefficients per CTA
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(bar)), "r"(count));
@@ -332,47 +334,83 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
         : "memory");
 }
 
-__global__ void __launch_bounds__(2 * PM_TILE) k_pmac_tma(const __grid_constant__ CUtensorMap tmap,
-                                                           const u64* __restrict__ Y, u64* __restrict__ A, int G,
-                                                           int Beff, int l, int rows, int N, int L, int rshift, ModTab mt) {
+// A CTA owns (row r, PM_T2 coefficients); thread = (polynomial p, coefficient i) and carries PM_GT giant
+// groups at once, so one shared-memory read of a baby value feeds PM_GT multiply-accumulates.
+// Shared memory: baby tile [Gp][2][PM_T2] in split-30 form (Gp = G rounded up to 8, zero padded), and a
+// PM_STAGES-deep ring of diagonal boxes [PM_GT][Gp][W] filled by TMA (one 3-D box per giant group;
+// groups past the end of the diagonal set are zero-filled by the TMA unit).
+template <int FOLD>
+__global__ void __launch_bounds__(2 * PM_T2) k_pmac_tma(const __grid_constant__ CUtensorMap tmap,
+                                                         const u64* __restrict__ Y, u64* __restrict__ A, int G, int Gp,
+                                                         int Beff, int l, int rows, int N, int L, int rshift, ModTab mt) {
     extern __shared__ __align__(128) unsigned char smraw[];
-    const int W = PM_TILE >> rshift;                      // diagonal values per tile row
-    u64* dsm = reinterpret_cast<u64*>(smraw);             // [PM_STAGES][G][W]
-    u64* ysm = dsm + (size_t)PM_STAGES * G * W;           // [G][2][PM_TILE]
-    uint64_t* full = reinterpret_cast<uint64_t*>(ysm + (size_t)G * 2 * PM_TILE);
-    const int tid = threadIdx.x, p = tid / PM_TILE, i = tid % PM_TILE;
-    const int r = blockIdx.y, n0 = blockIdx.x * PM_TILE;
+    const int W = PM_T2 >> rshift;
+    u64* dsm = reinterpret_cast<u64*>(smraw);                         // [PM_STAGES][PM_GT][Gp][W]
+    u64* ysm = dsm + (size_t)PM_STAGES * PM_GT * Gp * W;              // [Gp][2][PM_T2]
+    uint64_t* full = reinterpret_cast<uint64_t*>(ysm + (size_t)Gp * 2 * PM_T2);
+    const int tid = threadIdx.x, p = tid / PM_T2, i = tid % PM_T2;
+    const int r = blockIdx.y, n0 = blockIdx.x * PM_T2;
     const int t = r < l ? r : L + (r - l);
-    const u32 stage_bytes = (u32)G * W * sizeof(u64);
+    const int iters = (Beff + PM_GT - 1) / PM_GT;
+    const size_t group_words = (size_t)Gp * W, stage_words = PM_GT * group_words;
+    const u32 stage_bytes = (u32)(PM_GT * G * W * sizeof(u64));
     if (tid == 0) {
         for (int s = 0; s < PM_STAGES; s++) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
-    if (tid == 0) {
-        for (int s = 0; s < PM_STAGES && s < Beff; s++) {
-            mbar_expect_tx(&full[s], stage_bytes);
-            tma_load_3d(dsm + (size_t)s * G * W, &tmap, n0 >> rshift, r, s * G, &full[s]);
-        }
+    // zero the padding rows (never written by TMA) and the padded baby rows
+    for (int e = tid; e < PM_STAGES * PM_GT * (Gp - G) * W; e += 2 * PM_T2) {
+        int slot = e / ((Gp - G) * W), rem = e % ((Gp - G) * W);
+        dsm[(size_t)slot * group_words + (size_t)G * W + rem] = 0;
     }
     const size_t pw = (size_t)rows * N, off = (size_t)r * N + n0 + i;
-    for (int b = 0; b < G; b++) ysm[(b * 2 + p) * PM_TILE + i] = Y[(size_t)(b * 2 + p) * pw + off];
+    for (int b = 0; b < Gp; b++)
+        ysm[(b * 2 + p) * PM_T2 + i] = b < G ? split30(Y[(size_t)(b * 2 + p) * pw + off]) : 0;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    auto issue = [&](int it) {
+        const int s = it % PM_STAGES;
+        mbar_expect_tx(&full[s], stage_bytes);
+        for (int k = 0; k < PM_GT; k++)
+            tma_load_3d(dsm + s * stage_words + k * group_words, &tmap, n0 >> rshift, r, (it * PM_GT + k) * G, &full[s]);
+    };
+    if (tid == 0)
+        for (int it = 0; it < PM_STAGES && it < iters; it++) issue(it);
     const u64 q = mt.q[t], r0 = mt.ratio0[t], r1 = mt.ratio1[t];
-    const u64* ycol = ysm + p * PM_TILE + i;
-    for (int g = 0; g < Beff; g++) {
-        const int s = g % PM_STAGES;
-        mbar_wait(&full[s], (g / PM_STAGES) & 1);
-        const u64* dg = dsm + (size_t)s * G * W + (i >> rshift);
-        u64 lo = 0, hi = 0;
-#pragma unroll 2
-        for (int b = 0; b < G; b++) mac128(lo, hi, ycol[b * 2 * PM_TILE], dg[b * W]);
-        A[(size_t)(g * 2 + p) * pw + off] = barrett128(lo, hi, q, r0, r1);
-        __syncthreads();   // every thread is done with stage s
-        if (tid == 0 && g + PM_STAGES < Beff) {
-            mbar_expect_tx(&full[s], stage_bytes);
-            tma_load_3d(dsm + (size_t)s * G * W, &tmap, n0 >> rshift, r, (g + PM_STAGES) * G, &full[s]);
+    const u64* ycol = ysm + p * PM_T2 + i;
+    for (int it = 0; it < iters; it++) {
+        const int s = it % PM_STAGES;
+        mbar_wait(&full[s], (it / PM_STAGES) & 1);
+        const u64* dg = dsm + s * stage_words + (i >> rshift);
+        Acc3 acc[PM_GT];
+        u64 lo[PM_GT], hi[PM_GT];
+#pragma unroll
+        for (int k = 0; k < PM_GT; k++) acc[k].s0 = acc[k].s1 = acc[k].s2 = 0, lo[k] = hi[k] = 0;
+        for (int b0 = 0; b0 < Gp; b0 += FOLD) {
+#pragma unroll
+            for (int j = 0; j < FOLD; j++) {
+                const int b = b0 + j;
+                const u64 y = ycol[b * 2 * PM_T2];
+#pragma unroll
+                for (int k = 0; k < PM_GT; k++) mac_split(acc[k], y, dg[k * group_words + (size_t)b * W]);
+            }
+#pragma unroll
+            for (int k = 0; k < PM_GT; k++) fold_split(lo[k], hi[k], acc[k]);
         }
+#pragma unroll
+        for (int k = 0; k < PM_GT; k++) {
+            const int g = it * PM_GT + k;
+            if (g < Beff) A[(size_t)(g * 2 + p) * pw + off] = barrett128(lo[k], hi[k], q, r0, r1);
+        }
+        __syncthreads();   // every thread is done with stage s
+        if (tid == 0 && it + PM_STAGES < iters) issue(it + PM_STAGES);
     }
+}
+
+// in-place conversion between canonical residues and the split-30 storage form
+__global__ void k_split30(u64* __restrict__ x, size_t n, int unsplit) {
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x)
+        x[e] = unsplit ? unsplit30(x[e]) : split30(x[e]);
 }
 
 }  // namespace
@@ -503,11 +541,12 @@ static EncodeTiledFn encode_tiled() {
 
 void pmac_hoisted(const Ctx* c, const u64* Y, const u64* diag, u64* A, int G, int B, int D, int l, int rshift,
                   cudaStream_t s) {
-    const int rows = l + c->P, dn = c->N >> rshift, W = PM_TILE >> rshift;
+    const int rows = l + c->P, dn = c->N >> rshift, W = PM_T2 >> rshift, Gp = (G + 15) / 16 * 16;
     REQUIRE(c->N % PM_TILE == 0, "N must be a multiple of %d", PM_TILE);
-    const size_t tma_smem = sizeof(u64) * ((size_t)PM_STAGES * G * W + (size_t)G * 2 * PM_TILE) + 64;
+    const size_t tma_smem =
+        sizeof(u64) * ((size_t)PM_STAGES * PM_GT * Gp * W + (size_t)Gp * 2 * PM_T2) + 8 * PM_STAGES + 64;
     ProfScope ps(c, PROF_PMAC, s);
-    if (rshift >= 1 && W * sizeof(u64) >= 16 && ((size_t)G * W * sizeof(u64)) % 128 == 0 && G <= 256 &&
+    if (rshift >= 1 && W * sizeof(u64) >= 16 && ((size_t)Gp * W * sizeof(u64)) % 128 == 0 && G <= 256 &&
         tma_smem <= 227 * 1024) {
         CUtensorMap tmap;
         cuuint64_t dims[3] = {(cuuint64_t)dn, (cuuint64_t)rows, (cuuint64_t)D};
@@ -518,13 +557,20 @@ void pmac_hoisted(const Ctx* c, const u64* Y, const u64* diag, u64* A, int G, in
                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
+        // partial sums of 30x30-bit products: 16 terms fit 64 bits when every q < 2^59, else 8
+        bool small = true;
+        for (u64 qq : c->q) small = small && qq < (1ull << 59);
         static bool attr = false;
         if (!attr) {
-            CUDA_CHECK(cudaFuncSetAttribute(k_pmac_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            CUDA_CHECK(cudaFuncSetAttribute(k_pmac_tma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            CUDA_CHECK(cudaFuncSetAttribute(k_pmac_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             attr = true;
         }
-        LAUNCH(k_pmac_tma, dim3(c->N / PM_TILE, rows), 2 * PM_TILE, tma_smem, s)(tmap, Y, A, G, B, l, rows, c->N, c->L,
-                                                                                 rshift, c->modtab());
+        dim3 grid(c->N / PM_T2, rows);
+        if (small)
+            LAUNCH(k_pmac_tma<16>, grid, 2 * PM_T2, tma_smem, s)(tmap, Y, A, G, Gp, B, l, rows, c->N, c->L, rshift, c->modtab());
+        else
+            LAUNCH(k_pmac_tma<8>, grid, 2 * PM_T2, tma_smem, s)(tmap, Y, A, G, Gp, B, l, rows, c->N, c->L, rshift, c->modtab());
         CUDA_CHECK(cudaGetLastError());
         return;
     }
@@ -538,6 +584,11 @@ void pmac_hoisted(const Ctx* c, const u64* Y, const u64* diag, u64* A, int G, in
     }
     LAUNCH(k_pmac_hoisted, dim3(c->N / PM_TILE, rows), PM_TILE, smem, s)(Y, diag, A, G, B, D, l, rows, c->N, c->L, rshift,
                                                                      c->modtab());
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void split30_inplace(const Ctx* c, u64* x, size_t n, bool unsplit, cudaStream_t s) {
+    LAUNCH(k_split30, grid_for(c, n), TPB, 0, s)(x, n, unsplit ? 1 : 0);
     CUDA_CHECK(cudaGetLastError());
 }
 
