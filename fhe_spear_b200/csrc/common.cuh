@@ -141,17 +141,19 @@ __device__ __forceinline__ void add128(u64& lo, u64& hi, u64 x) {
 __device__ __forceinline__ u64 split30(u64 x) { return ((x >> 30) << 32) | (x & 0x3FFFFFFFull); }
 __device__ __forceinline__ u64 unsplit30(u64 s) { return ((s >> 32) << 30) | (s & 0xFFFFFFFFull); }
 struct Acc3 {
-    u64 s0, s1, s2;
+    u64 s0, s1, s2;   // s1 holds the Karatsuba middle sum  sum (x0+x1)(y0+y1)  (mod 2^64)
 };
-__device__ __forceinline__ void mac_split(Acc3& a, u64 xs, u64 ys) {
-    const u32 x0 = (u32)xs, x1 = (u32)(xs >> 32), y0 = (u32)ys, y1 = (u32)(ys >> 32);
+// three 32x32+64 multiply-adds per term (IMAD.WIDE is the scarce pipe): xs = x0 + x1 is supplied by the caller
+__device__ __forceinline__ void mac_split(Acc3& a, u64 x, u32 xs, u64 y) {
+    const u32 x0 = (u32)x, x1 = (u32)(x >> 32), y0 = (u32)y, y1 = (u32)(y >> 32);
     a.s0 = (u64)x0 * y0 + a.s0;
-    a.s1 = (u64)x0 * y1 + a.s1;
-    a.s1 = (u64)x1 * y0 + a.s1;
     a.s2 = (u64)x1 * y1 + a.s2;
+    a.s1 = (u64)xs * (y0 + y1) + a.s1;
 }
-// (hi:lo) += s0 + s1 * 2^30 + s2 * 2^60 ; clears the partial sums
+// (hi:lo) += s0 + (s1 - s0 - s2) * 2^30 + s2 * 2^60 ; clears the partial sums.  The true middle sum is < 2^64,
+// so the wrapped subtraction is exact.
 __device__ __forceinline__ void fold_split(u64& lo, u64& hi, Acc3& a) {
+    const u64 m = a.s1 - a.s0 - a.s2;
     asm("add.cc.u64 %0, %0, %2;\n\t"
         "addc.u64 %1, %1, 0;\n\t"
         "add.cc.u64 %0, %0, %3;\n\t"
@@ -159,7 +161,7 @@ __device__ __forceinline__ void fold_split(u64& lo, u64& hi, Acc3& a) {
         "add.cc.u64 %0, %0, %5;\n\t"
         "addc.u64 %1, %1, %6;"
         : "+l"(lo), "+l"(hi)
-        : "l"(a.s0), "l"(a.s1 << 30), "l"(a.s1 >> 34), "l"(a.s2 << 60), "l"(a.s2 >> 4));
+        : "l"(a.s0), "l"(m << 30), "l"(m >> 34), "l"(a.s2 << 60), "l"(a.s2 >> 4));
     a.s0 = a.s1 = a.s2 = 0;
 }
 

@@ -339,12 +339,35 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
 // Shared memory: baby tile [Gp][2][PM_T2] in split-30 form (Gp = G rounded up to 8, zero padded), and a
 // PM_STAGES-deep ring of diagonal boxes [PM_GT][Gp][W] filled by TMA (one 3-D box per giant group;
 // groups past the end of the diagonal set are zero-filled by the TMA unit).
-template <int FOLD>
+// NG giant groups of one pipeline stage: A[g0 + k] = sum_b y_b * d_{k,b}
+template <int FOLD, int W, int NG>
+__device__ __forceinline__ void pmac_groups(const u64* __restrict__ ycol, const u64* __restrict__ dg, size_t group_words,
+                                            int Gp, u64* __restrict__ Aout, size_t a_stride, u64 q, u64 r0, u64 r1) {
+    Acc3 acc[NG];
+    u64 lo[NG], hi[NG];
+#pragma unroll
+    for (int k = 0; k < NG; k++) acc[k].s0 = acc[k].s1 = acc[k].s2 = 0, lo[k] = hi[k] = 0;
+    for (int b0 = 0; b0 < Gp; b0 += FOLD) {
+#pragma unroll
+        for (int j = 0; j < FOLD; j++) {
+            const u64 y = ycol[(b0 + j) * 2 * PM_T2];
+            const u32 ys = (u32)y + (u32)(y >> 32);
+#pragma unroll
+            for (int k = 0; k < NG; k++) mac_split(acc[k], y, ys, dg[k * group_words + (size_t)(b0 + j) * W]);
+        }
+#pragma unroll
+        for (int k = 0; k < NG; k++) fold_split(lo[k], hi[k], acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < NG; k++) Aout[k * a_stride] = barrett128(lo[k], hi[k], q, r0, r1);
+}
+
+template <int FOLD, int RSH>
 __global__ void __launch_bounds__(2 * PM_T2) k_pmac_tma(const __grid_constant__ CUtensorMap tmap,
                                                          const u64* __restrict__ Y, u64* __restrict__ A, int G, int Gp,
-                                                         int Beff, int l, int rows, int N, int L, int rshift, ModTab mt) {
+                                                         int Beff, int l, int rows, int N, int L, ModTab mt) {
     extern __shared__ __align__(128) unsigned char smraw[];
-    const int W = PM_T2 >> rshift;
+    constexpr int W = PM_T2 >> RSH;
     u64* dsm = reinterpret_cast<u64*>(smraw);                         // [PM_STAGES][PM_GT][Gp][W]
     u64* ysm = dsm + (size_t)PM_STAGES * PM_GT * Gp * W;              // [Gp][2][PM_T2]
     uint64_t* full = reinterpret_cast<uint64_t*>(ysm + (size_t)Gp * 2 * PM_T2);
@@ -353,7 +376,6 @@ __global__ void __launch_bounds__(2 * PM_T2) k_pmac_tma(const __grid_constant__ 
     const int t = r < l ? r : L + (r - l);
     const int iters = (Beff + PM_GT - 1) / PM_GT;
     const size_t group_words = (size_t)Gp * W, stage_words = PM_GT * group_words;
-    const u32 stage_bytes = (u32)(PM_GT * G * W * sizeof(u64));
     if (tid == 0) {
         for (int s = 0; s < PM_STAGES; s++) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -368,40 +390,25 @@ __global__ void __launch_bounds__(2 * PM_T2) k_pmac_tma(const __grid_constant__ 
         ysm[(b * 2 + p) * PM_T2 + i] = b < G ? split30(Y[(size_t)(b * 2 + p) * pw + off]) : 0;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    auto issue = [&](int it) {
-        const int s = it % PM_STAGES;
-        mbar_expect_tx(&full[s], stage_bytes);
-        for (int k = 0; k < PM_GT; k++)
-            tma_load_3d(dsm + s * stage_words + k * group_words, &tmap, n0 >> rshift, r, (it * PM_GT + k) * G, &full[s]);
+    auto issue = [&](int it) {   // only the groups that exist are fetched; expect_tx counts exactly those bytes
+        const int s = it % PM_STAGES, ng = min(PM_GT, Beff - it * PM_GT);
+        mbar_expect_tx(&full[s], (u32)(ng * G * W * sizeof(u64)));
+        for (int k = 0; k < ng; k++)
+            tma_load_3d(dsm + s * stage_words + k * group_words, &tmap, n0 >> RSH, r, (it * PM_GT + k) * G, &full[s]);
     };
     if (tid == 0)
         for (int it = 0; it < PM_STAGES && it < iters; it++) issue(it);
     const u64 q = mt.q[t], r0 = mt.ratio0[t], r1 = mt.ratio1[t];
     const u64* ycol = ysm + p * PM_T2 + i;
     for (int it = 0; it < iters; it++) {
-        const int s = it % PM_STAGES;
+        const int s = it % PM_STAGES, ng = min(PM_GT, Beff - it * PM_GT);
         mbar_wait(&full[s], (it / PM_STAGES) & 1);
-        const u64* dg = dsm + s * stage_words + (i >> rshift);
-        Acc3 acc[PM_GT];
-        u64 lo[PM_GT], hi[PM_GT];
-#pragma unroll
-        for (int k = 0; k < PM_GT; k++) acc[k].s0 = acc[k].s1 = acc[k].s2 = 0, lo[k] = hi[k] = 0;
-        for (int b0 = 0; b0 < Gp; b0 += FOLD) {
-#pragma unroll
-            for (int j = 0; j < FOLD; j++) {
-                const int b = b0 + j;
-                const u64 y = ycol[b * 2 * PM_T2];
-#pragma unroll
-                for (int k = 0; k < PM_GT; k++) mac_split(acc[k], y, dg[k * group_words + (size_t)b * W]);
-            }
-#pragma unroll
-            for (int k = 0; k < PM_GT; k++) fold_split(lo[k], hi[k], acc[k]);
-        }
-#pragma unroll
-        for (int k = 0; k < PM_GT; k++) {
-            const int g = it * PM_GT + k;
-            if (g < Beff) A[(size_t)(g * 2 + p) * pw + off] = barrett128(lo[k], hi[k], q, r0, r1);
-        }
+        const u64* dg = dsm + s * stage_words + (i >> RSH);
+        u64* Aout = A + (size_t)(it * PM_GT * 2 + p) * pw + off;
+        if (ng == PM_GT) pmac_groups<FOLD, W, PM_GT>(ycol, dg, group_words, Gp, Aout, 2 * pw, q, r0, r1);
+        else if (ng == 3) pmac_groups<FOLD, W, 3>(ycol, dg, group_words, Gp, Aout, 2 * pw, q, r0, r1);
+        else if (ng == 2) pmac_groups<FOLD, W, 2>(ycol, dg, group_words, Gp, Aout, 2 * pw, q, r0, r1);
+        else pmac_groups<FOLD, W, 1>(ycol, dg, group_words, Gp, Aout, 2 * pw, q, r0, r1);
         __syncthreads();   // every thread is done with stage s
         if (tid == 0 && it + PM_STAGES < iters) issue(it + PM_STAGES);
     }
@@ -546,7 +553,7 @@ void pmac_hoisted(const Ctx* c, const u64* Y, const u64* diag, u64* A, int G, in
     const size_t tma_smem =
         sizeof(u64) * ((size_t)PM_STAGES * PM_GT * Gp * W + (size_t)Gp * 2 * PM_T2) + 8 * PM_STAGES + 64;
     ProfScope ps(c, PROF_PMAC, s);
-    if (rshift >= 1 && W * sizeof(u64) >= 16 && ((size_t)Gp * W * sizeof(u64)) % 128 == 0 && G <= 256 &&
+    if (rshift >= 1 && rshift <= 5 && W * sizeof(u64) >= 16 && ((size_t)Gp * W * sizeof(u64)) % 128 == 0 && G <= 256 &&
         tma_smem <= 227 * 1024) {
         CUtensorMap tmap;
         cuuint64_t dims[3] = {(cuuint64_t)dn, (cuuint64_t)rows, (cuuint64_t)D};
@@ -560,17 +567,24 @@ void pmac_hoisted(const Ctx* c, const u64* Y, const u64* diag, u64* A, int G, in
         // partial sums of 30x30-bit products: 16 terms fit 64 bits when every q < 2^59, else 8
         bool small = true;
         for (u64 qq : c->q) small = small && qq < (1ull << 59);
-        static bool attr = false;
-        if (!attr) {
-            CUDA_CHECK(cudaFuncSetAttribute(k_pmac_tma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            CUDA_CHECK(cudaFuncSetAttribute(k_pmac_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr = true;
-        }
         dim3 grid(c->N / PM_T2, rows);
-        if (small)
-            LAUNCH(k_pmac_tma<16>, grid, 2 * PM_T2, tma_smem, s)(tmap, Y, A, G, Gp, B, l, rows, c->N, c->L, rshift, c->modtab());
-        else
-            LAUNCH(k_pmac_tma<8>, grid, 2 * PM_T2, tma_smem, s)(tmap, Y, A, G, Gp, B, l, rows, c->N, c->L, rshift, c->modtab());
+        const ModTab mt = c->modtab();
+        auto go = [&](auto kern) {
+            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            LAUNCH(kern, grid, 2 * PM_T2, tma_smem, s)(tmap, Y, A, G, Gp, B, l, rows, c->N, c->L, mt);
+        };
+        switch (rshift * 2 + (small ? 1 : 0)) {
+            case 2: go(k_pmac_tma<8, 1>); break;
+            case 3: go(k_pmac_tma<16, 1>); break;
+            case 4: go(k_pmac_tma<8, 2>); break;
+            case 5: go(k_pmac_tma<16, 2>); break;
+            case 6: go(k_pmac_tma<8, 3>); break;
+            case 7: go(k_pmac_tma<16, 3>); break;
+            case 8: go(k_pmac_tma<8, 4>); break;
+            case 9: go(k_pmac_tma<16, 4>); break;
+            case 10: go(k_pmac_tma<8, 5>); break;
+            default: go(k_pmac_tma<16, 5>); break;
+        }
         CUDA_CHECK(cudaGetLastError());
         return;
     }
