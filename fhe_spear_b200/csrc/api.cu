@@ -89,6 +89,8 @@ KSKey* gen_switch_key(Ctx* c, const SecretKey* sk, u64 tag, const u64* snew) {
         sampler::ksk_combine(c, k1, e, sk->d, snew, j, k0, c->stream);
     }
     c->free(e);
+    // resident keys use the split-30 storage form consumed by the inner-product kernels (common.cuh)
+    ops::split30_inplace(c, key->d, (size_t)c->beta * 2 * K * N, false, c->stream);
     return key.release();
 }
 
@@ -343,15 +345,27 @@ int spear_secret_key_export(const spear_secret_key* sk_, uint64_t* host, size_t 
     const SecretKey* sk = reinterpret_cast<const SecretKey*>(sk_);
     return export_words(sk->ctx, sk->d, (size_t)sk->ctx->K * sk->ctx->N, host, words);
 }
+static int export_key(const KSKey* k, uint64_t* host, size_t words) {
+    API_BEGIN
+    Ctx* c = k->ctx;
+    use(c);
+    const size_t have = (size_t)c->beta * 2 * c->K * c->N;
+    REQUIRE(words == have, "export: buffer holds %zu words, key has %zu", words, have);
+    u64* tmp = c->alloc(have);   // canonical residues for the caller
+    CUDA_CHECK(cudaMemcpyAsync(tmp, k->d, sizeof(u64) * have, cudaMemcpyDeviceToDevice, c->stream));
+    ops::split30_inplace(c, tmp, have, true, c->stream);
+    int rc = export_words(c, tmp, have, host, words);
+    c->free(tmp);
+    return rc;
+    API_END
+}
 int spear_kswitch_key_export(const spear_kswitch_key* k_, uint64_t* host, size_t words) {
-    const KSKey* k = reinterpret_cast<const KSKey*>(k_);
-    return export_words(k->ctx, k->d, (size_t)k->ctx->beta * 2 * k->ctx->K * k->ctx->N, host, words);
+    return export_key(reinterpret_cast<const KSKey*>(k_), host, words);
 }
 int spear_galois_key_export(const spear_galois_keys* gk_, uint32_t elt, uint64_t* host, size_t words) {
     API_BEGIN
     const GaloisKeys* gk = reinterpret_cast<const GaloisKeys*>(gk_);
-    const KSKey* k = find_key(gk, elt);
-    return export_words(k->ctx, k->d, (size_t)k->ctx->beta * 2 * k->ctx->K * k->ctx->N, host, words);
+    return export_key(find_key(gk, elt), host, words);
     API_END
 }
 int spear_public_key_export(const spear_public_key* pk_, uint64_t* host, size_t words) {

@@ -108,8 +108,10 @@ void bsgs_hoisted(const Ctx* c, const u64* ct, int l, const u64* diag, int rshif
     // 1-2. hoisted baby steps, kept in basis Q_l * P
     ops::decompose(c, c1, l, x, E, s);
     ops::pscale(c, ct, Y, l, s);
+    c->l2_pin(s, E, sizeof(u64) * beta * pw);   // the digits are gathered by all G-1 baby kernels
     for (int b = 1; b < G; b++)
         ops::ks_inner(c, E, bkey[b], Y + (size_t)b * 2 * pw, l, belt[b], c0, l, 1, 0, s);
+    c->l2_pin(s, nullptr, 0);
     // 3. diagonal multiply-accumulate for every giant group
     ops::pmac_hoisted(c, Y, diag, A, G, Beff, D, l, rshift, s);
     // 4. giant steps: R (= A[0], in place) += (pi_g(A_g.0) + <pi_g(F), k0>, <pi_g(F), k1>)

@@ -3,6 +3,7 @@
 // gpu/phantom_binding.cu:81-98 of the reference (create_coeff_modulus, params, context).
 #include <cmath>
 #include <cstdarg>
+#include <algorithm>
 #include <cstring>
 
 #include "engine.h"
@@ -117,6 +118,19 @@ u64* Ctx::alloc(size_t n_u64) const {
     CUDA_CHECK(cudaMallocAsync(&p, sizeof(u64) * (n_u64 ? n_u64 : 1), stream));
     return (u64*)p;
 }
+void Ctx::l2_pin(cudaStream_t s, const void* p, size_t bytes) const {
+    if (!l2_persist_max || !l2_window_max) return;
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof v);
+    size_t win = bytes < l2_window_max ? bytes : l2_window_max;
+    v.accessPolicyWindow.base_ptr = const_cast<void*>(p);
+    v.accessPolicyWindow.num_bytes = win;
+    v.accessPolicyWindow.hitRatio = bytes ? (float)std::min(1.0, (double)l2_persist_max / (double)std::max<size_t>(win, 1)) : 0.f;
+    v.accessPolicyWindow.hitProp = bytes ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
+    v.accessPolicyWindow.missProp = bytes ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
+    cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v);
+    if (!bytes) cudaCtxResetPersistingL2Cache();
+}
 void Ctx::free(void* p) const {
     if (p) cudaFreeAsync(p, stream);
 }
@@ -148,6 +162,14 @@ Ctx* ctx_create(u64 N, const u64* moduli, int K, int P, int device) {
     unsigned long long keep = ~0ull;   // cache freed blocks: ~4k temporaries per mat-vec in the op-by-op path
     CUDA_CHECK(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep));
     CUDA_CHECK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    {   // reserve the largest persisting-L2 carve-out: the hoisted digits are re-read by every baby-step kernel
+        int pmax = 0, wmax = 0;
+        cudaDeviceGetAttribute(&pmax, cudaDevAttrMaxPersistingL2CacheSize, device);
+        cudaDeviceGetAttribute(&wmax, cudaDevAttrMaxAccessPolicyWindowSize, device);
+        if (pmax > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)pmax) == cudaSuccess)
+            c->l2_persist_max = (size_t)pmax, c->l2_window_max = (size_t)wmax;
+        cudaGetLastError();
+    }
 
     const int L = c->L, beta = c->beta;
     std::vector<u64> r0(K), r1(K);
@@ -194,7 +216,7 @@ Ctx* ctx_create(u64 N, const u64* moduli, int K, int P, int device) {
                     u64 qt = c->q[t], ht = 1;
                     for (int b = lo; b < hi; b++)
                         if (b != a) ht = mulm(ht, c->q[b] % qt, qt);
-                    up_hat[e * K + t] = ht;
+                    up_hat[e * K + t] = ((ht >> 30) << 32) | (ht & 0x3FFFFFFFull);   // split-30 (common.cuh)
                 }
             }
         }
@@ -217,7 +239,7 @@ Ctx* ctx_create(u64 N, const u64* moduli, int K, int P, int device) {
             u64 qi = c->q[i], hi = 1;
             for (int k2 = 0; k2 < P; k2++)
                 if (k2 != k) hi = mulm(hi, c->q[L + k2] % qi, qi);
-            dn_hat[(size_t)k * K + i] = hi;
+            dn_hat[(size_t)k * K + i] = ((hi >> 30) << 32) | (hi & 0x3FFFFFFFull);   // split-30
         }
     }
     for (int i = 0; i < K; i++) dn_half[i] = half_mod(c->q[i]);

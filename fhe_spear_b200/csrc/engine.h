@@ -22,6 +22,7 @@ struct Ctx {
     cudaEvent_t ev_aux[3] = {nullptr, nullptr, nullptr};
     cudaMemPool_t pool = nullptr;
     int sm_count = 148;
+    size_t l2_persist_max = 0, l2_window_max = 0;   // persisting-L2 carve-out and access-window limits
 
     // device tables
     u64 *d_q = nullptr, *d_ratio0 = nullptr, *d_ratio1 = nullptr;
@@ -56,6 +57,8 @@ struct Ctx {
     mutable bool profiling = false;
     mutable std::vector<ProfRec> prof;
 
+    // keep [p, p+bytes) L2-resident for the kernels that follow on `s` (bytes = 0 clears the window)
+    void l2_pin(cudaStream_t s, const void* p, size_t bytes) const;
     u64* alloc(size_t n_u64) const;   // stream-ordered
     void free(void* p) const;
 };

@@ -73,6 +73,8 @@ __global__ void k_galois(const u64* __restrict__ in, u64* __restrict__ out, int 
 // ---- ModUp --------------------------------------------------------------------------------
 // x: [l][N] coefficient form; cin: [l][N] the same polynomial in NTT form (copied into own-digit rows)
 // E: [beta][rows][N]; rows != own are left in coefficient form for the batched NTT that follows.
+// hat tables are stored split-30, so the <= P products per target accumulate carry-free (mac_split).
+template <int A>
 __global__ void __launch_bounds__(TPB) k_modup(const u64* __restrict__ x, const u64* __restrict__ cin,
                                                 u64* __restrict__ E, int l, int N, int L, int P, int K, ModTab mt,
                                                 const ulonglong2* __restrict__ hatinv, const u64* __restrict__ hat) {
@@ -80,13 +82,17 @@ __global__ void __launch_bounds__(TPB) k_modup(const u64* __restrict__ x, const 
     const int rows = l + P, lo = j * P, hi = min(lo + P, l), a = hi - lo;
     hatinv += (size_t)j * P;
     hat += (size_t)j * P * K;
-    u64 y[MAX_ALPHA];
+    u64 y[A];
+    u32 ys[A];
 #pragma unroll
-    for (int i = 0; i < MAX_ALPHA; i++)
+    for (int i = 0; i < A; i++) {
+        y[i] = 0, ys[i] = 0;
         if (i < a) {
             ulonglong2 h = hatinv[i];
-            y[i] = mul_shoup(x[(size_t)(lo + i) * N + n], h.x, h.y, mt.q[lo + i]);
+            y[i] = split30(mul_shoup(x[(size_t)(lo + i) * N + n], h.x, h.y, mt.q[lo + i]));
+            ys[i] = (u32)y[i] + (u32)(y[i] >> 32);
         }
+    }
     u64* Ej = E + (size_t)j * rows * N + n;
     for (int r = 0; r < rows; r++) {
         int t = r < l ? r : L + (r - l);
@@ -94,12 +100,61 @@ __global__ void __launch_bounds__(TPB) k_modup(const u64* __restrict__ x, const 
             Ej[(size_t)r * N] = cin[(size_t)t * N + n];
             continue;
         }
-        u64 alo = 0, ahi = 0;
+        Acc3 acc = {0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < MAX_ALPHA; i++)
-            if (i < a) mac128(alo, ahi, y[i], hat[(size_t)i * K + t]);
+        for (int i = 0; i < A; i++) mac_split(acc, y[i], ys[i], hat[(size_t)i * K + t]);   // rows i >= a hold zeros
+        u64 alo = 0, ahi = 0;
+        fold_split(alo, ahi, acc);
         Ej[(size_t)r * N] = barrett128(alo, ahi, mt.q[t], mt.ratio0[t], mt.ratio1[t]);
     }
+}
+
+// ---- TMA / mbarrier / cache-policy helpers ------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(bar)),
+                 "r"(bytes));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, u32 parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"((u32)__cvta_generic_to_shared(bar)),
+        "r"(parity));
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            (u32)__cvta_generic_to_shared(dst)),
+        "l"(map), "r"((u32)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                                 uint64_t* bar, u64 policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, "
+        "%5}], [%2], %6;" ::"r"((u32)__cvta_generic_to_shared(dst)),
+        "l"(map), "r"((u32)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ u64 evict_last_policy() {
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ u64 ld_keep(const u64* p, u64 pol) {
+    u64 v;
+    asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_stream(u64* p, u64 v, u64 pol) {
+    asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
 }
 
 // ---- key-switch inner product -----------------------------------------------------------------
@@ -128,7 +183,7 @@ __global__ void __launch_bounds__(TPB) k_ks_inner(KsArgs a, ModTab mt, const ulo
 #pragma unroll 4
     for (int j = 0; j < a.beta; j++) {
         u64 d = e[j * es];
-        u64 k0 = ld_stream(k + (size_t)(2 * j) * ks, pol), k1 = ld_stream(k + (size_t)(2 * j + 1) * ks, pol);
+        u64 k0 = unsplit30(ld_stream(k + (size_t)(2 * j) * ks, pol)), k1 = unsplit30(ld_stream(k + (size_t)(2 * j + 1) * ks, pol));
         mac128(lo0, hi0, d, k0);
         mac128(lo1, hi1, d, k1);
     }
@@ -140,6 +195,77 @@ __global__ void __launch_bounds__(TPB) k_ks_inner(KsArgs a, ModTab mt, const ulo
             c = mul_shoup(c, pm.x, pm.y, q);
         }
         v0 = add_mod(v0, c, q);
+    }
+    u64* o0 = a.out + (size_t)r * a.N + n;
+    u64* o1 = o0 + es;
+    if (a.accumulate) {
+        v0 = add_mod(v0, *o0, q);
+        v1 = add_mod(v1, *o1, q);
+    }
+    *o0 = v0;
+    *o1 = v1;
+}
+
+// TMA-staged variant (keys stored split-30): one CTA = (row r, 256 coefficients).  The whole key tile of the
+// row -- 2*beta rows of 2 KB, one 3-D box [2*beta][1][256] -- is fetched by a single UTMALDG with an
+// L2 evict-first policy while the threads gather their digit values (L2-resident, evict-last); two to
+// three CTAs per SM keep ~100 KB of key bytes in flight per SM.
+constexpr int KS_TILE = 256;
+template <int FOLD>
+__global__ void __launch_bounds__(KS_TILE, 4) k_ks_inner_tma(const __grid_constant__ CUtensorMap kmap, KsArgs a, ModTab mt,
+                                                           const ulonglong2* __restrict__ pmod) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    u64* ksm = reinterpret_cast<u64*>(smraw);                       // [2*beta][KS_TILE]
+    uint64_t* full = reinterpret_cast<uint64_t*>(ksm + (size_t)2 * a.beta * KS_TILE);
+    const int r = blockIdx.y, n0 = blockIdx.x * KS_TILE, n = n0 + threadIdx.x;
+    const int t = r < a.l ? r : a.L + (r - a.l);
+    if (threadIdx.x == 0) {
+        mbar_init(full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(full, (u32)(2 * a.beta * KS_TILE * sizeof(u64)));
+        tma_load_3d_hint(ksm, &kmap, n0, t, 0, full, evict_first_policy());
+    }
+    const u32 src = a.elt ? galois_src((u32)n, a.elt, a.logn) : (u32)n;
+    const u64 q = mt.q[t], r0 = mt.ratio0[t], r1 = mt.ratio1[t];
+    const u64 keep = evict_last_policy();
+    const u64* e = a.E + (size_t)r * a.N + src;
+    const size_t es = (size_t)a.rows * a.N;
+    u64 c0add = 0;
+    if (a.addp && r < a.add_rows) c0add = a.addp[(size_t)r * a.N + src];
+    __syncthreads();   // barrier initialised before anybody waits on it
+    u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+    Acc3 acc0 = {0, 0, 0}, acc1 = {0, 0, 0};
+    bool waited = false;
+    constexpr int CH = 8;   // digits gathered per batch (registers), folded every FOLD terms
+    for (int j0 = 0; j0 < a.beta; j0 += CH) {
+        u64 d[CH];
+#pragma unroll
+        for (int j = 0; j < CH; j++) d[j] = (j0 + j < a.beta) ? ld_keep(e + (size_t)(j0 + j) * es, keep) : 0;
+        if (!waited) {
+            mbar_wait(full, 0);
+            waited = true;
+        }
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            if (j0 + j < a.beta) {
+                const u64 ds = split30(d[j]);
+                const u32 dsum = (u32)ds + (u32)(ds >> 32);
+                mac_split(acc0, ds, dsum, ksm[(size_t)(2 * (j0 + j)) * KS_TILE + threadIdx.x]);
+                mac_split(acc1, ds, dsum, ksm[(size_t)(2 * (j0 + j) + 1) * KS_TILE + threadIdx.x]);
+            }
+        }
+        if (((j0 + CH) % FOLD) == 0 || j0 + CH >= a.beta) {
+            fold_split(lo0, hi0, acc0);
+            fold_split(lo1, hi1, acc1);
+        }
+    }
+    u64 v0 = barrett128(lo0, hi0, q, r0, r1), v1 = barrett128(lo1, hi1, q, r0, r1);
+    if (a.addp && r < a.add_rows) {
+        if (a.add_pscale) {
+            ulonglong2 pm = pmod[t];
+            c0add = mul_shoup(c0add, pm.x, pm.y, q);
+        }
+        v0 = add_mod(v0, c0add, q);
     }
     u64* o0 = a.out + (size_t)r * a.N + n;
     u64* o1 = o0 + es;
@@ -171,26 +297,32 @@ __global__ void k_pscale(const u64* __restrict__ x, u64* __restrict__ y, int l, 
 // ---- ModDown --------------------------------------------------------------------------------
 // in: [polys][rows][N] with the P special rows already in coefficient form.
 // tmp[p][i][n] = sum_k [ (sp_k + half_k) * hatinv_k ]_{p_k} * hat[k][i]  - half_i   (mod q_i), coefficient form
+template <int A>
 __global__ void __launch_bounds__(TPB) k_moddown_conv(const u64* __restrict__ in, u64* __restrict__ tmp, int l,
                                                        int N, int L, int P, int K, size_t in_pstride, ModTab mt,
                                                        const ulonglong2* __restrict__ hatinv,
                                                        const u64* __restrict__ half, const u64* __restrict__ hat) {
     const int p = blockIdx.y, n = blockIdx.x * TPB + threadIdx.x;
     const u64* sp = in + (size_t)p * in_pstride + (size_t)l * N + n;
-    u64 y[MAX_ALPHA];
+    u64 y[A];
+    u32 ys[A];
 #pragma unroll
-    for (int k = 0; k < MAX_ALPHA; k++)
+    for (int k = 0; k < A; k++) {
+        y[k] = 0, ys[k] = 0;
         if (k < P) {
             u64 pk = mt.q[L + k];
             ulonglong2 h = hatinv[k];
-            y[k] = mul_shoup(add_mod(sp[(size_t)k * N], half[L + k], pk), h.x, h.y, pk);
+            y[k] = split30(mul_shoup(add_mod(sp[(size_t)k * N], half[L + k], pk), h.x, h.y, pk));
+            ys[k] = (u32)y[k] + (u32)(y[k] >> 32);
         }
+    }
     u64* o = tmp + (size_t)p * l * N + n;
     for (int i = 0; i < l; i++) {
-        u64 alo = 0, ahi = 0;
+        Acc3 acc = {0, 0, 0};
 #pragma unroll
-        for (int k = 0; k < MAX_ALPHA; k++)
-            if (k < P) mac128(alo, ahi, y[k], hat[(size_t)k * K + i]);
+        for (int k = 0; k < A; k++) mac_split(acc, y[k], ys[k], hat[(size_t)k * K + i]);
+        u64 alo = 0, ahi = 0;
+        fold_split(alo, ahi, acc);
         u64 q = mt.q[i];
         o[(size_t)i * N] = sub_mod(barrett128(alo, ahi, q, mt.ratio0[i], mt.ratio1[i]), half[i], q);
     }
@@ -309,31 +441,6 @@ constexpr int PM_STAGES = 2;
 constexpr int PM_GT = 4;        // giant groups per pipeline stage (register tile over g)
 constexpr int PM_T2 = 64;       // coefficients per CTA
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, u32 bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(bar)),
-                 "r"(bytes));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, u32 parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" ::"r"((u32)__cvta_generic_to_shared(bar)),
-        "r"(parity));
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-            (u32)__cvta_generic_to_shared(dst)),
-        "l"(map), "r"((u32)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-
 // A CTA owns (row r, PM_T2 coefficients); thread = (polynomial p, coefficient i) and carries PM_GT giant
 // groups at once, so one shared-memory read of a baby value feeds PM_GT multiply-accumulates.
 // Shared memory: baby tile [Gp][2][PM_T2] in split-30 form (Gp = G rounded up to 8, zero padded), and a
@@ -427,6 +534,22 @@ __global__ void k_split30(u64* __restrict__ x, size_t n, int unsplit) {
 // ===============================================================================================
 namespace ops {
 
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st));
+        REQUIRE(p && st == cudaDriverEntryPointSuccess, "CUDA driver does not provide cuTensorMapEncodeTiled");
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
 static int grid_for(const Ctx* c, size_t total) {
     size_t blocks = (total + TPB - 1) / TPB;
     size_t cap = (size_t)c->sm_count * 16;
@@ -464,9 +587,16 @@ void decompose(const Ctx* c, const u64* cin, int l, u64* x, u64* E, cudaStream_t
     ntt_inverse(c, x, l, RowMap{l, l, c->L, 0}, N, s);
     {
         ProfScope ps(c, PROF_MODUP, s);
-        LAUNCH(k_modup, dim3(N / TPB, beta), TPB, 0, s)(x, cin, E, l, N, c->L, P, c->K, c->modtab(),
-                                                 c->d_up_hatinv + (size_t)l * c->beta * P,
-                                                 c->d_up_hat + (size_t)l * c->beta * P * c->K);
+        auto go = [&](auto kern) {
+            LAUNCH(kern, dim3(N / TPB, beta), TPB, 0, s)(x, cin, E, l, N, c->L, P, c->K, c->modtab(),
+                                                         c->d_up_hatinv + (size_t)l * c->beta * P,
+                                                         c->d_up_hat + (size_t)l * c->beta * P * c->K);
+        };
+        if (P == 1) go(k_modup<1>);
+        else if (P == 2) go(k_modup<2>);
+        else if (P == 3) go(k_modup<3>);
+        else if (P == 4) go(k_modup<4>);
+        else go(k_modup<MAX_ALPHA>);
     }
     ntt_forward(c, E, beta * rows, RowMap{rows, l, c->L, 0}, N, s, P);
     CUDA_CHECK(cudaGetLastError());
@@ -479,6 +609,28 @@ void ks_inner(const Ctx* c, const u64* E, const u64* key, u64* out, int l, u32 e
     a.accumulate = accumulate, a.beta = c->digits(l), a.l = l, a.rows = l + c->P, a.N = c->N, a.logn = c->logn;
     a.L = c->L, a.K = c->K, a.elt = elt;
     ProfScope ps(c, PROF_KS_INNER, s);
+    if (c->N % KS_TILE == 0 && 2 * a.beta <= 256 && (size_t)2 * a.beta * KS_TILE * sizeof(u64) + 64 <= 200 * 1024) {
+        CUtensorMap kmap;
+        cuuint64_t dims[3] = {(cuuint64_t)c->N, (cuuint64_t)c->K, (cuuint64_t)(2 * c->beta)};
+        cuuint64_t strides[2] = {(cuuint64_t)c->N * sizeof(u64), (cuuint64_t)c->K * c->N * sizeof(u64)};
+        cuuint32_t box[3] = {(cuuint32_t)KS_TILE, 1, (cuuint32_t)(2 * a.beta)};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult rc = encode_tiled()(&kmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, (void*)key, dims, strides, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
+        bool small = true;
+        for (u64 qq : c->q) small = small && qq < (1ull << 59);
+        const size_t smem = (size_t)2 * a.beta * KS_TILE * sizeof(u64) + 64;
+        auto go = [&](auto kern) {
+            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            LAUNCH(kern, dim3(c->N / KS_TILE, a.rows), KS_TILE, smem, s)(kmap, a, c->modtab(), c->d_pmod);
+        };
+        if (small) go(k_ks_inner_tma<16>);
+        else go(k_ks_inner_tma<8>);
+        CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     LAUNCH(k_ks_inner, dim3(c->N / TPB, a.rows), TPB, 0, s)(a, c->modtab(), c->d_pmod);
     CUDA_CHECK(cudaGetLastError());
 }
@@ -497,8 +649,15 @@ void moddown(const Ctx* c, u64* in, size_t in_pstride, int polys, int l, u64* tm
         ntt_inverse(c, in + (size_t)p * in_pstride + (size_t)l * N, P, RowMap{P, 0, c->L, 0}, N, s);
     {
         ProfScope ps(c, PROF_MODDOWN, s);
-        LAUNCH(k_moddown_conv, dim3(N / TPB, polys), TPB, 0, s)(in, tmp, l, N, c->L, P, c->K, in_pstride, c->modtab(),
-                                                         c->d_dn_hatinv, c->d_dn_half, c->d_dn_hat);
+        auto go = [&](auto kern) {
+            LAUNCH(kern, dim3(N / TPB, polys), TPB, 0, s)(in, tmp, l, N, c->L, P, c->K, in_pstride, c->modtab(),
+                                                          c->d_dn_hatinv, c->d_dn_half, c->d_dn_hat);
+        };
+        if (P == 1) go(k_moddown_conv<1>);
+        else if (P == 2) go(k_moddown_conv<2>);
+        else if (P == 3) go(k_moddown_conv<3>);
+        else if (P == 4) go(k_moddown_conv<4>);
+        else go(k_moddown_conv<MAX_ALPHA>);
     }
     ntt_forward(c, tmp, polys * l, RowMap{l, l, c->L, 0}, N, s);
     ProfScope ps(c, PROF_MODDOWN, s);
@@ -528,22 +687,6 @@ void pmac_list(const Ctx* c, const u64* const* baby, const u64* const* pt, int n
     ProfScope ps(c, PROF_PMAC, s);
     LAUNCH(k_pmac_list, dim3(c->N / TPB, l), TPB, 0, s)(p, nb, out, l, c->N, c->modtab());
     CUDA_CHECK(cudaGetLastError());
-}
-
-// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult st;
-        CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st));
-        REQUIRE(p && st == cudaDriverEntryPointSuccess, "CUDA driver does not provide cuTensorMapEncodeTiled");
-        fn = (EncodeTiledFn)p;
-    }
-    return fn;
 }
 
 void pmac_hoisted(const Ctx* c, const u64* Y, const u64* diag, u64* A, int G, int B, int D, int l, int rshift,
