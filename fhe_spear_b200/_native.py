@@ -78,10 +78,16 @@ _SIG = {
     "spear_hoisted_rotations": (C.c_int, [vp, vp, u32p, C.c_int, vp, vpp]),
     "spear_bsgs_multiply_accumulate": (C.c_int, [vp, vpp, C.c_int, vpp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vpp]),
     "spear_diagset_encode": (C.c_int, [vp, f64p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, vpp]),
+    "spear_diagset_encode_shard": (C.c_int, [vp, f64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                            C.c_int, C.c_int, vpp]),
     "spear_diagset_destroy": (None, [vp]),
     "spear_diagset_info": (C.c_int, [vp, ip, ip, ip, ip, ip, f64p, u64p]),
     "spear_diagset_export": (C.c_int, [vp, vp, C.c_size_t]),
     "spear_bsgs_hoisted": (C.c_int, [vp, vp, vp, vp, vpp]),
+    "spear_bsgs_hoisted_partial": (C.c_int, [vp, vp, vp, vp, vpp]),
+    "spear_bsgs_finish": (C.c_int, [vp, vp, vpp]),
+    "spear_obj_reduce": (C.c_int, [vp, vp]),
+    "spear_obj_device_ptr": (vp, [vp]),
     "spear_ntt_host": (C.c_int, [vp, vp, C.c_int, ip, C.c_int, C.c_int]),
 }
 

@@ -19,9 +19,10 @@ void relinearize(const Ctx* c, const u64* ct3, int l, const u64* rlk, u64* out, 
 void rescale(const Ctx* c, const u64* in, int polys, int l, u64* out, cudaStream_t s);
 void bsgs_exact(const Ctx* c, const u64* const* baby, const u64* const* pts, int G, int B, int D, int l,
                 const u32* gelt, const u64* const* gkey, u64* out, cudaStream_t s);
-void bsgs_hoisted(const Ctx* c, const u64* ct, int l, const u64* diag, int rshift, int G, int B, int D,
-                  const u32* belt, const u64* const* bkey, const u32* gelt, const u64* const* gkey, u64* out,
-                  cudaStream_t s);
+void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, int rshift, int G, int n_groups,
+                          int n_diags, int g_first, int g_stride, const u32* belt, const u64* const* bkey,
+                          const u32* gelt, const u64* const* gkey, u64* R, cudaStream_t s);
+void bsgs_finish(const Ctx* c, u64* R, int l, u64* out, cudaStream_t s);
 }  // namespace eng
 
 namespace {
@@ -499,27 +500,28 @@ static int addsub(spear_context* ctx, const spear_obj* a_, const spear_obj* b_, 
     Ctx* c = C_(ctx);
     use(c);
     const Obj *a = O_(a_), *b = O_(b_);
-    check_ct(a, "add/sub");
-    check_ct(b, "add/sub");
+    REQUIRE(a && b && a->size >= 2 && b->size >= 2 && a->n == c->N && b->n == c->N && a->ext == b->ext,
+            "add/sub: expected two ciphertexts in the same basis");
     REQUIRE(a->l == b->l, "add/sub: chain_index mismatch (%d vs %d limbs)", a->l, b->l);
     // a is the larger one
     const bool swap = b->size > a->size;
     const Obj *big = swap ? b : a, *small = swap ? a : b;
-    std::unique_ptr<Obj> o(new_obj(c, big->size, a->l, false, c->N, a->scale));
-    const size_t pw = (size_t)a->l * c->N;
-    RowMap rm = data_rows(c, a->l);
+    std::unique_ptr<Obj> o(new_obj(c, big->size, a->l, a->ext, c->N, a->scale));
+    const int nr = a->rows();
+    const size_t pw = (size_t)nr * c->N;
+    RowMap rm{nr, a->l, c->L, 0};
     if (!is_sub) {
-        ops::add(c, big->d, small->d, o->d, small->size, a->l, c->N, rm, small->size, c->stream);
+        ops::add(c, big->d, small->d, o->d, small->size, nr, c->N, rm, small->size, c->stream);
         if (big->size > small->size)
             CUDA_CHECK(cudaMemcpyAsync(o->d + small->size * pw, big->d + small->size * pw,
                                        sizeof(u64) * (big->size - small->size) * pw, cudaMemcpyDeviceToDevice, c->stream));
     } else {
-        ops::sub(c, a->d, b->d, o->d, small->size, a->l, c->N, rm, small->size, c->stream);
+        ops::sub(c, a->d, b->d, o->d, small->size, nr, c->N, rm, small->size, c->stream);
         if (a->size > b->size)
             CUDA_CHECK(cudaMemcpyAsync(o->d + small->size * pw, a->d + small->size * pw,
                                        sizeof(u64) * (a->size - b->size) * pw, cudaMemcpyDeviceToDevice, c->stream));
         else if (b->size > a->size)
-            ops::neg(c, b->d + small->size * pw, o->d + small->size * pw, b->size - a->size, a->l, c->N, rm, c->stream);
+            ops::neg(c, b->d + small->size * pw, o->d + small->size * pw, b->size - a->size, nr, c->N, rm, c->stream);
     }
     *out = H_(o.release());
     API_END
@@ -694,45 +696,55 @@ int spear_bsgs_multiply_accumulate(spear_context* ctx, spear_obj* const* ct_baby
     API_END
 }
 
-int spear_diagset_encode(spear_context* ctx, const double* diags, int D, int G, int B, double scale, int chain_index,
-                         int compress, spear_diagset** out) {
+int spear_diagset_encode_shard(spear_context* ctx, const double* diags, int n_diags, int D, int G, int B, int g_first,
+                               int g_stride, double scale, int chain_index, int compress, spear_diagset** out) {
     API_BEGIN
     Ctx* c = C_(ctx);
     use(c);
     REQUIRE(D >= 1 && G >= 1 && B >= 1 && (size_t)G * B >= (size_t)D && D <= c->N / 2, "diagset: bad D/G/B");
+    REQUIRE(g_first >= 0 && g_stride >= 1 && n_diags >= 0 && n_diags <= D, "diagset: bad shard");
     REQUIRE(chain_index >= 1 && chain_index <= c->L, "diagset: chain_index out of range");
+    {   // the shard must hold exactly the diagonals of groups g_first, g_first + g_stride, ...
+        int expect = 0;
+        for (int g = g_first; g < B && g * G < D; g += g_stride) expect += std::min(G, D - g * G);
+        REQUIRE(expect == n_diags, "diagset: shard (first %d, stride %d) holds %d diagonals, got %d", g_first, g_stride,
+                expect, n_diags);
+    }
     const int slots = c->N / 2, l = c->limbs_at(chain_index), rows = l + c->P;
     const bool pow2 = (D & (D - 1)) == 0;
     REQUIRE(!compress || pow2, "diagset: sub-ring compression needs D to be a power of two");
     const int n = (compress && pow2 && D >= 2) ? 2 * D : c->N;
     std::unique_ptr<DiagSet> ds(new DiagSet);
     ds->bind(c), ds->D = D, ds->G = G, ds->B = B, ds->l = l, ds->n = n, ds->scale = scale;
+    ds->n_diags = n_diags, ds->g_first = g_first, ds->g_stride = g_stride;
     ds->rshift = 0;
     while ((n << ds->rshift) < c->N) ds->rshift++;
-    ds->d = c->alloc((size_t)D * rows * n);
-    double2* dv = (double2*)c->alloc((size_t)D * D * 2);
-    CUDA_CHECK(cudaMemcpyAsync(dv, diags, sizeof(double2) * D * D, cudaMemcpyHostToDevice, c->stream));
-    if (n == 2 * D) {
-        const int chunk = std::max(1, std::min(D, (int)((32u << 20) / ((size_t)n))));
-        for (int v0 = 0; v0 < D; v0 += chunk) {
-            int nv = std::min(chunk, D - v0);
-            encoder::encode(c, dv + (size_t)v0 * D, nv, n, scale, l, true, ds->d + (size_t)v0 * rows * n, c->stream);
+    ds->d = c->alloc((size_t)std::max(n_diags, 1) * rows * n);
+    if (n_diags > 0) {
+        double2* dv = (double2*)c->alloc((size_t)n_diags * D * 2);
+        CUDA_CHECK(cudaMemcpyAsync(dv, diags, sizeof(double2) * n_diags * D, cudaMemcpyHostToDevice, c->stream));
+        const int chunk = std::max(1, std::min(n_diags, (int)((32u << 20) / ((size_t)n))));
+        double2* full = n == 2 * D ? nullptr : (double2*)c->alloc((size_t)chunk * slots * 2);
+        for (int v0 = 0; v0 < n_diags; v0 += chunk) {
+            int nv = std::min(chunk, n_diags - v0);
+            const double2* src = dv + (size_t)v0 * D;
+            if (full) {   // replicate the period-D vector over all slots (reference :371-378)
+                LAUNCH(k_tile, c->sm_count * 8, 256, 0, c->stream)(src, full, nv, D, slots);
+                src = full;
+            }
+            encoder::encode(c, src, nv, n, scale, l, true, ds->d + (size_t)v0 * rows * n, c->stream);
         }
-    } else {
-        const int chunk = std::max(1, std::min(D, (int)((32u << 20) / ((size_t)n))));
-        double2* full = (double2*)c->alloc((size_t)chunk * slots * 2);
-        for (int v0 = 0; v0 < D; v0 += chunk) {
-            int nv = std::min(chunk, D - v0);
-            LAUNCH(k_tile, c->sm_count * 8, 256, 0, c->stream)(dv + (size_t)v0 * D, full, nv, D, slots);
-            encoder::encode(c, full, nv, n, scale, l, true, ds->d + (size_t)v0 * rows * n, c->stream);
-        }
-        c->free(full);
+        if (full) c->free(full);
+        c->free(dv);
+        // the diagonal MAC kernels consume the split-30 storage form (common.cuh)
+        ops::split30_inplace(c, ds->d, (size_t)n_diags * rows * n, false, c->stream);
     }
-    c->free(dv);
-    // the diagonal MAC kernels consume the split-30 storage form (common.cuh)
-    ops::split30_inplace(c, ds->d, (size_t)D * rows * n, false, c->stream);
     *out = reinterpret_cast<spear_diagset*>(ds.release());
     API_END
+}
+int spear_diagset_encode(spear_context* ctx, const double* diags, int D, int G, int B, double scale, int chain_index,
+                         int compress, spear_diagset** out) {
+    return spear_diagset_encode_shard(ctx, diags, D, D, G, B, 0, 1, scale, chain_index, compress, out);
 }
 void spear_diagset_destroy(spear_diagset* d) { delete reinterpret_cast<DiagSet*>(d); }
 int spear_diagset_info(const spear_diagset* d_, int* D, int* G, int* B, int* limbs, int* ring_n, double* scale,
@@ -746,7 +758,7 @@ int spear_diagset_info(const spear_diagset* d_, int* D, int* G, int* B, int* lim
     if (limbs) *limbs = d->l;
     if (ring_n) *ring_n = d->n;
     if (scale) *scale = d->scale;
-    if (bytes) *bytes = sizeof(u64) * (size_t)d->D * (d->l + d->ctx->P) * d->n;
+    if (bytes) *bytes = sizeof(u64) * (size_t)d->n_diags * (d->l + d->ctx->P) * d->n;
     API_END
 }
 int spear_diagset_export(const spear_diagset* d_, uint64_t* host, size_t words) {
@@ -754,7 +766,7 @@ int spear_diagset_export(const spear_diagset* d_, uint64_t* host, size_t words) 
     const DiagSet* d = reinterpret_cast<const DiagSet*>(d_);
     Ctx* c = d->ctx;
     use(c);
-    const size_t have = (size_t)d->D * (d->l + c->P) * d->n;
+    const size_t have = (size_t)d->n_diags * (d->l + c->P) * d->n;
     REQUIRE(words == have, "export: buffer holds %zu words, diagonal set has %zu", words, have);
     u64* tmp = c->alloc(have);   // canonical residues for the caller; the resident copy stays split-30
     CUDA_CHECK(cudaMemcpyAsync(tmp, d->d, sizeof(u64) * have, cudaMemcpyDeviceToDevice, c->stream));
@@ -765,35 +777,71 @@ int spear_diagset_export(const spear_diagset* d_, uint64_t* host, size_t words) 
     API_END
 }
 
+static Obj* bsgs_partial(Ctx* c, const Obj* ct, const DiagSet* ds, const GaloisKeys* gk) {
+    check_ct(ct, "bsgs_hoisted");
+    REQUIRE(ct->size == 2, "bsgs_hoisted: relinearize first");
+    REQUIRE(ds->l == ct->l, "bsgs_hoisted: diagonals encoded for %d limbs, ciphertext has %d", ds->l, ct->l);
+    const int G = std::min(ds->G, ds->D), B = ds->B, D = ds->D, l = ct->l;
+    std::vector<u32> belt(G, 0), gelt;
+    std::vector<const u64*> bkey(G, nullptr), gkey;
+    for (int b = 1; b < G; b++) {
+        belt[b] = (u32)elt_from_step(b, c->N);
+        bkey[b] = find_key(gk, belt[b])->d;
+    }
+    for (int g = ds->g_first; g < B && g * ds->G < D; g += ds->g_stride) {
+        gelt.push_back(g ? (u32)elt_from_step(g * ds->G, c->N) : 0);
+        gkey.push_back(g ? find_key(gk, gelt.back())->d : nullptr);
+    }
+    std::unique_ptr<Obj> R(new_obj(c, 2, l, true, c->N, ct->scale * ds->scale));
+    eng::bsgs_hoisted_partial(c, ct->d, l, ds->d, ds->rshift, G, (int)gelt.size(), ds->n_diags, ds->g_first,
+                              ds->g_stride, belt.data(), bkey.data(), gelt.data(), gkey.data(), R->d, c->stream);
+    return R.release();
+}
+static Obj* bsgs_finish(Ctx* c, Obj* R) {
+    REQUIRE(R && R->size == 2 && R->ext && R->n == c->N, "bsgs_finish: expected an accumulator in basis Q_l*P");
+    REQUIRE(R->l >= 2, "bsgs: no level left for the final rescale");
+    std::unique_ptr<Obj> o(new_obj(c, 2, R->l - 1, false, c->N, R->scale / (double)c->q[R->l - 1]));
+    eng::bsgs_finish(c, R->d, R->l, o->d, c->stream);
+    return o.release();
+}
+
 int spear_bsgs_hoisted(spear_context* ctx, const spear_obj* ct_, const spear_diagset* ds_, const spear_galois_keys* gk_,
                        spear_obj** out) {
     API_BEGIN
     Ctx* c = C_(ctx);
     use(c);
-    const Obj* ct = O_(ct_);
     const DiagSet* ds = reinterpret_cast<const DiagSet*>(ds_);
-    const GaloisKeys* gk = reinterpret_cast<const GaloisKeys*>(gk_);
-    check_ct(ct, "bsgs_hoisted");
-    REQUIRE(ct->size == 2, "bsgs_hoisted: relinearize first");
-    REQUIRE(ds->l == ct->l, "bsgs_hoisted: diagonals encoded for %d limbs, ciphertext has %d", ds->l, ct->l);
-    REQUIRE(ct->l >= 2, "bsgs_hoisted: no level left for the final rescale");
-    const int G = ds->G, B = ds->B, D = ds->D, l = ct->l;
-    std::vector<u32> belt(G, 0), gelt(B, 0);
-    std::vector<const u64*> bkey(G, nullptr), gkey(B, nullptr);
-    for (int b = 1; b < G && b < D; b++) {
-        belt[b] = (u32)elt_from_step(b, c->N);
-        bkey[b] = find_key(gk, belt[b])->d;
-    }
-    for (int g = 1; g < B && g * G < D; g++) {
-        gelt[g] = (u32)elt_from_step(g * G, c->N);
-        gkey[g] = find_key(gk, gelt[g])->d;
-    }
-    std::unique_ptr<Obj> o(new_obj(c, 2, l - 1, false, c->N, ct->scale * ds->scale / (double)c->q[l - 1]));
-    eng::bsgs_hoisted(c, ct->d, l, ds->d, ds->rshift, std::min(G, D), B, D, belt.data(), bkey.data(), gelt.data(),
-                      gkey.data(), o->d, c->stream);
-    *out = H_(o.release());
+    REQUIRE(ds->g_first == 0 && ds->g_stride == 1, "bsgs_hoisted: sharded diagonal set (use bsgs_hoisted_partial)");
+    REQUIRE(O_(ct_)->l >= 2, "bsgs_hoisted: no level left for the final rescale");
+    std::unique_ptr<Obj> R(bsgs_partial(c, O_(ct_), ds, reinterpret_cast<const GaloisKeys*>(gk_)));
+    *out = H_(bsgs_finish(c, R.get()));
     API_END
 }
+int spear_bsgs_hoisted_partial(spear_context* ctx, const spear_obj* ct_, const spear_diagset* ds_,
+                               const spear_galois_keys* gk_, spear_obj** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    *out = H_(bsgs_partial(c, O_(ct_), reinterpret_cast<const DiagSet*>(ds_), reinterpret_cast<const GaloisKeys*>(gk_)));
+    API_END
+}
+int spear_bsgs_finish(spear_context* ctx, spear_obj* acc, spear_obj** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    *out = H_(bsgs_finish(c, reinterpret_cast<Obj*>(acc)));
+    API_END
+}
+int spear_obj_reduce(spear_context* ctx, spear_obj* o_) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    Obj* o = reinterpret_cast<Obj*>(o_);
+    REQUIRE(o && o->n == c->N, "reduce: bad operand");
+    ops::reduce_inplace(c, o->d, o->size, o->rows(), RowMap{o->rows(), o->l, c->L, 0}, c->stream);
+    API_END
+}
+void* spear_obj_device_ptr(spear_obj* o) { return reinterpret_cast<Obj*>(o)->d; }
 
 int spear_ntt_host(spear_context* ctx, uint64_t* data, int rows, const int* limb_ids, int ring_n, int inverse) {
     API_BEGIN

@@ -90,19 +90,19 @@ void bsgs_exact(const Ctx* c, const u64* const* baby, const u64* const* pts, int
     rescale(c, res, 2, l, out, s);
 }
 
-// ct [2][l][N]; diag [D][l+P][N >> rshift]; bkey[b] (1 <= b < G), gkey[g] (1 <= g < B); out [2][l-1][N]
-void bsgs_hoisted(const Ctx* c, const u64* ct, int l, const u64* diag, int rshift, int G, int B, int D,
-                  const u32* belt, const u64* const* bkey, const u32* gelt, const u64* const* gkey, u64* out,
-                  cudaStream_t s) {
+// ct [2][l][N]; diag [n_diags][l+P][N >> rshift] holds the giant groups g_first + k*g_stride (k < n_groups);
+// bkey[b] (1 <= b < G); gelt/gkey indexed by LOCAL group k (unused where the global group is 0).
+// R [2][l+P][N]: this shard's accumulator in basis Q_l*P (sum over shards, mod q, = the full accumulator).
+void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, int rshift, int G, int n_groups,
+                          int n_diags, int g_first, int g_stride, const u32* belt, const u64* const* bkey,
+                          const u32* gelt, const u64* const* gkey, u64* R, cudaStream_t s) {
     const size_t N = c->N, rows = l + c->P, pw = rows * N;
     const int beta = c->digits(l);
     Scratch sc(c);
     u64* x = sc.get(l * N);
     u64* E = sc.get(beta * pw);
     u64* Y = sc.get((size_t)G * 2 * pw);
-    const int Beff = (D + G - 1) / G;
-    REQUIRE(Beff <= B, "bsgs: D=%d needs more than B=%d giant steps of G=%d", D, B, G);
-    u64* A = sc.get((size_t)Beff * 2 * pw);
+    u64* A = sc.get((size_t)n_groups * 2 * pw);
     const u64 *c0 = ct, *c1 = ct + l * N;
 
     // 1-2. hoisted baby steps, kept in basis Q_l * P
@@ -112,19 +112,32 @@ void bsgs_hoisted(const Ctx* c, const u64* ct, int l, const u64* diag, int rshif
     for (int b = 1; b < G; b++)
         ops::ks_inner(c, E, bkey[b], Y + (size_t)b * 2 * pw, l, belt[b], c0, l, 1, 0, s);
     c->l2_pin(s, nullptr, 0);
-    // 3. diagonal multiply-accumulate for every giant group
-    ops::pmac_hoisted(c, Y, diag, A, G, Beff, D, l, rshift, s);
-    // 4. giant steps: R (= A[0], in place) += (pi_g(A_g.0) + <pi_g(F), k0>, <pi_g(F), k1>)
-    u64* R = A;
+    // 3. diagonal multiply-accumulate for every local giant group
+    ops::pmac_hoisted(c, Y, diag, A, G, n_groups, n_diags, l, rshift, s);
+    // 4. giant steps: R = sum_k (pi_g(A_k.0) + <pi_g(F), k0>, <pi_g(F), k1>)   (g = g_first + k*g_stride; g = 0: R = A_k)
     u64* t = sc.get(l * N);
     u64* tmp = sc.get(2 * l * N);
-    for (int g = 1; g < Beff; g++) {
-        u64* Ag = A + (size_t)g * 2 * pw;
-        ops::moddown(c, Ag + pw, pw, 1, l, tmp, nullptr, t, s);
-        ops::decompose(c, t, l, x, E, s);
-        ops::ks_inner(c, E, gkey[g], R, l, gelt[g], Ag, (int)rows, 0, 1, s);
+    bool have = false;
+    for (int k = 0; k < n_groups; k++) {
+        u64* Ak = A + (size_t)k * 2 * pw;
+        if (g_first + k * g_stride == 0) {
+            REQUIRE(!have, "bsgs: group 0 must come first");
+            CUDA_CHECK(cudaMemcpyAsync(R, Ak, sizeof(u64) * 2 * pw, cudaMemcpyDeviceToDevice, s));
+        } else {
+            ops::moddown(c, Ak + pw, pw, 1, l, tmp, nullptr, t, s);
+            ops::decompose(c, t, l, x, E, s);
+            ops::ks_inner(c, E, gkey[k], R, l, gelt[k], Ak, (int)rows, 0, have ? 1 : 0, s);
+        }
+        have = true;
     }
-    // 5. one ModDown, one rescale
+    if (!have) CUDA_CHECK(cudaMemsetAsync(R, 0, sizeof(u64) * 2 * pw, s));
+}
+
+// R [2][l+P][N] (destroyed) -> out [2][l-1][N]: one ModDown, one rescale
+void bsgs_finish(const Ctx* c, u64* R, int l, u64* out, cudaStream_t s) {
+    const size_t N = c->N, pw = (l + c->P) * N;
+    Scratch sc(c);
+    u64* tmp = sc.get(2 * l * N);
     u64* full = sc.get(2 * l * N);
     ops::moddown(c, R, pw, 2, l, tmp, nullptr, full, s);
     rescale(c, full, 2, l, out, s);

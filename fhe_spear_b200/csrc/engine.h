@@ -124,7 +124,9 @@ struct PublicKey : CtxRef {
 
 // pre-encoded, pre-rotated BSGS diagonals in basis Q_l * P (hoisted path)
 struct DiagSet : CtxRef {
-    int D = 0, G = 0, B = 0;
+    int D = 0, G = 0, B = 0;   // period (matrix dimension), baby steps per group, giant groups of the whole matrix
+    int n_diags = 0;           // diagonals stored here: the groups g_first, g_first + g_stride, ... (< B)
+    int g_first = 0, g_stride = 1;
     int l = 0;       // data limbs
     int n = 0;       // coefficients stored per row (N >> rshift)
     int rshift = 0;

@@ -44,6 +44,15 @@ __global__ void k_ew(const u64* __restrict__ a, const u64* __restrict__ b, u64* 
     }
 }
 
+// x[p][r][i] = x[p][r][i] mod q_r  for lazily summed residues (e.g. a u64 all-reduce of <= 16 shards)
+__global__ void k_reduce(u64* __restrict__ x, int polys, int rows, int n, RowMap rm, ModTab mt) {
+    size_t total = (size_t)polys * rows * n;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        int limb = rm.limb((int)((e / n) % rows));
+        x[e] = barrett64(x[e], mt.q[limb], mt.ratio1[limb]);
+    }
+}
+
 // tensor product of two size-2 ciphertexts -> size 3
 __global__ void k_tensor(const u64* __restrict__ a, const u64* __restrict__ b, u64* __restrict__ out, int l, int n,
                          ModTab mt) {
@@ -570,6 +579,10 @@ void neg(const Ctx* c, const u64* a, u64* out, int polys, int rows, int n, RowMa
 void mul(const Ctx* c, const u64* a, const u64* b, u64* out, int polys, int rows, int n, RowMap rm, int b_polys,
          cudaStream_t s) {
     LAUNCH(k_ew<EW_MUL>, grid_for(c, (size_t)polys * rows * n), TPB, 0, s)(a, b, out, polys, rows, n, rm, c->modtab(), b_polys);
+}
+void reduce_inplace(const Ctx* c, u64* x, int polys, int rows, RowMap rm, cudaStream_t s) {
+    LAUNCH(k_reduce, grid_for(c, (size_t)polys * rows * c->N), TPB, 0, s)(x, polys, rows, c->N, rm, c->modtab());
+    CUDA_CHECK(cudaGetLastError());
 }
 void tensor(const Ctx* c, const u64* a, const u64* b, u64* out, int l, cudaStream_t s) {
     LAUNCH(k_tensor, grid_for(c, (size_t)l * c->N), TPB, 0, s)(a, b, out, l, c->N, c->modtab());

@@ -605,19 +605,26 @@ context.__init__ = _ctx_init_track
 
 # ---- fast path (not in the reference): pre-encoded diagonal sets + hoisted BSGS -------------------------
 class diagonal_set:
-    """D pre-rotated period-D diagonals encoded in basis Q_l*P, sub-ring compressed when D is a power of two."""
+    """Pre-rotated period-D diagonals encoded in basis Q_l*P, sub-ring compressed when D is a power of two.
 
-    def __init__(self, ctx, diags, G, B, scale, chain_index=1, compress=True):
-        d = np.ascontiguousarray(np.asarray(diags, dtype=np.complex128))
-        D = d.shape[0]
+    `diags` is the full (D, D) array of pre-rotated diagonals; with shard=(rank, world) only the giant
+    groups g = rank, rank + world, ... are encoded and stored (giant-step sharding over GPUs)."""
+
+    def __init__(self, ctx, diags, G, B, scale, chain_index=1, compress=True, shard=(0, 1)):
+        d = np.asarray(diags, dtype=np.complex128)
+        D = d.shape[1]
         if d.shape != (D, D):
             raise RuntimeError("diagonal_set expects a (D, D) array of pre-rotated diagonals")
+        first, stride = int(shard[0]), int(shard[1])
+        rows = [k for g in range(first, int(B), stride) for k in range(g * G, min((g + 1) * G, D))]
+        part = np.ascontiguousarray(d[rows]) if rows else np.zeros((0, D), dtype=np.complex128)
         compress = bool(compress) and (D & (D - 1)) == 0 and D >= 2
         h = C.c_void_p()
-        _check(_lib.spear_diagset_encode(ctx._h, d.view(np.float64).ctypes.data_as(_n.f64p), D, int(G), int(B),
-                                         float(scale), int(chain_index), int(compress), C.byref(h)))
+        _check(_lib.spear_diagset_encode_shard(ctx._h, part.view(np.float64).ctypes.data_as(_n.f64p), len(rows), D,
+                                               int(G), int(B), first, stride, float(scale), int(chain_index),
+                                               int(compress), C.byref(h)))
         self._ctx, self._h = ctx, h
-        self.D, self.G, self.B = D, int(G), int(B)
+        self.D, self.G, self.B, self.shard, self.rows = D, int(G), int(B), (first, stride), rows
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -634,9 +641,27 @@ class diagonal_set:
 
     def to_numpy(self):
         i = self.info()
-        out = np.empty((i["D"], i["limbs"] + self._ctx.P, i["ring_n"]), dtype=np.uint64)
+        out = np.empty((len(self.rows), i["limbs"] + self._ctx.P, i["ring_n"]), dtype=np.uint64)
         _check(_lib.spear_diagset_export(self._h, out.ctypes.data_as(C.c_void_p), out.size))
         return out
+
+
+def bsgs_hoisted_partial(ctx, ct, shard, gk):
+    """This shard's accumulator in basis Q_l*P (ciphertext object with the special limbs)."""
+    return _new(ciphertext, ctx, _lib.spear_bsgs_hoisted_partial, ct._h, shard._h, gk._h)
+
+
+def bsgs_finish(ctx, acc):
+    """ModDown + rescale of a (summed) accumulator; the accumulator's contents are consumed."""
+    return _new(ciphertext, ctx, _lib.spear_bsgs_finish, acc._h)
+
+
+def reduce_inplace(ctx, obj):
+    _check(_lib.spear_obj_reduce(ctx._h, obj._h))
+
+
+def device_ptr(obj):
+    return int(_lib.spear_obj_device_ptr(obj._h))
 
 
 def bsgs_hoisted(ctx, ct, diags, gk):

@@ -148,6 +148,10 @@ int spear_bsgs_multiply_accumulate(spear_context* ctx, spear_obj* const* ct_baby
  *  (re, im).  compress != 0 stores the sub-ring form (ring 2D, N/(2D)-fold smaller). */
 int spear_diagset_encode(spear_context* ctx, const double* diags, int D, int G, int B, double scale, int chain_index,
                          int compress, spear_diagset** out);
+/* one shard of the same set for giant-step sharding over GPUs: only the giant groups
+ * g_first, g_first + g_stride, ... are stored; `diags` holds their n_diags rows in that order. */
+int spear_diagset_encode_shard(spear_context* ctx, const double* diags, int n_diags, int D, int G, int B, int g_first,
+                               int g_stride, double scale, int chain_index, int compress, spear_diagset** out);
 void spear_diagset_destroy(spear_diagset* d);
 int spear_diagset_info(const spear_diagset* d, int* D, int* G, int* B, int* limbs, int* ring_n, double* scale,
                        uint64_t* bytes);
@@ -156,6 +160,14 @@ int spear_diagset_export(const spear_diagset* d, uint64_t* host, size_t words); 
  * [ref: fork-only ph.bsgs_complete_from_cpu(ctx, ct_x, ...), bootstrap_generation.py:242] */
 int spear_bsgs_hoisted(spear_context* ctx, const spear_obj* ct, const spear_diagset* diags,
                        const spear_galois_keys* gk, spear_obj** out);
+
+/* Sharded form: the shard's accumulator in basis Q_l*P (size 2, ext).  Accumulators of all shards are summed
+ * (spear_add, or an integer all-reduce over spear_obj_device_ptr followed by spear_obj_reduce) and finished once. */
+int spear_bsgs_hoisted_partial(spear_context* ctx, const spear_obj* ct, const spear_diagset* shard,
+                               const spear_galois_keys* gk, spear_obj** out);
+int spear_bsgs_finish(spear_context* ctx, spear_obj* acc, spear_obj** out);   /* ModDown + rescale; clobbers acc */
+int spear_obj_reduce(spear_context* ctx, spear_obj* o);                       /* every residue mod its modulus, in place */
+void* spear_obj_device_ptr(spear_obj* o);                                     /* device address of the limbs */
 
 /* ---- raw transforms (tests / profiling) ------------------------------------------------------------- */
 /* in-place on a host buffer of `rows` x ring_n residues whose row r uses modulus limb_ids[r] */

@@ -118,7 +118,7 @@ class Oracle:
         """values: complex/real array of n/2 slots (n = N unless sub-ring)."""
         n = self.N if n is None else int(n)
         v = np.asarray(values)
-        assert v.shape[0] == n // 2
+        assert v.shape[0] == n // 2 and n & (n - 1) == 0 and n <= self.N, "ring size must be a power of two"
         re = np.ascontiguousarray(v.real, dtype=np.float64)
         im = np.ascontiguousarray(v.imag, dtype=np.float64) if np.iscomplexobj(v) else None
         rows = self.rows(l, ext)
@@ -276,12 +276,7 @@ class Oracle:
                                 _p(elts, u32p), kp, _p(out))
         return out
 
-    def bsgs_hoisted(self, ct, diags, G, B, D, keys):
-        """ct: (2,l,N); diags: (D, l+P, N >> rshift); keys: {elt: key}."""
-        ct, diags = _u64(ct), _u64(diags)
-        l = ct.shape[1]
-        dn = diags.shape[2]
-        rshift = (self.N // dn).bit_length() - 1
+    def _hoisted_args(self, G, B, keys):
         belts = np.zeros(G, dtype=np.uint32)
         gelts = np.zeros(B, dtype=np.uint32)
         bk = (u64p * G)()
@@ -291,8 +286,35 @@ class Oracle:
             bk[b] = _p(keys[int(belts[b])])
         for g in range(1, B):
             gelts[g] = self.elt_from_step(g * G)
-            gk[g] = _p(keys[int(gelts[g])])
+            if int(gelts[g]) in keys:
+                gk[g] = _p(keys[int(gelts[g])])
+        return belts, bk, gelts, gk
+
+    def bsgs_hoisted(self, ct, diags, G, B, D, keys):
+        """ct: (2,l,N); diags: (D, l+P, N >> rshift); keys: {elt: key}."""
+        return self.bsgs_finish(self.bsgs_hoisted_partial(ct, diags, G, B, D, keys))
+
+    def bsgs_hoisted_partial(self, ct, diags, G, B, D, keys, g_first=0, g_stride=1):
+        """Shard accumulator (2, l+P, N) in basis Q_l*P; diags holds the rows of groups g_first, g_first+g_stride, ..."""
+        ct, diags = _u64(ct), _u64(diags)
+        l = ct.shape[1]
+        dn = diags.shape[2]
+        rshift = (self.N // dn).bit_length() - 1
+        belts, bk, gelts, gk = self._hoisted_args(G, B, keys)
+        R = np.empty((2, l + self.P, self.N), dtype=np.uint64)
+        self.lib.orc_bsgs_hoisted_partial(self.ctx, int(l), _p(ct), _p(diags), int(rshift), int(G), int(B), int(D),
+                                          int(g_first), int(g_stride), _p(belts, u32p), bk, _p(gelts, u32p), gk, _p(R))
+        return R
+
+    def bsgs_finish(self, R):
+        R = _u64(R)
+        l = R.shape[1] - self.P
         out = np.empty((2, l - 1, self.N), dtype=np.uint64)
-        self.lib.orc_bsgs_hoisted(self.ctx, int(l), _p(ct), _p(diags), int(rshift), int(G), int(B), int(D),
-                                  _p(belts, u32p), bk, _p(gelts, u32p), gk, _p(out))
+        self.lib.orc_bsgs_finish(self.ctx, int(l), _p(R), _p(out))
         return out
+
+    def reduce_rows(self, x, ext):
+        x = _u64(x).copy()
+        l = x.shape[1] - (self.P if ext else 0)
+        self.lib.orc_reduce_rows(self.ctx, int(l), int(bool(ext)), int(x.shape[0]), _p(x))
+        return x

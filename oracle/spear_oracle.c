@@ -842,18 +842,20 @@ void orc_bsgs_exact(const orc_ctx *c, int l, const u64 *ct_baby, const u64 *pts,
 /*  5. out = rescale(ModDown(R))                                       */
 /* diags[D][l+P][N >> rshift]; baby_elts[b], bkeys[b] for b = 1..G-1    */
 /* ------------------------------------------------------------------ */
-void orc_bsgs_hoisted(const orc_ctx *c, int l, const u64 *ct, const u64 *diags, int rshift,
-                      int G, int B, int D,
-                      const u32 *baby_elts, const u64 *const *bkeys,
-                      const u32 *giant_elts, const u64 *const *gkeys, u64 *out) {
+/* shard form: diags holds only the giant groups g = g_first + k*g_stride (k = 0,1,...) in that order;
+ * R[2][l+P][N] is the shard's accumulator in basis Q_l*P (the sum over all shards mod q is the full one) */
+void orc_bsgs_hoisted_partial(const orc_ctx *c, int l, const u64 *ct, const u64 *diags, int rshift,
+                              int G, int B, int D, int g_first, int g_stride,
+                              const u32 *baby_elts, const u64 *const *bkeys,
+                              const u32 *giant_elts, const u64 *const *gkeys, u64 *R) {
     u64 N = c->N; int rows = l + c->P, beta = n_digits(c, l);
     u64 polyw = (u64)rows * N, dn = N >> rshift;
     u64 *E = (u64 *)malloc(sizeof(u64) * polyw * beta);
     u64 *Y = (u64 *)malloc(sizeof(u64) * polyw * 2 * G);
     u64 *A = (u64 *)malloc(sizeof(u64) * polyw * 2);
-    u64 *R = (u64 *)calloc(polyw * 2, sizeof(u64));
     u64 *t = (u64 *)malloc(sizeof(u64) * N * l);
     const u64 *c0 = ct, *c1 = ct + (u64)l * N;
+    memset(R, 0, sizeof(u64) * 2 * polyw);
     orc_decompose(c, l, c1, E);
     for (int b = 0; b < G; b++) {
         u64 *Yb = Y + (u64)b * 2 * polyw;
@@ -866,20 +868,22 @@ void orc_bsgs_hoisted(const orc_ctx *c, int l, const u64 *ct, const u64 *diags, 
                 if (b == 0) Yb[polyw + (u64)i * N + n] = mulmod(pm, c1[(u64)i * N + n], q);
             } }
     }
-    for (int g = 0; g < B; g++) {
+    u64 row0 = 0;   /* first stored diagonal of the current group */
+    for (int g = g_first; g < B; g += g_stride) {
         memset(A, 0, sizeof(u64) * 2 * polyw);
-        int any = 0;
+        int any = 0, used = 0;
         for (int b = 0; b < G; b++) {
             int k = g * G + b; if (k >= D) continue;
-            any = 1;
-            const u64 *Yb = Y + (u64)b * 2 * polyw, *pt = diags + (u64)k * rows * dn;
+            any = 1; used++;
+            const u64 *Yb = Y + (u64)b * 2 * polyw, *pt = diags + (row0 + (u64)b) * rows * dn;
             #pragma omp parallel for schedule(static) collapse(2)
             for (int p = 0; p < 2; p++) for (int r = 0; r < rows; r++) { u64 q = c->q[row_limb(c, l, r)];
                 for (u64 n = 0; n < N; n++) { u64 x = (u64)p * polyw + (u64)r * N + n;
                     A[x] = addmod(A[x], mulmod(Yb[x], pt[(u64)r * dn + (n >> rshift)], q), q); } }
         }
+        row0 += (u64)used;
         if (!any) continue;
-        if (g == 0) { for (u64 x = 0; x < 2 * polyw; x++) R[x] = A[x]; continue; }
+        if (g == 0) { for (u64 x = 0; x < 2 * polyw; x++) R[x] = addmod(R[x], A[x], c->q[row_limb(c, l, (int)((x / N) % rows))]); continue; }
         moddown_poly(c, l, A + polyw, t);
         orc_decompose(c, l, t, E);
         ks_inner(c, l, E, giant_elts[g], gkeys[g], R, 1);
@@ -889,9 +893,29 @@ void orc_bsgs_hoisted(const orc_ctx *c, int l, const u64 *ct, const u64 *diags, 
                 R[(u64)r * N + n] = addmod(R[(u64)r * N + n], A[(u64)r * N + src], q);
             } }
     }
+    free(E); free(Y); free(A); free(t);
+}
+/* R[2][l+P][N] -> out[2][l-1][N]: ModDown both polynomials, rescale */
+void orc_bsgs_finish(const orc_ctx *c, int l, const u64 *R, u64 *out) {
+    u64 N = c->N, polyw = (u64)(l + c->P) * N;
     u64 *full = (u64 *)malloc(sizeof(u64) * 2 * l * N);
     moddown_poly(c, l, R, full);
     moddown_poly(c, l, R + polyw, full + (u64)l * N);
     orc_rescale(c, l, 2, full, out);
-    free(E); free(Y); free(A); free(R); free(t); free(full);
+    free(full);
+}
+void orc_bsgs_hoisted(const orc_ctx *c, int l, const u64 *ct, const u64 *diags, int rshift,
+                      int G, int B, int D,
+                      const u32 *baby_elts, const u64 *const *bkeys,
+                      const u32 *giant_elts, const u64 *const *gkeys, u64 *out) {
+    u64 *R = (u64 *)malloc(sizeof(u64) * 2 * (u64)(l + c->P) * c->N);
+    orc_bsgs_hoisted_partial(c, l, ct, diags, rshift, G, B, D, 0, 1, baby_elts, bkeys, giant_elts, gkeys, R);
+    orc_bsgs_finish(c, l, R, out);
+    free(R);
+}
+/* x mod q per row (rows follow row_limb), for lazily summed accumulators */
+void orc_reduce_rows(const orc_ctx *c, int l, int ext, int polys, u64 *x) {
+    int rows = l + (ext ? c->P : 0);
+    for (int p = 0; p < polys; p++) for (int r = 0; r < rows; r++) { u64 q = c->q[row_limb(c, l, r)];
+        for (u64 n = 0; n < c->N; n++) x[((u64)p * rows + r) * c->N + n] %= q; }
 }

@@ -1,0 +1,87 @@
+"""World-size-2 gloo tests of the giant-step sharding logic (host side of SURVEY.md section 8e).
+
+The arithmetic of each rank is done by the CPU oracle (this is a CPU test); what is under test is the
+shard plan of fhe_spear_b200.sharding, the lazy integer all-reduce of the Q_l*P accumulators over
+torch.distributed, and that reduce + one ModDown/rescale reproduces the unsharded ciphertext bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import SEED, Setup, bsgs_params, rolled_diagonals, tile
+
+
+def test_shard_plan_partitions_the_matrix():
+    from fhe_spear_b200 import sharding as sh
+    for D in (16, 20, 2048):
+        G, B = bsgs_params(D)
+        for world in (1, 2, 3, 8):
+            rows = [sh.shard_rows(D, G, B, r, world) for r in range(world)]
+            assert sorted(k for part in rows for k in part) == list(range(D))
+            groups = [sh.giant_groups(B, r, world) for r in range(world)]
+            assert sorted(g for part in groups for g in part) == list(range(B))
+            for r in range(world):
+                steps = sh.shard_steps(D, G, B, r, world)
+                assert set(range(1, G)) <= set(steps)
+                assert {g * G for g in groups[r] if g} == set(steps) - set(range(1, G))
+    assert [sh.projection_owner(i, 3) for i in range(8)] == [0, 1, 2, 0, 1, 2, 0, 1]
+    q59 = [(1 << 59) - 1] * 4
+    assert sh.lazy_sum_is_safe(q59, 8) and not sh.lazy_sum_is_safe([(1 << 60) - 1], 16)
+
+
+def _worker(rank, world, port, D, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fhe_spear_b200 import sharding as sh
+    S = Setup(N=512, bits=(59,) * 5, P=2)
+    o = S.o
+    G, B = bsgs_params(D)
+    rng = np.random.default_rng(5)
+    W, x = rng.standard_normal((D, D)) * 0.1, rng.standard_normal(D)
+    rolled = rolled_diagonals(W, D, G, B)
+    keys = S.keys_for_steps(sh.shard_steps(D, G, B, rank, world))
+    ct = o.encrypt_symmetric(SEED, 1, S.sk, o.encode(tile(x, S.N // 2), S.scale, S.L))
+    rows = sh.shard_rows(D, G, B, rank, world)
+    pow2 = D & (D - 1) == 0
+
+    def enc(v):    # sub-ring form when D is a power of two, else the full ring
+        if pow2:
+            return o.encode(v.astype(complex), S.scale, S.L, ext=True, n=2 * D)
+        return o.encode(tile(v, S.N // 2), S.scale, S.L, ext=True)
+    diag = np.stack([enc(rolled[k]) for k in rows])
+    acc = o.bsgs_hoisted_partial(ct, diag, G, B, D, keys, g_first=rank, g_stride=world)
+    assert sh.lazy_sum_is_safe(S.q, world)
+    t = torch.from_numpy(acc.view(np.int64))
+    sh.allreduce_residues(t)                       # plain integer sum over ranks
+    y = o.bsgs_finish(o.reduce_rows(acc, ext=True))
+    if rank == 0:
+        all_keys = S.keys_for_steps(list(range(1, G)) + [g * G for g in range(1, B)])
+        full = np.stack([enc(r) for r in rolled])
+        ref = o.bsgs_hoisted(ct, full, G, B, D, all_keys)
+        dec = o.decode(o.decrypt(S.sk, y), S.scale ** 2 / float(S.q[S.L - 1]))[:D].real
+        out.put((bool(np.array_equal(y, ref)), float(np.abs(dec - W @ x).max())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("D", [16, 20])
+def test_two_rank_giant_sharding_matches_unsharded(D):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, D, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    same, err = out.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert same, "sharded ciphertext differs from the unsharded one"
+    assert err < 1e-9
