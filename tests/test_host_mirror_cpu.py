@@ -64,5 +64,5 @@ def test_chunk_packing_reproduces_projection():
             lo1, hi1 = c2 * D, min((c2 + 1) * D, F)
             x1[:hi1 - lo1] = xf[lo1:hi1]
             M1n = hb._val_chunk(Wv, c2, D, F, -1.0)
-            down += ((M0 - 1j * M1n) @ (x0 + 1j * x1)).real     # Enc(x0 + i x1) * (d0 - i d1)
+            down += ((M0 + 1j * M1n) @ (x0 + 1j * x1)).real     # diagonals d0 + i*(-d1): Enc(x0 + i x1) * (d0 - i d1)
     assert np.allclose(down, xf @ Wv)
