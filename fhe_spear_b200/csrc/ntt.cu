@@ -33,6 +33,44 @@ __device__ __forceinline__ void gs_butterfly(u64& x, u64& y, ulonglong2 w, u64 q
     y = mul_shoup_lazy(d, w.x, w.y, q);
 }
 
+// ---- lazy forward butterflies for q < 2^59 (31q < 2^64) -------------------------------------------------
+// No conditional subtraction at all: the twiddle product uses an approximate Shoup quotient (three 32x32
+// products instead of a full 64x64 high half, error <= 2, result in [0,4q)), so a value grows by at most 4q
+// per stage; 7 such stages plus one exact-Shoup stage stay below 31q, and each pass ends with one cheap
+// reduction (the Barrett ratio floor(2^64/q) fits 32 bits).
+__device__ __forceinline__ u64 mul_shoup_apx(u64 a, u64 w, u64 wp, u64 q) {
+    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), p0 = (u32)wp, p1 = (u32)(wp >> 32);
+    const u64 Q = (u64)a1 * p1 + (((u64)a0 * p1) >> 32) + (((u64)a1 * p0) >> 32);
+    return a * w - Q * q;
+}
+template <bool LAZY>
+__device__ __forceinline__ void fwd_bf(u64& x, u64& y, ulonglong2 w, u64 q, u64 q2, u64 q4) {
+    if (LAZY) {
+        const u64 t = mul_shoup_apx(y, w.x, w.y, q);
+        y = x - t + q4;
+        x = x + t;
+    } else {
+        ct_butterfly(x, y, w, q, q2);
+    }
+}
+// last stage of a lazy pass: exact Shoup product (grows by 2q only)
+template <bool LAZY>
+__device__ __forceinline__ void fwd_bf_last(u64& x, u64& y, ulonglong2 w, u64 q, u64 q2, u64 q4) {
+    if (LAZY) {
+        const u64 t = mul_shoup_lazy(y, w.x, w.y, q);
+        y = x - t + q2;
+        x = x + t;
+    } else {
+        ct_butterfly(x, y, w, q, q2);
+    }
+}
+// x < 2^64 -> [0, q);  r1 = floor(2^64/q) < 2^32
+__device__ __forceinline__ u64 reduce_small_ratio(u64 x, u64 q, u32 r1) {
+    const u64 h = ((u64)(u32)(x >> 32) * r1 + (((u64)(u32)x * r1) >> 32)) >> 32;
+    u64 r = x - h * q;            // in [0, 2q)
+    return r >= q ? r - q : r;
+}
+
 // ---- forward, pass A: stages 0..sA-1 on a [2^sA][COLS] tile --------------------------------
 __global__ void __launch_bounds__(TPB) ntt_fwd_a(u64* __restrict__ data, RowMap rm, NttTab tb, int N, int n,
                                                   int sA, int skip_alpha) {
@@ -179,18 +217,10 @@ constexpr int WB = 4;   // warps (= chunks) per pass-B CTA
 
 __device__ __forceinline__ int swz(int x) { return x ^ (((x >> 4) & 7) | ((x >> 2) & 8)); }
 
-__global__ void __launch_bounds__(WB * 32) ntt_fwd_b2(u64* __restrict__ data, RowMap rm, NttTab tb, int N, int n,
-                                                       int sA, int skip_alpha) {
-    __shared__ u64 smem[WB][256];
-    const int row = blockIdx.y;
-    const int limb = rm.limb(row);
-    if (skip_alpha && limb < rm.L && limb / skip_alpha == row / rm.rpp) return;
-    const u64 q = tb.q[limb], q2 = q << 1;
-    const ulonglong2* __restrict__ tw = tb.psi + (size_t)limb * N;
-    const int warp = threadIdx.x >> 5, j = threadIdx.x & 31;
-    const int gc = blockIdx.x * WB + warp;
-    u64* base = data + (size_t)row * n + (size_t)gc * 256;
-    u64* s = smem[warp];
+template <bool LAZY>
+__device__ __forceinline__ void fwd_b2_body(u64* __restrict__ base, u64* __restrict__ s,
+                                            const ulonglong2* __restrict__ tw, u64 q, int sA, int gc, int j) {
+    const u64 q2 = q << 1, q4 = q << 2;
     u64 v[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) v[k] = base[j + 32 * k];
@@ -198,14 +228,14 @@ __global__ void __launch_bounds__(WB * 32) ntt_fwd_b2(u64* __restrict__ data, Ro
     {   // x = j + 32k ; t = 128, 64, 32
         ulonglong2 w = tw[m + gc];
 #pragma unroll
-        for (int k = 0; k < 4; k++) ct_butterfly(v[k], v[k + 4], w, q, q2);
+        for (int k = 0; k < 4; k++) fwd_bf<LAZY>(v[k], v[k + 4], w, q, q2, q4);
         m <<= 1;
         ulonglong2 w0 = tw[m + 2 * gc], w1 = tw[m + 2 * gc + 1];
-        ct_butterfly(v[0], v[2], w0, q, q2), ct_butterfly(v[1], v[3], w0, q, q2);
-        ct_butterfly(v[4], v[6], w1, q, q2), ct_butterfly(v[5], v[7], w1, q, q2);
+        fwd_bf<LAZY>(v[0], v[2], w0, q, q2, q4), fwd_bf<LAZY>(v[1], v[3], w0, q, q2, q4);
+        fwd_bf<LAZY>(v[4], v[6], w1, q, q2, q4), fwd_bf<LAZY>(v[5], v[7], w1, q, q2, q4);
         m <<= 1;
 #pragma unroll
-        for (int k = 0; k < 4; k++) ct_butterfly(v[2 * k], v[2 * k + 1], tw[m + 4 * gc + k], q, q2);
+        for (int k = 0; k < 4; k++) fwd_bf<LAZY>(v[2 * k], v[2 * k + 1], tw[m + 4 * gc + k], q, q2, q4);
     }
 #pragma unroll
     for (int k = 0; k < 8; k++) s[swz(j + 32 * k)] = v[k];
@@ -220,9 +250,9 @@ __global__ void __launch_bounds__(WB * 32) ntt_fwd_b2(u64* __restrict__ data, Ro
 #pragma unroll
             for (int i = 0; i < 4; i++) e[i] = s[swz(32 * blk + b + 8 * i)];
             ulonglong2 w = tw[m + 8 * gc + blk];
-            ct_butterfly(e[0], e[2], w, q, q2), ct_butterfly(e[1], e[3], w, q, q2);
+            fwd_bf<LAZY>(e[0], e[2], w, q, q2, q4), fwd_bf<LAZY>(e[1], e[3], w, q, q2, q4);
             ulonglong2 wa = tw[2 * m + 16 * gc + 2 * blk], wb = tw[2 * m + 16 * gc + 2 * blk + 1];
-            ct_butterfly(e[0], e[1], wa, q, q2), ct_butterfly(e[2], e[3], wb, q, q2);
+            fwd_bf<LAZY>(e[0], e[1], wa, q, q2, q4), fwd_bf<LAZY>(e[2], e[3], wb, q, q2, q4);
 #pragma unroll
             for (int i = 0; i < 4; i++) s[swz(32 * blk + b + 8 * i)] = e[i];
         }
@@ -235,24 +265,45 @@ __global__ void __launch_bounds__(WB * 32) ntt_fwd_b2(u64* __restrict__ data, Ro
         m <<= 1;
         ulonglong2 w = tw[m + 32 * gc + j];
 #pragma unroll
-        for (int k = 0; k < 4; k++) ct_butterfly(v[k], v[k + 4], w, q, q2);
+        for (int k = 0; k < 4; k++) fwd_bf<LAZY>(v[k], v[k + 4], w, q, q2, q4);
         m <<= 1;
         ulonglong2 w0 = tw[m + 64 * gc + 2 * j], w1 = tw[m + 64 * gc + 2 * j + 1];
-        ct_butterfly(v[0], v[2], w0, q, q2), ct_butterfly(v[1], v[3], w0, q, q2);
-        ct_butterfly(v[4], v[6], w1, q, q2), ct_butterfly(v[5], v[7], w1, q, q2);
+        fwd_bf<LAZY>(v[0], v[2], w0, q, q2, q4), fwd_bf<LAZY>(v[1], v[3], w0, q, q2, q4);
+        fwd_bf<LAZY>(v[4], v[6], w1, q, q2, q4), fwd_bf<LAZY>(v[5], v[7], w1, q, q2, q4);
         m <<= 1;
 #pragma unroll
-        for (int k = 0; k < 4; k++) ct_butterfly(v[2 * k], v[2 * k + 1], tw[m + 128 * gc + 4 * j + k], q, q2);
+        for (int k = 0; k < 4; k++) fwd_bf_last<LAZY>(v[2 * k], v[2 * k + 1], tw[m + 128 * gc + 4 * j + k], q, q2, q4);
+        if (LAZY) {
+            const u32 r1 = (u32)(0xFFFFFFFFFFFFFFFFull / q);
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            u64 x = v[i];
-            x = x >= q2 ? x - q2 : x;
-            s[swz(8 * j + i)] = x >= q ? x - q : x;
+            for (int i = 0; i < 8; i++) s[swz(8 * j + i)] = reduce_small_ratio(v[i], q, r1);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                u64 x = v[i];
+                x = x >= q2 ? x - q2 : x;
+                s[swz(8 * j + i)] = x >= q ? x - q : x;
+            }
         }
     }
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 8; k++) base[j + 32 * k] = s[swz(j + 32 * k)];
+}
+
+__global__ void __launch_bounds__(WB * 32) ntt_fwd_b2(u64* __restrict__ data, RowMap rm, NttTab tb, int N, int n,
+                                                       int sA, int skip_alpha) {
+    __shared__ u64 smem[WB][256];
+    const int row = blockIdx.y;
+    const int limb = rm.limb(row);
+    if (skip_alpha && limb < rm.L && limb / skip_alpha == row / rm.rpp) return;
+    const u64 q = tb.q[limb];
+    const ulonglong2* __restrict__ tw = tb.psi + (size_t)limb * N;
+    const int warp = threadIdx.x >> 5, j = threadIdx.x & 31;
+    const int gc = blockIdx.x * WB + warp;
+    u64* base = data + (size_t)row * n + (size_t)gc * 256;
+    if (q < (1ull << 59) && q > (1ull << 33)) fwd_b2_body<true>(base, smem[warp], tw, q, sA, gc, j);
+    else fwd_b2_body<false>(base, smem[warp], tw, q, sA, gc, j);
 }
 
 __global__ void __launch_bounds__(WB * 32) ntt_inv_b2(u64* __restrict__ data, RowMap rm, NttTab tb, int N, int n,
@@ -332,19 +383,11 @@ __global__ void __launch_bounds__(WB * 32) ntt_inv_b2(u64* __restrict__ data, Ro
 }
 
 // pass A, forward: SA stages on a [R = 2^SA][16] tile, 2R threads, thread = (column c, row group g)
-template <int SA>
-__global__ void __launch_bounds__(2 << SA) ntt_fwd_a2(u64* __restrict__ data, RowMap rm, NttTab tb, int N, int n,
-                                                       int skip_alpha) {
+template <int SA, bool LAZY>
+__device__ __forceinline__ void fwd_a2_body(u64* __restrict__ base, u64* __restrict__ sm,
+                                            const ulonglong2* __restrict__ tw, u64 q, int S, int c, int g) {
     constexpr int R = 1 << SA;
-    __shared__ u64 sm[R * COLS];
-    const int row = blockIdx.y;
-    const int limb = rm.limb(row);
-    if (skip_alpha && limb < rm.L && limb / skip_alpha == row / rm.rpp) return;
-    const u64 q = tb.q[limb], q2 = q << 1;
-    const ulonglong2* __restrict__ tw = tb.psi + (size_t)limb * N;
-    const int c = threadIdx.x & (COLS - 1), g = threadIdx.x >> 4;
-    const int S = n >> SA;
-    u64* base = data + (size_t)row * n + blockIdx.x * COLS + c;
+    const u64 q2 = q << 1, q4 = q << 2;
     u64 v[8];
 #pragma unroll
     for (int s0 = 0; s0 < SA; s0 += 3) {
@@ -366,20 +409,43 @@ __global__ void __launch_bounds__(2 << SA) ntt_fwd_a2(u64* __restrict__ data, Ro
                 for (int k = 0; k < 8; k++) {
                     if (!(k & kgap)) {
                         const int r = rowbase + k * gbot;
-                        ct_butterfly(v[k], v[k + kgap], tw[(1 << st) + (r >> (SA - st))], q, q2);
+                        const ulonglong2 w = tw[(1 << st) + (r >> (SA - st))];
+                        if (SA == 8 && st == SA - 1) fwd_bf_last<LAZY>(v[k], v[k + kgap], w, q, q2, q4);   // 8 stages: keep < 31q
+                        else fwd_bf<LAZY>(v[k], v[k + kgap], w, q, q2, q4);
                     }
                 }
             }
         }
         if (s0 + 3 >= SA) {
+            if (LAZY) {   // hand pass B canonical residues
+                const u32 r1 = (u32)(0xFFFFFFFFFFFFFFFFull / q);
 #pragma unroll
-            for (int k = 0; k < 8; k++) base[(size_t)(rowbase + k * gbot) * S] = v[k];
+                for (int k = 0; k < 8; k++) base[(size_t)(rowbase + k * gbot) * S] = reduce_small_ratio(v[k], q, r1);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; k++) base[(size_t)(rowbase + k * gbot) * S] = v[k];
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < 8; k++) sm[(rowbase + k * gbot) * COLS + c] = v[k];
             __syncthreads();
         }
     }
+}
+template <int SA>
+__global__ void __launch_bounds__(2 << SA) ntt_fwd_a2(u64* __restrict__ data, RowMap rm, NttTab tb, int N, int n,
+                                                       int skip_alpha) {
+    constexpr int R = 1 << SA;
+    __shared__ u64 sm[R * COLS];
+    const int row = blockIdx.y;
+    const int limb = rm.limb(row);
+    if (skip_alpha && limb < rm.L && limb / skip_alpha == row / rm.rpp) return;
+    const u64 q = tb.q[limb];
+    const ulonglong2* __restrict__ tw = tb.psi + (size_t)limb * N;
+    const int c = threadIdx.x & (COLS - 1), g = threadIdx.x >> 4;
+    u64* base = data + (size_t)row * n + blockIdx.x * COLS + c;
+    if (q < (1ull << 59) && q > (1ull << 33)) fwd_a2_body<SA, true>(base, sm, tw, q, n >> SA, c, g);
+    else fwd_a2_body<SA, false>(base, sm, tw, q, n >> SA, c, g);
 }
 
 // pass A, inverse: row gaps 1, 2, ..., R/2, then n^-1
