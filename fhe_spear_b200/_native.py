@@ -84,6 +84,7 @@ _SIG = {
     "spear_diagset_info": (C.c_int, [vp, ip, ip, ip, ip, ip, f64p, u64p]),
     "spear_diagset_export": (C.c_int, [vp, vp, C.c_size_t]),
     "spear_bsgs_hoisted": (C.c_int, [vp, vp, vp, vp, vpp]),
+    "spear_bsgs_hoisted_batch": (C.c_int, [vp, vpp, vpp, C.c_int, vp, vpp]),
     "spear_bsgs_hoisted_partial": (C.c_int, [vp, vp, vp, vp, vpp]),
     "spear_bsgs_finish": (C.c_int, [vp, vp, vpp]),
     "spear_obj_reduce": (C.c_int, [vp, vp]),

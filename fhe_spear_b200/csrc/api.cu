@@ -21,7 +21,7 @@ void bsgs_exact(const Ctx* c, const u64* const* baby, const u64* const* pts, int
                 const u32* gelt, const u64* const* gkey, u64* out, cudaStream_t s);
 void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, int rshift, int G, int n_groups,
                           int n_diags, int g_first, int g_stride, const u32* belt, const u64* const* bkey,
-                          const u32* gelt, const u64* const* gkey, u64* R, cudaStream_t s);
+                          const u32* gelt, const u64* const* gkey, u64* R, cudaStream_t s, bool pin_l2);
 void bsgs_finish(const Ctx* c, u64* R, int l, u64* out, cudaStream_t s);
 }  // namespace eng
 
@@ -46,10 +46,10 @@ inline Ctx* C_(spear_context* c) { return reinterpret_cast<Ctx*>(c); }
 inline const Obj* O_(const spear_obj* o) { return reinterpret_cast<const Obj*>(o); }
 inline spear_obj* H_(Obj* o) { return reinterpret_cast<spear_obj*>(o); }
 
-Obj* new_obj(Ctx* c, int size, int l, bool ext, int n, double scale) {
+Obj* new_obj(Ctx* c, int size, int l, bool ext, int n, double scale, cudaStream_t s = nullptr) {
     std::unique_ptr<Obj> o(new Obj);
     o->bind(c), o->size = size, o->l = l, o->ext = ext, o->n = n, o->scale = scale;
-    o->d = c->alloc(o->words());
+    o->d = c->alloc(o->words(), s);   // ordered on the stream that first writes it
     return o.release();
 }
 void use(Ctx* c) { CUDA_CHECK(cudaSetDevice(c->device)); }
@@ -777,7 +777,9 @@ int spear_diagset_export(const spear_diagset* d_, uint64_t* host, size_t words) 
     API_END
 }
 
-static Obj* bsgs_partial(Ctx* c, const Obj* ct, const DiagSet* ds, const GaloisKeys* gk) {
+static Obj* bsgs_partial(Ctx* c, const Obj* ct, const DiagSet* ds, const GaloisKeys* gk, cudaStream_t s = nullptr,
+                         bool pin_l2 = true) {
+    if (!s) s = c->stream;
     check_ct(ct, "bsgs_hoisted");
     REQUIRE(ct->size == 2, "bsgs_hoisted: relinearize first");
     REQUIRE(ds->l == ct->l, "bsgs_hoisted: diagonals encoded for %d limbs, ciphertext has %d", ds->l, ct->l);
@@ -792,16 +794,17 @@ static Obj* bsgs_partial(Ctx* c, const Obj* ct, const DiagSet* ds, const GaloisK
         gelt.push_back(g ? (u32)elt_from_step(g * ds->G, c->N) : 0);
         gkey.push_back(g ? find_key(gk, gelt.back())->d : nullptr);
     }
-    std::unique_ptr<Obj> R(new_obj(c, 2, l, true, c->N, ct->scale * ds->scale));
+    std::unique_ptr<Obj> R(new_obj(c, 2, l, true, c->N, ct->scale * ds->scale, s));
     eng::bsgs_hoisted_partial(c, ct->d, l, ds->d, ds->rshift, G, (int)gelt.size(), ds->n_diags, ds->g_first,
-                              ds->g_stride, belt.data(), bkey.data(), gelt.data(), gkey.data(), R->d, c->stream);
+                              ds->g_stride, belt.data(), bkey.data(), gelt.data(), gkey.data(), R->d, s, pin_l2);
     return R.release();
 }
-static Obj* bsgs_finish(Ctx* c, Obj* R) {
+static Obj* bsgs_finish(Ctx* c, Obj* R, cudaStream_t s = nullptr) {
+    if (!s) s = c->stream;
     REQUIRE(R && R->size == 2 && R->ext && R->n == c->N, "bsgs_finish: expected an accumulator in basis Q_l*P");
     REQUIRE(R->l >= 2, "bsgs: no level left for the final rescale");
-    std::unique_ptr<Obj> o(new_obj(c, 2, R->l - 1, false, c->N, R->scale / (double)c->q[R->l - 1]));
-    eng::bsgs_finish(c, R->d, R->l, o->d, c->stream);
+    std::unique_ptr<Obj> o(new_obj(c, 2, R->l - 1, false, c->N, R->scale / (double)c->q[R->l - 1], s));
+    eng::bsgs_finish(c, R->d, R->l, o->d, s);
     return o.release();
 }
 
@@ -815,6 +818,33 @@ int spear_bsgs_hoisted(spear_context* ctx, const spear_obj* ct_, const spear_dia
     REQUIRE(O_(ct_)->l >= 2, "bsgs_hoisted: no level left for the final rescale");
     std::unique_ptr<Obj> R(bsgs_partial(c, O_(ct_), ds, reinterpret_cast<const GaloisKeys*>(gk_)));
     *out = H_(bsgs_finish(c, R.get()));
+    API_END
+}
+int spear_bsgs_hoisted_batch(spear_context* ctx, spear_obj* const* cts, spear_diagset* const* dss, int count,
+                             const spear_galois_keys* gk_, spear_obj** outs) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    REQUIRE(count >= 1, "bsgs_hoisted_batch: empty batch");
+    const GaloisKeys* gk = reinterpret_cast<const GaloisKeys*>(gk_);
+    std::vector<std::unique_ptr<Obj>> acc(count), res(count);
+    // independent mat-vecs on the auxiliary streams: the HBM-bound key streams of one overlap the
+    // integer-bound NTT / MAC phases of the others
+    CUDA_CHECK(cudaEventRecord(c->ev_main, c->stream));
+    for (int i = 0; i < count; i++) {
+        const DiagSet* ds = reinterpret_cast<const DiagSet*>(dss[i]);
+        REQUIRE(ds->g_first == 0 && ds->g_stride == 1, "bsgs_hoisted_batch: sharded diagonal set");
+        cudaStream_t s = count == 1 ? c->stream : c->aux[i % 3];
+        if (count > 1 && i < 3) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_main, 0));
+        acc[i].reset(bsgs_partial(c, O_(cts[i]), ds, gk, s, count == 1));
+        res[i].reset(bsgs_finish(c, acc[i].get(), s));
+    }
+    if (count > 1)
+        for (int k = 0; k < 3 && k < count; k++) {
+            CUDA_CHECK(cudaEventRecord(c->ev_aux[k], c->aux[k]));
+            CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_aux[k], 0));
+        }
+    for (int i = 0; i < count; i++) outs[i] = H_(res[i].release());
     API_END
 }
 int spear_bsgs_hoisted_partial(spear_context* ctx, const spear_obj* ct_, const spear_diagset* ds_,

@@ -13,24 +13,25 @@
 
 namespace eng {
 
-struct Scratch {   // stream-ordered temporaries, released on scope exit
+struct Scratch {   // temporaries ordered on the stream that uses them, released on scope exit
     const Ctx* c;
+    cudaStream_t s;
     std::vector<void*> ptrs;
-    explicit Scratch(const Ctx* c_) : c(c_) {}
+    Scratch(const Ctx* c_, cudaStream_t s_) : c(c_), s(s_) {}
     u64* get(size_t words) {
-        u64* p = c->alloc(words);
+        u64* p = c->alloc(words, s);
         ptrs.push_back(p);
         return p;
     }
     ~Scratch() {
-        for (void* p : ptrs) c->free(p);
+        for (void* p : ptrs) c->free(p, s);
     }
 };
 
 // out[2][l][N] = ModDown(<decompose(cin), key>)  (+ add0[l][N] into polynomial 0)
 void keyswitch(const Ctx* c, const u64* cin, int l, const u64* key, const u64* add0, u64* out, cudaStream_t s) {
     const size_t N = c->N, rows = l + c->P;
-    Scratch sc(c);
+    Scratch sc(c, s);
     u64* x = sc.get(l * N);
     u64* E = sc.get(c->digits(l) * rows * N);
     u64* acc = sc.get(2 * rows * N);
@@ -44,7 +45,7 @@ void keyswitch(const Ctx* c, const u64* cin, int l, const u64* key, const u64* a
 // reference op order: permute both polynomials, key-switch the permuted c1, add the permuted c0
 void apply_galois(const Ctx* c, const u64* ct, int l, u32 elt, const u64* key, u64* out, cudaStream_t s) {
     const size_t N = c->N;
-    Scratch sc(c);
+    Scratch sc(c, s);
     u64* perm = sc.get(2 * l * N);
     ops::galois(c, ct, perm, 2 * l, elt, s);
     keyswitch(c, perm + l * N, l, key, perm, out, s);
@@ -59,7 +60,7 @@ void relinearize(const Ctx* c, const u64* ct3, int l, const u64* rlk, u64* out, 
 
 void rescale(const Ctx* c, const u64* in, int polys, int l, u64* out, cudaStream_t s) {
     const size_t N = c->N;
-    Scratch sc(c);
+    Scratch sc(c, s);
     u64* last = sc.get(polys * N);
     u64* tmp = sc.get((size_t)polys * (l - 1) * N);
     ops::rescale(c, in, polys, l, last, tmp, out, s);
@@ -69,7 +70,7 @@ void rescale(const Ctx* c, const u64* in, int polys, int l, u64* out, cudaStream
 void bsgs_exact(const Ctx* c, const u64* const* baby, const u64* const* pts, int G, int B, int D, int l,
                 const u32* gelt, const u64* const* gkey, u64* out, cudaStream_t s) {
     const size_t N = c->N, ctw = 2 * l * N;
-    Scratch sc(c);
+    Scratch sc(c, s);
     u64* inner = sc.get(ctw);
     u64* rot = sc.get(ctw);
     u64* res = sc.get(ctw);
@@ -95,10 +96,10 @@ void bsgs_exact(const Ctx* c, const u64* const* baby, const u64* const* pts, int
 // R [2][l+P][N]: this shard's accumulator in basis Q_l*P (sum over shards, mod q, = the full accumulator).
 void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, int rshift, int G, int n_groups,
                           int n_diags, int g_first, int g_stride, const u32* belt, const u64* const* bkey,
-                          const u32* gelt, const u64* const* gkey, u64* R, cudaStream_t s) {
+                          const u32* gelt, const u64* const* gkey, u64* R, cudaStream_t s, bool pin_l2) {
     const size_t N = c->N, rows = l + c->P, pw = rows * N;
     const int beta = c->digits(l);
-    Scratch sc(c);
+    Scratch sc(c, s);
     u64* x = sc.get(l * N);
     u64* E = sc.get(beta * pw);
     u64* Y = sc.get((size_t)G * 2 * pw);
@@ -108,10 +109,10 @@ void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, i
     // 1-2. hoisted baby steps, kept in basis Q_l * P
     ops::decompose(c, c1, l, x, E, s);
     ops::pscale(c, ct, Y, l, s);
-    c->l2_pin(s, E, sizeof(u64) * beta * pw);   // the digits are gathered by all G-1 baby kernels
+    if (pin_l2) c->l2_pin(s, E, sizeof(u64) * beta * pw);   // the digits are gathered by all G-1 baby kernels
     for (int b = 1; b < G; b++)
         ops::ks_inner(c, E, bkey[b], Y + (size_t)b * 2 * pw, l, belt[b], c0, l, 1, 0, s);
-    c->l2_pin(s, nullptr, 0);
+    if (pin_l2) c->l2_pin(s, nullptr, 0);
     // 3. diagonal multiply-accumulate for every local giant group
     ops::pmac_hoisted(c, Y, diag, A, G, n_groups, n_diags, l, rshift, s);
     // 4. giant steps: R = sum_k (pi_g(A_k.0) + <pi_g(F), k0>, <pi_g(F), k1>)   (g = g_first + k*g_stride; g = 0: R = A_k)
@@ -136,7 +137,7 @@ void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, i
 // R [2][l+P][N] (destroyed) -> out [2][l-1][N]: one ModDown, one rescale
 void bsgs_finish(const Ctx* c, u64* R, int l, u64* out, cudaStream_t s) {
     const size_t N = c->N, pw = (l + c->P) * N;
-    Scratch sc(c);
+    Scratch sc(c, s);
     u64* tmp = sc.get(2 * l * N);
     u64* full = sc.get(2 * l * N);
     ops::moddown(c, R, pw, 2, l, tmp, nullptr, full, s);

@@ -113,9 +113,9 @@ int create_coeff_modulus(u64 N, const int* bits, int n, u64* out) {
     return 0;
 }
 
-u64* Ctx::alloc(size_t n_u64) const {
+u64* Ctx::alloc(size_t n_u64, cudaStream_t s) const {
     void* p = nullptr;
-    CUDA_CHECK(cudaMallocAsync(&p, sizeof(u64) * (n_u64 ? n_u64 : 1), stream));
+    CUDA_CHECK(cudaMallocAsync(&p, sizeof(u64) * (n_u64 ? n_u64 : 1), s ? s : stream));
     return (u64*)p;
 }
 void Ctx::l2_pin(cudaStream_t s, const void* p, size_t bytes) const {
@@ -131,8 +131,8 @@ void Ctx::l2_pin(cudaStream_t s, const void* p, size_t bytes) const {
     cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v);
     if (!bytes) cudaCtxResetPersistingL2Cache();
 }
-void Ctx::free(void* p) const {
-    if (p) cudaFreeAsync(p, stream);
+void Ctx::free(void* p, cudaStream_t s) const {
+    if (p) cudaFreeAsync(p, s ? s : stream);
 }
 
 Ctx* ctx_create(u64 N, const u64* moduli, int K, int P, int device) {

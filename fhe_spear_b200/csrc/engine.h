@@ -59,8 +59,8 @@ struct Ctx {
 
     // keep [p, p+bytes) L2-resident for the kernels that follow on `s` (bytes = 0 clears the window)
     void l2_pin(cudaStream_t s, const void* p, size_t bytes) const;
-    u64* alloc(size_t n_u64) const;   // stream-ordered
-    void free(void* p) const;
+    u64* alloc(size_t n_u64, cudaStream_t s = nullptr) const;   // stream-ordered (default: the main stream)
+    void free(void* p, cudaStream_t s = nullptr) const;
 };
 
 // Objects keep their context alive: destroying the context handle first (Python GC order is arbitrary)

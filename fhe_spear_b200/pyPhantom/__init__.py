@@ -646,6 +646,15 @@ class diagonal_set:
         return out
 
 
+def bsgs_hoisted_batch(ctx, cts, diag_sets, gk):
+    """Independent mat-vecs (e.g. r, k, v of one block) run concurrently on separate streams."""
+    n = len(cts)
+    outs = (C.c_void_p * n)()
+    _check(_lib.spear_bsgs_hoisted_batch(ctx._h, (C.c_void_p * n)(*[c._h for c in cts]),
+                                         (C.c_void_p * n)(*[d._h for d in diag_sets]), n, gk._h, outs))
+    return [ciphertext(ctx, C.c_void_p(h)) for h in outs]
+
+
 def bsgs_hoisted_partial(ctx, ct, shard, gk):
     """This shard's accumulator in basis Q_l*P (ciphertext object with the special limbs)."""
     return _new(ciphertext, ctx, _lib.spear_bsgs_hoisted_partial, ct._h, shard._h, gk._h)

@@ -161,6 +161,11 @@ int spear_diagset_export(const spear_diagset* d, uint64_t* host, size_t words); 
 int spear_bsgs_hoisted(spear_context* ctx, const spear_obj* ct, const spear_diagset* diags,
                        const spear_galois_keys* gk, spear_obj** out);
 
+/* `count` independent mat-vecs (e.g. the r, k, v projections of one block: same keys, different inputs and
+ * diagonal sets, reference bootstrap_generation.py:784-792) issued on separate streams so that key streaming of
+ * one overlaps the transforms of the others.  outs receives `count` ciphertexts. */
+int spear_bsgs_hoisted_batch(spear_context* ctx, spear_obj* const* cts, spear_diagset* const* diags, int count,
+                             const spear_galois_keys* gk, spear_obj** outs);
 /* Sharded form: the shard's accumulator in basis Q_l*P (size 2, ext).  Accumulators of all shards are summed
  * (spear_add, or an integer all-reduce over spear_obj_device_ptr followed by spear_obj_reduce) and finished once. */
 int spear_bsgs_hoisted_partial(spear_context* ctx, const spear_obj* ct, const spear_diagset* shard,

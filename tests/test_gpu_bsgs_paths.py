@@ -165,3 +165,24 @@ def test_full_size_c3_properties():
     # D -> 2D complex-packed and 2D -> D conjugate-packed projections (config C3's FFN key / value shapes, scaled to one call each)
     Wk = rng.standard_normal((D, 2 * D)) * 0.02
     assert np.abs(hb.fhe_projection_bsgs(ckks, x1, Wk, D, 2 * D) - x1 @ Wk).max() < 1e-9
+
+
+def test_batched_matvecs_match_single_calls():
+    """bsgs_hoisted_batch (three independent projections on separate streams) == three single calls."""
+    from fhe_spear_b200 import bsgs as hb
+    from fhe_spear_b200 import pyPhantom as ph
+    D = 64
+    ckks = hb.CKKSBootstrapContext(poly_degree=4096, L0=6, prime_bits=59, special_mod_size=3, max_rot_dim=1,
+                                   bsgs_dim=[D], skip_bootstrap=True, seed=SEED, verbose=False)
+    G, B = hb.compute_bsgs_params(D)
+    rng = np.random.default_rng(3)
+    Ws = [rng.standard_normal((D, D)) * 0.1 for _ in range(4)]
+    xs = [rng.standard_normal(D) for _ in range(4)]
+    sets = [hb.pre_encode_real_diags(ckks, W, D, G, B, level=1) for W in Ws]
+    cts = [ckks.encrypt_replicated(x) for x in xs]
+    for rep in range(3):                               # repeated: exercises stream reuse and the pool
+        singles = [ph.bsgs_hoisted(ckks.ctx, c, s, ckks.gk) for c, s in zip(cts, sets)]
+        batch = ph.bsgs_hoisted_batch(ckks.ctx, cts, sets, ckks.gk)
+        for a, b, W, x in zip(singles, batch, Ws, xs):
+            assert np.array_equal(a.to_numpy(), b.to_numpy())
+            assert np.abs(ckks.decrypt_vec(b, D) - W @ x).max() < 1e-9
