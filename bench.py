@@ -209,6 +209,12 @@ def run_ours(args):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+            torch.cuda.synchronize()   # the barrier itself (and NCCL's lazy set-up) must be over before timing
+
+    if world > 1:                      # bring the communicator up outside every timed region
+        warm = torch.zeros(1, device="cuda")
+        dist.all_reduce(warm)
+        barrier()
 
     def step():
         return ph.bsgs_hoisted_batch(ctx, cts, dsets, ckks.gk)
