@@ -46,18 +46,29 @@ def workload_name(cfg):
 
 # ---- clocks -----------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """nvidia-smi polled in the background.  It is started well before the timed region (its start-up takes the
+    driver lock for a while, which would stall kernel launches) and samples are filtered to the timed window."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.t0 = self.t1 = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                        "-lms", "100", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
@@ -69,23 +80,25 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]),
+                             {n for n, v in zip(names, parts[4:8]) if v.lower().startswith("active")}))
             except ValueError:
                 continue
-            for name, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
         os.unlink(self.f.name)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.05 <= r[0] <= (self.t1 or 1e18) + 0.05]
+        use = inside or rows
+        if use:
+            out.update(sm_mhz=float(np.median([r[1] for r in use])), sm_max_mhz=float(max(r[2] for r in use)),
+                       reasons=sorted(set().union(*[r[3] for r in use])), samples=len(use),
+                       window="timed region" if inside else "whole run (no sample fell inside the timed region)")
         return out
 
 
@@ -222,15 +235,18 @@ def run_ours(args):
     def single():
         return ph.bsgs_hoisted(ctx, ct_x, diags, ckks.gk)
 
+    clocks = ClockSampler(local)
+    time.sleep(1.0)                       # let nvidia-smi finish starting up before anything is timed
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    clocks = ClockSampler(local)
     launches0 = _native.launch_count()
+    clocks.mark_start()
     ctx.timer_start()
     for _ in range(args.steps):
         step()
     ms = ctx.timer_stop()
+    clocks.mark_end()
     launches = _native.launch_count() - launches0
     barrier()
     clk = clocks.stop()

@@ -158,7 +158,8 @@ struct ProfScope {   // brackets the launches of one kernel class with an event 
 
 // ---- launchers (ntt.cu) --------------------------------------------------------------------
 // rows x n in-place transforms; `n` may be a power-of-two prefix size (sub-ring) <= N
-void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s, int skip_digit_alpha = 0);
+void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s, int skip_digit_alpha = 0,
+                 bool split30_out = false);
 void ntt_inverse(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s);
 
 // ---- stream ids shared with the oracle ------------------------------------------------------

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(TPB) ntt_fwd_a(u64* __restrict__ data, RowMap 
 
 // ---- forward, pass B: stages sA..logn-1 on contiguous chunks of M = 2^sB -------------------
 __global__ void __launch_bounds__(TPB) ntt_fwd_b(u64* __restrict__ data, RowMap rm, NttTab tb, int N, int n,
-                                                  int sA, int sB, int skip_alpha) {
+                                                  int sA, int sB, int skip_alpha, int split) {
     extern __shared__ u64 sm[];
     const int row = blockIdx.y;
     const int limb = rm.limb(row);
@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(TPB) ntt_fwd_b(u64* __restrict__ data, RowMap 
     for (int e = threadIdx.x; e < elems; e += TPB) {
         u64 v = sm[e];
         v = v >= q2 ? v - q2 : v;
-        base[e] = v >= q ? v - q : v;
+        v = v >= q ? v - q : v;
+        base[e] = split ? split30(v) : v;
     }
 }
 
@@ -219,7 +220,8 @@ __device__ __forceinline__ int swz(int x) { return x ^ (((x >> 4) & 7) | ((x >> 
 
 template <bool LAZY>
 __device__ __forceinline__ void fwd_b2_body(u64* __restrict__ base, u64* __restrict__ s,
-                                            const ulonglong2* __restrict__ tw, u64 q, int sA, int gc, int j) {
+                                            const ulonglong2* __restrict__ tw, u64 q, int sA, int gc, int j,
+                                            bool split) {
     const u64 q2 = q << 1, q4 = q << 2;
     u64 v[8];
 #pragma unroll
@@ -276,13 +278,17 @@ __device__ __forceinline__ void fwd_b2_body(u64* __restrict__ base, u64* __restr
         if (LAZY) {
             const u32 r1 = (u32)(0xFFFFFFFFFFFFFFFFull / q);
 #pragma unroll
-            for (int i = 0; i < 8; i++) s[swz(8 * j + i)] = reduce_small_ratio(v[i], q, r1);
+            for (int i = 0; i < 8; i++) {
+                const u64 x = reduce_small_ratio(v[i], q, r1);
+                s[swz(8 * j + i)] = split ? split30(x) : x;
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 u64 x = v[i];
                 x = x >= q2 ? x - q2 : x;
-                s[swz(8 * j + i)] = x >= q ? x - q : x;
+                x = x >= q ? x - q : x;
+                s[swz(8 * j + i)] = split ? split30(x) : x;
             }
         }
     }
@@ -292,7 +298,7 @@ __device__ __forceinline__ void fwd_b2_body(u64* __restrict__ base, u64* __restr
 }
 
 __global__ void __launch_bounds__(WB * 32) ntt_fwd_b2(u64* __restrict__ data, RowMap rm, NttTab tb, int N, int n,
-                                                       int sA, int skip_alpha) {
+                                                       int sA, int skip_alpha, int split) {
     __shared__ u64 smem[WB][256];
     const int row = blockIdx.y;
     const int limb = rm.limb(row);
@@ -302,8 +308,8 @@ __global__ void __launch_bounds__(WB * 32) ntt_fwd_b2(u64* __restrict__ data, Ro
     const int warp = threadIdx.x >> 5, j = threadIdx.x & 31;
     const int gc = blockIdx.x * WB + warp;
     u64* base = data + (size_t)row * n + (size_t)gc * 256;
-    if (q < (1ull << 59) && q > (1ull << 33)) fwd_b2_body<true>(base, smem[warp], tw, q, sA, gc, j);
-    else fwd_b2_body<false>(base, smem[warp], tw, q, sA, gc, j);
+    if (q < (1ull << 59) && q > (1ull << 33)) fwd_b2_body<true>(base, smem[warp], tw, q, sA, gc, j, split != 0);
+    else fwd_b2_body<false>(base, smem[warp], tw, q, sA, gc, j, split != 0);
 }
 
 __global__ void __launch_bounds__(WB * 32) ntt_inv_b2(u64* __restrict__ data, RowMap rm, NttTab tb, int N, int n,
@@ -519,7 +525,7 @@ inline void split(int logn, int& sA, int& sB) {
 
 }  // namespace
 
-void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s, int skip_alpha) {
+void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s, int skip_alpha, bool split30_out) {
     int logn = 0;
     while ((1 << logn) < n) logn++;
     REQUIRE((1 << logn) == n && n <= c->N && logn <= 16 && n >= 2, "ntt: bad size %d", n);
@@ -537,7 +543,7 @@ void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream
             case 7: launch_fwd_a2<7>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
             default: launch_fwd_a2<8>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
         }
-        LAUNCH(ntt_fwd_b2, dim3(n / (256 * WB), rows), WB * 32, 0, s)(data, rm, tb, c->N, n, sA, skip_alpha);
+        LAUNCH(ntt_fwd_b2, dim3(n / (256 * WB), rows), WB * 32, 0, s)(data, rm, tb, c->N, n, sA, skip_alpha, split30_out ? 1 : 0);
         CUDA_CHECK(cudaGetLastError());
         return;
     }
@@ -547,7 +553,7 @@ void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream
     }
     int elems = n < B_ELEMS ? n : B_ELEMS;
     dim3 grid(n / elems, rows);
-    LAUNCH(ntt_fwd_b, grid, TPB, sizeof(u64) * elems, s)(data, rm, tb, c->N, n, sA, sB, skip_alpha);
+    LAUNCH(ntt_fwd_b, grid, TPB, sizeof(u64) * elems, s)(data, rm, tb, c->N, n, sA, sB, skip_alpha, split30_out ? 1 : 0);
     CUDA_CHECK(cudaGetLastError());
 }
 

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(TPB) k_modup(const u64* __restrict__ x, const 
     for (int r = 0; r < rows; r++) {
         int t = r < l ? r : L + (r - l);
         if (t >= lo && t < hi) {
-            Ej[(size_t)r * N] = cin[(size_t)t * N + n];
+            Ej[(size_t)r * N] = split30(cin[(size_t)t * N + n]);   // digits are consumed in split-30 form
             continue;
         }
         Acc3 acc = {0, 0, 0};
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(TPB) k_ks_inner(KsArgs a, ModTab mt, const ulo
     const u64 pol = evict_first_policy();
 #pragma unroll 4
     for (int j = 0; j < a.beta; j++) {
-        u64 d = e[j * es];
+        u64 d = unsplit30(e[j * es]);
         u64 k0 = unsplit30(ld_stream(k + (size_t)(2 * j) * ks, pol)), k1 = unsplit30(ld_stream(k + (size_t)(2 * j + 1) * ks, pol));
         mac128(lo0, hi0, d, k0);
         mac128(lo1, hi1, d, k1);
@@ -220,22 +220,24 @@ __global__ void __launch_bounds__(TPB) k_ks_inner(KsArgs a, ModTab mt, const ulo
 // L2 evict-first policy while the threads gather their digit values (L2-resident, evict-last); two to
 // three CTAs per SM keep ~100 KB of key bytes in flight per SM.
 constexpr int KS_TILE = 256;
-template <int FOLD>
+// BETA > 0: digit count known at compile time (fully unrolled, no predication); BETA == 0: runtime loop.
+// The digits E arrive in split-30 form (written that way by ModUp / the forward NTT), like the keys.
+template <int FOLD, int BETA>
 __global__ void __launch_bounds__(KS_TILE, 4) k_ks_inner_tma(const __grid_constant__ CUtensorMap kmap, KsArgs a, ModTab mt,
-                                                           const ulonglong2* __restrict__ pmod) {
+                                                              const ulonglong2* __restrict__ pmod) {
     extern __shared__ __align__(128) unsigned char smraw[];
+    const int beta = BETA ? BETA : a.beta;
     u64* ksm = reinterpret_cast<u64*>(smraw);                       // [2*beta][KS_TILE]
-    uint64_t* full = reinterpret_cast<uint64_t*>(ksm + (size_t)2 * a.beta * KS_TILE);
+    uint64_t* full = reinterpret_cast<uint64_t*>(ksm + (size_t)2 * beta * KS_TILE);
     const int r = blockIdx.y, n0 = blockIdx.x * KS_TILE, n = n0 + threadIdx.x;
     const int t = r < a.l ? r : a.L + (r - a.l);
     if (threadIdx.x == 0) {
         mbar_init(full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(full, (u32)(2 * a.beta * KS_TILE * sizeof(u64)));
+        mbar_expect_tx(full, (u32)(2 * beta * KS_TILE * sizeof(u64)));
         tma_load_3d_hint(ksm, &kmap, n0, t, 0, full, evict_first_policy());
     }
     const u32 src = a.elt ? galois_src((u32)n, a.elt, a.logn) : (u32)n;
-    const u64 q = mt.q[t], r0 = mt.ratio0[t], r1 = mt.ratio1[t];
     const u64 keep = evict_last_policy();
     const u64* e = a.E + (size_t)r * a.N + src;
     const size_t es = (size_t)a.rows * a.N;
@@ -244,30 +246,38 @@ __global__ void __launch_bounds__(KS_TILE, 4) k_ks_inner_tma(const __grid_consta
     __syncthreads();   // barrier initialised before anybody waits on it
     u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
     Acc3 acc0 = {0, 0, 0}, acc1 = {0, 0, 0};
-    bool waited = false;
-    constexpr int CH = 8;   // digits gathered per batch (registers), folded every FOLD terms
-    for (int j0 = 0; j0 < a.beta; j0 += CH) {
-        u64 d[CH];
+    const u64* kcol = ksm + threadIdx.x;
+    if (BETA) {
+        u64 d[BETA ? BETA : 1];
 #pragma unroll
-        for (int j = 0; j < CH; j++) d[j] = (j0 + j < a.beta) ? ld_keep(e + (size_t)(j0 + j) * es, keep) : 0;
-        if (!waited) {
-            mbar_wait(full, 0);
-            waited = true;
-        }
+        for (int j = 0; j < BETA; j++) d[j] = ld_keep(e + (size_t)j * es, keep);
+        mbar_wait(full, 0);
 #pragma unroll
-        for (int j = 0; j < CH; j++) {
-            if (j0 + j < a.beta) {
-                const u64 ds = split30(d[j]);
-                const u32 dsum = (u32)ds + (u32)(ds >> 32);
-                mac_split(acc0, ds, dsum, ksm[(size_t)(2 * (j0 + j)) * KS_TILE + threadIdx.x]);
-                mac_split(acc1, ds, dsum, ksm[(size_t)(2 * (j0 + j) + 1) * KS_TILE + threadIdx.x]);
+        for (int j = 0; j < BETA; j++) {
+            const u32 dsum = (u32)d[j] + (u32)(d[j] >> 32);
+            mac_split(acc0, d[j], dsum, kcol[(2 * j) * KS_TILE]);
+            mac_split(acc1, d[j], dsum, kcol[(2 * j + 1) * KS_TILE]);
+            if ((j + 1) % FOLD == 0 && j + 1 < BETA) {
+                fold_split(lo0, hi0, acc0);
+                fold_split(lo1, hi1, acc1);
             }
         }
-        if (((j0 + CH) % FOLD) == 0 || j0 + CH >= a.beta) {
-            fold_split(lo0, hi0, acc0);
-            fold_split(lo1, hi1, acc1);
+    } else {
+        mbar_wait(full, 0);
+        for (int j = 0; j < beta; j++) {
+            const u64 dj = ld_keep(e + (size_t)j * es, keep);
+            const u32 dsum = (u32)dj + (u32)(dj >> 32);
+            mac_split(acc0, dj, dsum, kcol[(size_t)(2 * j) * KS_TILE]);
+            mac_split(acc1, dj, dsum, kcol[(size_t)(2 * j + 1) * KS_TILE]);
+            if ((j + 1) % FOLD == 0) {
+                fold_split(lo0, hi0, acc0);
+                fold_split(lo1, hi1, acc1);
+            }
         }
     }
+    fold_split(lo0, hi0, acc0);
+    fold_split(lo1, hi1, acc1);
+    const u64 q = mt.q[t], r0 = mt.ratio0[t], r1 = mt.ratio1[t];
     u64 v0 = barrett128(lo0, hi0, q, r0, r1), v1 = barrett128(lo1, hi1, q, r0, r1);
     if (a.addp && r < a.add_rows) {
         if (a.add_pscale) {
@@ -611,7 +621,7 @@ void decompose(const Ctx* c, const u64* cin, int l, u64* x, u64* E, cudaStream_t
         else if (P == 4) go(k_modup<4>);
         else go(k_modup<MAX_ALPHA>);
     }
-    ntt_forward(c, E, beta * rows, RowMap{rows, l, c->L, 0}, N, s, P);
+    ntt_forward(c, E, beta * rows, RowMap{rows, l, c->L, 0}, N, s, P, /*split30_out=*/true);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -639,8 +649,18 @@ void ks_inner(const Ctx* c, const u64* E, const u64* key, u64* out, int l, u32 e
             CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             LAUNCH(kern, dim3(c->N / KS_TILE, a.rows), KS_TILE, smem, s)(kmap, a, c->modtab(), c->d_pmod);
         };
-        if (small) go(k_ks_inner_tma<16>);
-        else go(k_ks_inner_tma<8>);
+#define KS_CASE(B)                                 \
+    case B:                                        \
+        if (small) go(k_ks_inner_tma<16, B>);      \
+        else go(k_ks_inner_tma<8, B>);             \
+        break;
+        switch (a.beta) {
+            KS_CASE(1) KS_CASE(2) KS_CASE(3) KS_CASE(4) KS_CASE(5) KS_CASE(6) KS_CASE(7) KS_CASE(8)
+            default:
+                if (small) go(k_ks_inner_tma<16, 0>);
+                else go(k_ks_inner_tma<8, 0>);
+        }
+#undef KS_CASE
         CUDA_CHECK(cudaGetLastError());
         return;
     }
