@@ -109,10 +109,10 @@ void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, i
     // 1-2. hoisted baby steps, kept in basis Q_l * P
     ops::decompose(c, c1, l, x, E, s);
     ops::pscale(c, ct, Y, l, s);
-    if (pin_l2) c->l2_pin(s, E, sizeof(u64) * beta * pw);   // the digits are gathered by all G-1 baby kernels
-    for (int b = 1; b < G; b++)
-        ops::ks_inner(c, E, bkey[b], Y + (size_t)b * 2 * pw, l, belt[b], c0, l, 1, 0, s);
-    if (pin_l2) c->l2_pin(s, nullptr, 0);
+    if (G > 1 && !ops::ks_baby_fused(c, E, bkey + 1, belt + 1, G - 1, Y + 2 * pw, l, c0, s))
+        for (int b = 1; b < G; b++)
+            ops::ks_inner(c, E, bkey[b], Y + (size_t)b * 2 * pw, l, belt[b], c0, l, 1, 0, s);
+    (void)pin_l2;
     // 3. diagonal multiply-accumulate for every local giant group
     ops::pmac_hoisted(c, Y, diag, A, G, n_groups, n_diags, l, rshift, s);
     // 4. giant steps: R = sum_k (pi_g(A_k.0) + <pi_g(F), k0>, <pi_g(F), k1>)   (g = g_first + k*g_stride; g = 0: R = A_k)

@@ -138,7 +138,7 @@ struct DiagSet : CtxRef {
 };
 
 enum { PROF_KS_INNER = 0, PROF_PMAC = 1, PROF_NTT = 2, PROF_MODUP = 3, PROF_MODDOWN = 4, PROF_RESCALE = 5,
-       PROF_OTHER = 6, PROF_CLASSES = 7 };
+       PROF_KS_BABY = 6, PROF_CLASSES = 7 };
 struct ProfScope {   // brackets the launches of one kernel class with an event pair when profiling is on
     const Ctx* c;
     cudaStream_t s;

@@ -219,81 +219,141 @@ __global__ void __launch_bounds__(TPB) k_ks_inner(KsArgs a, ModTab mt, const ulo
 // row -- 2*beta rows of 2 KB, one 3-D box [2*beta][1][256] -- is fetched by a single UTMALDG with an
 // L2 evict-first policy while the threads gather their digit values (L2-resident, evict-last); two to
 // three CTAs per SM keep ~100 KB of key bytes in flight per SM.
-constexpr int KS_TILE = 256;
+constexpr int KS_TILE = 128;
 // BETA > 0: digit count known at compile time (fully unrolled, no predication); BETA == 0: runtime loop.
 // The digits E arrive in split-30 form (written that way by ModUp / the forward NTT), like the keys.
+// One CTA walks KS_TPC consecutive 256-coefficient tiles of one (rotation, row) with a two-stage TMA ring:
+// the key box of tile i+2 is in flight while tile i is multiplied, so every SM keeps several 32 KB boxes
+// outstanding all the time (3 CTAs x 2 stages per SM).
+constexpr int KS_TPC = 8;
 template <int FOLD, int BETA>
-__global__ void __launch_bounds__(KS_TILE, 4) k_ks_inner_tma(const __grid_constant__ CUtensorMap kmap, KsArgs a, ModTab mt,
-                                                              const ulonglong2* __restrict__ pmod) {
+__device__ __forceinline__ void ks_tile_body(const CUtensorMap* kmap, const KsArgs& a, const ModTab& mt,
+                                             const ulonglong2* __restrict__ pmod, int r, int tile0, u32 elt,
+                                             u64* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smraw[];
     const int beta = BETA ? BETA : a.beta;
-    u64* ksm = reinterpret_cast<u64*>(smraw);                       // [2*beta][KS_TILE]
-    uint64_t* full = reinterpret_cast<uint64_t*>(ksm + (size_t)2 * beta * KS_TILE);
-    const int r = blockIdx.y, n0 = blockIdx.x * KS_TILE, n = n0 + threadIdx.x;
+    const size_t stage_words = (size_t)2 * beta * KS_TILE;
+    u64* ksm = reinterpret_cast<u64*>(smraw);                       // [2 stages][2*beta][KS_TILE]
+    uint64_t* full = reinterpret_cast<uint64_t*>(ksm + 2 * stage_words);
     const int t = r < a.l ? r : a.L + (r - a.l);
+    const int ntiles = min(KS_TPC, a.N / KS_TILE - tile0);
+    const u32 stage_bytes = (u32)(stage_words * sizeof(u64));
+    u64 pol_first = 0;
     if (threadIdx.x == 0) {
-        mbar_init(full, 1);
+        pol_first = evict_first_policy();
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(full, (u32)(2 * beta * KS_TILE * sizeof(u64)));
-        tma_load_3d_hint(ksm, &kmap, n0, t, 0, full, evict_first_policy());
+        for (int i = 0; i < 2 && i < ntiles; i++) {
+            mbar_expect_tx(&full[i], stage_bytes);
+            tma_load_3d_hint(ksm + i * stage_words, kmap, (tile0 + i) * KS_TILE, t, 0, &full[i], pol_first);
+        }
     }
-    const u32 src = a.elt ? galois_src((u32)n, a.elt, a.logn) : (u32)n;
     const u64 keep = evict_last_policy();
-    const u64* e = a.E + (size_t)r * a.N + src;
     const size_t es = (size_t)a.rows * a.N;
-    u64 c0add = 0;
-    if (a.addp && r < a.add_rows) c0add = a.addp[(size_t)r * a.N + src];
-    __syncthreads();   // barrier initialised before anybody waits on it
-    u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
-    Acc3 acc0 = {0, 0, 0}, acc1 = {0, 0, 0};
-    const u64* kcol = ksm + threadIdx.x;
-    if (BETA) {
-        u64 d[BETA ? BETA : 1];
-#pragma unroll
-        for (int j = 0; j < BETA; j++) d[j] = ld_keep(e + (size_t)j * es, keep);
-        mbar_wait(full, 0);
-#pragma unroll
-        for (int j = 0; j < BETA; j++) {
-            const u32 dsum = (u32)d[j] + (u32)(d[j] >> 32);
-            mac_split(acc0, d[j], dsum, kcol[(2 * j) * KS_TILE]);
-            mac_split(acc1, d[j], dsum, kcol[(2 * j + 1) * KS_TILE]);
-            if ((j + 1) % FOLD == 0 && j + 1 < BETA) {
-                fold_split(lo0, hi0, acc0);
-                fold_split(lo1, hi1, acc1);
-            }
-        }
-    } else {
-        mbar_wait(full, 0);
-        for (int j = 0; j < beta; j++) {
-            const u64 dj = ld_keep(e + (size_t)j * es, keep);
-            const u32 dsum = (u32)dj + (u32)(dj >> 32);
-            mac_split(acc0, dj, dsum, kcol[(size_t)(2 * j) * KS_TILE]);
-            mac_split(acc1, dj, dsum, kcol[(size_t)(2 * j + 1) * KS_TILE]);
-            if ((j + 1) % FOLD == 0) {
-                fold_split(lo0, hi0, acc0);
-                fold_split(lo1, hi1, acc1);
-            }
-        }
-    }
-    fold_split(lo0, hi0, acc0);
-    fold_split(lo1, hi1, acc1);
     const u64 q = mt.q[t], r0 = mt.ratio0[t], r1 = mt.ratio1[t];
-    u64 v0 = barrett128(lo0, hi0, q, r0, r1), v1 = barrett128(lo1, hi1, q, r0, r1);
-    if (a.addp && r < a.add_rows) {
-        if (a.add_pscale) {
-            ulonglong2 pm = pmod[t];
-            c0add = mul_shoup(c0add, pm.x, pm.y, q);
+    const bool has_add = a.addp && r < a.add_rows;
+    ulonglong2 pm = make_ulonglong2(0, 0);
+    if (has_add && a.add_pscale) pm = pmod[t];
+    __syncthreads();   // barriers initialised before anybody waits on them
+    // digits (and the c0 term) of tile i+1 are gathered from L2 while tile i is multiplied
+    u64 dn[BETA ? BETA : 1];
+    u64 c0n = 0;
+    u32 srcn = 0;
+    auto gather = [&](int i) {
+        const int n = (tile0 + i) * KS_TILE + threadIdx.x;
+        srcn = elt ? galois_src((u32)n, elt, a.logn) : (u32)n;
+        const u64* e = a.E + (size_t)r * a.N + srcn;
+        if (BETA) {
+#pragma unroll
+            for (int j = 0; j < BETA; j++) dn[j] = ld_keep(e + (size_t)j * es, keep);
         }
-        v0 = add_mod(v0, c0add, q);
+        c0n = has_add ? a.addp[(size_t)r * a.N + srcn] : 0;
+    };
+    gather(0);
+    for (int i = 0; i < ntiles; i++) {
+        const int n = (tile0 + i) * KS_TILE + threadIdx.x;
+        const u32 src = srcn;
+        const u64* e = a.E + (size_t)r * a.N + src;
+        const u64* kcol = ksm + (i & 1) * stage_words + threadIdx.x;
+        u64 c0add = c0n;
+        u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+        Acc3 acc0 = {0, 0, 0}, acc1 = {0, 0, 0};
+        if (BETA) {
+            u64 d[BETA ? BETA : 1];
+#pragma unroll
+            for (int j = 0; j < BETA; j++) d[j] = dn[j];
+            if (i + 1 < ntiles) gather(i + 1);
+            mbar_wait(&full[i & 1], (i >> 1) & 1);
+#pragma unroll
+            for (int j = 0; j < BETA; j++) {
+                const u32 dsum = (u32)d[j] + (u32)(d[j] >> 32);
+                mac_split(acc0, d[j], dsum, kcol[(2 * j) * KS_TILE]);
+                mac_split(acc1, d[j], dsum, kcol[(2 * j + 1) * KS_TILE]);
+                if ((j + 1) % FOLD == 0 && j + 1 < BETA) {
+                    fold_split(lo0, hi0, acc0);
+                    fold_split(lo1, hi1, acc1);
+                }
+            }
+        } else {
+            if (i + 1 < ntiles) gather(i + 1);
+            mbar_wait(&full[i & 1], (i >> 1) & 1);
+            for (int j = 0; j < beta; j++) {
+                const u64 dj = ld_keep(e + (size_t)j * es, keep);
+                const u32 dsum = (u32)dj + (u32)(dj >> 32);
+                mac_split(acc0, dj, dsum, kcol[(size_t)(2 * j) * KS_TILE]);
+                mac_split(acc1, dj, dsum, kcol[(size_t)(2 * j + 1) * KS_TILE]);
+                if ((j + 1) % FOLD == 0) {
+                    fold_split(lo0, hi0, acc0);
+                    fold_split(lo1, hi1, acc1);
+                }
+            }
+        }
+        fold_split(lo0, hi0, acc0);
+        fold_split(lo1, hi1, acc1);
+        u64 v0 = barrett128(lo0, hi0, q, r0, r1), v1 = barrett128(lo1, hi1, q, r0, r1);
+        if (has_add) {
+            if (a.add_pscale) c0add = mul_shoup(c0add, pm.x, pm.y, q);
+            v0 = add_mod(v0, c0add, q);
+        }
+        u64* o0 = out + (size_t)r * a.N + n;
+        u64* o1 = o0 + es;
+        if (a.accumulate) {
+            v0 = add_mod(v0, *o0, q);
+            v1 = add_mod(v1, *o1, q);
+        }
+        *o0 = v0;
+        *o1 = v1;
+        if (i + 2 < ntiles) {
+            __syncthreads();   // every thread is done reading stage i & 1
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&full[i & 1], stage_bytes);
+                tma_load_3d_hint(ksm + (i & 1) * stage_words, kmap, (tile0 + i + 2) * KS_TILE, t, 0, &full[i & 1],
+                                 pol_first);
+            }
+        }
     }
-    u64* o0 = a.out + (size_t)r * a.N + n;
-    u64* o1 = o0 + es;
-    if (a.accumulate) {
-        v0 = add_mod(v0, *o0, q);
-        v1 = add_mod(v1, *o1, q);
-    }
-    *o0 = v0;
-    *o1 = v1;
+}
+
+template <int FOLD, int BETA>
+__global__ void __launch_bounds__(KS_TILE, 6) k_ks_inner_tma(const __grid_constant__ CUtensorMap kmap, KsArgs a, ModTab mt,
+                                                              const ulonglong2* __restrict__ pmod) {
+    ks_tile_body<FOLD, BETA>(&kmap, a, mt, pmod, blockIdx.y, blockIdx.x * KS_TPC, a.elt, a.out);
+}
+
+// All hoisted baby steps in ONE launch: grid (tiles, babies, rows) is dispatched row-major, so the ~2 MB of
+// digits of a row stay L2-resident while the (G-1) rotation keys stream past them exactly once.
+constexpr int KS_MAX_BABY = 96;
+struct BabyTab {
+    CUtensorMap map[KS_MAX_BABY];   // key of baby step blockIdx.y + 1
+    u32 elt[KS_MAX_BABY];
+};
+template <int FOLD, int BETA>
+__global__ void __launch_bounds__(KS_TILE, 6) k_ks_baby_fused(const __grid_constant__ BabyTab tab, KsArgs a, ModTab mt,
+                                                               const ulonglong2* __restrict__ pmod) {
+    const int b = blockIdx.y;
+    ks_tile_body<FOLD, BETA>(&tab.map[b], a, mt, pmod, blockIdx.z, blockIdx.x * KS_TPC, tab.elt[b],
+                             a.out + (size_t)b * 2 * a.rows * a.N);
 }
 
 // y[p][r][n] = x[p][r][n] * (P mod q_r)  on data rows, 0 on special rows (the b = 0 baby "rotation")
@@ -632,7 +692,7 @@ void ks_inner(const Ctx* c, const u64* E, const u64* key, u64* out, int l, u32 e
     a.accumulate = accumulate, a.beta = c->digits(l), a.l = l, a.rows = l + c->P, a.N = c->N, a.logn = c->logn;
     a.L = c->L, a.K = c->K, a.elt = elt;
     ProfScope ps(c, PROF_KS_INNER, s);
-    if (c->N % KS_TILE == 0 && 2 * a.beta <= 256 && (size_t)2 * a.beta * KS_TILE * sizeof(u64) + 64 <= 200 * 1024) {
+    if (c->N % KS_TILE == 0 && 2 * a.beta <= 256 && (size_t)4 * a.beta * KS_TILE * sizeof(u64) + 64 <= 200 * 1024) {
         CUtensorMap kmap;
         cuuint64_t dims[3] = {(cuuint64_t)c->N, (cuuint64_t)c->K, (cuuint64_t)(2 * c->beta)};
         cuuint64_t strides[2] = {(cuuint64_t)c->N * sizeof(u64), (cuuint64_t)c->K * c->N * sizeof(u64)};
@@ -644,10 +704,11 @@ void ks_inner(const Ctx* c, const u64* E, const u64* key, u64* out, int l, u32 e
         REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
         bool small = true;
         for (u64 qq : c->q) small = small && qq < (1ull << 59);
-        const size_t smem = (size_t)2 * a.beta * KS_TILE * sizeof(u64) + 64;
+        const size_t smem = (size_t)4 * a.beta * KS_TILE * sizeof(u64) + 64;
+        const int gx = (c->N / KS_TILE + KS_TPC - 1) / KS_TPC;
         auto go = [&](auto kern) {
             CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            LAUNCH(kern, dim3(c->N / KS_TILE, a.rows), KS_TILE, smem, s)(kmap, a, c->modtab(), c->d_pmod);
+            LAUNCH(kern, dim3(gx, a.rows), KS_TILE, smem, s)(kmap, a, c->modtab(), c->d_pmod);
         };
 #define KS_CASE(B)                                 \
     case B:                                        \
@@ -666,6 +727,47 @@ void ks_inner(const Ctx* c, const u64* E, const u64* key, u64* out, int l, u32 e
     }
     LAUNCH(k_ks_inner, dim3(c->N / TPB, a.rows), TPB, 0, s)(a, c->modtab(), c->d_pmod);
     CUDA_CHECK(cudaGetLastError());
+}
+
+// Y[b] for b = 1..nb (out points at Y[1]): all hoisted baby steps against their keys in one launch.
+// Returns false when the fused path does not apply (caller falls back to one launch per baby step).
+bool ks_baby_fused(const Ctx* c, const u64* E, const u64* const* keys, const u32* elts, int nb, u64* out, int l,
+                   const u64* c0, cudaStream_t s) {
+    const int beta = c->digits(l), rows = l + c->P;
+    if (nb < 1 || nb > KS_MAX_BABY || beta > 8 || c->N % KS_TILE != 0) return false;
+    static thread_local BabyTab tab;   // 12.6 KB by-value kernel parameter
+    cuuint64_t dims[3] = {(cuuint64_t)c->N, (cuuint64_t)c->K, (cuuint64_t)(2 * c->beta)};
+    cuuint64_t strides[2] = {(cuuint64_t)c->N * sizeof(u64), (cuuint64_t)c->K * c->N * sizeof(u64)};
+    cuuint32_t box[3] = {(cuuint32_t)KS_TILE, 1, (cuuint32_t)(2 * beta)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    for (int b = 0; b < nb; b++) {
+        CUresult rc = encode_tiled()(&tab.map[b], CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, (void*)keys[b], dims, strides, box,
+                                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
+        tab.elt[b] = elts[b];
+    }
+    KsArgs a;
+    a.E = E, a.key = nullptr, a.out = out, a.addp = c0, a.add_rows = l, a.add_pscale = 1, a.accumulate = 0;
+    a.beta = beta, a.l = l, a.rows = rows, a.N = c->N, a.logn = c->logn, a.L = c->L, a.K = c->K, a.elt = 0;
+    bool small = true;
+    for (u64 qq : c->q) small = small && qq < (1ull << 59);
+    const size_t smem = (size_t)4 * beta * KS_TILE * sizeof(u64) + 64;
+    const int gx = (c->N / KS_TILE + KS_TPC - 1) / KS_TPC;
+    ProfScope ps(c, PROF_KS_BABY, s);
+    auto go = [&](auto kern) {
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        LAUNCH(kern, dim3(gx, nb, rows), KS_TILE, smem, s)(tab, a, c->modtab(), c->d_pmod);
+    };
+#define KB_CASE(B)                                  \
+    case B:                                         \
+        if (small) go(k_ks_baby_fused<16, B>);      \
+        else go(k_ks_baby_fused<8, B>);             \
+        break;
+    switch (beta) { KB_CASE(1) KB_CASE(2) KB_CASE(3) KB_CASE(4) KB_CASE(5) KB_CASE(6) KB_CASE(7) KB_CASE(8) }
+#undef KB_CASE
+    CUDA_CHECK(cudaGetLastError());
+    return true;
 }
 
 void pscale(const Ctx* c, const u64* x, u64* y, int l, cudaStream_t s) {

@@ -13,6 +13,8 @@ void galois(const Ctx* c, const u64* in, u64* out, int rows, u32 elt, cudaStream
 void decompose(const Ctx* c, const u64* cin, int l, u64* x, u64* E, cudaStream_t s);
 void ks_inner(const Ctx* c, const u64* E, const u64* key, u64* out, int l, u32 elt, const u64* addp, int add_rows,
               int add_pscale, int accumulate, cudaStream_t s);
+bool ks_baby_fused(const Ctx* c, const u64* E, const u64* const* keys, const u32* elts, int nb, u64* out, int l,
+                   const u64* c0, cudaStream_t s);
 void pscale(const Ctx* c, const u64* x, u64* y, int l, cudaStream_t s);
 void moddown(const Ctx* c, u64* in, size_t in_pstride, int polys, int l, u64* tmp, const u64* add, u64* out, cudaStream_t s);
 void rescale(const Ctx* c, const u64* in, int polys, int l, u64* last, u64* tmp, u64* out, cudaStream_t s);

@@ -58,7 +58,8 @@ void* spear_context_stream(spear_context* ctx);   /* cudaStream_t */
 int spear_timer_start(spear_context* ctx);
 int spear_timer_stop(spear_context* ctx, float* elapsed_ms);
 /* per-kernel-class device timing (event pair around every launch of the class) for the roofline line:
- * classes 0 key-switch inner product, 1 diagonal MAC, 2 NTT/INTT, 3 ModUp, 4 ModDown, 5 rescale, 6 other */
+ * classes 0 key inner product (one rotation per launch), 1 diagonal MAC, 2 NTT/INTT, 3 ModUp, 4 ModDown, 5 rescale,
+ * 6 fused hoisted baby-step key inner product (G-1 rotations per launch) */
 int spear_profile_enable(spear_context* ctx, int on);
 int spear_profile_read(spear_context* ctx, double* ms, uint64_t* launches, int classes);
 /* pinned host buffers for the host<->device legs of the end-to-end path */
