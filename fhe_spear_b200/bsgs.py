@@ -27,18 +27,21 @@ def compute_rotation_galois_elements(poly_degree, max_dim):
     return list(elts)
 
 
-def compute_bsgs_params(D):
-    G = int(np.ceil(np.sqrt(D)))          # baby steps
-    return G, int(np.ceil(D / G))         # giant steps
+def compute_bsgs_params(D, baby_weight=1.0):
+    """(G baby steps, B giant steps).  baby_weight = 1 is the reference's split G = ceil(sqrt(D)) [ref: :29-32].
+    Hoisted baby steps only stream a key while every giant step pays a full decomposition, so the hoisted
+    path is faster with more baby steps: baby_weight = 2 gives G = ceil(sqrt(2 D)) (D=2048: 64 x 32)."""
+    G = int(np.ceil(np.sqrt(D * baby_weight)))
+    return G, int(np.ceil(D / G))
 
 
-def bsgs_steps(D):
-    G, B = compute_bsgs_params(D)
+def bsgs_steps(D, baby_weight=1.0):
+    G, B = compute_bsgs_params(D, baby_weight)
     return list(range(1, G)) + [g * G for g in range(1, B)]
 
 
-def compute_bsgs_galois_elements(poly_degree, D):
-    return ph.get_elts_from_steps(bsgs_steps(D), poly_degree)
+def compute_bsgs_galois_elements(poly_degree, D, baby_weight=1.0):
+    return ph.get_elts_from_steps(bsgs_steps(D, baby_weight), poly_degree)
 
 
 def compute_diagonals(W, D):
@@ -58,7 +61,8 @@ def _replicate_to_slots(vec, slots):
 # ---- context wrapper  [ref: :61-154] -----------------------------------------------------------------
 class CKKSBootstrapContext:
     def __init__(self, poly_degree=32768, L0=24, prime_bits=59, special_mod_size=3, level_budget=None,
-                 max_rot_dim=256, bsgs_dim=0, skip_bootstrap=False, seed=None, device=None, verbose=True):
+                 max_rot_dim=256, bsgs_dim=0, skip_bootstrap=False, seed=None, device=None, verbose=True,
+                 baby_weights=(1.0,)):
         if not skip_bootstrap:
             raise RuntimeError("Bootstrap not available in this build (pass skip_bootstrap=True)")
         say = print if verbose else (lambda *a, **k: None)
@@ -67,10 +71,11 @@ class CKKSBootstrapContext:
         dims = bsgs_dim if isinstance(bsgs_dim, (list, tuple)) else [bsgs_dim]
         bsgs_elts = set()
         for d in sorted({d for d in dims if d > 0}):
-            elts = compute_bsgs_galois_elements(poly_degree, d)
-            bsgs_elts.update(elts)
-            G, B = compute_bsgs_params(d)
-            say(f"[CKKS] BSGS: D={d}, G={G} baby, B={B} giant, {len(elts)} galois elements")
+            for w in baby_weights:          # extra (G, B) splits only add the keys they need
+                elts = compute_bsgs_galois_elements(poly_degree, d, w)
+                bsgs_elts.update(elts)
+                G, B = compute_bsgs_params(d, w)
+                say(f"[CKKS] BSGS: D={d}, G={G} baby, B={B} giant, {len(elts)} galois elements")
         all_elts = sorted(set(rot_elts) | bsgs_elts)
         say(f"[CKKS] Galois elements: 0 boot + {len(rot_elts)} rot + {len(bsgs_elts)} bsgs = {len(all_elts)} total")
 

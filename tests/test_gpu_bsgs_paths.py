@@ -186,3 +186,46 @@ def test_batched_matvecs_match_single_calls():
         for a, b, W, x in zip(singles, batch, Ws, xs):
             assert np.array_equal(a.to_numpy(), b.to_numpy())
             assert np.abs(ckks.decrypt_vec(b, D) - W @ x).max() < 1e-9
+
+
+def test_fully_encrypted_ffn_block_flow():
+    """The call sequence of the reference's fully_encrypted_ffn_block (test_fully_enc_bsgs.py:26-118) at small
+    size: shared baby rotations, per-chunk BSGS for the FFN key, CT-CT square + relinearize + rescale, BSGS
+    for the FFN value, level alignment with mod_switch_to_next, set_scale and residual add -- 3 levels per block,
+    two blocks back to back, checked against the float64 block (corr > 0.999 is the reference's own bar, :298)."""
+    from fhe_spear_b200 import bsgs as hb
+    from fhe_spear_b200 import pyPhantom as ph
+    D, F, L0 = 16, 32, 8
+    ckks = hb.CKKSBootstrapContext(poly_degree=4096, L0=L0, prime_bits=59, special_mod_size=2, max_rot_dim=D,
+                                   bsgs_dim=[D], skip_bootstrap=True, seed=SEED, verbose=False)
+    G, B = hb.compute_bsgs_params(D)
+    rng = np.random.default_rng(42)
+    x = rng.standard_normal(D) * 0.1
+    ct = ckks.encrypt_replicated(x)
+    ref = x.copy()
+    for blk in range(2):
+        Wk, Wv = rng.standard_normal((D, F)) * 0.2, rng.standard_normal((F, D)) * 0.2
+        start = ct.chain_index()
+        n_chunks = F // D
+        ct_baby = hb._compute_baby_rotations(ckks, ct, G)
+        sq = []
+        for c in range(n_chunks):
+            M = Wk[:, c * D:(c + 1) * D].T.copy()
+            fk = hb.fhe_matmul_bsgs(ckks, ct, M, D, G, B, ct_baby)          # reference-order path (plaintext list)
+            s = ph.rescale_to_next(ckks.ctx, ph.relinearize(ckks.ctx, ph.multiply(ckks.ctx, fk, fk), ckks.rlk))
+            sq.append(s)
+        acc = None
+        for c, s in enumerate(sq):
+            M = Wv[c * D:(c + 1) * D, :].T.copy()
+            part = hb.fhe_matmul_bsgs(ckks, s, M, D)                        # hoisted path at a lower level
+            acc = part if acc is None else ph.add(ckks.ctx, acc, part)
+        xa = ct
+        while xa.chain_index() < acc.chain_index():
+            xa = ph.mod_switch_to_next(ckks.ctx, xa)
+        acc.set_scale(xa.scale())
+        ct = ph.add(ckks.ctx, xa, acc)
+        assert ct.chain_index() == start + 3
+        ref = ref + ((ref @ Wk) ** 2) @ Wv
+        got = ckks.decrypt_vec(ct, D)
+        assert np.corrcoef(got, ref)[0, 1] > 0.999999
+        assert np.abs(got - ref).max() < 1e-6      # set_scale fudges the scale by q_i/2^59 - 1 ~ 1e-13 relative

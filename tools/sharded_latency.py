@@ -1,0 +1,65 @@
+#!/usr/bin/env python3
+"""Giant-step-sharded single mat-vec over the ranks of one node (second level):
+torchrun --nproc-per-node N tools/sharded_latency.py.  Checks the result against the unsharded mat-vec
+on every rank and prints the latency (CUDA events, max over ranks)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    from fhe_spear_b200 import bsgs as hb
+    from fhe_spear_b200 import pyPhantom as ph
+    from fhe_spear_b200.sharding import ShardedMatvec
+    cfg = sys.argv[1] if len(sys.argv) > 1 else "c3"
+    N, L0, P, D = bench.CONFIGS[cfg]
+    G, B = hb.compute_bsgs_params(D)
+    ckks = hb.CKKSBootstrapContext(poly_degree=N, L0=L0, prime_bits=59, special_mod_size=P, max_rot_dim=1, bsgs_dim=[D],
+                                   skip_bootstrap=True, seed=bytes(range(32)), device=local, verbose=False)
+    rng = np.random.default_rng(7)                      # same matrix and input on every rank
+    W, x = rng.standard_normal((D, D)) * 0.02, rng.standard_normal(D) * 0.1
+    ct = ckks.encrypt_replicated(x)                     # same seed, same enc counter -> identical ciphertext
+    mv = ShardedMatvec(ckks, W, D)
+    y = mv(ct)
+    full = hb.pre_encode_real_diags(ckks, W, D, G, B, level=1)
+    ref = ph.bsgs_hoisted(ckks.ctx, ct, full, ckks.gk)
+    same = bool(np.array_equal(y.to_numpy(), ref.to_numpy()))
+    err = float(np.abs(ckks.decrypt_vec(y, D) - W @ x).max())
+    for _ in range(3):
+        mv(ct)
+    ckks.ctx.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    steps = 10
+    import time
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        mv(ct)
+    ckks.ctx.synchronize()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps * 1e3
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ok = torch.tensor([1.0 if same else 0.0], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(json.dumps({"what": "giant-step-sharded single mat-vec latency", "config": cfg, "n_gpus": world,
+                          "ms_per_matvec": float(t.item()), "bit_identical_to_unsharded_on_all_ranks": bool(ok.item() > 0.5),
+                          "max_abs_err_vs_float64": err, "shard_diag_bytes": mv.shard.info()["bytes"]}))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
