@@ -13,6 +13,19 @@
 
 namespace eng {
 
+struct Arena {   // bump allocator over the stream's grow-only workspace (hot path: no allocator calls)
+    u64* p;
+    size_t left;
+    Arena(const Ctx* c, cudaStream_t s, size_t words) : p(c->workspace(s, words)), left(words) {}
+    u64* get(size_t words) {
+        words = (words + 31) & ~(size_t)31;   // keep 256-byte alignment
+        REQUIRE(words <= left, "internal: workspace under-estimated");
+        u64* r = p;
+        p += words, left -= words;
+        return r;
+    }
+};
+
 struct Scratch {   // temporaries ordered on the stream that uses them, released on scope exit
     const Ctx* c;
     cudaStream_t s;
@@ -99,7 +112,9 @@ void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, i
                           const u32* gelt, const u64* const* gkey, u64* R, cudaStream_t s, bool pin_l2) {
     const size_t N = c->N, rows = l + c->P, pw = rows * N;
     const int beta = c->digits(l);
-    Scratch sc(c, s);
+    const int k0 = (g_first == 0) ? 1 : 0;          // group 0 (if owned) needs no rotation
+    const int nrot = n_groups > k0 ? n_groups - k0 : 0;
+    Arena sc(c, s, l * N + beta * pw + (size_t)G * 2 * pw + (size_t)n_groups * 2 * pw + 3 * (size_t)nrot * l * N + 32 * 8);
     u64* x = sc.get(l * N);
     u64* E = sc.get(beta * pw);
     u64* Y = sc.get((size_t)G * 2 * pw);
@@ -116,20 +131,28 @@ void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, i
     // 3. diagonal multiply-accumulate for every local giant group
     ops::pmac_hoisted(c, Y, diag, A, G, n_groups, n_diags, l, rshift, s);
     // 4. giant steps: R = sum_k (pi_g(A_k.0) + <pi_g(F), k0>, <pi_g(F), k1>)   (g = g_first + k*g_stride; g = 0: R = A_k)
-    u64* t = sc.get(l * N);
-    u64* tmp = sc.get(2 * l * N);
+    //    The ModDown of every A_k.1 and the INTT that starts its decomposition are batched over all groups
+    //    (few large launches instead of ~10 small ones per giant step); ModUp + NTT + key product stay per group
+    //    so that the 57 MB of digits never leave L2.
     bool have = false;
-    for (int k = 0; k < n_groups; k++) {
-        u64* Ak = A + (size_t)k * 2 * pw;
-        if (g_first + k * g_stride == 0) {
-            REQUIRE(!have, "bsgs: group 0 must come first");
-            CUDA_CHECK(cudaMemcpyAsync(R, Ak, sizeof(u64) * 2 * pw, cudaMemcpyDeviceToDevice, s));
-        } else {
-            ops::moddown(c, Ak + pw, pw, 1, l, tmp, nullptr, t, s);
-            ops::decompose(c, t, l, x, E, s);
-            ops::ks_inner(c, E, gkey[k], R, l, gelt[k], Ak, (int)rows, 0, have ? 1 : 0, s);
-        }
+    if (g_first == 0 && n_groups > 0) {
+        CUDA_CHECK(cudaMemcpyAsync(R, A, sizeof(u64) * 2 * pw, cudaMemcpyDeviceToDevice, s));
         have = true;
+    }
+    if (nrot > 0) {
+        u64* t_all = sc.get((size_t)nrot * l * N);      // ModDown(A_k.1), NTT form
+        u64* x_all = sc.get((size_t)nrot * l * N);      // the same, coefficient form
+        u64* tmp = sc.get((size_t)nrot * l * N);
+        ops::moddown(c, A + (size_t)k0 * 2 * pw + pw, 2 * pw, nrot, l, tmp, nullptr, t_all, s);
+        CUDA_CHECK(cudaMemcpyAsync(x_all, t_all, sizeof(u64) * nrot * l * N, cudaMemcpyDeviceToDevice, s));
+        ntt_inverse(c, x_all, nrot * l, RowMap{l, l, c->L, 0}, (int)N, s);
+        for (int k = k0; k < n_groups; k++) {
+            u64* Ak = A + (size_t)k * 2 * pw;
+            const size_t o = (size_t)(k - k0) * l * N;
+            ops::decompose_from(c, t_all + o, x_all + o, l, E, s);
+            ops::ks_inner(c, E, gkey[k], R, l, gelt[k], Ak, (int)rows, 0, have ? 1 : 0, s);
+            have = true;
+        }
     }
     if (!have) CUDA_CHECK(cudaMemsetAsync(R, 0, sizeof(u64) * 2 * pw, s));
 }

@@ -71,9 +71,14 @@ struct RowMap {
     int l;     // data rows per polynomial
     int L;     // index of the first special limb
     int base;  // limb id of data row 0
+    size_t pstride;   // words between consecutive polynomials (0: rows are contiguous, rpp * n)
     __host__ __device__ __forceinline__ int limb(int row) const {
         int idx = row % rpp;
         return idx < l ? base + idx : L + (idx - l);
+    }
+    // word offset of row `row` of a batch whose rows hold n coefficients
+    __host__ __device__ __forceinline__ size_t offset(int row, int n) const {
+        return pstride ? (size_t)(row / rpp) * pstride + (size_t)(row % rpp) * n : (size_t)row * n;
     }
 };
 

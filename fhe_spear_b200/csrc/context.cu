@@ -118,6 +118,21 @@ u64* Ctx::alloc(size_t n_u64, cudaStream_t s) const {
     CUDA_CHECK(cudaMallocAsync(&p, sizeof(u64) * (n_u64 ? n_u64 : 1), s ? s : stream));
     return (u64*)p;
 }
+u64* Ctx::workspace(cudaStream_t s, size_t words) const {
+    int slot = 0;
+    for (int i = 0; i < 3; i++)
+        if (s == aux[i]) slot = i + 1;
+    if (ws_cap[slot] < words) {   // rare: first call, or a larger problem than any before on this stream
+        cudaStream_t st = slot ? aux[slot - 1] : stream;
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (ws_base[slot]) CUDA_CHECK(cudaFree(ws_base[slot]));
+        ws_base[slot] = nullptr, ws_cap[slot] = 0;
+        void* p = nullptr;
+        CUDA_CHECK(cudaMalloc(&p, sizeof(u64) * words));
+        ws_base[slot] = (u64*)p, ws_cap[slot] = words;
+    }
+    return ws_base[slot];
+}
 void Ctx::l2_pin(cudaStream_t s, const void* p, size_t bytes) const {
     if (!l2_persist_max || !l2_window_max) return;
     cudaStreamAttrValue v;
@@ -283,6 +298,7 @@ void ctx_destroy(Ctx* c) {
                     (void*)c->d_dn_hatinv, (void*)c->d_dn_half, (void*)c->d_dn_hat, (void*)c->d_rs_inv,
                     (void*)c->d_garner, (void*)c->d_zeta})
         cudaFree(p);
+    for (int i = 0; i < 4; i++) cudaFree(c->ws_base[i]);
     for (int i = 0; i < 3; i++) {
         cudaStreamDestroy(c->aux[i]);
         cudaEventDestroy(c->ev_aux[i]);

@@ -57,6 +57,10 @@ struct Ctx {
     mutable bool profiling = false;
     mutable std::vector<ProfRec> prof;
 
+    // grow-only scratch arena of a stream (main or aux[i]) for the fused BSGS call: no allocator traffic on the hot path
+    u64* workspace(cudaStream_t s, size_t words) const;
+    mutable u64* ws_base[4] = {nullptr, nullptr, nullptr, nullptr};
+    mutable size_t ws_cap[4] = {0, 0, 0, 0};
     // keep [p, p+bytes) L2-resident for the kernels that follow on `s` (bytes = 0 clears the window)
     void l2_pin(cudaStream_t s, const void* p, size_t bytes) const;
     u64* alloc(size_t n_u64, cudaStream_t s = nullptr) const;   // stream-ordered (default: the main stream)

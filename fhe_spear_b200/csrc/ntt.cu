@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(TPB) ntt_fwd_a(u64* __restrict__ data, RowMap 
     if (skip_alpha && limb < rm.L && limb / skip_alpha == row / rm.rpp) return;
     const u64 q = tb.q[limb], q2 = q << 1;
     const ulonglong2* __restrict__ tw = tb.psi + (size_t)limb * N;
-    u64* base = data + (size_t)row * n;
+    u64* base = data + rm.offset(row, n);
     const int R = 1 << sA, S = n >> sA, c0 = blockIdx.x * COLS;
     for (int e = threadIdx.x; e < R * COLS; e += TPB) sm[e] = base[(size_t)(e / COLS) * S + c0 + (e % COLS)];
     __syncthreads();
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(TPB) ntt_fwd_b(u64* __restrict__ data, RowMap 
     const ulonglong2* __restrict__ tw = tb.psi + (size_t)limb * N;
     const int M = 1 << sB;
     const int elems = n < B_ELEMS ? n : B_ELEMS;
-    u64* base = data + (size_t)row * n + (size_t)blockIdx.x * elems;
+    u64* base = data + rm.offset(row, n) + (size_t)blockIdx.x * elems;
     const int gc0 = blockIdx.x * (elems >> sB);   // first global chunk of this CTA
     for (int e = threadIdx.x; e < elems; e += TPB) sm[e] = base[e];
     __syncthreads();
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(TPB) ntt_inv_b(u64* __restrict__ data, RowMap 
     const ulonglong2* __restrict__ tw = tb.ipsi + (size_t)limb * N;
     const int M = 1 << sB;
     const int elems = n < B_ELEMS ? n : B_ELEMS;
-    u64* base = data + (size_t)row * n + (size_t)blockIdx.x * elems;
+    u64* base = data + rm.offset(row, n) + (size_t)blockIdx.x * elems;
     const int gc0 = blockIdx.x * (elems >> sB);
     for (int e = threadIdx.x; e < elems; e += TPB) sm[e] = base[e];
     __syncthreads();
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(TPB) ntt_inv_a(u64* __restrict__ data, RowMap 
     const int limb = rm.limb(row);
     const u64 q = tb.q[limb], q2 = q << 1;
     const ulonglong2* __restrict__ tw = tb.ipsi + (size_t)limb * N;
-    u64* base = data + (size_t)row * n;
+    u64* base = data + rm.offset(row, n);
     const int R = 1 << sA, S = n >> sA, c0 = blockIdx.x * COLS;
     for (int e = threadIdx.x; e < R * COLS; e += TPB) sm[e] = base[(size_t)(e / COLS) * S + c0 + (e % COLS)];
     __syncthreads();
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(WB * 32) ntt_fwd_b2(u64* __restrict__ data, Ro
     const ulonglong2* __restrict__ tw = tb.psi + (size_t)limb * N;
     const int warp = threadIdx.x >> 5, j = threadIdx.x & 31;
     const int gc = blockIdx.x * WB + warp;
-    u64* base = data + (size_t)row * n + (size_t)gc * 256;
+    u64* base = data + rm.offset(row, n) + (size_t)gc * 256;
     if (q < (1ull << 59) && q > (1ull << 33)) fwd_b2_body<true>(base, smem[warp], tw, q, sA, gc, j, split != 0);
     else fwd_b2_body<false>(base, smem[warp], tw, q, sA, gc, j, split != 0);
 }
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(WB * 32) ntt_inv_b2(u64* __restrict__ data, Ro
     const ulonglong2* __restrict__ tw = tb.ipsi + (size_t)limb * N;
     const int warp = threadIdx.x >> 5, j = threadIdx.x & 31;
     const int gc = blockIdx.x * WB + warp;
-    u64* base = data + (size_t)row * n + (size_t)gc * 256;
+    u64* base = data + rm.offset(row, n) + (size_t)gc * 256;
     u64* s = smem[warp];
     u64 v[8];
 #pragma unroll
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(2 << SA) ntt_fwd_a2(u64* __restrict__ data, Ro
     const u64 q = tb.q[limb];
     const ulonglong2* __restrict__ tw = tb.psi + (size_t)limb * N;
     const int c = threadIdx.x & (COLS - 1), g = threadIdx.x >> 4;
-    u64* base = data + (size_t)row * n + blockIdx.x * COLS + c;
+    u64* base = data + rm.offset(row, n) + blockIdx.x * COLS + c;
     if (q < (1ull << 59) && q > (1ull << 33)) fwd_a2_body<SA, true>(base, sm, tw, q, n >> SA, c, g);
     else fwd_a2_body<SA, false>(base, sm, tw, q, n >> SA, c, g);
 }
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(2 << SA) ntt_inv_a2(u64* __restrict__ data, Ro
     const ulonglong2* __restrict__ tw = tb.ipsi + (size_t)limb * N;
     const int c = threadIdx.x & (COLS - 1), g = threadIdx.x >> 4;
     const int S = n >> SA;
-    u64* base = data + (size_t)row * n + blockIdx.x * COLS + c;
+    u64* base = data + rm.offset(row, n) + blockIdx.x * COLS + c;
     const ulonglong2 ninv = tb.invn[limb * 17 + logn];
     u64 v[8];
     // a partial round (SA % 3 stages) comes first, where the 8 rows of a thread are contiguous

@@ -663,11 +663,15 @@ void galois(const Ctx* c, const u64* in, u64* out, int rows, u32 elt, cudaStream
 
 // cin [l][N] NTT form -> E [digits(l)][l+P][N] NTT form (scratch x: [l][N])
 void decompose(const Ctx* c, const u64* cin, int l, u64* x, u64* E, cudaStream_t s) {
+    CUDA_CHECK(cudaMemcpyAsync(x, cin, sizeof(u64) * l * c->N, cudaMemcpyDeviceToDevice, s));
+    ntt_inverse(c, x, l, RowMap{l, l, c->L, 0}, c->N, s);
+    decompose_from(c, cin, x, l, E, s);
+}
+// same, given both forms of the polynomial: cin (NTT) and x (coefficients)
+void decompose_from(const Ctx* c, const u64* cin, const u64* x, int l, u64* E, cudaStream_t s) {
     const int N = c->N, P = c->P, rows = l + P, beta = c->digits(l);
     REQUIRE(P <= MAX_ALPHA, "special_modulus_size > %d not supported", MAX_ALPHA);
     REQUIRE(N % TPB == 0, "N must be a multiple of %d", TPB);
-    CUDA_CHECK(cudaMemcpyAsync(x, cin, sizeof(u64) * l * N, cudaMemcpyDeviceToDevice, s));
-    ntt_inverse(c, x, l, RowMap{l, l, c->L, 0}, N, s);
     {
         ProfScope ps(c, PROF_MODUP, s);
         auto go = [&](auto kern) {
@@ -780,8 +784,7 @@ void pscale(const Ctx* c, const u64* x, u64* y, int l, cudaStream_t s) {
 void moddown(const Ctx* c, u64* in, size_t in_pstride, int polys, int l, u64* tmp, const u64* add, u64* out,
              cudaStream_t s) {
     const int N = c->N, P = c->P;
-    for (int p = 0; p < polys; p++)
-        ntt_inverse(c, in + (size_t)p * in_pstride + (size_t)l * N, P, RowMap{P, 0, c->L, 0}, N, s);
+    ntt_inverse(c, in + (size_t)l * N, polys * P, RowMap{P, 0, c->L, 0, in_pstride}, N, s);   // special rows of every polynomial
     {
         ProfScope ps(c, PROF_MODDOWN, s);
         auto go = [&](auto kern) {
