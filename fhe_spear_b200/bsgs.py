@@ -280,6 +280,41 @@ def fhe_projection_bsgs(ckks, x, W, D_in, D_out, label="", preencoded_diags=None
                                cpu_offloaded=pick(cpu_offloaded_diags, 0))
         return ckks.decrypt_vec(ct_y, D_in)
 
+    all_sets = bool(preencoded_diags) and all(isinstance(p, ph.diagonal_set) for p in preencoded_diags)
+    if D_out > D_in and all_sets:
+        # every chunk pair is an independent mat-vec on the same input: one batched call, then unpack (re, im)
+        D, F = D_in, D_out
+        pairs = _chunk_pairs(F, D)
+        ct_x = ckks.encrypt_replicated(x)
+        outs = ph.bsgs_hoisted_batch(ckks.ctx, [ct_x] * len(pairs), list(preencoded_diags[:len(pairs)]), ckks.gk)
+        result = np.zeros(F)
+        for (c, c2), ct_y in zip(pairs, outs):
+            lo1, hi1 = c * D, min((c + 1) * D, F)
+            if c2 is None:
+                result[lo1:hi1] = ckks.decrypt_vec(ct_y, D)[:hi1 - lo1]
+            else:
+                lo2, hi2 = c2 * D, min((c2 + 1) * D, F)
+                vals = ckks.decrypt_vec_complex(ct_y, D)
+                result[lo1:hi1], result[lo2:hi2] = vals.real[:hi1 - lo1], vals.imag[:hi2 - lo2]
+        return result
+    if D_out < D_in and all_sets:
+        # conjugate-packed input chunk pairs: independent mat-vecs whose real parts are summed in plaintext
+        D, F = D_out, D_in
+        pairs = _chunk_pairs(F, D)
+        cts = []
+        for c, c2 in pairs:
+            x0, x1 = np.zeros(D), np.zeros(D)
+            lo, hi = c * D, min((c + 1) * D, F)
+            x0[:hi - lo] = x[lo:hi]
+            if c2 is None:
+                cts.append(ckks.encrypt_replicated(x0))
+            else:
+                lo1, hi1 = c2 * D, min((c2 + 1) * D, F)
+                x1[:hi1 - lo1] = x[lo1:hi1]
+                cts.append(ckks.encrypt_replicated_complex(x0, x1))
+        outs = ph.bsgs_hoisted_batch(ckks.ctx, cts, list(preencoded_diags[:len(pairs)]), ckks.gk)
+        return sum(ckks.decrypt_vec_complex(ct_y, D).real for ct_y in outs)
+
     if D_out > D_in:
         D, F = D_in, D_out
         G, B = compute_bsgs_params(D)
@@ -289,12 +324,14 @@ def fhe_projection_bsgs(ckks, x, W, D_in, D_out, label="", preencoded_diags=None
         ct_baby = _compute_baby_rotations(ckks, ct_x, G) if need_baby else None
         for i, (c, c2) in enumerate(_chunk_pairs(F, D)):
             pe, cpu = pick(preencoded_diags, i), pick(cpu_offloaded_diags, i)
+            have = pe is not None or cpu is not None          # chunk matrices are only built when they must be encoded
             lo1, hi1 = c * D, min((c + 1) * D, F)
-            M1 = _key_chunk(W, c, D, F)
+            M1 = None if have else _key_chunk(W, c, D, F)
             if c2 is not None:
                 lo2, hi2 = c2 * D, min((c2 + 1) * D, F)
-                ct_y = fhe_matmul_bsgs_complex(ckks, ct_x, M1, _key_chunk(W, c2, D, F), D, G, B, ct_baby=ct_baby,
-                                               preencoded=pe, cpu_offloaded=cpu)
+                M2 = None if have else _key_chunk(W, c2, D, F)
+                ct_y = fhe_matmul_bsgs_complex(ckks, ct_x, M1, M2, D, G, B, ct_baby=ct_baby, preencoded=pe,
+                                               cpu_offloaded=cpu)
                 vals = ckks.decrypt_vec_complex(ct_y, D)
                 result[lo1:hi1] = vals.real[:hi1 - lo1]
                 result[lo2:hi2] = vals.imag[:hi2 - lo2]
@@ -308,17 +345,19 @@ def fhe_projection_bsgs(ckks, x, W, D_in, D_out, label="", preencoded_diags=None
     result = np.zeros(D)
     for i, (c, c2) in enumerate(_chunk_pairs(F, D)):
         pe, cpu = pick(preencoded_diags, i), pick(cpu_offloaded_diags, i)
+        have = pe is not None or cpu is not None
         x0 = np.zeros(D)
         lo, hi = c * D, min((c + 1) * D, F)
         x0[:hi - lo] = x[lo:hi]
-        M0 = _val_chunk(W, c, D, F)
+        M0 = None if have else _val_chunk(W, c, D, F)
         if c2 is not None:
             x1 = np.zeros(D)
             lo1, hi1 = c2 * D, min((c2 + 1) * D, F)
             x1[:hi1 - lo1] = x[lo1:hi1]
             # Enc(x0 + i x1) * (d0 - i d1): real part = M0 x0 + M1 x1  [ref: :630-642]
-            ct_y = fhe_matmul_bsgs_complex(ckks, ckks.encrypt_replicated_complex(x0, x1), M0,
-                                           _val_chunk(W, c2, D, F, -1.0), D, G, B, preencoded=pe, cpu_offloaded=cpu)
+            M1n = None if have else _val_chunk(W, c2, D, F, -1.0)
+            ct_y = fhe_matmul_bsgs_complex(ckks, ckks.encrypt_replicated_complex(x0, x1), M0, M1n, D, G, B,
+                                           preencoded=pe, cpu_offloaded=cpu)
             result += ckks.decrypt_vec_complex(ct_y, D).real
         else:
             ct_y = fhe_matmul_bsgs(ckks, ckks.encrypt_replicated(x0), M0, D, G, B, preencoded=pe, cpu_offloaded=cpu)

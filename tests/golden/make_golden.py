@@ -237,6 +237,25 @@ def main():
     assert np.abs(out["proj_down"] - x2 @ Wv).max() < 1e-9
     assert np.abs(out["proj_same"] - x @ W).max() < 1e-9
     np.savez_compressed(os.path.join(HERE, "bsgs_loop.npz"), **out)
+
+    # ---- the reference's float64 RWKV-7 block (plaintext_block :902-980) on seeded random weights -------------
+    from fhe_spear_b200.rwkv_block import RWKVBlockWeights as MyWeights
+    Db, Fb, Hb, Sb = 16, 64, 2, 8
+    blk = {}
+    rngb = np.random.default_rng(99)
+    xb = rngb.standard_normal(Db)
+    xpa, xpf = rngb.standard_normal(Db) * 0.1, rngb.standard_normal(Db) * 0.1
+    st = rngb.standard_normal((Hb, Sb, Sb)) * 0.1
+    vf = rngb.standard_normal(Db) * 0.1
+    for idx in (0, 1):
+        mine = MyWeights.random(Db, Fb, Hb, Sb, block_idx=idx, seed=5 + idx)
+        ref_block = object.__new__(bg.RWKVBlockWeights)          # the reference class, filled with the same tensors
+        ref_block.__dict__.update(mine.__dict__)
+        o = bg.plaintext_block(ref_block, xb, xpa, xpf, st, vf)
+        for name, val in zip(("x", "xpa", "xpf", "state", "v_first"), o):
+            blk[f"b{idx}_{name}"] = np.asarray(val)
+    blk.update(x=xb, x_prev_att=xpa, x_prev_ffn=xpf, state=st, v_first=vf, dims=np.array([Db, Fb, Hb, Sb]))
+    np.savez_compressed(os.path.join(HERE, "rwkv_block.npz"), **blk)
     print("golden fixtures written to", HERE)
 
 

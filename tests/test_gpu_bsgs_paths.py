@@ -229,3 +229,28 @@ def test_fully_encrypted_ffn_block_flow():
         got = ckks.decrypt_vec(ct, D)
         assert np.corrcoef(got, ref)[0, 1] > 0.999999
         assert np.abs(got - ref).max() < 1e-6      # set_scale fudges the scale by q_i/2^59 - 1 ~ 1e-13 relative
+
+
+def test_client_aided_rwkv_block_matches_plaintext_block():
+    """Two chained RWKV-7 blocks (reference client_aided_block, scripts/bootstrap_generation.py:756-899) with the
+    eight projections per block on the GPU, pre-encoded and on-the-fly, against the float64 plaintext_block."""
+    from fhe_spear_b200 import bsgs as hb
+    from fhe_spear_b200.rwkv_block import RWKVBlockWeights, client_aided_block, plaintext_block
+    D, F, H, S = 16, 64, 2, 8
+    ckks = hb.CKKSBootstrapContext(poly_degree=2048, L0=3, prime_bits=59, special_mod_size=1, max_rot_dim=1,
+                                   bsgs_dim=[D], skip_bootstrap=True, seed=SEED, verbose=False)
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(D)
+    xf, xp = x.copy(), x.copy()
+    st_f = st_p = np.zeros((H, S, S))
+    pa_f = pa_p = pf_f = pf_p = np.zeros(D)
+    vf_f = vf_p = None
+    for idx in range(2):
+        blk = RWKVBlockWeights.random(D, F, H, S, block_idx=idx, seed=20 + idx)
+        pe = hb.pre_encode_block(ckks, blk, D, F) if idx == 0 else None     # block 1 encodes its diagonals on the fly
+        xf, pa_f, pf_f, st_f, vf_f, tm = client_aided_block(ckks, blk, xf, pa_f, pf_f, st_f, vf_f, use_bsgs=True,
+                                                            preencoded_block=pe)
+        xp, pa_p, pf_p, st_p, vf_p = plaintext_block(blk, xp, pa_p, pf_p, st_p, vf_p)
+        assert set(tm) >= {"server_rkv", "server_wo", "server_ffn_key", "server_ffn_val"}
+        assert np.abs(xf - xp).max() < 1e-7 and np.abs(st_f - st_p).max() < 1e-7
+        assert np.corrcoef(xf, xp)[0, 1] > 0.999999

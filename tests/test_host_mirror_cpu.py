@@ -66,3 +66,16 @@ def test_chunk_packing_reproduces_projection():
             M1n = hb._val_chunk(Wv, c2, D, F, -1.0)
             down += ((M0 + 1j * M1n) @ (x0 + 1j * x1)).real     # diagonals d0 + i*(-d1): Enc(x0 + i x1) * (d0 - i d1)
     assert np.allclose(down, xf @ Wv)
+
+
+def test_plaintext_block_matches_reference():
+    """tests/golden/rwkv_block.npz: outputs of the reference's plaintext_block (bootstrap_generation.py:902-980)
+    on the seeded random weights of RWKVBlockWeights.random; the mirror must agree to rounding."""
+    from fhe_spear_b200.rwkv_block import RWKVBlockWeights, plaintext_block
+    g = np.load(os.path.join(GOLD, "rwkv_block.npz"))
+    D, F, H, S = (int(v) for v in g["dims"])
+    for idx in (0, 1):
+        blk = RWKVBlockWeights.random(D, F, H, S, block_idx=idx, seed=5 + idx)
+        out = plaintext_block(blk, g["x"], g["x_prev_att"], g["x_prev_ffn"], g["state"], g["v_first"])
+        for name, val in zip(("x", "xpa", "xpf", "state", "v_first"), out):
+            assert np.abs(np.asarray(val) - g[f"b{idx}_{name}"]).max() < 1e-12, (idx, name)
