@@ -156,21 +156,22 @@ def _batch_encode_diags_complex(ckks, diags1, diags2, D, G, slots, level):
     return ckks.encoder.encode_complex_vector_batch(ckks.ctx, vecs, ckks.diag_scale, chain_index=level)
 
 
-def pre_encode_real_diags(ckks, W, D, G, B, level, as_plaintexts=False, compress=True):
+def pre_encode_real_diags(ckks, W, D, G, B, level, as_plaintexts=False, compress=True, shard=(0, 1)):
+    """shard = (rank, world): keep only this rank's giant groups (giant-step sharding over GPUs)."""
     diags = _extract_diagonals(np.asarray(W, dtype=np.float64), D)
     if as_plaintexts:
         return _batch_encode_diags_real(ckks, diags, D, G, ckks.slots, level)
     return ph.diagonal_set(ckks.ctx, _pre_rotate(diags, D, G), G, B, ckks.diag_scale, chain_index=level,
-                           compress=compress)
+                           compress=compress, shard=shard)
 
 
-def pre_encode_complex_diags(ckks, W1, W2, D, G, B, level, as_plaintexts=False, compress=True):
+def pre_encode_complex_diags(ckks, W1, W2, D, G, B, level, as_plaintexts=False, compress=True, shard=(0, 1)):
     d1 = _extract_diagonals(np.asarray(W1, dtype=np.float64), D)
     d2 = _extract_diagonals(np.asarray(W2, dtype=np.float64), D)
     if as_plaintexts:
         return _batch_encode_diags_complex(ckks, d1, d2, D, G, ckks.slots, level)
     return ph.diagonal_set(ckks.ctx, _pre_rotate(d1, D, G) + 1j * _pre_rotate(d2, D, G), G, B, ckks.diag_scale,
-                           chain_index=level, compress=compress)
+                           chain_index=level, compress=compress, shard=shard)
 
 
 def _chunk_pairs(F, D):
@@ -195,12 +196,12 @@ def _val_chunk(W, c, D, F, sign=1.0):
     return M
 
 
-def pre_encode_block(ckks, block, D, F, G=None, B=None, as_plaintexts=False):
+def pre_encode_block(ckks, block, D, F, G=None, B=None, as_plaintexts=False, shard=(0, 1)):
     """All 8 diagonal sets of one RWKV-7 block at the level of a fresh ciphertext  [ref: :265-333]"""
     if G is None or B is None:
         G, B = compute_bsgs_params(D)
     level = ckks.encrypt_replicated(np.zeros(1)).chain_index()
-    kw = dict(as_plaintexts=as_plaintexts)
+    kw = dict(as_plaintexts=as_plaintexts, shard=shard)
     pe = {name: pre_encode_real_diags(ckks, W.T, D, G, B, level, **kw)
           for name, W in (("r", block.W_r), ("k", block.W_k), ("v", block.W_v), ("o", block.W_o))}
     pe["ffn_key"] = []
@@ -245,6 +246,9 @@ def _matmul(ckks, ct_x_rep, make_set, make_pts, D, G, B, ct_baby, preencoded, cp
     if preencoded is None:
         preencoded = make_set(level) if ct_baby is None else make_pts(level)
     if isinstance(preencoded, ph.diagonal_set):
+        if preencoded.shard[1] > 1:      # giant-step shard: partial accumulator, all-reduce over the ranks, finish
+            from .sharding import sharded_matvec
+            return sharded_matvec(ckks, ct_x_rep, preencoded)
         return ph.bsgs_hoisted(ckks.ctx, ct_x_rep, preencoded, ckks.gk)
     if ct_baby is None:
         ct_baby = _compute_baby_rotations(ckks, ct_x_rep, G)
@@ -280,7 +284,7 @@ def fhe_projection_bsgs(ckks, x, W, D_in, D_out, label="", preencoded_diags=None
                                cpu_offloaded=pick(cpu_offloaded_diags, 0))
         return ckks.decrypt_vec(ct_y, D_in)
 
-    all_sets = bool(preencoded_diags) and all(isinstance(p, ph.diagonal_set) for p in preencoded_diags)
+    all_sets = bool(preencoded_diags) and all(isinstance(p, ph.diagonal_set) and p.shard[1] == 1 for p in preencoded_diags)
     if D_out > D_in and all_sets:
         # every chunk pair is an independent mat-vec on the same input: one batched call, then unpack (re, im)
         D, F = D_in, D_out

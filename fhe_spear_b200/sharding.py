@@ -56,6 +56,25 @@ class _DevView:
                                          "strides": None}
 
 
+def sharded_matvec(ckks, ct, shard_set, group=None):
+    """One giant-step-sharded mat-vec: this rank's accumulator, integer all-reduce, Barrett pass, ModDown + rescale.
+    Every rank ends with the same ciphertext (bit-identical to the unsharded result)."""
+    import torch
+    import torch.distributed as dist
+    from . import pyPhantom as ph
+    ctx = ckks.ctx
+    acc = ph.bsgs_hoisted_partial(ctx, ct, shard_set, ckks.gk)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        size, limbs, ext, ring, _, _ = acc._info()
+        count = size * (limbs + ctx.P) * ring
+        ctx.synchronize()                                   # engine stream -> torch stream hand-off
+        t = torch.as_tensor(_DevView(ph.device_ptr(acc), count), device=f"cuda:{ctx.device}")
+        allreduce_residues(t, group)
+        torch.cuda.synchronize(ctx.device)
+        ph.reduce_inplace(ctx, acc)
+    return ph.bsgs_finish(ctx, acc)
+
+
 class ShardedMatvec:
     """Giant-step-sharded hoisted BSGS mat-vec  Enc(x) -> Enc(W @ x)  over the ranks of `group`.
 
@@ -77,15 +96,4 @@ class ShardedMatvec:
                                      shard=(self.rank, self.world))
 
     def __call__(self, ct):
-        import torch
-        ph, ctx = self.ph, self.ckks.ctx
-        acc = ph.bsgs_hoisted_partial(ctx, ct, self.shard, self.ckks.gk)
-        if self.world > 1:
-            size, limbs, ext, ring, _, _ = acc._info()
-            count = size * (limbs + ctx.P) * ring
-            ctx.synchronize()                                   # engine stream -> torch stream hand-off
-            t = torch.as_tensor(_DevView(ph.device_ptr(acc), count), device=f"cuda:{ctx.device}")
-            allreduce_residues(t, self.group)
-            torch.cuda.synchronize(ctx.device)
-            ph.reduce_inplace(ctx, acc)
-        return ph.bsgs_finish(ctx, acc)
+        return sharded_matvec(self.ckks, ct, self.shard, self.group)
