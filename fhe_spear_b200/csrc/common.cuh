@@ -55,6 +55,7 @@ struct ModTab {
     const u64* q;          // [K]
     const u64* ratio0;     // [K] low  word of floor(2^128/q)
     const u64* ratio1;     // [K] high word of floor(2^128/q)
+    const u64* rwide;      // [K] floor(2^(s+64)/q), s = bitlength(q) - 1   (reduce_wide)
 };
 
 struct NttTab {
@@ -119,6 +120,18 @@ __device__ __forceinline__ u64 barrett128(u64 lo, u64 hi, u64 q, u64 r0, u64 r1)
     carry = t2hi + (tmp1 < t2lo);
     tmp1 = hi * r1 + tmp3 + carry;
     u64 r = lo - tmp1 * q;
+    return r >= q ? r - q : r;
+}
+// (hi:lo) mod q for (hi:lo) < 2^(s+64), s = bitlength(q) - 1 -- e.g. a sum of up to 8 products of residues.
+// One 64x64 high product on the top 64 significant bits (R = floor(2^(s+64)/q)): the quotient estimate is at
+// most 2 short, so two conditional subtractions finish the job.  About half the instructions of barrett128.
+__device__ __forceinline__ u64 reduce_wide(u64 lo, u64 hi, u64 q, u64 R) {
+    const int s = 63 - __clzll((long long)q);
+    const u64 top = (hi << (64 - s)) | (lo >> s);
+    const u64 Q = __umul64hi(top, R);
+    u64 r = lo - Q * q;
+    const u64 q2 = q << 1;
+    r = r >= q2 ? r - q2 : r;
     return r >= q ? r - q : r;
 }
 __device__ __forceinline__ u64 mul_mod(u64 a, u64 b, u64 q, u64 r0, u64 r1) {

@@ -187,12 +187,16 @@ Ctx* ctx_create(u64 N, const u64* moduli, int K, int P, int device) {
     }
 
     const int L = c->L, beta = c->beta;
-    std::vector<u64> r0(K), r1(K);
+    std::vector<u64> r0(K), r1(K), rw(K);
     std::vector<ulonglong2> psi((size_t)K * N), ipsi((size_t)K * N), invn((size_t)K * 17);
     for (int i = 0; i < K; i++) {
         u64 q = c->q[i];
         u128 ratio = ~(u128)0 / q;
         r0[i] = (u64)ratio, r1[i] = (u64)(ratio >> 64);
+        {
+            int sbits = 63 - __builtin_clzll(q);
+            rw[i] = (u64)((((u128)1 << (sbits + 64)) - 1) / q);   // q odd, so this equals floor(2^(s+64)/q)
+        }
         u64 w = min_root(N, q), iw = invm(w, q), p = 1, ip = 1;
         for (u64 k = 0; k < N; k++) {
             u32 r = brev((u32)k, c->logn);
@@ -202,7 +206,7 @@ Ctx* ctx_create(u64 N, const u64* moduli, int K, int P, int device) {
         }
         for (int k = 0; k <= 16; k++) invn[i * 17 + k] = with_shoup(invm((1ull << k) % q, q), q);
     }
-    c->d_q = upload(c->q), c->d_ratio0 = upload(r0), c->d_ratio1 = upload(r1);
+    c->d_q = upload(c->q), c->d_ratio0 = upload(r0), c->d_ratio1 = upload(r1), c->d_rwide = upload(rw);
     c->d_psi = upload(psi), c->d_ipsi = upload(ipsi), c->d_invn = upload(invn);
 
     // P mod q_i and its inverse
@@ -293,7 +297,7 @@ void ctx_destroy(Ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (void* p : {(void*)c->d_q, (void*)c->d_ratio0, (void*)c->d_ratio1, (void*)c->d_psi, (void*)c->d_ipsi,
+    for (void* p : {(void*)c->d_q, (void*)c->d_ratio0, (void*)c->d_ratio1, (void*)c->d_rwide, (void*)c->d_psi, (void*)c->d_ipsi,
                     (void*)c->d_invn, (void*)c->d_pmod, (void*)c->d_pinv, (void*)c->d_up_hatinv, (void*)c->d_up_hat,
                     (void*)c->d_dn_hatinv, (void*)c->d_dn_half, (void*)c->d_dn_hat, (void*)c->d_rs_inv,
                     (void*)c->d_garner, (void*)c->d_zeta})

@@ -25,7 +25,7 @@ struct Ctx {
     size_t l2_persist_max = 0, l2_window_max = 0;   // persisting-L2 carve-out and access-window limits
 
     // device tables
-    u64 *d_q = nullptr, *d_ratio0 = nullptr, *d_ratio1 = nullptr;
+    u64 *d_q = nullptr, *d_ratio0 = nullptr, *d_ratio1 = nullptr, *d_rwide = nullptr;
     ulonglong2 *d_psi = nullptr, *d_ipsi = nullptr, *d_invn = nullptr;
     // per data limb i: P mod q_i, P^-1 mod q_i (with Shoup companions)
     ulonglong2 *d_pmod = nullptr, *d_pinv = nullptr;
@@ -43,7 +43,7 @@ struct Ctx {
     // encoder: complex roots zeta^{bitrev(i)}, slot index maps are computed in-kernel
     double2* d_zeta = nullptr;
 
-    ModTab modtab() const { return ModTab{d_q, d_ratio0, d_ratio1}; }
+    ModTab modtab() const { return ModTab{d_q, d_ratio0, d_ratio1, d_rwide}; }
     NttTab ntttab() const { return NttTab{d_psi, d_ipsi, d_invn, d_q}; }
     int digits(int l) const { return (l + P - 1) / P; }
     int limbs_at(int chain_index) const { return chain_index == 0 ? K : L - (chain_index - 1); }

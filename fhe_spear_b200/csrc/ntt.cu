@@ -40,7 +40,7 @@ __device__ __forceinline__ void gs_butterfly(u64& x, u64& y, ulonglong2 w, u64 q
 // reduction (the Barrett ratio floor(2^64/q) fits 32 bits).
 __device__ __forceinline__ u64 mul_shoup_apx(u64 a, u64 w, u64 wp, u64 q) {
     const u32 a0 = (u32)a, a1 = (u32)(a >> 32), p0 = (u32)wp, p1 = (u32)(wp >> 32);
-    const u64 Q = (u64)a1 * p1 + (((u64)a0 * p1) >> 32) + (((u64)a1 * p0) >> 32);
+    const u64 Q = (u64)a1 * p1 + (u64)__umulhi(a0, p1) + (u64)__umulhi(a1, p0);
     return a * w - Q * q;
 }
 template <bool LAZY>

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(TPB) k_modup(const u64* __restrict__ x, const 
         for (int i = 0; i < A; i++) mac_split(acc, y[i], ys[i], hat[(size_t)i * K + t]);   // rows i >= a hold zeros
         u64 alo = 0, ahi = 0;
         fold_split(alo, ahi, acc);
-        Ej[(size_t)r * N] = barrett128(alo, ahi, mt.q[t], mt.ratio0[t], mt.ratio1[t]);
+        Ej[(size_t)r * N] = reduce_wide(alo, ahi, mt.q[t], mt.rwide[t]);
     }
 }
 
@@ -251,7 +251,7 @@ __device__ __forceinline__ void ks_tile_body(const CUtensorMap* kmap, const KsAr
     }
     const u64 keep = evict_last_policy();
     const size_t es = (size_t)a.rows * a.N;
-    const u64 q = mt.q[t], r0 = mt.ratio0[t], r1 = mt.ratio1[t];
+    const u64 q = mt.q[t], r0 = mt.ratio0[t], r1 = mt.ratio1[t], rw = mt.rwide[t];
     const bool has_add = a.addp && r < a.add_rows;
     ulonglong2 pm = make_ulonglong2(0, 0);
     if (has_add && a.add_pscale) pm = pmod[t];
@@ -311,7 +311,12 @@ __device__ __forceinline__ void ks_tile_body(const CUtensorMap* kmap, const KsAr
         }
         fold_split(lo0, hi0, acc0);
         fold_split(lo1, hi1, acc1);
-        u64 v0 = barrett128(lo0, hi0, q, r0, r1), v1 = barrett128(lo1, hi1, q, r0, r1);
+        u64 v0, v1;
+        if (FOLD == 16 && BETA != 0) {   // q < 2^59 and <= 8 digits: the sum is below 2^(s+64)
+            v0 = reduce_wide(lo0, hi0, q, rw), v1 = reduce_wide(lo1, hi1, q, rw);
+        } else {
+            v0 = barrett128(lo0, hi0, q, r0, r1), v1 = barrett128(lo1, hi1, q, r0, r1);
+        }
         if (has_add) {
             if (a.add_pscale) c0add = mul_shoup(c0add, pm.x, pm.y, q);
             v0 = add_mod(v0, c0add, q);
@@ -403,7 +408,7 @@ __global__ void __launch_bounds__(TPB) k_moddown_conv(const u64* __restrict__ in
         u64 alo = 0, ahi = 0;
         fold_split(alo, ahi, acc);
         u64 q = mt.q[i];
-        o[(size_t)i * N] = sub_mod(barrett128(alo, ahi, q, mt.ratio0[i], mt.ratio1[i]), half[i], q);
+        o[(size_t)i * N] = sub_mod(reduce_wide(alo, ahi, q, mt.rwide[i]), half[i], q);
     }
 }
 // out[p][i][n] = (in[p][i][n] - tmp[p][i][n]) * P^-1  (+ add[p][i][n])
