@@ -254,3 +254,60 @@ def test_client_aided_rwkv_block_matches_plaintext_block():
         assert set(tm) >= {"server_rkv", "server_wo", "server_ffn_key", "server_ffn_val"}
         assert np.abs(xf - xp).max() < 1e-7 and np.abs(st_f - st_p).max() < 1e-7
         assert np.corrcoef(xf, xp)[0, 1] > 0.999999
+
+
+def test_retrieval_wrapper_flow():
+    """The call sequence of the reference's PhantomFHE retrieval wrapper (fhe_common.py:83-194; BASELINE config 1
+    uses the same primitives): N=8192, primes [60, 40, 40, 60], P=1, asymmetric encryption, complex-packed
+    Lorentz vectors, batched CT-PT and CT-CT dot products.  Scores must match the plaintext Lorentz inner
+    product (tolerance 1e-5 at scale 2^40)."""
+    from fhe_spear_b200 import pyPhantom as ph
+    parms = ph.params(ph.scheme_type.ckks)
+    parms.set_poly_modulus_degree(8192)
+    parms.set_coeff_modulus(ph.create_coeff_modulus(8192, [60, 40, 40, 60]))
+    parms.set_special_modulus_size(1)                       # after set_coeff_modulus, as the reference does
+    ctx = ph.context(parms)
+    sk = ph.secret_key(ctx, seed=SEED)
+    pk, rlk, enc = sk.gen_publickey(ctx), sk.gen_relinkey(ctx), ph.ckks_encoder(ctx)
+    scale, slots = 2.0 ** 40, enc.slot_count()
+    rng = np.random.default_rng(12)
+
+    def lorentz(v):
+        return np.concatenate([np.sqrt(1 + (v ** 2).sum(-1, keepdims=True)), v], axis=-1)
+
+    def pack(v, conj=False):
+        v = np.concatenate([v, [0.0]]) if len(v) % 2 else v
+        return v[0::2] + (-1j if conj else 1j) * v[1::2]
+
+    docs = rng.standard_normal((300, 64))
+    docs /= np.linalg.norm(docs, axis=1, keepdims=True)
+    q = rng.standard_normal(64)
+    q /= np.linalg.norm(q)
+    ql, dl = lorentz(q), lorentz(docs)
+    sign = np.concatenate([[-1.0], np.ones(64)])
+    truth = dl @ (ql * sign)
+    qp = pack(ql * sign, conj=True)                          # conj-packed query: Re(q_conj * d) sums both halves
+    dp = [pack(d) for d in dl]
+    spd = len(qp)
+    per = slots // spd
+    scores_pt, scores_ct = [], []
+    for s0 in range(0, len(dp), per):
+        batch = dp[s0:s0 + per]
+        qs = np.zeros(slots, dtype=complex)
+        ds = np.zeros(slots, dtype=complex)
+        for i, d in enumerate(batch):
+            qs[i * spd:(i + 1) * spd] = qp
+            ds[i * spd:(i + 1) * spd] = d
+        enc_q = pk.encrypt_asymmetric(ctx, enc.encode_complex_vector(ctx, list(qs), scale))
+        d_pt = enc.encode_complex_vector(ctx, list(ds), scale)
+        r1 = ph.rescale_to_next(ctx, ph.multiply_plain(ctx, enc_q, d_pt))
+        v1 = enc.decode_complex_vector(ctx, sk.decrypt(ctx, r1))
+        enc_d = pk.encrypt_asymmetric(ctx, d_pt)
+        r2 = ph.rescale_to_next(ctx, ph.relinearize(ctx, ph.multiply(ctx, enc_q, enc_d), rlk))
+        v2 = enc.decode_complex_vector(ctx, sk.decrypt(ctx, r2))
+        for i in range(len(batch)):
+            scores_pt.append(sum(c.real for c in v1[i * spd:(i + 1) * spd]))
+            scores_ct.append(sum(c.real for c in v2[i * spd:(i + 1) * spd]))
+    assert np.abs(np.array(scores_pt) - truth).max() < 1e-5
+    assert np.abs(np.array(scores_ct) - truth).max() < 1e-5
+    assert int(np.argmax(scores_pt)) == int(np.argmax(truth)) == int(np.argmax(scores_ct))
