@@ -21,7 +21,7 @@ void bsgs_exact(const Ctx* c, const u64* const* baby, const u64* const* pts, int
                 const u32* gelt, const u64* const* gkey, u64* out, cudaStream_t s);
 void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, int rshift, int G, int n_groups,
                           int n_diags, int g_first, int g_stride, const u32* belt, const u64* const* bkey,
-                          const u32* gelt, const u64* const* gkey, u64* R, cudaStream_t s, bool pin_l2);
+                          const u32* gelt, const u64* const* gkey, u64* R, cudaStream_t s);
 void bsgs_finish(const Ctx* c, u64* R, int l, u64* out, cudaStream_t s);
 }  // namespace eng
 
@@ -777,8 +777,7 @@ int spear_diagset_export(const spear_diagset* d_, uint64_t* host, size_t words) 
     API_END
 }
 
-static Obj* bsgs_partial(Ctx* c, const Obj* ct, const DiagSet* ds, const GaloisKeys* gk, cudaStream_t s = nullptr,
-                         bool pin_l2 = true) {
+static Obj* bsgs_partial(Ctx* c, const Obj* ct, const DiagSet* ds, const GaloisKeys* gk, cudaStream_t s = nullptr) {
     if (!s) s = c->stream;
     check_ct(ct, "bsgs_hoisted");
     REQUIRE(ct->size == 2, "bsgs_hoisted: relinearize first");
@@ -796,7 +795,7 @@ static Obj* bsgs_partial(Ctx* c, const Obj* ct, const DiagSet* ds, const GaloisK
     }
     std::unique_ptr<Obj> R(new_obj(c, 2, l, true, c->N, ct->scale * ds->scale, s));
     eng::bsgs_hoisted_partial(c, ct->d, l, ds->d, ds->rshift, G, (int)gelt.size(), ds->n_diags, ds->g_first,
-                              ds->g_stride, belt.data(), bkey.data(), gelt.data(), gkey.data(), R->d, s, pin_l2);
+                              ds->g_stride, belt.data(), bkey.data(), gelt.data(), gkey.data(), R->d, s);
     return R.release();
 }
 static Obj* bsgs_finish(Ctx* c, Obj* R, cudaStream_t s = nullptr) {
@@ -836,7 +835,7 @@ int spear_bsgs_hoisted_batch(spear_context* ctx, spear_obj* const* cts, spear_di
         REQUIRE(ds->g_first == 0 && ds->g_stride == 1, "bsgs_hoisted_batch: sharded diagonal set");
         cudaStream_t s = count == 1 ? c->stream : c->aux[i % 3];
         if (count > 1 && i < 3) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_main, 0));
-        acc[i].reset(bsgs_partial(c, O_(cts[i]), ds, gk, s, count == 1));
+        acc[i].reset(bsgs_partial(c, O_(cts[i]), ds, gk, s));
         res[i].reset(bsgs_finish(c, acc[i].get(), s));
     }
     if (count > 1)

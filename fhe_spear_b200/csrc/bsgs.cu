@@ -109,7 +109,7 @@ void bsgs_exact(const Ctx* c, const u64* const* baby, const u64* const* pts, int
 // R [2][l+P][N]: this shard's accumulator in basis Q_l*P (sum over shards, mod q, = the full accumulator).
 void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, int rshift, int G, int n_groups,
                           int n_diags, int g_first, int g_stride, const u32* belt, const u64* const* bkey,
-                          const u32* gelt, const u64* const* gkey, u64* R, cudaStream_t s, bool pin_l2) {
+                          const u32* gelt, const u64* const* gkey, u64* R, cudaStream_t s) {
     const size_t N = c->N, rows = l + c->P, pw = rows * N;
     const int beta = c->digits(l);
     const int k0 = (g_first == 0) ? 1 : 0;          // group 0 (if owned) needs no rotation
@@ -127,7 +127,6 @@ void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, i
     if (G > 1 && !ops::ks_baby_fused(c, E, bkey + 1, belt + 1, G - 1, Y + 2 * pw, l, c0, s))
         for (int b = 1; b < G; b++)
             ops::ks_inner(c, E, bkey[b], Y + (size_t)b * 2 * pw, l, belt[b], c0, l, 1, 0, s);
-    (void)pin_l2;
     // 3. diagonal multiply-accumulate for every local giant group
     ops::pmac_hoisted(c, Y, diag, A, G, n_groups, n_diags, l, rshift, s);
     // 4. giant steps: R = sum_k (pi_g(A_k.0) + <pi_g(F), k0>, <pi_g(F), k1>)   (g = g_first + k*g_stride; g = 0: R = A_k)

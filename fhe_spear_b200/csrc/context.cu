@@ -133,19 +133,6 @@ u64* Ctx::workspace(cudaStream_t s, size_t words) const {
     }
     return ws_base[slot];
 }
-void Ctx::l2_pin(cudaStream_t s, const void* p, size_t bytes) const {
-    if (!l2_persist_max || !l2_window_max) return;
-    cudaStreamAttrValue v;
-    memset(&v, 0, sizeof v);
-    size_t win = bytes < l2_window_max ? bytes : l2_window_max;
-    v.accessPolicyWindow.base_ptr = const_cast<void*>(p);
-    v.accessPolicyWindow.num_bytes = win;
-    v.accessPolicyWindow.hitRatio = bytes ? (float)std::min(1.0, (double)l2_persist_max / (double)std::max<size_t>(win, 1)) : 0.f;
-    v.accessPolicyWindow.hitProp = bytes ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
-    v.accessPolicyWindow.missProp = bytes ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
-    cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v);
-    if (!bytes) cudaCtxResetPersistingL2Cache();
-}
 void Ctx::free(void* p, cudaStream_t s) const {
     if (p) cudaFreeAsync(p, s ? s : stream);
 }
@@ -177,14 +164,6 @@ Ctx* ctx_create(u64 N, const u64* moduli, int K, int P, int device) {
     unsigned long long keep = ~0ull;   // cache freed blocks: ~4k temporaries per mat-vec in the op-by-op path
     CUDA_CHECK(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep));
     CUDA_CHECK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
-    {   // reserve the largest persisting-L2 carve-out: the hoisted digits are re-read by every baby-step kernel
-        int pmax = 0, wmax = 0;
-        cudaDeviceGetAttribute(&pmax, cudaDevAttrMaxPersistingL2CacheSize, device);
-        cudaDeviceGetAttribute(&wmax, cudaDevAttrMaxAccessPolicyWindowSize, device);
-        if (pmax > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)pmax) == cudaSuccess)
-            c->l2_persist_max = (size_t)pmax, c->l2_window_max = (size_t)wmax;
-        cudaGetLastError();
-    }
 
     const int L = c->L, beta = c->beta;
     std::vector<u64> r0(K), r1(K), rw(K);

@@ -22,7 +22,6 @@ struct Ctx {
     cudaEvent_t ev_aux[3] = {nullptr, nullptr, nullptr};
     cudaMemPool_t pool = nullptr;
     int sm_count = 148;
-    size_t l2_persist_max = 0, l2_window_max = 0;   // persisting-L2 carve-out and access-window limits
 
     // device tables
     u64 *d_q = nullptr, *d_ratio0 = nullptr, *d_ratio1 = nullptr, *d_rwide = nullptr;
@@ -47,7 +46,6 @@ struct Ctx {
     NttTab ntttab() const { return NttTab{d_psi, d_ipsi, d_invn, d_q}; }
     int digits(int l) const { return (l + P - 1) / P; }
     int limbs_at(int chain_index) const { return chain_index == 0 ? K : L - (chain_index - 1); }
-    int chain_of(int l, bool key_level) const { return key_level ? 0 : L - l + 1; }
 
     // optional per-kernel-class timing (CUDA events on the launching stream), used by bench.py
     struct ProfRec {
@@ -61,8 +59,6 @@ struct Ctx {
     u64* workspace(cudaStream_t s, size_t words) const;
     mutable u64* ws_base[4] = {nullptr, nullptr, nullptr, nullptr};
     mutable size_t ws_cap[4] = {0, 0, 0, 0};
-    // keep [p, p+bytes) L2-resident for the kernels that follow on `s` (bytes = 0 clears the window)
-    void l2_pin(cudaStream_t s, const void* p, size_t bytes) const;
     u64* alloc(size_t n_u64, cudaStream_t s = nullptr) const;   // stream-ordered (default: the main stream)
     void free(void* p, cudaStream_t s = nullptr) const;
 };

@@ -162,10 +162,6 @@ __device__ __forceinline__ u64 ld_keep(const u64* p, u64 pol) {
     asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
     return v;
 }
-__device__ __forceinline__ void st_stream(u64* p, u64 v, u64 pol) {
-    asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
-}
-
 // ---- key-switch inner product -----------------------------------------------------------------
 // out[p][r][n] (+)= sum_j E[j][r][src(n)] * key[j][p][limb(r)][n]  (+ addp[r][src(n)] (* P) into p = 0)
 struct KsArgs {

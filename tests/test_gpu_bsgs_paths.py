@@ -311,3 +311,34 @@ def test_retrieval_wrapper_flow():
     assert np.abs(np.array(scores_pt) - truth).max() < 1e-5
     assert np.abs(np.array(scores_ct) - truth).max() < 1e-5
     assert int(np.argmax(scores_pt)) == int(np.argmax(truth)) == int(np.argmax(scores_ct))
+
+
+@pytest.mark.parametrize("L0,P", [(12, 1), (20, 2), (9, 4)])
+def test_many_digit_parameter_sets_match_oracle(L0, P):
+    """More than 8 key-switch digits (config C5 has beta = 12) takes the generic, non-unrolled kernel paths;
+    P = 4 exercises a wider digit.  Rotation, exact BSGS and hoisted BSGS must stay bit-exact with the oracle."""
+    S = Setup(N=1024, bits=(59,) * (L0 + P), P=P)
+    D = 16
+    G, B = bsgs_params(D)
+    steps = list(range(1, G)) + [g * G for g in range(1, B)]
+    ph, ctx, sk = S.gpu(steps)
+    gk = sk.create_galois_keys(ctx)
+    enc = ph.ckks_encoder(ctx)
+    keys = S.keys_for_steps(steps)
+    rng = np.random.default_rng(L0)
+    W, x = rng.standard_normal((D, D)) * 0.1, rng.standard_normal(D)
+    rolled = rolled_diagonals(W, D, G, B)
+    ct = sk.encrypt_symmetric(ctx, enc.encode_double_vector(ctx, tile(x, S.N // 2), S.scale), enc_id=5)
+    cto = ct.to_numpy()
+    r = ph.rotate(ctx, ct, 3, gk)
+    assert np.array_equal(r.to_numpy(), S.o.apply_galois(cto, S.o.elt_from_step(3), S.key(S.o.elt_from_step(3))))
+    ds = ph.diagonal_set(ctx, rolled, G, B, S.scale)
+    diag_o = np.stack([S.o.encode(v.astype(complex), S.scale, S.L, ext=True, n=2 * D) for v in rolled])
+    y = ph.bsgs_hoisted(ctx, ct, ds, gk)
+    assert np.array_equal(y.to_numpy(), S.o.bsgs_hoisted(cto, diag_o, G, B, D, keys))
+    assert np.abs(np.array(enc.decode_double_vector(ctx, sk.decrypt(ctx, y)))[:D] - W @ x).max() < 1e-9
+    pts = enc.encode_double_vector_batch(ctx, np.stack([tile(v, S.N // 2) for v in rolled]), S.scale, chain_index=1)
+    baby = [ct] + [ph.rotate(ctx, ct, b, gk) for b in range(1, G)]
+    ye = ph.bsgs_multiply_accumulate(ctx, baby, pts, G, B, D, gk)
+    assert np.array_equal(ye.to_numpy(), S.o.bsgs_exact(np.stack([c.to_numpy() for c in baby]),
+                                                         np.stack([p.to_numpy()[0] for p in pts]), G, B, D, keys))
