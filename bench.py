@@ -190,7 +190,7 @@ def run_ours(args):
     N, L0, P, D = CONFIGS[args.config]
     G, B = hb.compute_bsgs_params(D)
     t_setup = time.perf_counter()
-    weights = (1.0,) if args.no_tuned else (1.0, 2.0)
+    weights = (1.0,) if args.no_tuned else (1.0, args.tuned_weight)
     ckks = hb.CKKSBootstrapContext(poly_degree=N, L0=L0, prime_bits=59, special_mod_size=P, max_rot_dim=1,
                                    bsgs_dim=[D], skip_bootstrap=True, seed=bytes(range(32)), device=local,
                                    verbose=(rank == 0 and args.verbose), baby_weights=weights)
@@ -305,10 +305,10 @@ def run_ours(args):
     e2e_value = world * args.steps * nb / float(te.item())
     assert np.array_equal(h_out[0], y.to_numpy()), "e2e result differs from the resident-input result"
 
-    # secondary measurement (not the headline): the same mat-vecs with the hoisting-aware split G = ceil(sqrt(2D))
+    # secondary measurement (not the headline): the same mat-vecs with a hoisting-aware split G = ceil(sqrt(w D))
     tuned = None
     if not args.no_tuned:
-        G2, B2 = hb.compute_bsgs_params(D, 2.0)
+        G2, B2 = hb.compute_bsgs_params(D, args.tuned_weight)
         dsets2 = [hb.pre_encode_real_diags(ckks, Wm, D, G2, B2, level=1) for Wm in Ws]
         ys2 = ph.bsgs_hoisted_batch(ctx, cts, dsets2, ckks.gk)
         err2 = max(float(np.abs(ckks.decrypt_vec(yy, D) - WW @ xx).max()) for yy, WW, xx in zip(ys2, Ws, xs))
@@ -414,7 +414,8 @@ def main():
     ap.add_argument("--full-diagonals", action="store_true", help="store diagonals on the full ring (12.9+ GB at C3)")
     ap.add_argument("--batch", type=int, default=3, help="independent projections per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-tuned", action="store_true", help="skip the secondary G=ceil(sqrt(2D)) measurement")
+    ap.add_argument("--no-tuned", action="store_true", help="skip the secondary hoisting-aware-split measurement")
+    ap.add_argument("--tuned-weight", type=float, default=8.0, help="secondary split: G = ceil(sqrt(weight * D))")
     ap.add_argument("--cpu-reps", type=int, default=3)
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()

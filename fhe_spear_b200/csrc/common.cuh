@@ -162,11 +162,26 @@ struct Acc3 {
     u64 s0, s1, s2;   // s1 holds the Karatsuba middle sum  sum (x0+x1)(y0+y1)  (mod 2^64)
 };
 // three 32x32+64 multiply-adds per term (IMAD.WIDE is the scarce pipe): xs = x0 + x1 is supplied by the caller
+__device__ __forceinline__ u64 mul_wide(u32 a, u32 b) {
+    u64 r;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
+    return r;
+}
+// high word of a 32x32 product through the wide multiplier (kept as IMAD.WIDE by ptxas, not IMAD.HI)
+__device__ __forceinline__ u32 hi_of_wide(u32 a, u32 b) {
+    u32 hi;
+    asm("{ .reg .u64 t; .reg .u32 lo; mul.wide.u32 t, %1, %2; mov.b64 {lo, %0}, t; }" : "=r"(hi) : "r"(a), "r"(b));
+    return hi;
+}
 __device__ __forceinline__ void mac_split(Acc3& a, u64 x, u32 xs, u64 y) {
-    const u32 x0 = (u32)x, x1 = (u32)(x >> 32), y0 = (u32)y, y1 = (u32)(y >> 32);
-    a.s0 = (u64)x0 * y0 + a.s0;
-    a.s2 = (u64)x1 * y1 + a.s2;
-    a.s1 = (u64)xs * (y0 + y1) + a.s1;
+    // explicit PTX: written as (u64)x0 * y0 in C, the front end widens the products to 64-bit multiplies of masked
+    // operands and ptxas then emits a stray 32-bit add per product; mul.wide + add folds to one IMAD.WIDE each
+    u32 x0, x1, y0, y1;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(x0), "=r"(x1) : "l"(x));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(y0), "=r"(y1) : "l"(y));
+    a.s0 += mul_wide(x0, y0);
+    a.s2 += mul_wide(x1, y1);
+    a.s1 += mul_wide(xs, y0 + y1);
 }
 // (hi:lo) += s0 + (s1 - s0 - s2) * 2^30 + s2 * 2^60 ; clears the partial sums.  The true middle sum is < 2^64,
 // so the wrapped subtraction is exact.

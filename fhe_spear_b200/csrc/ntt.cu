@@ -39,8 +39,10 @@ __device__ __forceinline__ void gs_butterfly(u64& x, u64& y, ulonglong2 w, u64 q
 // per stage; 7 such stages plus one exact-Shoup stage stay below 31q, and each pass ends with one cheap
 // reduction (the Barrett ratio floor(2^64/q) fits 32 bits).
 __device__ __forceinline__ u64 mul_shoup_apx(u64 a, u64 w, u64 wp, u64 q) {
+    // the two cross terms only need their high halves; a non-accumulating IMAD.WIDE costs 2 issue cycles on
+    // sm_100a, IMAD.HI costs 5 (tools/ubench/imad.cu), so take the high word of mul.wide instead of __umulhi
     const u32 a0 = (u32)a, a1 = (u32)(a >> 32), p0 = (u32)wp, p1 = (u32)(wp >> 32);
-    const u64 Q = (u64)a1 * p1 + (u64)__umulhi(a0, p1) + (u64)__umulhi(a1, p0);
+    const u64 Q = (u64)a1 * p1 + (u64)hi_of_wide(a0, p1) + (u64)hi_of_wide(a1, p0);
     return a * w - Q * q;
 }
 template <bool LAZY>

@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(KS_TILE, 6) k_ks_inner_tma(const __grid_consta
 
 // All hoisted baby steps in ONE launch: grid (tiles, babies, rows) is dispatched row-major, so the ~2 MB of
 // digits of a row stay L2-resident while the (G-1) rotation keys stream past them exactly once.
-constexpr int KS_MAX_BABY = 96;
+constexpr int KS_MAX_BABY = 224;   // 224 x (128 B tensor map + element) = 29.6 KB of the 32 KB parameter space
 struct BabyTab {
     CUtensorMap map[KS_MAX_BABY];   // key of baby step blockIdx.y + 1
     u32 elt[KS_MAX_BABY];
@@ -523,18 +523,22 @@ constexpr int PM_T2 = 64;       // coefficients per CTA
 
 // A CTA owns (row r, PM_T2 coefficients); thread = (polynomial p, coefficient i) and carries PM_GT giant
 // groups at once, so one shared-memory read of a baby value feeds PM_GT multiply-accumulates.
-// Shared memory: baby tile [Gp][2][PM_T2] in split-30 form (Gp = G rounded up to 8, zero padded), and a
-// PM_STAGES-deep ring of diagonal boxes [PM_GT][Gp][W] filled by TMA (one 3-D box per giant group;
-// groups past the end of the diagonal set are zero-filled by the TMA unit).
-// NG giant groups of one pipeline stage: A[g0 + k] = sum_b y_b * d_{k,b}
+// One launch covers the baby steps [b0, b0 + nbc) of every group (Gc = chunk height, a multiple of 16): sets with
+// many baby steps (hoisting-aware splits, G > 64) are walked in chunks so the shared-memory tile stays small
+// enough for two to three CTAs per SM; later chunks add onto A.
+// Shared memory: baby tile [Gc][2][PM_T2] in split-30 form (rows >= nbc zero), and a PM_STAGES-deep ring of
+// diagonal boxes [PM_GT][Gc][W] filled by TMA (one 3-D box per giant group; a box may run past its group or
+// past the end of the set -- those rows meet zero baby values / are zero-filled by the TMA unit).
+// NG giant groups of one pipeline stage: A[g0 + k] (+)= sum_b y_b * d_{k,b}
 template <int FOLD, int W, int NG>
 __device__ __forceinline__ void pmac_groups(const u64* __restrict__ ycol, const u64* __restrict__ dg, size_t group_words,
-                                            int Gp, u64* __restrict__ Aout, size_t a_stride, u64 q, u64 r0, u64 r1) {
+                                            int Gc, u64* __restrict__ Aout, size_t a_stride, u64 q, u64 r0, u64 r1,
+                                            bool accumulate) {
     Acc3 acc[NG];
     u64 lo[NG], hi[NG];
 #pragma unroll
     for (int k = 0; k < NG; k++) acc[k].s0 = acc[k].s1 = acc[k].s2 = 0, lo[k] = hi[k] = 0;
-    for (int b0 = 0; b0 < Gp; b0 += FOLD) {
+    for (int b0 = 0; b0 < Gc; b0 += FOLD) {
 #pragma unroll
         for (int j = 0; j < FOLD; j++) {
             const u64 y = ycol[(b0 + j) * 2 * PM_T2];
@@ -546,56 +550,59 @@ __device__ __forceinline__ void pmac_groups(const u64* __restrict__ ycol, const 
         for (int k = 0; k < NG; k++) fold_split(lo[k], hi[k], acc[k]);
     }
 #pragma unroll
-    for (int k = 0; k < NG; k++) Aout[k * a_stride] = barrett128(lo[k], hi[k], q, r0, r1);
+    for (int k = 0; k < NG; k++) {
+        u64 v = barrett128(lo[k], hi[k], q, r0, r1);
+        if (accumulate) v = add_mod(v, Aout[k * a_stride], q);
+        Aout[k * a_stride] = v;
+    }
 }
 
+// Threads: (h, p, i) -- polynomial p, coefficient i, and h in [0, PM_HS) takes the giant groups h*PM_GT/PM_HS ... of
+// every stage: the baby column of (p, i) is shared by PM_HS threads, which doubles the warps per SM for the same
+// shared-memory footprint (the MAC loop is latency-bound at 2-3 warps per scheduler).
+constexpr int PM_HS = 2;
+constexpr int PM_NG = PM_GT / PM_HS;   // groups per thread and stage
 template <int FOLD, int RSH>
-__global__ void __launch_bounds__(2 * PM_T2) k_pmac_tma(const __grid_constant__ CUtensorMap tmap,
-                                                         const u64* __restrict__ Y, u64* __restrict__ A, int G, int Gp,
-                                                         int Beff, int l, int rows, int N, int L, ModTab mt) {
+__global__ void __launch_bounds__(2 * PM_T2 * PM_HS) k_pmac_tma(const __grid_constant__ CUtensorMap tmap,
+                                                                 const u64* __restrict__ Y, u64* __restrict__ A, int G,
+                                                                 int Gc, int b0, int nbc, int accumulate, int Beff, int l,
+                                                                 int rows, int N, int L, ModTab mt) {
     extern __shared__ __align__(128) unsigned char smraw[];
     constexpr int W = PM_T2 >> RSH;
-    u64* dsm = reinterpret_cast<u64*>(smraw);                         // [PM_STAGES][PM_GT][Gp][W]
-    u64* ysm = dsm + (size_t)PM_STAGES * PM_GT * Gp * W;              // [Gp][2][PM_T2]
-    uint64_t* full = reinterpret_cast<uint64_t*>(ysm + (size_t)Gp * 2 * PM_T2);
-    const int tid = threadIdx.x, p = tid / PM_T2, i = tid % PM_T2;
+    u64* dsm = reinterpret_cast<u64*>(smraw);                         // [PM_STAGES][PM_GT][Gc][W]
+    u64* ysm = dsm + (size_t)PM_STAGES * PM_GT * Gc * W;              // [Gc][2][PM_T2]
+    uint64_t* full = reinterpret_cast<uint64_t*>(ysm + (size_t)Gc * 2 * PM_T2);
+    const int tid = threadIdx.x, h = tid / (2 * PM_T2), p = (tid / PM_T2) & 1, i = tid % PM_T2;
     const int r = blockIdx.y, n0 = blockIdx.x * PM_T2;
     const int t = r < l ? r : L + (r - l);
     const int iters = (Beff + PM_GT - 1) / PM_GT;
-    const size_t group_words = (size_t)Gp * W, stage_words = PM_GT * group_words;
+    const size_t group_words = (size_t)Gc * W, stage_words = PM_GT * group_words;
     if (tid == 0) {
         for (int s = 0; s < PM_STAGES; s++) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // zero the padding rows (never written by TMA) and the padded baby rows
-    for (int e = tid; e < PM_STAGES * PM_GT * (Gp - G) * W; e += 2 * PM_T2) {
-        int slot = e / ((Gp - G) * W), rem = e % ((Gp - G) * W);
-        dsm[(size_t)slot * group_words + (size_t)G * W + rem] = 0;
-    }
     const size_t pw = (size_t)rows * N, off = (size_t)r * N + n0 + i;
-    for (int b = 0; b < Gp; b++)
-        ysm[(b * 2 + p) * PM_T2 + i] = b < G ? split30(Y[(size_t)(b * 2 + p) * pw + off]) : 0;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int b = h; b < Gc; b += PM_HS)
+        ysm[(b * 2 + p) * PM_T2 + i] = b < nbc ? split30(Y[(size_t)((b0 + b) * 2 + p) * pw + off]) : 0;
     __syncthreads();
     auto issue = [&](int it) {   // only the groups that exist are fetched; expect_tx counts exactly those bytes
         const int s = it % PM_STAGES, ng = min(PM_GT, Beff - it * PM_GT);
-        mbar_expect_tx(&full[s], (u32)(ng * G * W * sizeof(u64)));
+        mbar_expect_tx(&full[s], (u32)(ng * Gc * W * sizeof(u64)));
         for (int k = 0; k < ng; k++)
-            tma_load_3d(dsm + s * stage_words + k * group_words, &tmap, n0 >> RSH, r, (it * PM_GT + k) * G, &full[s]);
+            tma_load_3d(dsm + s * stage_words + k * group_words, &tmap, n0 >> RSH, r, (it * PM_GT + k) * G + b0, &full[s]);
     };
     if (tid == 0)
         for (int it = 0; it < PM_STAGES && it < iters; it++) issue(it);
     const u64 q = mt.q[t], r0 = mt.ratio0[t], r1 = mt.ratio1[t];
     const u64* ycol = ysm + p * PM_T2 + i;
+    const bool acc = accumulate != 0;
     for (int it = 0; it < iters; it++) {
-        const int s = it % PM_STAGES, ng = min(PM_GT, Beff - it * PM_GT);
+        const int s = it % PM_STAGES, ng = min(PM_NG, Beff - it * PM_GT - h * PM_NG);   // this thread's groups
         mbar_wait(&full[s], (it / PM_STAGES) & 1);
-        const u64* dg = dsm + s * stage_words + (i >> RSH);
-        u64* Aout = A + (size_t)(it * PM_GT * 2 + p) * pw + off;
-        if (ng == PM_GT) pmac_groups<FOLD, W, PM_GT>(ycol, dg, group_words, Gp, Aout, 2 * pw, q, r0, r1);
-        else if (ng == 3) pmac_groups<FOLD, W, 3>(ycol, dg, group_words, Gp, Aout, 2 * pw, q, r0, r1);
-        else if (ng == 2) pmac_groups<FOLD, W, 2>(ycol, dg, group_words, Gp, Aout, 2 * pw, q, r0, r1);
-        else pmac_groups<FOLD, W, 1>(ycol, dg, group_words, Gp, Aout, 2 * pw, q, r0, r1);
+        const u64* dg = dsm + s * stage_words + (size_t)h * PM_NG * group_words + (i >> RSH);
+        u64* Aout = A + (size_t)((it * PM_GT + h * PM_NG) * 2 + p) * pw + off;
+        if (ng >= PM_NG) pmac_groups<FOLD, W, PM_NG>(ycol, dg, group_words, Gc, Aout, 2 * pw, q, r0, r1, acc);
+        else if (ng == 1) pmac_groups<FOLD, W, 1>(ycol, dg, group_words, Gc, Aout, 2 * pw, q, r0, r1, acc);
         __syncthreads();   // every thread is done with stage s
         if (tid == 0 && it + PM_STAGES < iters) issue(it + PM_STAGES);
     }
@@ -757,7 +764,12 @@ bool ks_baby_fused(const Ctx* c, const u64* E, const u64* const* keys, const u32
     a.beta = beta, a.l = l, a.rows = rows, a.N = c->N, a.logn = c->logn, a.L = c->L, a.K = c->K, a.elt = 0;
     bool small = true;
     for (u64 qq : c->q) small = small && qq < (1ull << 59);
-    const size_t smem = (size_t)4 * beta * KS_TILE * sizeof(u64) + 64;
+    size_t smem = (size_t)4 * beta * KS_TILE * sizeof(u64) + 64;
+    static const size_t pad_to = [] {   // experiment: cap CTAs/SM by padding dynamic shared memory
+        const char* e = getenv("SPEAR_KS_SMEM_KB");
+        return e ? (size_t)atoi(e) * 1024 : (size_t)0;
+    }();
+    smem = std::max(smem, pad_to);
     const int gx = (c->N / KS_TILE + KS_TPC - 1) / KS_TPC;
     ProfScope ps(c, PROF_KS_BABY, s);
     auto go = [&](auto kern) {
@@ -830,17 +842,19 @@ void pmac_list(const Ctx* c, const u64* const* baby, const u64* const* pt, int n
 
 void pmac_hoisted(const Ctx* c, const u64* Y, const u64* diag, u64* A, int G, int B, int D, int l, int rshift,
                   cudaStream_t s) {
-    const int rows = l + c->P, dn = c->N >> rshift, W = PM_T2 >> rshift, Gp = (G + 15) / 16 * 16;
+    const int rows = l + c->P, dn = c->N >> rshift, W = PM_T2 >> rshift;
+    // baby steps are walked in chunks of Gc <= 64 rows (a multiple of 16) so that 2-3 CTAs fit per SM
+    const int nchunks = (G + 63) / 64, Gc = ((G + nchunks - 1) / nchunks + 15) / 16 * 16;
     REQUIRE(c->N % PM_TILE == 0, "N must be a multiple of %d", PM_TILE);
     const size_t tma_smem =
-        sizeof(u64) * ((size_t)PM_STAGES * PM_GT * Gp * W + (size_t)Gp * 2 * PM_T2) + 8 * PM_STAGES + 64;
+        sizeof(u64) * ((size_t)PM_STAGES * PM_GT * Gc * W + (size_t)Gc * 2 * PM_T2) + 8 * PM_STAGES + 64;
     ProfScope ps(c, PROF_PMAC, s);
-    if (rshift >= 1 && rshift <= 5 && W * sizeof(u64) >= 16 && ((size_t)Gp * W * sizeof(u64)) % 128 == 0 && G <= 256 &&
-        tma_smem <= 227 * 1024) {
+    if (rshift >= 1 && rshift <= 5 && W * sizeof(u64) >= 16 && ((size_t)Gc * W * sizeof(u64)) % 128 == 0 &&
+        Gc <= D && tma_smem <= 227 * 1024) {
         CUtensorMap tmap;
         cuuint64_t dims[3] = {(cuuint64_t)dn, (cuuint64_t)rows, (cuuint64_t)D};
         cuuint64_t strides[2] = {(cuuint64_t)dn * sizeof(u64), (cuuint64_t)rows * dn * sizeof(u64)};
-        cuuint32_t box[3] = {(cuuint32_t)W, 1, (cuuint32_t)G};
+        cuuint32_t box[3] = {(cuuint32_t)W, 1, (cuuint32_t)Gc};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult rc = encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, (void*)diag, dims, strides, box, estr,
                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -853,7 +867,9 @@ void pmac_hoisted(const Ctx* c, const u64* Y, const u64* diag, u64* A, int G, in
         const ModTab mt = c->modtab();
         auto go = [&](auto kern) {
             CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            LAUNCH(kern, grid, 2 * PM_T2, tma_smem, s)(tmap, Y, A, G, Gp, B, l, rows, c->N, c->L, mt);
+            for (int b0 = 0; b0 < G; b0 += Gc)
+                LAUNCH(kern, grid, 2 * PM_T2 * PM_HS, tma_smem, s)(tmap, Y, A, G, Gc, b0, std::min(Gc, G - b0), b0 > 0 ? 1 : 0, B, l,
+                                                           rows, c->N, c->L, mt);
         };
         switch (rshift * 2 + (small ? 1 : 0)) {
             case 2: go(k_pmac_tma<8, 1>); break;

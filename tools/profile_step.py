@@ -20,14 +20,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--count-only", action="store_true")
     ap.add_argument("--mode", default="hoisted", choices=["hoisted", "exact"])
+    ap.add_argument("--weight", type=float, default=1.0, help="split G = ceil(sqrt(weight * D)); 1 = the reference's")
+    ap.add_argument("--classes", action="store_true", help="print per-kernel-class times (event pair around each launch)")
     a = ap.parse_args()
     from fhe_spear_b200 import _native
     from fhe_spear_b200 import bsgs as hb
     from fhe_spear_b200 import pyPhantom as ph
     N, L0, P, D = bench.CONFIGS[a.config]
-    G, B = hb.compute_bsgs_params(D)
+    G, B = hb.compute_bsgs_params(D, a.weight)
     ckks = hb.CKKSBootstrapContext(poly_degree=N, L0=L0, prime_bits=59, special_mod_size=P, max_rot_dim=1,
-                                   bsgs_dim=[D], skip_bootstrap=True, seed=bytes(range(32)), verbose=False)
+                                   bsgs_dim=[D], skip_bootstrap=True, seed=bytes(range(32)), verbose=False,
+                                   baby_weights=(a.weight,))
     rng = np.random.default_rng(1000)
     W, x = rng.standard_normal((D, D)) * 0.02, rng.standard_normal(D) * 0.1
     diags = hb.pre_encode_real_diags(ckks, W, D, G, B, level=1)
@@ -38,9 +41,19 @@ def main():
     if a.count_only:
         print(_native.launch_count())
         return
+    if a.classes:
+        ckks.ctx.timer_start()
+        for _ in range(a.steps):
+            ph.bsgs_hoisted(ckks.ctx, ct, diags, ckks.gk)
+        print(f"G={G} B={B}: {ckks.ctx.timer_stop() / a.steps:.3f} ms per mat-vec")
+        ckks.ctx.profile(True)
     for _ in range(a.steps):
         y = ph.bsgs_hoisted(ckks.ctx, ct, diags, ckks.gk)
     ckks.ctx.synchronize()
+    if a.classes:
+        for k, v in ckks.ctx.profile_read().items():
+            print(f"  {k:14s} {v['ms'] / a.steps:8.3f} ms  {v['launches'] // a.steps:4d} launches")
+        ckks.ctx.profile(False)
     err = float(np.abs(ckks.decrypt_vec(y, D) - W @ x).max())
     print(f"steps={a.steps} max_abs_err={err:.3e} launches={_native.launch_count()}")
 
