@@ -86,6 +86,7 @@ _SIG = {
     "spear_bsgs_hoisted": (C.c_int, [vp, vp, vp, vp, vpp]),
     "spear_bsgs_hoisted_batch": (C.c_int, [vp, vpp, vpp, C.c_int, vp, vpp]),
     "spear_bsgs_hoisted_partial": (C.c_int, [vp, vp, vp, vp, vpp]),
+    "spear_bsgs_hoisted_partial_batch": (C.c_int, [vp, vpp, vpp, C.c_int, vp, vpp]),
     "spear_bsgs_finish": (C.c_int, [vp, vp, vpp]),
     "spear_obj_reduce": (C.c_int, [vp, vp]),
     "spear_obj_device_ptr": (vp, [vp]),

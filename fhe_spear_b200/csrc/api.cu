@@ -854,6 +854,28 @@ int spear_bsgs_hoisted_partial(spear_context* ctx, const spear_obj* ct_, const s
     *out = H_(bsgs_partial(c, O_(ct_), reinterpret_cast<const DiagSet*>(ds_), reinterpret_cast<const GaloisKeys*>(gk_)));
     API_END
 }
+int spear_bsgs_hoisted_partial_batch(spear_context* ctx, spear_obj* const* cts, spear_diagset* const* dss, int count,
+                                     const spear_galois_keys* gk_, spear_obj** outs) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    REQUIRE(count >= 1, "bsgs_hoisted_partial_batch: empty batch");
+    const GaloisKeys* gk = reinterpret_cast<const GaloisKeys*>(gk_);
+    std::vector<std::unique_ptr<Obj>> acc(count);
+    CUDA_CHECK(cudaEventRecord(c->ev_main, c->stream));
+    for (int i = 0; i < count; i++) {
+        cudaStream_t s = count == 1 ? c->stream : c->aux[i % 3];
+        if (count > 1 && i < 3) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_main, 0));
+        acc[i].reset(bsgs_partial(c, O_(cts[i]), reinterpret_cast<const DiagSet*>(dss[i]), gk, s));
+    }
+    if (count > 1)
+        for (int k = 0; k < 3 && k < count; k++) {
+            CUDA_CHECK(cudaEventRecord(c->ev_aux[k], c->aux[k]));
+            CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_aux[k], 0));
+        }
+    for (int i = 0; i < count; i++) outs[i] = H_(acc[i].release());
+    API_END
+}
 int spear_bsgs_finish(spear_context* ctx, spear_obj* acc, spear_obj** out) {
     API_BEGIN
     Ctx* c = C_(ctx);

@@ -660,6 +660,15 @@ def bsgs_hoisted_partial(ctx, ct, shard, gk):
     return _new(ciphertext, ctx, _lib.spear_bsgs_hoisted_partial, ct._h, shard._h, gk._h)
 
 
+def bsgs_hoisted_partial_batch(ctx, cts, shards, gk):
+    """Shard accumulators of several independent mat-vecs, computed concurrently on separate streams."""
+    n = len(cts)
+    outs = (C.c_void_p * n)()
+    _check(_lib.spear_bsgs_hoisted_partial_batch(ctx._h, (C.c_void_p * n)(*[c._h for c in cts]),
+                                                 (C.c_void_p * n)(*[d._h for d in shards]), n, gk._h, outs))
+    return [ciphertext(ctx, C.c_void_p(h)) for h in outs]
+
+
 def bsgs_finish(ctx, acc):
     """ModDown + rescale of a (summed) accumulator; the accumulator's contents are consumed."""
     return _new(ciphertext, ctx, _lib.spear_bsgs_finish, acc._h)

@@ -117,10 +117,14 @@ def client_aided_block(ckks, block, x, x_prev_att, x_prev_ffn, state, v_first, u
     tm["client_mix"] = time.perf_counter() - t0
 
     t0 = time.perf_counter()
-    if pe and all(isinstance(pe[n], ph.diagonal_set) and pe[n].shard[1] == 1 for n in "rkv"):
+    if pe and all(isinstance(pe[n], ph.diagonal_set) for n in "rkv"):
         # server round 1 as one batched call: three independent mat-vecs sharing the keys
         cts = [ckks.encrypt_replicated(mixed[n]) for n in "rkv"]
-        outs = ph.bsgs_hoisted_batch(ckks.ctx, cts, [pe[n] for n in "rkv"], ckks.gk)
+        if any(pe[n].shard[1] > 1 for n in "rkv"):
+            from .sharding import sharded_matvec_batch
+            outs = sharded_matvec_batch(ckks, cts, [pe[n] for n in "rkv"])
+        else:
+            outs = ph.bsgs_hoisted_batch(ckks.ctx, cts, [pe[n] for n in "rkv"], ckks.gk)
         r, k, v = (ckks.decrypt_vec(o, D) for o in outs)
     else:
         r, k, v = (hb.fhe_projection_bsgs(ckks, mixed[n], getattr(block, "W_" + n), D, D, n,

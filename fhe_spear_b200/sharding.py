@@ -75,12 +75,36 @@ def sharded_matvec(ckks, ct, shard_set, group=None):
     return ph.bsgs_finish(ctx, acc)
 
 
+def sharded_matvec_batch(ckks, cts, shard_sets, group=None):
+    """The independent mat-vecs of one block phase (r, k, v | the ffn chunk pairs), giant-step sharded: all shard
+    accumulators are computed concurrently on the engine's streams, then one host hand-off, the all-reduces issued
+    back to back, one Barrett pass and the ModDown + rescale of each.  Same results as sharded_matvec per item."""
+    import torch
+    import torch.distributed as dist
+    from . import pyPhantom as ph
+    ctx = ckks.ctx
+    accs = ph.bsgs_hoisted_partial_batch(ctx, list(cts), list(shard_sets), ckks.gk)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        ctx.synchronize()
+        works = []
+        for acc in accs:
+            size, limbs, ext, ring, _, _ = acc._info()
+            t = torch.as_tensor(_DevView(ph.device_ptr(acc), size * (limbs + ctx.P) * ring), device=f"cuda:{ctx.device}")
+            works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True))
+        for w in works:
+            w.wait()
+        torch.cuda.synchronize(ctx.device)
+        for acc in accs:
+            ph.reduce_inplace(ctx, acc)
+    return [ph.bsgs_finish(ctx, acc) for acc in accs]
+
+
 class ShardedMatvec:
     """Giant-step-sharded hoisted BSGS mat-vec  Enc(x) -> Enc(W @ x)  over the ranks of `group`.
 
     `ckks` is a fhe_spear_b200.bsgs.CKKSBootstrapContext built identically (same seed) on every rank."""
 
-    def __init__(self, ckks, W, D, level=1, group=None, compress=True):
+    def __init__(self, ckks, W, D, level=1, group=None, compress=True, baby_weight=1.0):
         import torch.distributed as dist
         from . import bsgs as hb
         from . import pyPhantom as ph
@@ -89,7 +113,7 @@ class ShardedMatvec:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         if not lazy_sum_is_safe(ckks.ctx.moduli, self.world):
             raise RuntimeError("too many shards for a lazy 64-bit sum of residues")
-        G, B = hb.compute_bsgs_params(D)
+        G, B = hb.compute_bsgs_params(D, baby_weight)   # the context must hold the keys of this split
         rolled = hb._pre_rotate(hb._extract_diagonals(np.asarray(W, dtype=np.float64), D), D, G)
         self.D, self.G, self.B = D, G, B
         self.shard = ph.diagonal_set(ckks.ctx, rolled, G, B, ckks.diag_scale, chain_index=level, compress=compress,

@@ -171,6 +171,10 @@ int spear_bsgs_hoisted_batch(spear_context* ctx, spear_obj* const* cts, spear_di
  * (spear_add, or an integer all-reduce over spear_obj_device_ptr followed by spear_obj_reduce) and finished once. */
 int spear_bsgs_hoisted_partial(spear_context* ctx, const spear_obj* ct, const spear_diagset* shard,
                                const spear_galois_keys* gk, spear_obj** out);
+/* `count` shard accumulators at once, on separate streams like spear_bsgs_hoisted_batch (the independent
+ * projections of one block phase); their all-reduces are then issued back to back. */
+int spear_bsgs_hoisted_partial_batch(spear_context* ctx, spear_obj* const* cts, spear_diagset* const* shards, int count,
+                                     const spear_galois_keys* gk, spear_obj** outs);
 int spear_bsgs_finish(spear_context* ctx, spear_obj* acc, spear_obj** out);   /* ModDown + rescale; clobbers acc */
 int spear_obj_reduce(spear_context* ctx, spear_obj* o);                       /* every residue mod its modulus, in place */
 void* spear_obj_device_ptr(spear_obj* o);                                     /* device address of the limbs */

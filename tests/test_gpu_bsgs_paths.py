@@ -79,6 +79,10 @@ def test_giant_sharding_on_one_gpu(D, world):
         exp = S.o.bsgs_hoisted_partial(ct.to_numpy(), shard.to_numpy(), G, B, D, keys, g_first=r, g_stride=world)
         assert np.array_equal(acc.to_numpy(), exp), r
         accs.append(acc)
+    shards = [ph.diagonal_set(ctx, rolled, G, B, S.scale, shard=(r, world)) for r in range(world)]
+    batch = ph.bsgs_hoisted_partial_batch(ctx, [ct] * world, shards, gk)   # same accumulators, concurrent streams
+    for a, b in zip(accs, batch):
+        assert np.array_equal(a.to_numpy(), b.to_numpy())
     lazy = sum(a.to_numpy().astype(object) for a in accs)            # what an integer all-reduce would hold
     assert int(lazy.max()) < 1 << 63
     total = accs[0]

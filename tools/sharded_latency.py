@@ -23,15 +23,22 @@ def main():
     from fhe_spear_b200 import bsgs as hb
     from fhe_spear_b200 import pyPhantom as ph
     from fhe_spear_b200.sharding import ShardedMatvec
-    cfg = sys.argv[1] if len(sys.argv) > 1 else "c3"
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("config", nargs="?", default="c3")
+    ap.add_argument("--weight", type=float, default=0.0, help="split G = ceil(sqrt(weight * D)); 0 = 8 / world")
+    a = ap.parse_args()
+    cfg = a.config
+    weight = a.weight if a.weight > 0 else max(1.0, 8.0 / world)
     N, L0, P, D = bench.CONFIGS[cfg]
-    G, B = hb.compute_bsgs_params(D)
+    G, B = hb.compute_bsgs_params(D, weight)
     ckks = hb.CKKSBootstrapContext(poly_degree=N, L0=L0, prime_bits=59, special_mod_size=P, max_rot_dim=1, bsgs_dim=[D],
-                                   skip_bootstrap=True, seed=bytes(range(32)), device=local, verbose=False)
+                                   skip_bootstrap=True, seed=bytes(range(32)), device=local, verbose=False,
+                                   baby_weights=(weight,))
     rng = np.random.default_rng(7)                      # same matrix and input on every rank
     W, x = rng.standard_normal((D, D)) * 0.02, rng.standard_normal(D) * 0.1
     ct = ckks.encrypt_replicated(x)                     # same seed, same enc counter -> identical ciphertext
-    mv = ShardedMatvec(ckks, W, D)
+    mv = ShardedMatvec(ckks, W, D, baby_weight=weight)
     y = mv(ct)
     full = hb.pre_encode_real_diags(ckks, W, D, G, B, level=1)
     ref = ph.bsgs_hoisted(ckks.ctx, ct, full, ckks.gk)
@@ -50,13 +57,39 @@ def main():
     ckks.ctx.synchronize()
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / steps * 1e3
+    # phase breakdown (host clock, synchronised after every phase)
+    from fhe_spear_b200.sharding import _DevView, allreduce_residues
+    ctx = ckks.ctx
+    ph_ms = {"partial": 0.0, "allreduce": 0.0, "reduce_finish": 0.0}
+    for _ in range(steps):
+        dist.barrier()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        acc = ph.bsgs_hoisted_partial(ctx, ct, mv.shard, ckks.gk)
+        ctx.synchronize()
+        t2 = time.perf_counter()
+        size, limbs, ext, ring, _, _ = acc._info()
+        tt = torch.as_tensor(_DevView(ph.device_ptr(acc), size * (limbs + ctx.P) * ring), device=f"cuda:{ctx.device}")
+        allreduce_residues(tt)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        ph.reduce_inplace(ctx, acc)
+        ph.bsgs_finish(ctx, acc)
+        ctx.synchronize()
+        t4 = time.perf_counter()
+        ph_ms["partial"] += (t2 - t1) * 1e3 / steps
+        ph_ms["allreduce"] += (t3 - t2) * 1e3 / steps
+        ph_ms["reduce_finish"] += (t4 - t3) * 1e3 / steps
+    pt = torch.tensor([ph_ms["partial"], ph_ms["allreduce"], ph_ms["reduce_finish"]], dtype=torch.float64, device="cuda")
+    dist.all_reduce(pt, op=dist.ReduceOp.MAX)
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ok = torch.tensor([1.0 if same else 0.0], device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps({"what": "giant-step-sharded single mat-vec latency", "config": cfg, "n_gpus": world,
-                          "ms_per_matvec": float(t.item()), "bit_identical_to_unsharded_on_all_ranks": bool(ok.item() > 0.5),
+                          "split": f"G={G} B={B}", "ms_per_matvec": float(t.item()),
+                          "phase_ms_max_over_ranks": dict(zip(("partial", "allreduce", "reduce_finish"), [float(v) for v in pt.tolist()])), "bit_identical_to_unsharded_on_all_ranks": bool(ok.item() > 0.5),
                           "max_abs_err_vs_float64": err, "shard_diag_bytes": mv.shard.info()["bytes"]}))
     dist.destroy_process_group()
 

@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--N", type=int, default=32768)
     ap.add_argument("--L0", type=int, default=24)
     ap.add_argument("--P", type=int, default=3)
+    ap.add_argument("--weight", type=float, default=0.0,
+                    help="BSGS split G = ceil(sqrt(weight * D)); 1 = the reference's, 0 = hoisting-aware (8 / world)")
     a = ap.parse_args()
     from fhe_spear_b200 import bsgs as hb
     from fhe_spear_b200 import rwkv_block as rb
@@ -41,10 +43,13 @@ def main():
     D, F = a.embed_dim, a.ffn_dim
     H, S = max(1, D // 64), min(64, D)
     t0 = time.perf_counter()
+    weight = a.weight if a.weight > 0 else hb.hoisting_weight(world)
+    G, B = hb.compute_bsgs_params(D, weight)
     ckks = hb.CKKSBootstrapContext(poly_degree=a.N, L0=a.L0, prime_bits=59, special_mod_size=a.P, max_rot_dim=1,
-                                   bsgs_dim=[D], skip_bootstrap=True, seed=bytes(range(32)), verbose=False, device=local)
+                                   bsgs_dim=[D], skip_bootstrap=True, seed=bytes(range(32)), verbose=False, device=local,
+                                   baby_weights=(weight,))
     base = rb.RWKVBlockWeights.random(D, F, H, S, block_idx=0, seed=0)
-    pe = hb.pre_encode_block(ckks, base, D, F, shard=(rank, world))
+    pe = hb.pre_encode_block(ckks, base, D, F, G=G, B=B, shard=(rank, world))
     ckks.ctx.synchronize()
     setup_s = time.perf_counter() - t0
     blocks = []
@@ -85,9 +90,9 @@ def main():
             dist.destroy_process_group()
             return
     print(json.dumps({"metric": "server ms per RWKV-7 token (client-aided, BSGS, pre-encoded diagonals)", "n_gpus": world,
-                      "parallelism": "giant steps of every mat-vec sharded over the ranks; one int64 all-reduce per mat-vec" if world > 1 else "1 GPU",
+                      "parallelism": "giant steps of every mat-vec sharded over the ranks; the mat-vecs of a block phase run together, one int64 all-reduce each" if world > 1 else "1 GPU",
                       "config": {"embed_dim": D, "ffn_dim": F, "num_blocks": a.num_blocks, "N": a.N, "L0": a.L0, "P": a.P,
-                                 "matvecs_per_token": 8 * a.num_blocks,
+                                 "matvecs_per_token": 8 * a.num_blocks, "split": f"G={G} B={B} ({G + B - 2} rotations)",
                                  "note": "server_* timings as in the reference: they include client encode+encrypt and decrypt+decode of every projection"},
                       "server_ms_per_token": best, "tokens": rows, "setup_s": setup_s}))
     if world > 1:
