@@ -112,6 +112,8 @@ def client_aided_block(ckks, block, x, x_prev_att, x_prev_ffn, state, v_first, u
     D, F = block.D, block.F
     pe, cpu = preencoded_block, cpu_offloaded_block
     tm = {}
+    if hasattr(pe, "rkv"):       # sharding.HybridBlock: the phases are served by rank groups
+        return _client_aided_block_hybrid(block, pe, x, x_prev_att, x_prev_ffn, state, v_first)
     t0 = time.perf_counter()
     x_ln, mixed = _time_mix_inputs(block, x, x_prev_att)
     tm["client_mix"] = time.perf_counter() - t0
@@ -162,6 +164,40 @@ def client_aided_block(ckks, block, x, x_prev_att, x_prev_ffn, state, v_first, u
                                    cpu_offloaded_diags=cpu.get("ffn_val") if cpu else None)
     tm["server_ffn_val"] = time.perf_counter() - t0
 
+    t0 = time.perf_counter()
+    x = x + v_ffn
+    tm["client_residual"] = time.perf_counter() - t0
+    return x, x_ln, x_ffn_ln, new_state, v_first_out, tm
+
+
+def _client_aided_block_hybrid(block, server, x, x_prev_att, x_prev_ffn, state, v_first):
+    """Same flow as client_aided_block with the four server rounds answered by a sharding.HybridBlock."""
+    tm = {}
+    t0 = time.perf_counter()
+    x_ln, mixed = _time_mix_inputs(block, x, x_prev_att)
+    tm["client_mix"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    r, k, v = server.rkv(mixed)
+    tm["server_rkv"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    gated, new_state, v_first_out = _wkv_and_gate(block, mixed, r, k, v, state, v_first)
+    tm["client_wkv_gate"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    att_out = server.o(gated)
+    tm["server_wo"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    x = x + att_out
+    x_ffn_ln, x_k_ffn = _ffn_input(block, x, x_prev_ffn)
+    tm["client_ffn_prep"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    fk = server.ffn_key(x_k_ffn)
+    tm["server_ffn_key"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    fk_sq = np.maximum(fk, 0.0) ** 2
+    tm["client_relu_sq"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    v_ffn = server.ffn_val(fk_sq)
+    tm["server_ffn_val"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     x = x + v_ffn
     tm["client_residual"] = time.perf_counter() - t0

@@ -5,6 +5,9 @@ Two levels, no parameter exchange after setup:
   * across mat-vecs -- the projections of one RWKV-7 block (r, k, v | o | 2 x ffn_key | 2 x ffn_val,
     reference scripts/bootstrap_generation.py:784-893) are independent: `projection_owner` deals them
     round-robin over the ranks; no collective on the data path (weak scaling, what bench.py --gpus N times).
+    `PhasePlan` / `HybridBlock` combine the two levels for token latency: the k independent mat-vecs of a phase
+    are dealt to k rank groups, each group shards its mat-vec by giant step; the decrypted vectors (a few KB) are
+    exchanged with one small all-reduce per phase.
   * within a mat-vec -- giant groups g = rank, rank + world, ... (`giant_groups`).  Every rank runs the
     hoisted baby steps, the diagonal MAC and the giant key switches of its groups on its own shard of the
     diagonals (`pyPhantom.diagonal_set(..., shard=(rank, world))`) and ends with an accumulator in basis
@@ -121,3 +124,129 @@ class ShardedMatvec:
 
     def __call__(self, ct):
         return sharded_matvec(self.ckks, ct, self.shard, self.group)
+
+
+class PhasePlan:
+    """Deal the k independent mat-vecs of a block phase to rank groups: min(k, world) contiguous groups take one
+    mat-vec each per round; when fewer mat-vecs than groups remain (k = 3 on 2 GPUs) the rest is giant-step sharded
+    over all ranks, so every rank carries the same load."""
+
+    def __init__(self, k, world):
+        self.k, self.world = k, world
+        ng = min(k, world)
+        parts = [tuple(int(r) for r in part) for part in np.array_split(np.arange(world), ng)]
+        full = (k // ng) * ng
+        self.assign = [(j, parts[j % ng]) for j in range(full)] + [(j, tuple(range(world))) for j in range(full, k)]
+        self.groups = sorted({g for _, g in self.assign}, key=lambda g: (len(g), g))
+
+    def mine(self, rank):
+        """[(ranks of the group, [mat-vecs it serves])] for the groups `rank` belongs to, smallest group first"""
+        return [(g, [j for j, gj in self.assign if gj == g]) for g in self.groups if rank in g]
+
+    def leader(self, j):
+        return dict(self.assign)[j][0]
+
+
+class HybridBlock:
+    """The eight projections of one client-aided RWKV-7 block (reference scripts/bootstrap_generation.py:756-899)
+    served by all ranks: phases r,k,v | o | ffn_key pairs | ffn_val pairs, each phase planned by PhasePlan.
+    Every rank runs the same client code and ends every phase with the same plaintext vectors."""
+
+    PHASES = ("rkv", "o", "ffn_key", "ffn_val")
+
+    @staticmethod
+    def plans(world, D, F):
+        from . import bsgs as hb
+        npairs = len(hb._chunk_pairs(F, D))
+        return {"rkv": PhasePlan(3, world), "o": PhasePlan(1, world), "ffn_key": PhasePlan(npairs, world),
+                "ffn_val": PhasePlan(npairs, world)}
+
+    @staticmethod
+    def required_weights(world, D, F):
+        """baby weights (BSGS splits) whose rotation keys the context must hold"""
+        from . import bsgs as hb
+        return tuple(sorted({hb.hoisting_weight(len(g)) for p in HybridBlock.plans(world, D, F).values() for g in p.groups}))
+
+    def __init__(self, ckks, block, D, F, rank=0, world=1):
+        import torch.distributed as dist
+        from . import bsgs as hb
+        self.ckks, self.D, self.F, self.rank, self.world = ckks, D, F, rank, world
+        self.plan = self.plans(world, D, F)
+        self.pairs = hb._chunk_pairs(F, D)
+        self.seq = 1 << 20                                   # encryption counter shared by all ranks
+        level = ckks.encrypt_replicated(np.zeros(1)).chain_index()
+        # one process group per distinct rank group (every rank creates all of them, in the same order)
+        self.pg = {}
+        if world > 1:
+            for ranks in sorted({g for p in self.plan.values() for g in p.groups}):
+                self.pg[ranks] = dist.group.WORLD if len(ranks) == world else dist.new_group(list(ranks))
+        mats = {"rkv": [("real", block.W_r.T), ("real", block.W_k.T), ("real", block.W_v.T)], "o": [("real", block.W_o.T)],
+                "ffn_key": [], "ffn_val": []}
+        for c, c2 in self.pairs:
+            M1 = hb._key_chunk(block.W_key_ffn, c, D, F)
+            mats["ffn_key"].append(("real", M1) if c2 is None else ("complex", M1, hb._key_chunk(block.W_key_ffn, c2, D, F)))
+            M0 = hb._val_chunk(block.W_val_ffn, c, D, F)
+            mats["ffn_val"].append(("real", M0) if c2 is None else ("complex", M0, hb._val_chunk(block.W_val_ffn, c2, D, F, -1.0)))
+        self.sets = {}
+        for phase in self.PHASES:
+            for ranks, js in self.plan[phase].mine(rank):
+                G, B = hb.compute_bsgs_params(D, hb.hoisting_weight(len(ranks)))
+                for j in js:
+                    m = mats[phase][j]
+                    enc = hb.pre_encode_real_diags if m[0] == "real" else hb.pre_encode_complex_diags
+                    self.sets[(phase, j)] = enc(ckks, *m[1:], D, G, B, level, shard=(ranks.index(rank), len(ranks)))
+
+    def _serve(self, phase, inputs):
+        """inputs: k complex (or real) vectors of length D -> k complex result vectors, identical on every rank"""
+        import torch
+        import torch.distributed as dist
+        ckks, D, plan = self.ckks, self.D, self.plan[phase]
+        base, self.seq = self.seq, self.seq + plan.k
+        res = np.zeros((plan.k, D), dtype=np.complex128)
+        for ranks, js in plan.mine(self.rank):
+            cts = []
+            for j in js:
+                rep = np.asarray(inputs[j], dtype=np.complex128)
+                rep = np.concatenate([np.tile(rep, ckks.slots // D), rep[:ckks.slots % D]])
+                cts.append(ckks.sk.encrypt_symmetric(ckks.ctx, ckks.encoder.encode_complex_vector(ckks.ctx, rep, ckks.scale),
+                                                     enc_id=base + j))   # identical ciphertext on every rank of the group
+            outs = sharded_matvec_batch(ckks, cts, [self.sets[(phase, j)] for j in js], group=self.pg.get(ranks))
+            for j, ct_y in zip(js, outs):
+                res[j] = ckks.decrypt_vec_complex(ct_y, D)
+        if self.world > 1 and any(len(g) < self.world for g in plan.groups):
+            keep = np.array([plan.leader(j) == self.rank for j in range(plan.k)])
+            res[~keep] = 0                                      # every result has exactly one contributing rank
+            t = torch.from_numpy(res.view(np.float64)).to(f"cuda:{ckks.ctx.device}")
+            dist.all_reduce(t)
+            res = t.cpu().numpy().view(np.complex128)
+        return res
+
+    def rkv(self, mixed):
+        out = self._serve("rkv", [mixed[n] for n in "rkv"])
+        return out[0].real, out[1].real, out[2].real
+
+    def o(self, gated):
+        return self._serve("o", [gated])[0].real
+
+    def ffn_key(self, x):
+        out = self._serve("ffn_key", [x] * len(self.pairs))
+        D, F, result = self.D, self.F, np.zeros(self.F)
+        for (c, c2), vals in zip(self.pairs, out):
+            lo1, hi1 = c * D, min((c + 1) * D, F)
+            result[lo1:hi1] = vals.real[:hi1 - lo1]
+            if c2 is not None:
+                lo2, hi2 = c2 * D, min((c2 + 1) * D, F)
+                result[lo2:hi2] = vals.imag[:hi2 - lo2]
+        return result
+
+    def ffn_val(self, x):
+        D, F, ins = self.D, self.F, []
+        for c, c2 in self.pairs:
+            v = np.zeros(D, dtype=np.complex128)
+            lo, hi = c * D, min((c + 1) * D, F)
+            v[:hi - lo] = x[lo:hi]
+            if c2 is not None:
+                lo1, hi1 = c2 * D, min((c2 + 1) * D, F)
+                v[:hi1 - lo1] += 1j * x[lo1:hi1]
+            ins.append(v)
+        return sum(vals.real for vals in self._serve("ffn_val", ins))

@@ -69,6 +69,30 @@ def _worker(rank, world, port, D, out):
     dist.destroy_process_group()
 
 
+
+
+def test_phase_plans_cover_every_matvec_once_and_balance_the_ranks():
+    from fhe_spear_b200 import sharding as sh
+    for world in (1, 2, 3, 4, 8):
+        for k in (1, 2, 3, 5):
+            plan = sh.PhasePlan(k, world)
+            assert sorted(j for j, _ in plan.assign) == list(range(k))
+            load = np.zeros(world)
+            for j, ranks in plan.assign:
+                assert len(set(ranks)) == len(ranks) and all(0 <= r < world for r in ranks)
+                load[list(ranks)] += 1.0 / len(ranks)
+                assert plan.leader(j) == ranks[0]
+            if world <= k or k == 1:
+                assert np.ptp(load) < 1e-12 or k % world                # equal shares when the phase fills the ranks
+            for rank in range(world):
+                mine = plan.mine(rank)
+                assert all(rank in g for g, _ in mine)
+                assert sum(len(js) for _, js in mine) == sum(1 for _, g in plan.assign if rank in g)
+    p = sh.PhasePlan(3, 2)      # r -> rank 0, k -> rank 1, v sharded over both: 1.5 mat-vecs each
+    assert p.assign == [(0, (0,)), (1, (1,)), (2, (0, 1))]
+    assert sh.HybridBlock.required_weights(8, 2048, 8192) == (1.0, 2.0, 8.0 / 3.0, 4.0)
+
+
 @pytest.mark.parametrize("D", [16, 20])
 def test_two_rank_giant_sharding_matches_unsharded(D):
     with socket.socket() as s:

@@ -26,6 +26,9 @@ def main():
     ap.add_argument("--N", type=int, default=32768)
     ap.add_argument("--L0", type=int, default=24)
     ap.add_argument("--P", type=int, default=3)
+    ap.add_argument("--plan", default="hybrid", choices=["hybrid", "giant"],
+                    help="hybrid: mat-vecs of a phase dealt to rank groups, giant steps sharded inside a group; "
+                         "giant: every mat-vec sharded by giant step over all ranks")
     ap.add_argument("--weight", type=float, default=0.0,
                     help="BSGS split G = ceil(sqrt(weight * D)); 1 = the reference's, 0 = hoisting-aware (8 / world)")
     a = ap.parse_args()
@@ -43,13 +46,19 @@ def main():
     D, F = a.embed_dim, a.ffn_dim
     H, S = max(1, D // 64), min(64, D)
     t0 = time.perf_counter()
+    from fhe_spear_b200.sharding import HybridBlock
+    hybrid = a.plan == "hybrid" and world > 1
     weight = a.weight if a.weight > 0 else hb.hoisting_weight(world)
     G, B = hb.compute_bsgs_params(D, weight)
+    weights = HybridBlock.required_weights(world, D, F) if hybrid else (weight,)
     ckks = hb.CKKSBootstrapContext(poly_degree=a.N, L0=a.L0, prime_bits=59, special_mod_size=a.P, max_rot_dim=1,
                                    bsgs_dim=[D], skip_bootstrap=True, seed=bytes(range(32)), verbose=False, device=local,
-                                   baby_weights=(weight,))
+                                   baby_weights=weights)
     base = rb.RWKVBlockWeights.random(D, F, H, S, block_idx=0, seed=0)
-    pe = hb.pre_encode_block(ckks, base, D, F, G=G, B=B, shard=(rank, world))
+    if hybrid:
+        pe = HybridBlock(ckks, base, D, F, rank, world)
+    else:
+        pe = hb.pre_encode_block(ckks, base, D, F, G=G, B=B, shard=(rank, world))
     ckks.ctx.synchronize()
     setup_s = time.perf_counter() - t0
     blocks = []
@@ -90,9 +99,11 @@ def main():
             dist.destroy_process_group()
             return
     print(json.dumps({"metric": "server ms per RWKV-7 token (client-aided, BSGS, pre-encoded diagonals)", "n_gpus": world,
-                      "parallelism": "giant steps of every mat-vec sharded over the ranks; the mat-vecs of a block phase run together, one int64 all-reduce each" if world > 1 else "1 GPU",
+                      "parallelism": ("1 GPU" if world == 1 else
+                                      "hybrid: the mat-vecs of a phase dealt to rank groups " + str({k: v.groups for k, v in pe.plan.items()}) + ", giant steps sharded inside a group" if hybrid else
+                                      "giant steps of every mat-vec sharded over all ranks; the mat-vecs of a block phase run together, one int64 all-reduce each"),
                       "config": {"embed_dim": D, "ffn_dim": F, "num_blocks": a.num_blocks, "N": a.N, "L0": a.L0, "P": a.P,
-                                 "matvecs_per_token": 8 * a.num_blocks, "split": f"G={G} B={B} ({G + B - 2} rotations)",
+                                 "matvecs_per_token": 8 * a.num_blocks, "split": "per group size: G = ceil(sqrt(8 / size * D))" if hybrid else f"G={G} B={B} ({G + B - 2} rotations)",
                                  "note": "server_* timings as in the reference: they include client encode+encrypt and decrypt+decode of every projection"},
                       "server_ms_per_token": best, "tokens": rows, "setup_s": setup_s}))
     if world > 1:
