@@ -39,11 +39,43 @@ __device__ __forceinline__ void gs_butterfly(u64& x, u64& y, ulonglong2 w, u64 q
 // per stage; 7 such stages plus one exact-Shoup stage stay below 31q, and each pass ends with one cheap
 // reduction (the Barrett ratio floor(2^64/q) fits 32 bits).
 __device__ __forceinline__ u64 mul_shoup_apx(u64 a, u64 w, u64 wp, u64 q) {
-    // the two cross terms only need their high halves; a non-accumulating IMAD.WIDE costs 2 issue cycles on
-    // sm_100a, IMAD.HI costs 5 (tools/ubench/imad.cu), so take the high word of mul.wide instead of __umulhi
-    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), p0 = (u32)wp, p1 = (u32)(wp >> 32);
-    const u64 Q = (u64)a1 * p1 + (u64)hi_of_wide(a0, p1) + (u64)hi_of_wide(a1, p0);
-    return a * w - Q * q;
+    // Written out in PTX so that the instruction selection is exactly: 4 IMAD.WIDE (two of them only for their high
+    // halves -- a non-accumulating IMAD.WIDE issues in 2 cycles on sm_100a, IMAD.HI in 5, tools/ubench/imad.cu),
+    // 1 accumulating IMAD.WIDE, 4 IMAD and 4 carry adds:
+    //   Q = a1*p1 + hi(a0*p1) + hi(a1*p0);   r = lo64(a*w) - lo64(Q*q)
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 a0, a1, w0, w1, p0, p1, q0, q1, h1, h2, z, Q0, Q1, T0, T1, U0, U1;\n\t"
+        ".reg .u64 t, Q, T, U;\n\t"
+        "mov.b64 {a0, a1}, %1;\n\t"
+        "mov.b64 {w0, w1}, %2;\n\t"
+        "mov.b64 {p0, p1}, %3;\n\t"
+        "mov.b64 {q0, q1}, %4;\n\t"
+        "mul.wide.u32 t, a0, p1;\n\t"
+        "mov.b64 {z, h1}, t;\n\t"
+        "mul.wide.u32 t, a1, p0;\n\t"
+        "mov.b64 {z, h2}, t;\n\t"
+        "mov.u32 z, 0;\n\t"
+        "mov.b64 t, {h1, z};\n\t"
+        "mad.wide.u32 Q, a1, p1, t;\n\t"
+        "mov.b64 {Q0, Q1}, Q;\n\t"
+        "add.cc.u32 Q0, Q0, h2;\n\t"
+        "addc.u32 Q1, Q1, 0;\n\t"
+        "mul.wide.u32 T, a0, w0;\n\t"
+        "mov.b64 {T0, T1}, T;\n\t"
+        "mad.lo.u32 T1, a0, w1, T1;\n\t"
+        "mad.lo.u32 T1, a1, w0, T1;\n\t"
+        "mul.wide.u32 U, Q0, q0;\n\t"
+        "mov.b64 {U0, U1}, U;\n\t"
+        "mad.lo.u32 U1, Q0, q1, U1;\n\t"
+        "mad.lo.u32 U1, Q1, q0, U1;\n\t"
+        "sub.cc.u32 T0, T0, U0;\n\t"
+        "subc.u32 T1, T1, U1;\n\t"
+        "mov.b64 %0, {T0, T1};\n\t"
+        "}"
+        : "=l"(r)
+        : "l"(a), "l"(w), "l"(wp), "l"(q));
+    return r;
 }
 template <bool LAZY>
 __device__ __forceinline__ void fwd_bf(u64& x, u64& y, ulonglong2 w, u64 q, u64 q2, u64 q4) {
