@@ -134,6 +134,15 @@ __device__ __forceinline__ u64 reduce_wide(u64 lo, u64 hi, u64 q, u64 R) {
     r = r >= q2 ? r - q2 : r;
     return r >= q ? r - q : r;
 }
+// same with s supplied (all moduli of a parameter set usually share their bit length: uniform shifts, no FLO)
+__device__ __forceinline__ u64 reduce_wide_s(u64 lo, u64 hi, u64 q, u64 R, int s) {
+    const u64 top = (hi << (64 - s)) | (lo >> s);
+    const u64 Q = __umul64hi(top, R);
+    u64 r = lo - Q * q;
+    const u64 q2 = q << 1;
+    r = r >= q2 ? r - q2 : r;
+    return r >= q ? r - q : r;
+}
 __device__ __forceinline__ u64 mul_mod(u64 a, u64 b, u64 q, u64 r0, u64 r1) {
     return barrett128(a * b, __umul64hi(a, b), q, r0, r1);
 }

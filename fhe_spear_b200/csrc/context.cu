@@ -186,6 +186,11 @@ Ctx* ctx_create(u64 N, const u64* moduli, int K, int P, int device) {
         for (int k = 0; k <= 16; k++) invn[i * 17 + k] = with_shoup(invm((1ull << k) % q, q), q);
     }
     c->d_q = upload(c->q), c->d_ratio0 = upload(r0), c->d_ratio1 = upload(r1), c->d_rwide = upload(rw);
+    {
+        auto bits = [](u64 v) { int b = 0; while (v) b++, v >>= 1; return b; };
+        c->sbits = bits(c->q[0]) - 1;
+        for (u64 qq : c->q) if (bits(qq) - 1 != c->sbits) c->sbits = 0;
+    }
     c->d_psi = upload(psi), c->d_ipsi = upload(ipsi), c->d_invn = upload(invn);
 
     // P mod q_i and its inverse

@@ -22,6 +22,7 @@ struct Ctx {
     cudaEvent_t ev_aux[3] = {nullptr, nullptr, nullptr};
     cudaMemPool_t pool = nullptr;
     int sm_count = 148;
+    int sbits = 0;   // bitlength(q) - 1 when every modulus has the same bit length, else 0
 
     // device tables
     u64 *d_q = nullptr, *d_ratio0 = nullptr, *d_ratio1 = nullptr, *d_rwide = nullptr;

@@ -86,11 +86,19 @@ __global__ void k_galois(const u64* __restrict__ in, u64* __restrict__ out, int 
 template <int A>
 __global__ void __launch_bounds__(TPB) k_modup(const u64* __restrict__ x, const u64* __restrict__ cin,
                                                 u64* __restrict__ E, int l, int N, int L, int P, int K, ModTab mt,
-                                                const ulonglong2* __restrict__ hatinv, const u64* __restrict__ hat) {
+                                                const ulonglong2* __restrict__ hatinv, const u64* __restrict__ hat,
+                                                int sbits) {
+    // per-row constants of this digit (hat_0..hat_{A-1}, q, floor(2^(s+64)/q)) staged once per CTA: the row loop
+    // then issues shared-memory broadcasts instead of five global loads with 64-bit address arithmetic per row
+    extern __shared__ u64 tab[];   // [rows][A + 2]
     const int j = blockIdx.y, n = blockIdx.x * TPB + threadIdx.x;
     const int rows = l + P, lo = j * P, hi = min(lo + P, l), a = hi - lo;
     hatinv += (size_t)j * P;
     hat += (size_t)j * P * K;
+    for (int e = threadIdx.x; e < rows * (A + 2); e += TPB) {
+        const int r = e / (A + 2), c = e % (A + 2), t = r < l ? r : L + (r - l);
+        tab[e] = c < A ? (c < a ? hat[(size_t)c * K + t] : 0) : c == A ? mt.q[t] : mt.rwide[t];
+    }
     u64 y[A];
     u32 ys[A];
 #pragma unroll
@@ -102,19 +110,22 @@ __global__ void __launch_bounds__(TPB) k_modup(const u64* __restrict__ x, const 
             ys[i] = (u32)y[i] + (u32)(y[i] >> 32);
         }
     }
+    __syncthreads();
     u64* Ej = E + (size_t)j * rows * N + n;
     for (int r = 0; r < rows; r++) {
-        int t = r < l ? r : L + (r - l);
+        const int t = r < l ? r : L + (r - l);
         if (t >= lo && t < hi) {
             Ej[(size_t)r * N] = split30(cin[(size_t)t * N + n]);   // digits are consumed in split-30 form
             continue;
         }
+        const u64* tr = tab + r * (A + 2);
         Acc3 acc = {0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < A; i++) mac_split(acc, y[i], ys[i], hat[(size_t)i * K + t]);   // rows i >= a hold zeros
+        for (int i = 0; i < A; i++) mac_split(acc, y[i], ys[i], tr[i]);   // rows i >= a hold zeros
         u64 alo = 0, ahi = 0;
         fold_split(alo, ahi, acc);
-        Ej[(size_t)r * N] = reduce_wide(alo, ahi, mt.q[t], mt.rwide[t]);
+        const u64 q = tr[A];
+        Ej[(size_t)r * N] = sbits > 0 ? reduce_wide_s(alo, ahi, q, tr[A + 1], sbits) : reduce_wide(alo, ahi, q, tr[A + 1]);
     }
 }
 
@@ -682,10 +693,11 @@ void decompose_from(const Ctx* c, const u64* cin, const u64* x, int l, u64* E, c
     REQUIRE(N % TPB == 0, "N must be a multiple of %d", TPB);
     {
         ProfScope ps(c, PROF_MODUP, s);
+        const size_t tab_bytes = sizeof(u64) * rows * ((P <= 4 ? P : MAX_ALPHA) + 2);
         auto go = [&](auto kern) {
-            LAUNCH(kern, dim3(N / TPB, beta), TPB, 0, s)(x, cin, E, l, N, c->L, P, c->K, c->modtab(),
-                                                         c->d_up_hatinv + (size_t)l * c->beta * P,
-                                                         c->d_up_hat + (size_t)l * c->beta * P * c->K);
+            LAUNCH(kern, dim3(N / TPB, beta), TPB, tab_bytes, s)(x, cin, E, l, N, c->L, P, c->K, c->modtab(),
+                                                                 c->d_up_hatinv + (size_t)l * c->beta * P,
+                                                                 c->d_up_hat + (size_t)l * c->beta * P * c->K, c->sbits);
         };
         if (P == 1) go(k_modup<1>);
         else if (P == 2) go(k_modup<2>);
@@ -764,12 +776,7 @@ bool ks_baby_fused(const Ctx* c, const u64* E, const u64* const* keys, const u32
     a.beta = beta, a.l = l, a.rows = rows, a.N = c->N, a.logn = c->logn, a.L = c->L, a.K = c->K, a.elt = 0;
     bool small = true;
     for (u64 qq : c->q) small = small && qq < (1ull << 59);
-    size_t smem = (size_t)4 * beta * KS_TILE * sizeof(u64) + 64;
-    static const size_t pad_to = [] {   // experiment: cap CTAs/SM by padding dynamic shared memory
-        const char* e = getenv("SPEAR_KS_SMEM_KB");
-        return e ? (size_t)atoi(e) * 1024 : (size_t)0;
-    }();
-    smem = std::max(smem, pad_to);
+    const size_t smem = (size_t)4 * beta * KS_TILE * sizeof(u64) + 64;
     const int gx = (c->N / KS_TILE + KS_TPC - 1) / KS_TPC;
     ProfScope ps(c, PROF_KS_BABY, s);
     auto go = [&](auto kern) {
