@@ -73,6 +73,7 @@ _SIG = {
     "spear_multiply_plain": (C.c_int, [vp, vp, vp, vpp]),
     "spear_relinearize": (C.c_int, [vp, vp, vp, vpp]),
     "spear_rescale_to_next": (C.c_int, [vp, vp, vpp]),
+    "spear_mod_raise": (C.c_int, [vp, vp, C.c_int, vpp]),
     "spear_mod_switch_to_next": (C.c_int, [vp, vp, vpp]),
     "spear_apply_galois": (C.c_int, [vp, vp, C.c_uint32, vp, vpp]),
     "spear_hoisted_rotations": (C.c_int, [vp, vp, u32p, C.c_int, vp, vpp]),

@@ -71,10 +71,12 @@ class CKKSBootstrapContext:
     def __init__(self, poly_degree=32768, L0=24, prime_bits=59, special_mod_size=3, level_budget=None,
                  max_rot_dim=256, bsgs_dim=0, skip_bootstrap=False, seed=None, device=None, verbose=True,
                  baby_weights=(1.0,)):
-        if not skip_bootstrap:
-            raise RuntimeError("Bootstrap not available in this build (pass skip_bootstrap=True)")
+        if level_budget is None:
+            level_budget = [2, 2]
         say = print if verbose else (lambda *a, **k: None)
-        say(f"[CKKS] Setting up: N={poly_degree}, L0={L0}, bits={prime_bits}, P={special_mod_size}")
+        say(f"[CKKS] Setting up: N={poly_degree}, L0={L0}, bits={prime_bits}, P={special_mod_size}"
+            + ("" if skip_bootstrap else f", budget={level_budget}"))
+        boot_elts = [] if skip_bootstrap else ph.ckks_bootstrapper.get_galois_elements(poly_degree, 0, level_budget)
         rot_elts = compute_rotation_galois_elements(poly_degree, max_dim=max_rot_dim)
         dims = bsgs_dim if isinstance(bsgs_dim, (list, tuple)) else [bsgs_dim]
         bsgs_elts = set()
@@ -84,8 +86,8 @@ class CKKSBootstrapContext:
                 bsgs_elts.update(elts)
                 G, B = compute_bsgs_params(d, w)
                 say(f"[CKKS] BSGS: D={d}, G={G} baby, B={B} giant, {len(elts)} galois elements")
-        all_elts = sorted(set(rot_elts) | bsgs_elts)
-        say(f"[CKKS] Galois elements: 0 boot + {len(rot_elts)} rot + {len(bsgs_elts)} bsgs = {len(all_elts)} total")
+        all_elts = sorted(set(boot_elts) | set(rot_elts) | bsgs_elts)
+        say(f"[CKKS] Galois elements: {len(boot_elts)} boot + {len(rot_elts)} rot + {len(bsgs_elts)} bsgs = {len(all_elts)} total")
 
         parms = ph.params(ph.scheme_type.ckks)
         parms.set_poly_modulus_degree(poly_degree)
@@ -104,6 +106,12 @@ class CKKSBootstrapContext:
         self.rlk = self.sk.gen_relinkey(self.ctx)
         self.gk = self.sk.create_galois_keys(self.ctx)
         self.bt = None
+        if not skip_bootstrap:                      # [ref: :110-116]
+            self.bt = ph.ckks_bootstrapper(self.encoder)
+            self.bt.setup(self.ctx, level_budget)
+            self.bt.impl.gk, self.bt.impl.rlk = self.gk, self.rlk     # the context's keys already cover the bootstrap elements
+            bt_depth = ph.ckks_bootstrapper.get_bootstrap_depth(level_budget, poly_degree)
+            say(f"[CKKS] Bootstrap depth={bt_depth}, post-bootstrap levels={L0 - bt_depth - 1}")
         say(f"[CKKS] Slots={self.slots}")
 
     def encrypt(self, vec):
@@ -129,7 +137,12 @@ class CKKSBootstrapContext:
         return self.encoder.decode_double_vector(self.ctx, self.sk.decrypt(self.ctx, ct))[0]
 
     def bootstrap(self, ct):
-        raise RuntimeError("Bootstrap not available (skip_bootstrap=True)")
+        """[ref: :149-154] mod-switch down to two limbs, then ckks_bootstrapper.bootstrap"""
+        if self.bt is None:
+            raise RuntimeError("Bootstrap not available (skip_bootstrap=True)")
+        while ct.coeff_modulus_size() > 2:
+            ct = ph.mod_switch_to_next(self.ctx, ct)
+        return self.bt.bootstrap(self.ctx, ct)
 
 
 # ---- diagonals  [ref: :198-203, :361-432] --------------------------------------------------------------

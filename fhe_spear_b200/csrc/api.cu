@@ -600,6 +600,22 @@ int spear_rescale_to_next(spear_context* ctx, const spear_obj* ct_, spear_obj** 
     *out = H_(o.release());
     API_END
 }
+int spear_mod_raise(spear_context* ctx, const spear_obj* ct_, int chain_index, spear_obj** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const Obj* ct = O_(ct_);
+    check_ct(ct, "mod_raise");
+    REQUIRE(ct->l == 1, "mod_raise: the ciphertext must be at the last level (one limb), has %d", ct->l);
+    const int l = c->L - chain_index + 1;
+    REQUIRE(chain_index >= 1 && l >= 1, "mod_raise: chain_index %d out of range", chain_index);
+    std::unique_ptr<Obj> o(new_obj(c, ct->size, l, false, c->N, ct->scale));
+    u64* x = c->alloc((size_t)ct->size * c->N);
+    ops::mod_raise(c, ct->d, ct->size, l, x, o->d, c->stream);
+    c->free(x);
+    *out = H_(o.release());
+    API_END
+}
 int spear_mod_switch_to_next(spear_context* ctx, const spear_obj* a_, spear_obj** out) {
     API_BEGIN
     Ctx* c = C_(ctx);

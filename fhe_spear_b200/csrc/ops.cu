@@ -435,6 +435,26 @@ __global__ void k_moddown_final(const u64* __restrict__ in, const u64* __restric
     }
 }
 
+// ---- ModRaise (bootstrapping) ---------------------------------------------------------------------
+// x: [polys][N] coefficient form modulo q_0; out[p][i][n] = centred representative of x modulo q_i (coefficient form)
+__global__ void __launch_bounds__(TPB) k_modraise(const u64* __restrict__ x, u64* __restrict__ out, int l, int N,
+                                                   ModTab mt) {
+    const int p = blockIdx.y, n = blockIdx.x * TPB + threadIdx.x;
+    const u64 q0 = mt.q[0], half = q0 >> 1, v = x[(size_t)p * N + n];
+    u64* o = out + (size_t)p * l * N + n;
+    for (int i = 0; i < l; i++) {
+        const u64 q = mt.q[i], r1 = mt.ratio1[i];
+        u64 r;
+        if (v > half) {   // negative representative v - q_0
+            const u64 d = barrett64(q0 - v, q, r1);
+            r = d ? q - d : 0;
+        } else {
+            r = barrett64(v, q, r1);
+        }
+        o[(size_t)i * N] = r;
+    }
+}
+
 // ---- rescale ---------------------------------------------------------------------------------
 // last: [polys][N] coefficient form of the dropped limb; tmp[p][i][n] = [(x + half)]_{q_i} - [half]_{q_i}
 __global__ void __launch_bounds__(TPB) k_rescale_conv(const u64* __restrict__ last, u64* __restrict__ tmp, int l,
@@ -835,6 +855,16 @@ void rescale(const Ctx* c, const u64* in, int polys, int l, u64* last, u64* tmp,
     ntt_forward(c, tmp, polys * (l - 1), RowMap{l - 1, l - 1, c->L, 0}, N, s);
     LAUNCH(k_rescale_final, grid_for(c, (size_t)polys * (l - 1) * N), TPB, 0, s)(in, tmp, out, polys, l, N, c->modtab(),
                                                                              c->d_rs_inv + (size_t)(l - 1) * c->K);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// in: [polys][1][N] (NTT form, modulus q_0) -> out: [polys][l][N] (NTT form); x: scratch [polys][N]
+void mod_raise(const Ctx* c, const u64* in, int polys, int l, u64* x, u64* out, cudaStream_t s) {
+    const int N = c->N;
+    CUDA_CHECK(cudaMemcpyAsync(x, in, sizeof(u64) * polys * N, cudaMemcpyDeviceToDevice, s));
+    ntt_inverse(c, x, polys, RowMap{1, 1, c->L, 0}, N, s);
+    LAUNCH(k_modraise, dim3(N / TPB, polys), TPB, 0, s)(x, out, l, N, c->modtab());
+    ntt_forward(c, out, polys * l, RowMap{l, l, c->L, 0}, N, s);
     CUDA_CHECK(cudaGetLastError());
 }
 

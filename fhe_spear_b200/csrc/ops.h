@@ -18,6 +18,7 @@ bool ks_baby_fused(const Ctx* c, const u64* E, const u64* const* keys, const u32
                    const u64* c0, cudaStream_t s);
 void pscale(const Ctx* c, const u64* x, u64* y, int l, cudaStream_t s);
 void moddown(const Ctx* c, u64* in, size_t in_pstride, int polys, int l, u64* tmp, const u64* add, u64* out, cudaStream_t s);
+void mod_raise(const Ctx* c, const u64* in, int polys, int l, u64* x, u64* out, cudaStream_t s);
 void rescale(const Ctx* c, const u64* in, int polys, int l, u64* last, u64* tmp, u64* out, cudaStream_t s);
 void pmac_list(const Ctx* c, const u64* const* baby, const u64* const* pt, int nb, u64* out, int l, cudaStream_t s);
 void split30_inplace(const Ctx* c, u64* x, size_t n, bool unsplit, cudaStream_t s);

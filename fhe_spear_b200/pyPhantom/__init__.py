@@ -492,6 +492,11 @@ def mod_switch_to_next(ctx, obj):
     return _new(type(obj), ctx, _lib.spear_mod_switch_to_next, obj._h)
 
 
+def mod_raise(ctx, ct, chain_index=1):
+    """ModRaise (bootstrapping entry): a one-limb ciphertext re-read modulo the primes of `chain_index`."""
+    return _new(ciphertext, ctx, _lib.spear_mod_raise, ct._h, int(chain_index))
+
+
 def mod_switch_to(ctx, obj, chain_index):
     cur = obj.chain_index()
     if chain_index < cur:
@@ -688,15 +693,44 @@ def bsgs_hoisted(ctx, ct, diags, gk):
 
 # ---- bootstrapping  [ref: fork-only ckks_bootstrapper, scripts/bootstrap_generation.py:72-75,110-116] ---
 class ckks_bootstrapper:
-    """Not built in this round; callers must pass skip_bootstrap=True."""
+    """CKKS bootstrapping (fhe_spear_b200/bootstrap.py): ModRaise -> CoeffToSlot -> EvalMod -> SlotToCoeff over the
+    evaluator of this module.  The reference's implementation sits in the absent phantom-fhe fork; interface and
+    call order follow its call sites, the algorithm is this build's own."""
+
+    DEFAULT_BUDGET = (2, 2)
 
     def __init__(self, encoder):
-        raise RuntimeError("ckks_bootstrapper is not implemented in this build (use skip_bootstrap=True / --no-bootstrap)")
+        self.encoder = encoder
+        self.impl = None
 
     @staticmethod
-    def get_galois_elements(poly_degree, flag, level_budget):
-        raise RuntimeError("ckks_bootstrapper is not implemented in this build (use skip_bootstrap=True / --no-bootstrap)")
+    def get_galois_elements(poly_degree, slots, level_budget):
+        """Galois elements of every rotation the linear transforms need, plus conjugation (slots = 0: all N/2)."""
+        from ..bootstrap import Bootstrapper
+        steps = Bootstrapper.rotation_steps(int(poly_degree), tuple(level_budget or ckks_bootstrapper.DEFAULT_BUDGET))
+        return sorted(set(get_elts_from_steps(steps, poly_degree)) | {2 * int(poly_degree) - 1})
 
     @staticmethod
-    def get_bootstrap_depth(level_budget):
-        raise RuntimeError("ckks_bootstrapper is not implemented in this build (use skip_bootstrap=True / --no-bootstrap)")
+    def get_bootstrap_depth(level_budget, poly_degree=32768):
+        """Levels between the raised ciphertext and the bootstrapped one (the reference passes the budget only: the
+        default degree is the largest ring of its configurations, smaller rings need at most as many levels)."""
+        from ..bootstrap import Bootstrapper
+        return Bootstrapper.depth_for(int(poly_degree), tuple(level_budget or ckks_bootstrapper.DEFAULT_BUDGET))
+
+    def setup(self, ctx, level_budget=None):
+        from ..bootstrap import Bootstrapper
+        import sys
+        self.impl = Bootstrapper(sys.modules[__name__], ctx, self.encoder, ctx.N, ctx.moduli, ctx.P,
+                                 tuple(level_budget or self.DEFAULT_BUDGET))
+
+    def keygen(self, ctx, sk):
+        if self.impl is None:
+            raise RuntimeError("ckks_bootstrapper.keygen: call setup(ctx, level_budget) first")
+        elts = self.get_galois_elements(ctx.N, 0, self.impl.budget)
+        self.impl.gk = sk.create_galois_keys(ctx, elts)
+        self.impl.rlk = sk.gen_relinkey(ctx)
+
+    def bootstrap(self, ctx, ct):
+        if self.impl is None or self.impl.gk is None:
+            raise RuntimeError("ckks_bootstrapper.bootstrap: call setup() and keygen() first")
+        return self.impl.bootstrap(ct)

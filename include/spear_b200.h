@@ -131,6 +131,10 @@ int spear_multiply(spear_context* ctx, const spear_obj* a, const spear_obj* b, s
 int spear_multiply_plain(spear_context* ctx, const spear_obj* ct, const spear_obj* pt, spear_obj** out);
 int spear_relinearize(spear_context* ctx, const spear_obj* ct3, const spear_kswitch_key* rlk, spear_obj** out);
 int spear_rescale_to_next(spear_context* ctx, const spear_obj* ct, spear_obj** out);
+/* ModRaise, the entry of CKKS bootstrapping [ref: inside the fork-only ckks_bootstrapper.bootstrap,
+ * scripts/bootstrap_generation.py:149-154]: a one-limb ciphertext re-read modulo the primes of `chain_index`
+ * (centred lift of every coefficient); it then decrypts to m + q_0 * I(X). */
+int spear_mod_raise(spear_context* ctx, const spear_obj* ct, int chain_index, spear_obj** out);
 int spear_mod_switch_to_next(spear_context* ctx, const spear_obj* o, spear_obj** out);   /* ct or pt */
 int spear_apply_galois(spear_context* ctx, const spear_obj* ct, uint32_t elt, const spear_galois_keys* gk,
                        spear_obj** out);

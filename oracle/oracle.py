@@ -223,6 +223,14 @@ class Oracle:
         self.lib.orc_rescale(self.ctx, int(l), int(size), _p(ct), _p(o))
         return o
 
+    def mod_raise(self, ct, l):
+        ct = _u64(ct)
+        size = ct.shape[0]
+        assert ct.shape[1] == 1
+        o = np.empty((size, l, self.N), dtype=np.uint64)
+        self.lib.orc_mod_raise(self.ctx, int(size), _p(ct), int(l), _p(o))
+        return o
+
     def decompose(self, cin):
         cin = _u64(cin)
         l = cin.shape[0]

@@ -780,6 +780,29 @@ void orc_rescale(const orc_ctx *c, int l, int size, const u64 *ct, u64 *out) {
     }
     free(x);
 }
+/* ModRaise (first step of CKKS bootstrapping): a ciphertext modulo q_0 alone, ct[size][1][N], is re-read modulo
+ * q_0..q_{l-1}: every coefficient is lifted to its centred representative in (-q_0/2, q_0/2] and reduced modulo each
+ * q_i.  The result decrypts to m + q_0 * I(X) with small integer I.  out[size][l][N], NTT form. */
+void orc_mod_raise(const orc_ctx *c, int size, const u64 *ct, int l, u64 *out) {
+    u64 N = c->N, q0 = c->q[0], half = q0 >> 1;
+    u64 *x = (u64 *)malloc(sizeof(u64) * N);
+    for (int p = 0; p < size; p++) {
+        memcpy(x, ct + (u64)p * N, sizeof(u64) * N);
+        orc_ntt_inv(c, 0, x);
+        #pragma omp parallel for schedule(static)
+        for (int i = 0; i < l; i++) {
+            u64 qi = c->q[i];
+            u64 *o = out + ((u64)p * l + i) * N;
+            for (u64 n = 0; n < N; n++) {
+                u64 v = x[n];
+                if (v > half) { u64 d = (q0 - v) % qi; o[n] = d ? qi - d : 0; }   /* negative representative v - q0 */
+                else o[n] = v % qi;
+            }
+            orc_ntt_fwd(c, i, o);
+        }
+    }
+    free(x);
+}
 /* element-wise helpers on [rows][N] blocks whose row r has limb id r (data limbs) */
 void orc_add(const orc_ctx *c, int rows_per_poly, int polys, const u64 *a, const u64 *b, u64 *o) {
     #pragma omp parallel for schedule(static) collapse(2)
