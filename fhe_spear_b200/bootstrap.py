@@ -133,7 +133,7 @@ class LinearTransform:
                             for g in self.giants for j in self.babies if (g + j) % self.n in self.diags}
         return self._pts[l]
 
-    def apply(self, bt, ct):
+    def apply(self, bt, ct, rescale=True):
         ph, ctx = bt.ph, bt.ctx
         pts = self.plaintexts(bt, ct.coeff_modulus_size())
         steps = [b for b in self.babies if b]
@@ -152,6 +152,8 @@ class LinearTransform:
             if g:
                 inner = ph.rotate(ctx, inner, g, bt.gk)
             acc = inner if acc is None else ph.add(ctx, acc, inner)
+        if not rescale:
+            return acc                                 # scale = scale(ct) * q_{l-1}: the caller rescales
         out = ph.rescale_to_next(ctx, acc)
         out.set_scale(ct.scale())
         return out
@@ -409,7 +411,9 @@ class Bootstrapper:
         return c
 
     # ---- the pipeline
-    def bootstrap(self, ct):
+    def bootstrap(self, ct, rescale_last=True):
+        """ct: at most ... two limbs.  rescale_last=False leaves the rescale of the last SlotToCoeff group to the caller
+        (the reference's convention: its call site rescales the bootstrapped ciphertext, test_fully_enc_bsgs.py:251-253)."""
         ph, ctx = self.ph, self.ctx
         while ct.coeff_modulus_size() > 2:
             ct = ph.mod_switch_to_next(ctx, ct)
@@ -432,7 +436,9 @@ class Bootstrapper:
         re, im = self._eval_mod(re), self._eval_mod(im)
         y = ph.add(ctx, re, ph.multiply_plain(ctx, im, self._const(1j, im.coeff_modulus_size(), 1.0)))
         y.set_scale(self.S)
-        for lt in self.s2c:
-            y = lt.apply(self, y)
-        y.set_scale(scale_in * self.S / self.q0)       # the message is back at (about) its original scale
+        for i, lt in enumerate(self.s2c):
+            y = lt.apply(self, y, rescale=rescale_last or i + 1 < len(self.s2c))
+        # relabel: the message is back at its original scale (times the pending prime when the rescale is left out)
+        pending = 1.0 if rescale_last else float(self.moduli[y.coeff_modulus_size() - 1])
+        y.set_scale(scale_in * pending)
         return y

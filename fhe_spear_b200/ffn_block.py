@@ -1,0 +1,60 @@
+"""Host mirror of the reference's fully encrypted FFN block (test_fully_enc_bsgs.py:26-125): x + ((x W_key)^2) W_val with
+the squared activation computed under encryption -- BSGS mat-vecs for the key chunks, CT-CT square + relinearize +
+rescale, BSGS mat-vecs for the value chunks, level alignment, residual add.  Three levels per block.
+
+The mat-vecs go through the hoisted path of this build (`fhe_matmul_bsgs` without baby ciphertexts: diagonals are
+encoded at the ciphertext's level and consumed by `spear_bsgs_hoisted`), so the separately rotated baby ciphertexts
+of the reference loop are not materialised."""
+import time
+
+import numpy as np
+
+from . import bsgs as hb
+from . import pyPhantom as ph
+
+
+def plaintext_ffn_block(x, W_key, W_val):
+    """[ref: :121-125]"""
+    return x + ((x @ W_key) ** 2) @ W_val
+
+
+def _align(ctx, a, b):
+    """bring two ciphertexts to the deeper of their levels  [ref: :83-91, :97-107]"""
+    while a.chain_index() < b.chain_index():
+        a = ph.mod_switch_to_next(ctx, a)
+    while b.chain_index() < a.chain_index():
+        b = ph.mod_switch_to_next(ctx, b)
+    return a, b
+
+
+def fully_encrypted_ffn_block(ckks, ct_x_rep, W_key, W_val, D, F, block_idx=0, split=None, verbose=False):
+    """Enc(x replicated) -> (Enc(x + ((x W_key)^2) W_val), levels used)  [ref: :26-118]"""
+    t0 = time.perf_counter()
+    G, B = split if split else hb.compute_bsgs_params(D)
+    n_chunks = int(np.ceil(F / D))
+    start_level = ct_x_rep.chain_index()
+    ct_sq = []
+    for c in range(n_chunks):                                   # FFN key: one mat-vec per chunk of D outputs
+        lo, hi = c * D, min((c + 1) * D, F)
+        M = np.zeros((D, D))
+        M[:hi - lo, :] = W_key[:, lo:hi].T
+        fk = hb.fhe_matmul_bsgs(ckks, ct_x_rep, M, D, G, B)
+        sq = ph.rescale_to_next(ckks.ctx, ph.relinearize(ckks.ctx, ph.multiply(ckks.ctx, fk, fk), ckks.rlk))
+        ct_sq.append(sq)
+    acc = None
+    for c, sq in enumerate(ct_sq):                              # FFN value: chunk partials summed homomorphically
+        lo, hi = c * D, min((c + 1) * D, F)
+        M = np.zeros((D, D))
+        M[:, :hi - lo] = W_val[lo:hi, :].T
+        part = hb.fhe_matmul_bsgs(ckks, sq, M, D, G, B)
+        if acc is None:
+            acc = part
+        else:
+            acc, part = _align(ckks.ctx, acc, part)
+            acc = ph.add(ckks.ctx, acc, part)
+    x_al, acc = _align(ckks.ctx, ct_x_rep, acc)
+    acc.set_scale(x_al.scale())
+    out = ph.add(ckks.ctx, x_al, acc)
+    if verbose:
+        print(f"  Block {block_idx}: levels {start_level} -> {out.chain_index()}, {time.perf_counter() - t0:.3f}s")
+    return out, out.chain_index() - start_level

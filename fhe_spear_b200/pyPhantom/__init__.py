@@ -731,6 +731,8 @@ class ckks_bootstrapper:
         self.impl.rlk = sk.gen_relinkey(ctx)
 
     def bootstrap(self, ctx, ct):
+        """Returns the refreshed ciphertext with one rescale pending (scale ~ (2^bits)^2), as the reference's call site
+        expects: it calls rescale_to_next right after (test_fully_enc_bsgs.py:251-253)."""
         if self.impl is None or self.impl.gk is None:
             raise RuntimeError("ckks_bootstrapper.bootstrap: call setup() and keygen() first")
-        return self.impl.bootstrap(ct)
+        return self.impl.bootstrap(ct, rescale_last=False)

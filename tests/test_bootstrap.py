@@ -127,7 +127,9 @@ def test_gpu_mod_raise_and_bootstrap_match_the_oracle_limb_for_limb():
     one_g = ph.mod_switch_to_next(ctx, ct_g)
     raised = ph.mod_raise(ctx, one_g, 1)
     assert np.array_equal(raised.to_numpy(), be.mod_raise(None, be.mod_switch_to_next(None, ct_o), 1).a)
-    out_g = bt.bootstrap(ctx, ct_g)
+    pending = bt.bootstrap(ctx, ct_g)                  # reference convention: one rescale left to the caller
+    assert abs(pending.scale() / (2.0 ** 59) ** 2 - 1) < 1e-6
+    out_g = ph.rescale_to_next(ctx, pending)
     out_o = bt_ref.bootstrap(ct_o)
     assert out_g.coeff_modulus_size() == out_o.coeff_modulus_size() == L0 - ph.ckks_bootstrapper.get_bootstrap_depth([2, 2], N)
     assert np.array_equal(out_g.to_numpy(), out_o.a)                             # bit-exact, ~1500 primitive calls deep
