@@ -79,6 +79,8 @@ _SIG = {
     "spear_hoisted_rotations": (C.c_int, [vp, vp, u32p, C.c_int, vp, vpp]),
     "spear_bsgs_multiply_accumulate": (C.c_int, [vp, vpp, C.c_int, vpp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vpp]),
     "spear_diagset_encode": (C.c_int, [vp, f64p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, vpp]),
+    "spear_diagset_encode_matrix": (C.c_int, [vp, f64p, f64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                               C.c_int, C.c_int, vpp]),
     "spear_diagset_encode_shard": (C.c_int, [vp, f64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                             C.c_int, C.c_int, vpp]),
     "spear_diagset_destroy": (None, [vp]),

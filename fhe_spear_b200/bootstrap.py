@@ -125,10 +125,10 @@ class LinearTransform:
         return sorted({b for b in self.babies if b} | {g for g in self.giants if g})
 
     def plaintexts(self, bt, l):
-        """Pre-rotated diagonals encoded for a ciphertext with l limbs at scale q_{l-1} (so that the rescale that
-        follows restores the ciphertext's scale exactly)."""
+        """Pre-rotated diagonals encoded for a ciphertext with l limbs at the scale that makes the rescaled product land
+        exactly on the ladder scale of level l-1."""
         if l not in self._pts:
-            sc, ci = float(bt.moduli[l - 1]), bt.L - l + 1
+            sc, ci = bt.S[l - 1] * float(bt.moduli[l - 1]) / bt.S[l], bt.L - l + 1
             self._pts[l] = {(g, j): bt.encoder.encode_complex_vector(bt.ctx, np.roll(self.diags[(g + j) % self.n], g), sc, ci)
                             for g in self.giants for j in self.babies if (g + j) % self.n in self.diags}
         return self._pts[l]
@@ -152,10 +152,12 @@ class LinearTransform:
             if g:
                 inner = ph.rotate(ctx, inner, g, bt.gk)
             acc = inner if acc is None else ph.add(ctx, acc, inner)
+        l = ct.coeff_modulus_size()
         if not rescale:
-            return acc                                 # scale = scale(ct) * q_{l-1}: the caller rescales
+            acc.set_scale(bt.S[l - 1] * float(bt.moduli[l - 1]))   # the caller rescales
+            return acc
         out = ph.rescale_to_next(ctx, acc)
-        out.set_scale(ct.scale())
+        out.set_scale(bt.S[l - 1])
         return out
 
 
@@ -285,6 +287,14 @@ class Bootstrapper:
         self.s2c = [LinearTransform(d, self.n) for d in
                     _merge(_s2c_stages(self.n, self.N), self.budget[1], self.n, scalar=self.post)]
         self.q0 = q0
+        # scale ladder: a ciphertext with l limbs always has scale S[l]; S[l-1] = S[l]^2 / q_{l-1}, so the product of two
+        # level-l ciphertexts lands exactly on the scale of level l-1 and every addition is between equal scales.  (The
+        # primes differ from one another by ~1e-11 relative; forcing one nominal scale instead loses ~1e-9 per
+        # bootstrap before the double-angle steps amplify it.)
+        self.S = [0.0] * (self.L + 1)
+        self.S[self.L] = q0
+        for l in range(self.L, 1, -1):
+            self.S[l - 1] = self.S[l] * self.S[l] / float(self.moduli[l - 1])
         self.gk = self.rlk = None
 
     # ---- static helpers of the reference interface
@@ -309,20 +319,31 @@ class Bootstrapper:
     def _baby_count(d):
         return 1 << max(1, int(math.ceil(math.log2(max(2, d + 1)) / 2)))
 
-    # ---- level / scale discipline: every ciphertext handed around has the nominal scale `self.S`
-    def _align(self, a, b):
+    # ---- level / scale discipline: a ciphertext with l limbs has exactly the scale self.S[l]
+    def _drop(self, a, l):
+        """Bring `a` down to l limbs and onto that level's ladder scale: plain limb drop to l+1, then one multiplication
+        by the constant 1 encoded at S[l] q_l / S[la] and a rescale."""
         ph, ctx = self.ph, self.ctx
-        la, lb = a.coeff_modulus_size(), b.coeff_modulus_size()
-        if la > lb:
-            a = ph.mod_switch_to(ctx, a, b.chain_index())
-        elif lb > la:
-            b = ph.mod_switch_to(ctx, b, a.chain_index())
-        return a, b
+        la = a.coeff_modulus_size()
+        if la == l:
+            return a
+        if la > l + 1:
+            a = ph.mod_switch_to(ctx, a, self.L - l)
+        one = self._const(1.0, l + 1, self.S[l] * float(self.moduli[l]) / self.S[la])
+        out = ph.rescale_to_next(ctx, ph.multiply_plain(ctx, a, one))
+        out.set_scale(self.S[l])
+        return out
+
+    def _align(self, a, b):
+        l = min(a.coeff_modulus_size(), b.coeff_modulus_size())
+        return self._drop(a, l), self._drop(b, l)
 
     def _mul(self, a, b):
         ph, ctx = self.ph, self.ctx
         a, b = self._align(a, b)
-        return ph.rescale_to_next(ctx, ph.relinearize(ctx, ph.multiply(ctx, a, b), self.rlk))   # true scale sa*sb/q_l
+        out = ph.rescale_to_next(ctx, ph.relinearize(ctx, ph.multiply(ctx, a, b), self.rlk))
+        out.set_scale(self.S[out.coeff_modulus_size()])          # S[l]^2 / q_{l-1} by construction of the ladder
+        return out
 
     def _add(self, a, b, sub=False):
         a, b = self._align(a, b)
@@ -340,26 +361,26 @@ class Bootstrapper:
         return self._add_const(self.ph.add(self.ctx, sq, sq), -1.0)
 
     def _linear_combination(self, terms, const):
-        """sum_k c_k * ct_k + const, one level.  Each constant is encoded at the scale S q_{l-1} / scale(ct_k), so every
-        product has exactly the scale S q_{l-1} whatever the (slightly different) scales of the ct_k, and the rescale
-        returns exactly S: the drift of ciphertext scales is absorbed here."""
+        """sum_k c_k * ct_k + const, one level below the deepest term.  Terms from higher levels are limb-dropped (scale
+        unchanged) and their constants encoded at S[l-1] q_{l-1} / scale(ct_k), so every product has the same scale."""
         ph, ctx = self.ph, self.ctx
         terms = [(c, t) for c, t in terms if abs(c) > 1e-300]
         if not terms:
             return None
         lmin = min(t.coeff_modulus_size() for _, t in terms)
-        ql = float(self.moduli[lmin - 1])
+        target = self.S[lmin - 1] * float(self.moduli[lmin - 1])
         acc = None
         for c, t in terms:
+            st = t.scale()
             if t.coeff_modulus_size() > lmin:
                 t = ph.mod_switch_to(ctx, t, self.L - lmin + 1)
-            p = ph.multiply_plain(ctx, t, self._const(c, lmin, self.S * ql / t.scale()))
+            p = ph.multiply_plain(ctx, t, self._const(c, lmin, target / st))
             acc = p if acc is None else ph.add(ctx, acc, p)
-        acc.set_scale(self.S * ql)
+        acc.set_scale(target)
         if const:
-            acc = ph.add_plain(ctx, acc, self._const(const, lmin, acc.scale()))
+            acc = ph.add_plain(ctx, acc, self._const(const, lmin, target))
         out = ph.rescale_to_next(ctx, acc)
-        out.set_scale(self.S)
+        out.set_scale(self.S[lmin - 1])
         return out
 
     # ---- Chebyshev series by baby-step / giant-step (Paterson-Stockmeyer in the Chebyshev basis)
@@ -424,21 +445,20 @@ class Bootstrapper:
         else:
             raise RuntimeError("bootstrap: the ciphertext must still have two limbs (one is spent scaling the message down)")
         raised = ph.mod_raise(ctx, ct, 1)
-        self.S = self.q0                               # relabel: slots are now (m + q0 I)/q0
-        raised.set_scale(self.S)
+        raised.set_scale(self.S[self.L])               # relabel (S[L] = q0): slots are now (m + q0 I)/q0
         x = raised
         for lt in self.c2s:                            # slots: (c_lo + i c_hi) / (2 K q0), bit-reversed order
             x = lt.apply(self, x)
         conj = ph.apply_galois(ctx, x, 2 * self.N - 1, self.gk)
         re = ph.add(ctx, x, conj)                      # c_lo / (K q0)
         im = ph.multiply_plain(ctx, ph.sub(ctx, x, conj), self._const(-1j, x.coeff_modulus_size(), 1.0))
-        im.set_scale(self.S)
+        im.set_scale(x.scale())
         re, im = self._eval_mod(re), self._eval_mod(im)
+        re, im = self._align(re, im)
         y = ph.add(ctx, re, ph.multiply_plain(ctx, im, self._const(1j, im.coeff_modulus_size(), 1.0)))
-        y.set_scale(self.S)
+        y.set_scale(re.scale())
         for i, lt in enumerate(self.s2c):
             y = lt.apply(self, y, rescale=rescale_last or i + 1 < len(self.s2c))
-        # relabel: the message is back at its original scale (times the pending prime when the rescale is left out)
-        pending = 1.0 if rescale_last else float(self.moduli[y.coeff_modulus_size() - 1])
-        y.set_scale(scale_in * pending)
+        # relabel: value * label = msg * scale_in * label / q0 (times the pending prime when the rescale is left out)
+        y.set_scale(scale_in * y.scale() / self.q0)
         return y

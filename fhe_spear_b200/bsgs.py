@@ -179,20 +179,20 @@ def _batch_encode_diags_complex(ckks, diags1, diags2, D, G, slots, level):
 
 def pre_encode_real_diags(ckks, W, D, G, B, level, as_plaintexts=False, compress=True, shard=(0, 1)):
     """shard = (rank, world): keep only this rank's giant groups (giant-step sharding over GPUs)."""
-    diags = _extract_diagonals(np.asarray(W, dtype=np.float64), D)
+    W = np.asarray(W, dtype=np.float64)
     if as_plaintexts:
-        return _batch_encode_diags_real(ckks, diags, D, G, ckks.slots, level)
-    return ph.diagonal_set(ckks.ctx, _pre_rotate(diags, D, G), G, B, ckks.diag_scale, chain_index=level,
-                           compress=compress, shard=shard)
+        return _batch_encode_diags_real(ckks, _extract_diagonals(W, D), D, G, ckks.slots, level)
+    # diagonal extraction and pre-rotation run on the device (the host gather alone took 0.19 s at D = 2048)
+    return ph.diagonal_set.from_matrix(ckks.ctx, W[:D, :D], G, B, ckks.diag_scale, chain_index=level, compress=compress,
+                                       shard=shard)
 
 
 def pre_encode_complex_diags(ckks, W1, W2, D, G, B, level, as_plaintexts=False, compress=True, shard=(0, 1)):
-    d1 = _extract_diagonals(np.asarray(W1, dtype=np.float64), D)
-    d2 = _extract_diagonals(np.asarray(W2, dtype=np.float64), D)
+    W1, W2 = np.asarray(W1, dtype=np.float64), np.asarray(W2, dtype=np.float64)
     if as_plaintexts:
-        return _batch_encode_diags_complex(ckks, d1, d2, D, G, ckks.slots, level)
-    return ph.diagonal_set(ckks.ctx, _pre_rotate(d1, D, G) + 1j * _pre_rotate(d2, D, G), G, B, ckks.diag_scale,
-                           chain_index=level, compress=compress, shard=shard)
+        return _batch_encode_diags_complex(ckks, _extract_diagonals(W1, D), _extract_diagonals(W2, D), D, G, ckks.slots, level)
+    return ph.diagonal_set.from_matrix(ckks.ctx, W1[:D, :D], G, B, ckks.diag_scale, chain_index=level, compress=compress,
+                                       shard=shard, M_imag=W2[:D, :D])
 
 
 def _chunk_pairs(F, D):

@@ -712,11 +712,10 @@ int spear_bsgs_multiply_accumulate(spear_context* ctx, spear_obj* const* ct_baby
     API_END
 }
 
-int spear_diagset_encode_shard(spear_context* ctx, const double* diags, int n_diags, int D, int G, int B, int g_first,
-                               int g_stride, double scale, int chain_index, int compress, spear_diagset** out) {
-    API_BEGIN
-    Ctx* c = C_(ctx);
-    use(c);
+// dv: [n_diags][D] complex rows on the device (pre-rotated diagonals of the shard's groups, in storage order), or
+// nullptr with `host` pointing at the same rows in host memory
+static DiagSet* diagset_build(Ctx* c, const double* host, double2* dv_in, int n_diags, int D, int G, int B, int g_first,
+                              int g_stride, double scale, int chain_index, int compress) {
     REQUIRE(D >= 1 && G >= 1 && B >= 1 && (size_t)G * B >= (size_t)D && D <= c->N / 2, "diagset: bad D/G/B");
     REQUIRE(g_first >= 0 && g_stride >= 1 && n_diags >= 0 && n_diags <= D, "diagset: bad shard");
     REQUIRE(chain_index >= 1 && chain_index <= c->L, "diagset: chain_index out of range");
@@ -737,8 +736,11 @@ int spear_diagset_encode_shard(spear_context* ctx, const double* diags, int n_di
     while ((n << ds->rshift) < c->N) ds->rshift++;
     ds->d = c->alloc((size_t)std::max(n_diags, 1) * rows * n);
     if (n_diags > 0) {
-        double2* dv = (double2*)c->alloc((size_t)n_diags * D * 2);
-        CUDA_CHECK(cudaMemcpyAsync(dv, diags, sizeof(double2) * n_diags * D, cudaMemcpyHostToDevice, c->stream));
+        double2* dv = dv_in;
+        if (!dv) {
+            dv = (double2*)c->alloc((size_t)n_diags * D * 2);
+            CUDA_CHECK(cudaMemcpyAsync(dv, host, sizeof(double2) * n_diags * D, cudaMemcpyHostToDevice, c->stream));
+        }
         const int chunk = std::max(1, std::min(n_diags, (int)((32u << 20) / ((size_t)n))));
         double2* full = n == 2 * D ? nullptr : (double2*)c->alloc((size_t)chunk * slots * 2);
         for (int v0 = 0; v0 < n_diags; v0 += chunk) {
@@ -751,11 +753,62 @@ int spear_diagset_encode_shard(spear_context* ctx, const double* diags, int n_di
             encoder::encode(c, src, nv, n, scale, l, true, ds->d + (size_t)v0 * rows * n, c->stream);
         }
         if (full) c->free(full);
-        c->free(dv);
+        if (!dv_in) c->free(dv);
         // the diagonal MAC kernels consume the split-30 storage form (common.cuh)
         ops::split30_inplace(c, ds->d, (size_t)n_diags * rows * n, false, c->stream);
     }
-    *out = reinterpret_cast<spear_diagset*>(ds.release());
+    return ds.release();
+}
+int spear_diagset_encode_shard(spear_context* ctx, const double* diags, int n_diags, int D, int G, int B, int g_first,
+                               int g_stride, double scale, int chain_index, int compress, spear_diagset** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    *out = reinterpret_cast<spear_diagset*>(
+        diagset_build(c, diags, nullptr, n_diags, D, G, B, g_first, g_stride, scale, chain_index, compress));
+    API_END
+}
+// rows of the shard's giant groups straight from the matrix: row (g, b), k = gG + b:
+//   out[row][t] = M[j][(j + k) mod D],  j = (t - gG) mod D     (diagonal k of y = M x, rolled right by gG)
+__global__ void k_diag_rows(const double* __restrict__ mre, const double* __restrict__ mim, double2* __restrict__ out,
+                            int n_diags, int D, int G, int B, int g_first, int g_stride) {
+    const size_t total = (size_t)n_diags * D;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int row = (int)(e / D), t = (int)(e % D);
+        // full groups hold G diagonals; only the last group of the matrix can be shorter, and it is last in the shard
+        const int gi = row / G, b = row % G, g = g_first + gi * g_stride, k = g * G + b;
+        int j = t - (g * G) % D;
+        if (j < 0) j += D;
+        const size_t at = (size_t)j * D + (j + k) % D;
+        out[e] = make_double2(mre[at], mim ? mim[at] : 0.0);
+    }
+}
+int spear_diagset_encode_matrix(spear_context* ctx, const double* m_re, const double* m_im, int D, int G, int B,
+                                int g_first, int g_stride, double scale, int chain_index, int compress,
+                                spear_diagset** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    REQUIRE(m_re && D >= 1 && G >= 1 && B >= 1 && g_first >= 0 && g_stride >= 1, "diagset: bad matrix arguments");
+    int n_diags = 0;
+    for (int g = g_first; g < B && g * G < D; g += g_stride) n_diags += std::min(G, D - g * G);
+    const size_t mw = (size_t)D * D;
+    double* dm = (double*)c->alloc(mw * (m_im ? 2 : 1));
+    CUDA_CHECK(cudaMemcpyAsync(dm, m_re, sizeof(double) * mw, cudaMemcpyHostToDevice, c->stream));
+    if (m_im) CUDA_CHECK(cudaMemcpyAsync(dm + mw, m_im, sizeof(double) * mw, cudaMemcpyHostToDevice, c->stream));
+    double2* dv = (double2*)c->alloc((size_t)std::max(n_diags, 1) * D * 2);
+    if (n_diags > 0)
+        LAUNCH(k_diag_rows, c->sm_count * 8, 256, 0, c->stream)(dm, m_im ? dm + mw : nullptr, dv, n_diags, D, G, B, g_first,
+                                                              g_stride);
+    DiagSet* ds = nullptr;
+    try {
+        ds = diagset_build(c, nullptr, dv, n_diags, D, G, B, g_first, g_stride, scale, chain_index, compress);
+    } catch (...) {
+        c->free(dv), c->free(dm);
+        throw;
+    }
+    c->free(dv), c->free(dm);
+    *out = reinterpret_cast<spear_diagset*>(ds);
     API_END
 }
 int spear_diagset_encode(spear_context* ctx, const double* diags, int D, int G, int B, double scale, int chain_index,

@@ -559,11 +559,21 @@ inline void split(int logn, int& sA, int& sB) {
 
 }  // namespace
 
+// grid.y carries the row index: batches beyond 65535 rows are split at polynomial boundaries
+static int max_rows_per_launch(const RowMap& rm) { return 65535 / rm.rpp * rm.rpp; }
+
 void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s, int skip_alpha, bool split30_out) {
     int logn = 0;
     while ((1 << logn) < n) logn++;
     REQUIRE((1 << logn) == n && n <= c->N && logn <= 16 && n >= 2, "ntt: bad size %d", n);
     if (rows == 0) return;
+    if (rows > 65535) {
+        const int step = max_rows_per_launch(rm);
+        REQUIRE(step > 0 && !skip_alpha, "ntt: %d rows per polynomial do not fit one launch", rm.rpp);
+        for (int r0 = 0; r0 < rows; r0 += step)
+            ntt_forward(c, data + rm.offset(r0, n), std::min(step, rows - r0), rm, n, s, skip_alpha, split30_out);
+        return;
+    }
     int sA, sB;
     split(logn, sA, sB);
     NttTab tb = c->ntttab();
@@ -596,6 +606,13 @@ void ntt_inverse(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream
     while ((1 << logn) < n) logn++;
     REQUIRE((1 << logn) == n && n <= c->N && logn <= 16 && n >= 2, "intt: bad size %d", n);
     if (rows == 0) return;
+    if (rows > 65535) {
+        const int step = max_rows_per_launch(rm);
+        REQUIRE(step > 0, "intt: %d rows per polynomial do not fit one launch", rm.rpp);
+        for (int r0 = 0; r0 < rows; r0 += step)
+            ntt_inverse(c, data + rm.offset(r0, n), std::min(step, rows - r0), rm, n, s);
+        return;
+    }
     int sA, sB;
     split(logn, sA, sB);
     NttTab tb = c->ntttab();

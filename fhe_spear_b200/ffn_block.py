@@ -27,26 +27,39 @@ def _align(ctx, a, b):
     return a, b
 
 
-def fully_encrypted_ffn_block(ckks, ct_x_rep, W_key, W_val, D, F, block_idx=0, split=None, verbose=False):
+def _matvecs(ckks, cts, mats, D, G, B, shard):
+    """The independent mat-vecs of one phase: diagonals encoded at the ciphertexts' level, then one batched call
+    (giant-step sharded over the ranks when shard = (rank, world) with world > 1)."""
+    level = cts[0].chain_index()
+    sets = [hb.pre_encode_real_diags(ckks, M, D, G, B, level, shard=shard) for M in mats]
+    if shard[1] > 1:
+        from .sharding import sharded_matvec_batch
+        return sharded_matvec_batch(ckks, cts, sets)
+    return ph.bsgs_hoisted_batch(ckks.ctx, cts, sets, ckks.gk)
+
+
+def fully_encrypted_ffn_block(ckks, ct_x_rep, W_key, W_val, D, F, block_idx=0, split=None, shard=(0, 1), verbose=False):
     """Enc(x replicated) -> (Enc(x + ((x W_key)^2) W_val), levels used)  [ref: :26-118]"""
     t0 = time.perf_counter()
     G, B = split if split else hb.compute_bsgs_params(D)
     n_chunks = int(np.ceil(F / D))
     start_level = ct_x_rep.chain_index()
-    ct_sq = []
+    mats = []
     for c in range(n_chunks):                                   # FFN key: one mat-vec per chunk of D outputs
         lo, hi = c * D, min((c + 1) * D, F)
         M = np.zeros((D, D))
         M[:hi - lo, :] = W_key[:, lo:hi].T
-        fk = hb.fhe_matmul_bsgs(ckks, ct_x_rep, M, D, G, B)
-        sq = ph.rescale_to_next(ckks.ctx, ph.relinearize(ckks.ctx, ph.multiply(ckks.ctx, fk, fk), ckks.rlk))
-        ct_sq.append(sq)
-    acc = None
-    for c, sq in enumerate(ct_sq):                              # FFN value: chunk partials summed homomorphically
+        mats.append(M)
+    ct_sq = [ph.rescale_to_next(ckks.ctx, ph.relinearize(ckks.ctx, ph.multiply(ckks.ctx, fk, fk), ckks.rlk))
+             for fk in _matvecs(ckks, [ct_x_rep] * n_chunks, mats, D, G, B, shard)]
+    mats = []
+    for c in range(n_chunks):                                   # FFN value: chunk partials summed homomorphically
         lo, hi = c * D, min((c + 1) * D, F)
         M = np.zeros((D, D))
         M[:, :hi - lo] = W_val[lo:hi, :].T
-        part = hb.fhe_matmul_bsgs(ckks, sq, M, D, G, B)
+        mats.append(M)
+    acc = None
+    for part in _matvecs(ckks, ct_sq, mats, D, G, B, shard):
         if acc is None:
             acc = part
         else:

@@ -631,6 +631,29 @@ class diagonal_set:
         self._ctx, self._h = ctx, h
         self.D, self.G, self.B, self.shard, self.rows = D, int(G), int(B), (first, stride), rows
 
+    @classmethod
+    def from_matrix(cls, ctx, M, G, B, scale, chain_index=1, compress=True, shard=(0, 1), M_imag=None):
+        """Same set from the matrix of y = M x (optionally M + i M_imag for the complex packing): diagonal extraction,
+        the +gG pre-rotation and the slot tiling run on the device; only D*D doubles cross the bus."""
+        M = np.ascontiguousarray(M, dtype=np.float64)
+        D = M.shape[0]
+        if M.shape != (D, D):
+            raise RuntimeError("diagonal_set.from_matrix expects a (D, D) matrix")
+        Mi = None if M_imag is None else np.ascontiguousarray(M_imag, dtype=np.float64)
+        if Mi is not None and Mi.shape != (D, D):
+            raise RuntimeError("diagonal_set.from_matrix: M_imag must have the shape of M")
+        first, stride = int(shard[0]), int(shard[1])
+        compress = bool(compress) and (D & (D - 1)) == 0 and D >= 2
+        h = C.c_void_p()
+        _check(_lib.spear_diagset_encode_matrix(ctx._h, M.ctypes.data_as(_n.f64p),
+                                                Mi.ctypes.data_as(_n.f64p) if Mi is not None else None, D, int(G), int(B),
+                                                first, stride, float(scale), int(chain_index), int(compress), C.byref(h)))
+        self = cls.__new__(cls)
+        self._ctx, self._h = ctx, h
+        self.D, self.G, self.B, self.shard = D, int(G), int(B), (first, stride)
+        self.rows = [k for g in range(first, int(B), stride) for k in range(g * int(G), min((g + 1) * int(G), D))]
+        return self
+
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:

@@ -157,6 +157,12 @@ int spear_diagset_encode(spear_context* ctx, const double* diags, int D, int G, 
  * g_first, g_first + g_stride, ... are stored; `diags` holds their n_diags rows in that order. */
 int spear_diagset_encode_shard(spear_context* ctx, const double* diags, int n_diags, int D, int G, int B, int g_first,
                                int g_stride, double scale, int chain_index, int compress, spear_diagset** out);
+/* the same from the matrix itself (row-major D x D, y = M x; m_im optional second matrix for the complex packing
+ * M_re + i M_im): diagonal extraction, the +gG pre-rotation and the slot tiling of _extract_diagonals /
+ * _batch_encode_diags_* [ref: bootstrap_generation.py:198-203, 361-432] run on the device. */
+int spear_diagset_encode_matrix(spear_context* ctx, const double* m_re, const double* m_im, int D, int G, int B,
+                                int g_first, int g_stride, double scale, int chain_index, int compress,
+                                spear_diagset** out);
 void spear_diagset_destroy(spear_diagset* d);
 int spear_diagset_info(const spear_diagset* d, int* D, int* G, int* B, int* limbs, int* ring_n, double* scale,
                        uint64_t* bytes);

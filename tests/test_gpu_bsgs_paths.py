@@ -127,8 +127,8 @@ def test_host_mirror_projections():
     # a second level: chain_index is preserved through the call surface (reference test_fully_enc_bsgs.py:32)
     y_ct = hb.fhe_matmul_bsgs(ckks, ct, W.T, D)
     assert y_ct.chain_index() == level + 1 and y_ct.coeff_modulus_size() == ckks.L0 - 1
-    with pytest.raises(RuntimeError):
-        hb.CKKSBootstrapContext(poly_degree=2048, L0=4, special_mod_size=2, skip_bootstrap=False)
+    with pytest.raises(RuntimeError):                      # [ref: :149-151] no bootstrapper without skip_bootstrap=False
+        ckks.bootstrap(ct)
 
 
 def test_full_size_c3_properties():

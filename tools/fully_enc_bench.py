@@ -26,6 +26,13 @@ def main():
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--weight", type=float, default=1.0, help="BSGS split G = ceil(sqrt(weight * D)); 1 = the reference's")
     a = ap.parse_args()
+    rank, world, local = 0, 1, int(os.environ.get("LOCAL_RANK", "0"))
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:      # torchrun: every mat-vec giant-step sharded over the ranks
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        rank, world = dist.get_rank(), dist.get_world_size()
     from fhe_spear_b200 import bsgs as hb
     from fhe_spear_b200 import pyPhantom as ph
     from fhe_spear_b200.ffn_block import fully_encrypted_ffn_block, plaintext_ffn_block
@@ -46,7 +53,7 @@ def main():
     ckks = hb.CKKSBootstrapContext(poly_degree=a.N, L0=L0, prime_bits=59, special_mod_size=a.P,
                                    level_budget=None if a.no_bootstrap else [2, 2], max_rot_dim=1, bsgs_dim=[D],
                                    skip_bootstrap=a.no_bootstrap, seed=bytes(range(32)), verbose=False,
-                                   baby_weights=(a.weight,))
+                                   baby_weights=(a.weight,), device=local)
     split = hb.compute_bsgs_params(D, a.weight)
     setup_s = time.perf_counter() - t0
     ct = ckks.encrypt_replicated(x0)
@@ -66,7 +73,8 @@ def main():
             boots.append({"before_block": b, "seconds": tb, "chain_index_after": ct.chain_index(), "max_abs_err": err})
         ckks.ctx.synchronize()
         tb = time.perf_counter()
-        ct, used = fully_encrypted_ffn_block(ckks, ct, W_keys[b], W_vals[b], D, F, block_idx=b, split=split)
+        ct, used = fully_encrypted_ffn_block(ckks, ct, W_keys[b], W_vals[b], D, F, block_idx=b, split=split,
+                                             shard=(rank, world))
         ckks.ctx.synchronize()
         tb = time.perf_counter() - tb
         got = ckks.decrypt_vec(ct, D)
@@ -74,9 +82,18 @@ def main():
                      "corr": float(np.corrcoef(got, ref[b + 1])[0, 1]), "max_abs_err": float(np.abs(got - ref[b + 1]).max())})
         done = b + 1
     total = time.perf_counter() - t_all
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total = float(t.item())
+        dist.destroy_process_group()
+        if rank != 0:
+            return
     print(json.dumps({"what": "fully encrypted FFN blocks (reference test_fully_enc_bsgs.py flow)",
                       "config": {"D": D, "F": F, "N": a.N, "L0": L0, "P": a.P, "num_blocks": a.num_blocks,
-                                 "bootstrap": not a.no_bootstrap, "split": f"G={split[0]} B={split[1]}"},
+                                 "bootstrap": not a.no_bootstrap, "split": f"G={split[0]} B={split[1]}", "n_gpus": world},
                       "blocks_completed": done, "bootstraps": len(boots), "total_s": total,
                       "s_per_block": float(np.mean([r["seconds"] for r in rows])) if rows else None,
                       "s_per_bootstrap": float(np.mean([r["seconds"] for r in boots])) if boots else None,
