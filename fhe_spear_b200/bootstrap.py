@@ -264,6 +264,7 @@ class Bootstrapper:
     look-alike), `encoder` the CKKS encoder, `moduli` the data primes q_0..q_{L-1} followed by the special ones."""
 
     RATIO_BITS = 12     # the message is scaled down by 2^RATIO_BITS before ModRaise so that sin(x) ~ x holds
+    CONST_CACHE_BYTES = 3 << 30
 
     def __init__(self, ph, ctx, encoder, N, moduli, special, level_budget=(2, 2), K=None, doublings=None,
                  ratio_bits=None):
@@ -296,6 +297,7 @@ class Bootstrapper:
         for l in range(self.L, 1, -1):
             self.S[l - 1] = self.S[l] * self.S[l] / float(self.moduli[l - 1])
         self.gk = self.rlk = None
+        self._consts, self._const_bytes = {}, 0
 
     # ---- static helpers of the reference interface
     @staticmethod
@@ -350,8 +352,17 @@ class Bootstrapper:
         return self.ph.sub(self.ctx, a, b) if sub else self.ph.add(self.ctx, a, b)
 
     def _const(self, value, l, scale):
-        return self.encoder.encode_complex_vector(self.ctx, np.full(self.n, value, dtype=np.complex128), float(scale),
-                                                  self.L - l + 1)
+        """Constant slot vector as a plaintext with l limbs.  The ladder makes (value, l, scale) repeat exactly from one
+        bootstrap to the next, so the encodings are kept (bounded by CONST_CACHE_BYTES)."""
+        key = (complex(value), int(l), float(scale))
+        pt = self._consts.get(key)
+        if pt is None:
+            pt = self.encoder.encode_complex_vector(self.ctx, np.full(self.n, value, dtype=np.complex128), float(scale),
+                                                    self.L - l + 1)
+            self._const_bytes += 8 * l * self.N
+            if self._const_bytes <= self.CONST_CACHE_BYTES:
+                self._consts[key] = pt
+        return pt
 
     def _add_const(self, a, value):
         return self.ph.add_plain(self.ctx, a, self._const(value, a.coeff_modulus_size(), a.scale()))

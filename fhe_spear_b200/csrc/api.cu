@@ -734,7 +734,9 @@ static DiagSet* diagset_build(Ctx* c, const double* host, double2* dv_in, int n_
     ds->n_diags = n_diags, ds->g_first = g_first, ds->g_stride = g_stride;
     ds->rshift = 0;
     while ((n << ds->rshift) < c->N) ds->rshift++;
-    ds->d = c->alloc((size_t)std::max(n_diags, 1) * rows * n);
+    // capacity of a set at the top level whatever `l` is: sets encoded on the fly at falling levels (fully encrypted
+    // blocks) then recycle the same pool block instead of growing the pool with a new size every time
+    ds->d = c->alloc((size_t)std::max(n_diags, 1) * (c->L + c->P) * n);
     if (n_diags > 0) {
         double2* dv = dv_in;
         if (!dv) {
