@@ -93,6 +93,11 @@ _SIG = {
     "spear_bsgs_finish": (C.c_int, [vp, vp, vpp]),
     "spear_obj_reduce": (C.c_int, [vp, vp]),
     "spear_obj_device_ptr": (vp, [vp]),
+    "spear_peer_window_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_char_p, vpp]),
+    "spear_peer_window_connect": (C.c_int, [vp, vp, C.c_char_p]),
+    "spear_peer_allreduce": (C.c_int, [vp, vp, C.c_int, vp]),
+    "spear_peer_window_status": (C.c_int, [vp]),
+    "spear_peer_window_destroy": (None, [vp]),
     "spear_ntt_host": (C.c_int, [vp, vp, C.c_int, ip, C.c_int, C.c_int]),
 }
 

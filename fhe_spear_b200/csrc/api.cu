@@ -119,6 +119,8 @@ __global__ void k_tile(const double2* __restrict__ in, double2* __restrict__ out
 
 }  // namespace
 
+void spear_set_last_error(const char* msg) { g_err = msg; }   // for the other translation units with entry points
+
 extern "C" {
 
 const char* spear_last_error(void) { return g_err.c_str(); }

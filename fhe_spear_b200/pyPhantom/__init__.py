@@ -710,6 +710,36 @@ def device_ptr(obj):
     return int(_lib.spear_obj_device_ptr(obj._h))
 
 
+class peer_window:
+    """Device memory of this rank mapped by the other ranks of its group (CUDA IPC) for the fused NVLink exchange of
+    shard accumulators (include/spear_b200.h "peer-memory exchange").  `handle` (64 bytes) goes to every other rank by
+    any host channel; connect() takes the handles of all ranks in rank order."""
+
+    def __init__(self, ctx, rank, world, slot_bytes, slots=3):
+        self._ctx, self.rank, self.world, self.slots = ctx, rank, world, slots
+        buf = C.create_string_buffer(64)
+        h = C.c_void_p()
+        _check(_lib.spear_peer_window_create(ctx._h, rank, world, int(slot_bytes), slots, buf, C.byref(h)))
+        self._h, self.handle = h, bytes(buf.raw)
+
+    def connect(self, handles):
+        if len(handles) != self.world or any(len(h) != 64 for h in handles):
+            raise RuntimeError("peer_window.connect: one 64-byte handle per rank expected")
+        _check(_lib.spear_peer_window_connect(self._ctx._h, self._h, b"".join(handles)))
+
+    def allreduce(self, acc, slot=0):
+        """acc <- sum over the ranks of the group, mod q, in place; asynchronous on the context's stream"""
+        _check(_lib.spear_peer_allreduce(self._ctx._h, self._h, slot, acc._h))
+
+    def status(self):
+        return int(_lib.spear_peer_window_status(self._h))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib.spear_peer_window_destroy(h)
+
+
 def bsgs_hoisted(ctx, ct, diags, gk):
     return _new(ciphertext, ctx, _lib.spear_bsgs_hoisted, ct._h, diags._h, gk._h)
 

@@ -11,11 +11,15 @@ Two levels, no parameter exchange after setup:
   * within a mat-vec -- giant groups g = rank, rank + world, ... (`giant_groups`).  Every rank runs the
     hoisted baby steps, the diagonal MAC and the giant key switches of its groups on its own shard of the
     diagonals (`pyPhantom.diagonal_set(..., shard=(rank, world))`) and ends with an accumulator in basis
-    Q_l*P.  The accumulators are summed with ONE integer all-reduce: residues are < 2^60, so the plain
-    uint64 sum of <= 8 shards cannot wrap (`lazy_sum_is_safe`), and a single Barrett pass
-    (`spear_obj_reduce`) turns it into the mod-q sum -- NCCL's own sum is not mod q, but it does not have
-    to be.  One ModDown + rescale then finishes the ciphertext on every rank.
+    Q_l*P.  The accumulators are summed mod q by the engine itself over NVLink peer memory (`PeerExchange`,
+    csrc/peer.cu): every rank maps the others' exchange windows through CUDA IPC and one kernel per rank does
+    reduce-scatter + Barrett + all-gather on the engine's stream, without a host hand-off.  Residues are < 2^60,
+    so the plain uint64 sum of <= 8 shards cannot wrap (`lazy_sum_is_safe`) and one Barrett step per element
+    gives the mod-q sum.  Where windows cannot be mapped (gloo CPU tests, GPUs hidden from each other) the same
+    sum is ONE integer all-reduce followed by a Barrett pass (`spear_obj_reduce`) -- NCCL's own sum is not mod q,
+    but it does not have to be.  One ModDown + rescale then finishes the ciphertext on every rank.
 """
+import os
 import numpy as np
 
 
@@ -59,15 +63,60 @@ class _DevView:
                                          "strides": None}
 
 
+class PeerExchange:
+    """The exchange windows of one rank group (pyPhantom.peer_window): created once per (context, group), handles
+    swapped with one all_gather_object over the group -- host plumbing only; the data path is csrc/peer.cu."""
+
+    _cache = {}
+
+    def __init__(self, ctx, group=None, slots=3):
+        import torch.distributed as dist
+        from . import pyPhantom as ph
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        slot_bytes = 2 * (ctx.L + ctx.P) * ctx.N * 8            # an accumulator at the top level
+        self.window = ph.peer_window(ctx, self.rank, self.world, slot_bytes, slots)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.window.handle, group=group)
+        self.window.connect(handles)
+        dist.barrier(group=group)                               # every window is mapped before anyone posts to it
+        self.slots = slots
+
+    @classmethod
+    def get(cls, ctx, group=None):
+        """The exchange of (ctx, group), or None when peer windows are switched off (SPEAR_PEER=0), not on CUDA
+        ranks, or cannot be mapped (then the callers use the integer all-reduce)."""
+        import torch.distributed as dist
+        if os.environ.get("SPEAR_PEER", "1") == "0" or not dist.is_initialized() or dist.get_world_size(group) < 2:
+            return None
+        key = (id(ctx), id(group) if group is not None else 0)
+        if key not in cls._cache:
+            try:
+                ok, ex = 1, cls(ctx, group)
+            except RuntimeError as e:   # every rank must take the same path: agree on the outcome below
+                ok, ex = 0, None
+                print(f"[spear] peer windows unavailable on rank {dist.get_rank()}: {e}; using the NCCL all-reduce")
+            flags = [None] * dist.get_world_size(group)
+            dist.all_gather_object(flags, ok, group=group)
+            cls._cache[key] = ex if all(flags) else None
+        return cls._cache[key]
+
+    def allreduce(self, acc, slot=0):
+        self.window.allreduce(acc, slot % self.slots)
+
+
 def sharded_matvec(ckks, ct, shard_set, group=None):
-    """One giant-step-sharded mat-vec: this rank's accumulator, integer all-reduce, Barrett pass, ModDown + rescale.
+    """One giant-step-sharded mat-vec: this rank's accumulator, the mod-q sum over the group (fused peer-memory
+    exchange; integer all-reduce + Barrett pass as the fallback), ModDown + rescale.
     Every rank ends with the same ciphertext (bit-identical to the unsharded result)."""
     import torch
     import torch.distributed as dist
     from . import pyPhantom as ph
     ctx = ckks.ctx
     acc = ph.bsgs_hoisted_partial(ctx, ct, shard_set, ckks.gk)
-    if dist.is_initialized() and dist.get_world_size(group) > 1:
+    ex = PeerExchange.get(ctx, group)
+    if ex is not None:
+        ex.allreduce(acc)
+    elif dist.is_initialized() and dist.get_world_size(group) > 1:
         size, limbs, ext, ring, _, _ = acc._info()
         count = size * (limbs + ctx.P) * ring
         ctx.synchronize()                                   # engine stream -> torch stream hand-off
@@ -87,7 +136,11 @@ def sharded_matvec_batch(ckks, cts, shard_sets, group=None):
     from . import pyPhantom as ph
     ctx = ckks.ctx
     accs = ph.bsgs_hoisted_partial_batch(ctx, list(cts), list(shard_sets), ckks.gk)
-    if dist.is_initialized() and dist.get_world_size(group) > 1:
+    ex = PeerExchange.get(ctx, group)
+    if ex is not None:
+        for i, acc in enumerate(accs):
+            ex.allreduce(acc, i)
+    elif dist.is_initialized() and dist.get_world_size(group) > 1:
         ctx.synchronize()
         works = []
         for acc in accs:

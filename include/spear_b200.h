@@ -189,6 +189,24 @@ int spear_bsgs_finish(spear_context* ctx, spear_obj* acc, spear_obj** out);   /*
 int spear_obj_reduce(spear_context* ctx, spear_obj* o);                       /* every residue mod its modulus, in place */
 void* spear_obj_device_ptr(spear_obj* o);                                     /* device address of the limbs */
 
+/* ---- peer-memory exchange of shard accumulators (one process per GPU) ---------------
+ * [ref: the reference has no multi-GPU path; BASELINE north_star: "partial ciphertexts are combined with ... P2P
+ *  over NVLink plus a modular-add kernel"]  A window is device memory of this rank that the other ranks of its
+ * group map through CUDA IPC.  create -> exchange the 64-byte handles by any host channel (torch.distributed
+ * all_gather in fhe_spear_b200/sharding.py) -> connect(handles of all ranks, rank-major).  spear_peer_allreduce then
+ * replaces acc (size 2, basis Q_l*P, same shape on every rank) by the sum over ranks mod q, in place, with one fused
+ * reduce-scatter + Barrett + all-gather kernel over NVLink, ordered on the context's stream (no host sync).
+ * Every rank of the group must call it with the same slot in the same order.  A peer that does not arrive within
+ * 20 s raises the window status (non-zero) instead of hanging; later calls on the window then fail. */
+typedef struct spear_peer_window spear_peer_window;
+#define SPEAR_IPC_HANDLE_BYTES 64
+int spear_peer_window_create(spear_context* ctx, int rank, int world, uint64_t slot_bytes, int slots,
+                             uint8_t* handle_out /* [SPEAR_IPC_HANDLE_BYTES] */, spear_peer_window** out);
+int spear_peer_window_connect(spear_context* ctx, spear_peer_window* w, const uint8_t* handles /* [world][64] */);
+int spear_peer_allreduce(spear_context* ctx, spear_peer_window* w, int slot, spear_obj* acc);
+int spear_peer_window_status(const spear_peer_window* w);   /* 0 = healthy; 1 + r = peer r timed out */
+void spear_peer_window_destroy(spear_peer_window* w);
+
 /* ---- raw transforms (tests / profiling) ------------------------------------------------------------- */
 /* in-place on a host buffer of `rows` x ring_n residues whose row r uses modulus limb_ids[r] */
 int spear_ntt_host(spear_context* ctx, uint64_t* data, int rows, const int* limb_ids, int ring_n, int inverse);
