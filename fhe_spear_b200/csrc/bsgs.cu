@@ -49,8 +49,9 @@ void keyswitch(const Ctx* c, const u64* cin, int l, const u64* key, const u64* a
     u64* E = sc.get(c->digits(l) * rows * N);
     u64* acc = sc.get(2 * rows * N);
     u64* tmp = sc.get(2 * l * N);
-    ops::decompose(c, cin, l, x, E, s);
-    ops::ks_inner(c, E, key, acc, l, 0, nullptr, 0, 0, 0, s);
+    CUDA_CHECK(cudaMemcpyAsync(x, cin, sizeof(u64) * l * N, cudaMemcpyDeviceToDevice, s));
+    ntt_inverse(c, x, l, RowMap{l, l, c->L, 0}, (int)N, s);
+    ops::decompose_ks(c, cin, x, l, E, key, acc, 0, nullptr, 0, 0, 0, s);
     ops::moddown(c, acc, rows * N, 2, l, tmp, nullptr, out, s);
     if (add0) ops::add(c, out, add0, out, 1, l, (int)N, RowMap{l, l, c->L, 0}, 1, s);
 }
@@ -148,8 +149,7 @@ void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, i
         for (int k = k0; k < n_groups; k++) {
             u64* Ak = A + (size_t)k * 2 * pw;
             const size_t o = (size_t)(k - k0) * l * N;
-            ops::decompose_from(c, t_all + o, x_all + o, l, E, s);
-            ops::ks_inner(c, E, gkey[k], R, l, gelt[k], Ak, (int)rows, 0, have ? 1 : 0, s);
+            ops::decompose_ks(c, t_all + o, x_all + o, l, E, gkey[k], R, gelt[k], Ak, (int)rows, 0, have ? 1 : 0, s);
             have = true;
         }
     }

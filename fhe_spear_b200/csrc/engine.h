@@ -139,7 +139,7 @@ struct DiagSet : CtxRef {
 };
 
 enum { PROF_KS_INNER = 0, PROF_PMAC = 1, PROF_NTT = 2, PROF_MODUP = 3, PROF_MODDOWN = 4, PROF_RESCALE = 5,
-       PROF_KS_BABY = 6, PROF_CLASSES = 7 };
+       PROF_KS_BABY = 6, PROF_NTT_KS = 7, PROF_CLASSES = 8 };
 struct ProfScope {   // brackets the launches of one kernel class with an event pair when profiling is on
     const Ctx* c;
     cudaStream_t s;
@@ -160,7 +160,10 @@ struct ProfScope {   // brackets the launches of one kernel class with an event 
 // ---- launchers (ntt.cu) --------------------------------------------------------------------
 // rows x n in-place transforms; `n` may be a power-of-two prefix size (sub-ring) <= N
 void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s, int skip_digit_alpha = 0,
-                 bool split30_out = false);
+                 bool split30_out = false, bool pass_a_only = false);
+// forward transform of freshly ModUp'd digits fused with the key inner product (ntt.cu); false: not applicable
+bool ntt_ks_fused(const Ctx* c, u64* E, const u64* key, u64* out, int l, u32 elt, const u64* addp, int add_rows,
+                  int add_pscale, int accumulate, cudaStream_t s);
 void ntt_inverse(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s);
 
 // ---- stream ids shared with the oracle ------------------------------------------------------

@@ -11,6 +11,8 @@
 // 2048 elements per CTA).  Each element crosses L2 twice per transform; twiddles are (w, shoup(w))
 // pairs fetched with one 16-byte load.
 #include "engine.h"
+#include "ops.h"
+#include "tma.cuh"
 
 namespace {
 
@@ -252,8 +254,9 @@ constexpr int WB = 4;   // warps (= chunks) per pass-B CTA
 
 __device__ __forceinline__ int swz(int x) { return x ^ (((x >> 4) & 7) | ((x >> 2) & 8)); }
 
-template <bool LAZY>
-__device__ __forceinline__ void fwd_b2_body(u64* __restrict__ base, u64* __restrict__ s,
+// STORE = false leaves the chunk in shared memory (element x at s[swz(x)]) for a fused consumer
+template <bool LAZY, bool STORE = true, typename PTR = u64*>
+__device__ __forceinline__ void fwd_b2_body(PTR __restrict__ base, u64* __restrict__ s,
                                             const ulonglong2* __restrict__ tw, u64 q, int sA, int gc, int j,
                                             bool split) {
     const u64 q2 = q << 1, q4 = q << 2;
@@ -326,9 +329,11 @@ __device__ __forceinline__ void fwd_b2_body(u64* __restrict__ base, u64* __restr
             }
         }
     }
-    __syncwarp();
+    if constexpr (STORE) {
+        __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 8; k++) base[j + 32 * k] = s[swz(j + 32 * k)];
+        for (int k = 0; k < 8; k++) base[j + 32 * k] = s[swz(j + 32 * k)];
+    }
 }
 
 __global__ void __launch_bounds__(WB * 32) ntt_fwd_b2(u64* __restrict__ data, RowMap rm, NttTab tb, int N, int n,
@@ -541,6 +546,110 @@ __global__ void __launch_bounds__(2 << SA) ntt_inv_a2(u64* __restrict__ data, Ro
     }
 }
 
+// =============================================================================================
+// Forward pass B fused with the key-switch inner product (giant steps, rotate, relinearize).
+// One CTA owns (row r, OUTPUT chunk of 256 coefficients).  The Galois permutation of the bit-reversed NTT domain maps
+// aligned blocks onto aligned blocks (common.cuh galois_src), so the digits it needs are one 256-coefficient chunk of
+// every digit: warp j runs the last eight butterfly stages of digit j's chunk and leaves it in shared memory -- the
+// transformed digits never travel to L2/HBM and back -- while the TMA engine fetches the [2*beta][256] box of the
+// rotation key, issued before the first butterfly, so the key stream (HBM) hides behind the transform (integer pipe).
+// Then every thread forms  sum_j E_j[src(n)] * key[j][p][n]  for its coefficient exactly like ks_tile_body (ops.cu).
+// =============================================================================================
+constexpr int FK_CHUNK = 256, FK_MAXW = 8;
+
+template <int FOLD>
+__global__ void __launch_bounds__(FK_MAXW * 32, 4) k_ntt_b_ks(const __grid_constant__ CUtensorMap kmap, KsArgs a, ModTab mt,
+                                                            NttTab tb, const ulonglong2* __restrict__ pmod, int sA,
+                                                            int alpha, int wide_ok) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const int beta = a.beta;
+    u64* ksm = reinterpret_cast<u64*>(smraw);                     // [2*beta][256]  key box (TMA destination)
+    u64* esm = ksm + (size_t)2 * beta * FK_CHUNK;                 // [beta][256]    transformed digits, swizzled per chunk
+    uint64_t* full = reinterpret_cast<uint64_t*>(esm + (size_t)beta * FK_CHUNK);
+    const int r = blockIdx.y, t = r < a.l ? r : a.L + (r - a.l);
+    const u32 n0 = blockIdx.x * FK_CHUNK;
+    if (threadIdx.x == 0) {
+        mbar_init(full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(full, (u32)(2 * beta * FK_CHUNK * sizeof(u64)));
+        tma_load_3d_hint(ksm, &kmap, (int)n0, t, 0, full, evict_first_policy());
+    }
+    const u32 csrc = (a.elt ? galois_src(n0, a.elt, a.logn) : n0) / FK_CHUNK;   // chunk the output chunk is gathered from
+    const bool has_add = a.addp && r < a.add_rows;
+    // the epilogue's read-modify-write operands are pulled into L2 now, a whole transform ahead of their use
+    for (int o = threadIdx.x; o < FK_CHUNK; o += blockDim.x) {
+        if (a.accumulate) {
+            const u64* o0 = a.out + (size_t)r * a.N + n0 + o;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(o0));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(o0 + (size_t)a.rows * a.N));
+        }
+        if (has_add) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.addp + (size_t)r * a.N + (size_t)csrc * FK_CHUNK + o));
+    }
+    const int own = r < a.l ? r / alpha : -1;   // the digit this row belongs to (ModUp wrote its NTT form already)
+    const u64 q = tb.q[t];
+    const ulonglong2* __restrict__ tw = tb.psi + (size_t)t * a.N;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const bool lazy = q < (1ull << 59) && q > (1ull << 33);
+    for (int j = warp; j < beta; j += nwarps) {
+        u64* s = esm + (size_t)j * FK_CHUNK;
+        const u64* base = a.E + ((size_t)j * a.rows + r) * a.N + (size_t)csrc * FK_CHUNK;
+        if (j == own) {   // own-digit row: ModUp already wrote the NTT form (split-30)
+#pragma unroll
+            for (int k = 0; k < 8; k++) s[swz(lane + 32 * k)] = base[lane + 32 * k];
+        } else if (lazy) {
+            fwd_b2_body<true, false, const u64*>(base, s, tw, q, sA, (int)csrc, lane, true);
+        } else {
+            fwd_b2_body<false, false, const u64*>(base, s, tw, q, sA, (int)csrc, lane, true);
+        }
+    }
+    __syncthreads();   // digits complete; mbarrier initialised before anybody waits on it
+    const size_t es = (size_t)a.rows * a.N;
+    const u64 r0 = mt.ratio0[t], r1 = mt.ratio1[t], rw = mt.rwide[t];
+    ulonglong2 pm = make_ulonglong2(0, 0);
+    if (has_add && a.add_pscale) pm = pmod[t];
+    mbar_wait(full, 0);
+    for (int o = threadIdx.x; o < FK_CHUNK; o += blockDim.x) {
+        const u32 n = n0 + o;
+        const u32 src = a.elt ? galois_src(n, a.elt, a.logn) : n;
+        const int sl = swz((int)(src & (FK_CHUNK - 1)));
+        u64 c0add = has_add ? a.addp[(size_t)r * a.N + src] : 0;
+        u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+        Acc3 acc0 = {0, 0, 0}, acc1 = {0, 0, 0};
+        const u64* kcol = ksm + o;
+#pragma unroll 4
+        for (int j = 0; j < beta; j++) {
+            const u64 dj = esm[(size_t)j * FK_CHUNK + sl];
+            const u32 dsum = (u32)dj + (u32)(dj >> 32);
+            mac_split(acc0, dj, dsum, kcol[(size_t)(2 * j) * FK_CHUNK]);
+            mac_split(acc1, dj, dsum, kcol[(size_t)(2 * j + 1) * FK_CHUNK]);
+            if ((j + 1) % FOLD == 0) {
+                fold_split(lo0, hi0, acc0);
+                fold_split(lo1, hi1, acc1);
+            }
+        }
+        fold_split(lo0, hi0, acc0);
+        fold_split(lo1, hi1, acc1);
+        u64 v0, v1;
+        if (wide_ok) {   // q < 2^59 and <= 8 digits: the sum is below 2^(s+64)
+            v0 = reduce_wide(lo0, hi0, q, rw), v1 = reduce_wide(lo1, hi1, q, rw);
+        } else {
+            v0 = barrett128(lo0, hi0, q, r0, r1), v1 = barrett128(lo1, hi1, q, r0, r1);
+        }
+        if (has_add) {
+            if (a.add_pscale) c0add = mul_shoup(c0add, pm.x, pm.y, q);
+            v0 = add_mod(v0, c0add, q);
+        }
+        u64* o0 = a.out + (size_t)r * a.N + n;
+        u64* o1 = o0 + es;
+        if (a.accumulate) {
+            v0 = add_mod(v0, *o0, q);
+            v1 = add_mod(v1, *o1, q);
+        }
+        *o0 = v0;
+        *o1 = v1;
+    }
+}
+
 template <int SA>
 void launch_fwd_a2(u64* data, int rows, RowMap rm, NttTab tb, int N, int n, int skip_alpha, cudaStream_t s) {
     dim3 grid((n >> SA) / COLS, rows);
@@ -562,7 +671,8 @@ inline void split(int logn, int& sA, int& sB) {
 // grid.y carries the row index: batches beyond 65535 rows are split at polynomial boundaries
 static int max_rows_per_launch(const RowMap& rm) { return 65535 / rm.rpp * rm.rpp; }
 
-void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s, int skip_alpha, bool split30_out) {
+void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s, int skip_alpha, bool split30_out,
+                 bool pass_a_only) {
     int logn = 0;
     while ((1 << logn) < n) logn++;
     REQUIRE((1 << logn) == n && n <= c->N && logn <= 16 && n >= 2, "ntt: bad size %d", n);
@@ -571,12 +681,14 @@ void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream
         const int step = max_rows_per_launch(rm);
         REQUIRE(step > 0 && !skip_alpha, "ntt: %d rows per polynomial do not fit one launch", rm.rpp);
         for (int r0 = 0; r0 < rows; r0 += step)
-            ntt_forward(c, data + rm.offset(r0, n), std::min(step, rows - r0), rm, n, s, skip_alpha, split30_out);
+            ntt_forward(c, data + rm.offset(r0, n), std::min(step, rows - r0), rm, n, s, skip_alpha, split30_out,
+                        pass_a_only);
         return;
     }
     int sA, sB;
     split(logn, sA, sB);
     NttTab tb = c->ntttab();
+    REQUIRE(!pass_a_only || sA >= 3, "ntt: pass A alone needs n >= 2048");
     ProfScope ps(c, PROF_NTT, s);
     if (sA >= 3) {   // n >= 2048: register-tiled kernels
         switch (sA) {
@@ -587,7 +699,8 @@ void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream
             case 7: launch_fwd_a2<7>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
             default: launch_fwd_a2<8>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
         }
-        LAUNCH(ntt_fwd_b2, dim3(n / (256 * WB), rows), WB * 32, 0, s)(data, rm, tb, c->N, n, sA, skip_alpha, split30_out ? 1 : 0);
+        if (!pass_a_only)
+            LAUNCH(ntt_fwd_b2, dim3(n / (256 * WB), rows), WB * 32, 0, s)(data, rm, tb, c->N, n, sA, skip_alpha, split30_out ? 1 : 0);
         CUDA_CHECK(cudaGetLastError());
         return;
     }
@@ -599,6 +712,38 @@ void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream
     dim3 grid(n / elems, rows);
     LAUNCH(ntt_fwd_b, grid, TPB, sizeof(u64) * elems, s)(data, rm, tb, c->N, n, sA, sB, skip_alpha, split30_out ? 1 : 0);
     CUDA_CHECK(cudaGetLastError());
+}
+
+// E: [beta][l+P][N] as ModUp leaves it (own-digit rows in NTT split-30 form, the others in coefficient form).
+// Runs the forward transform of the other rows and the key inner product (KsArgs semantics of ops::ks_inner) with
+// the last eight stages fused into the product.  Returns false when the fused path does not apply (N < 2048).
+bool ntt_ks_fused(const Ctx* c, u64* E, const u64* key, u64* out, int l, u32 elt, const u64* addp, int add_rows,
+                  int add_pscale, int accumulate, cudaStream_t s) {
+    const int beta = c->digits(l), rows = l + c->P;
+    const size_t smem = (size_t)3 * beta * FK_CHUNK * sizeof(u64) + 64;
+    int sA, sB;
+    split(c->logn, sA, sB);
+    if (sA < 3 || smem > 200 * 1024) return false;
+    ntt_forward(c, E, beta * rows, RowMap{rows, l, c->L, 0}, c->N, s, c->P, true, /*pass_a_only=*/true);
+    KsArgs a;
+    a.E = E, a.key = key, a.out = out, a.addp = addp, a.add_rows = add_rows, a.add_pscale = add_pscale;
+    a.accumulate = accumulate, a.beta = beta, a.l = l, a.rows = rows, a.N = c->N, a.logn = c->logn;
+    a.L = c->L, a.K = c->K, a.elt = elt;
+    CUtensorMap kmap;
+    ops::encode_key_map(c, key, FK_CHUNK, beta, &kmap);
+    bool small = true;
+    for (u64 qq : c->q) small = small && qq < (1ull << 59);
+    const int threads = 32 * std::min(beta, FK_MAXW);
+    ProfScope ps(c, PROF_NTT_KS, s);
+    auto go = [&](auto kern) {
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        LAUNCH(kern, dim3(c->N / FK_CHUNK, rows), threads, smem, s)(kmap, a, c->modtab(), c->ntttab(), c->d_pmod, sA, c->P,
+                                                                    small && beta <= 8 ? 1 : 0);
+    };
+    if (small) go(k_ntt_b_ks<16>);
+    else go(k_ntt_b_ks<8>);
+    CUDA_CHECK(cudaGetLastError());
+    return true;
 }
 
 void ntt_inverse(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s) {

@@ -6,10 +6,12 @@
 // diagonals) loaded with L1::no_allocate/L2::evict_first so the reused operands (decomposed digits,
 // baby ciphertexts) stay L2-resident.  Sums of products are accumulated lazily in 128 bits and
 // reduced once (Barrett-128).
+#include <cstdlib>
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include "engine.h"
 #include "ops.h"
+#include "tma.cuh"
 
 namespace {
 
@@ -129,63 +131,8 @@ __global__ void __launch_bounds__(TPB) k_modup(const u64* __restrict__ x, const 
     }
 }
 
-// ---- TMA / mbarrier / cache-policy helpers ------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, u32 bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(bar)),
-                 "r"(bytes));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, u32 parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" ::"r"((u32)__cvta_generic_to_shared(bar)),
-        "r"(parity));
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-            (u32)__cvta_generic_to_shared(dst)),
-        "l"(map), "r"((u32)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-
-__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
-                                                 uint64_t* bar, u64 policy) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, "
-        "%5}], [%2], %6;" ::"r"((u32)__cvta_generic_to_shared(dst)),
-        "l"(map), "r"((u32)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
-        : "memory");
-}
-__device__ __forceinline__ u64 evict_last_policy() {
-    u64 pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ u64 ld_keep(const u64* p, u64 pol) {
-    u64 v;
-    asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
-    return v;
-}
 // ---- key-switch inner product -----------------------------------------------------------------
 // out[p][r][n] (+)= sum_j E[j][r][src(n)] * key[j][p][limb(r)][n]  (+ addp[r][src(n)] (* P) into p = 0)
-struct KsArgs {
-    const u64* E;      // [beta][rows][N]
-    const u64* key;    // [beta_key][2][K][N]
-    u64* out;          // [2][rows][N]
-    const u64* addp;   // optional polynomial added (after the same permutation) to out poly 0
-    int add_rows;      // rows of addp (l: data limbs only; rows: extended)
-    int add_pscale;    // multiply addp by P mod q first
-    int accumulate;    // out += instead of out =
-    int beta, l, rows, N, logn, L, K;
-    u32 elt;           // 0: identity
-};
 __global__ void __launch_bounds__(TPB) k_ks_inner(KsArgs a, ModTab mt, const ulonglong2* __restrict__ pmod) {
     const int r = blockIdx.y, n = blockIdx.x * TPB + threadIdx.x;
     const int t = r < a.l ? r : a.L + (r - a.l);
@@ -668,6 +615,18 @@ static EncodeTiledFn encode_tiled() {
     return fn;
 }
 
+// tensor map over one switching key [2*beta_key][K][N] with boxes [2*beta][1][box_n] (shared with ntt.cu's fused kernel)
+void encode_key_map(const Ctx* c, const u64* key, int box_n, int beta, CUtensorMap* out) {
+    cuuint64_t dims[3] = {(cuuint64_t)c->N, (cuuint64_t)c->K, (cuuint64_t)(2 * c->beta)};
+    cuuint64_t strides[2] = {(cuuint64_t)c->N * sizeof(u64), (cuuint64_t)c->K * c->N * sizeof(u64)};
+    cuuint32_t box[3] = {(cuuint32_t)box_n, 1, (cuuint32_t)(2 * beta)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult rc = encode_tiled()(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, (void*)key, dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
+}
+
 static int grid_for(const Ctx* c, size_t total) {
     size_t blocks = (total + TPB - 1) / TPB;
     size_t cap = (size_t)c->sm_count * 16;
@@ -707,7 +666,7 @@ void decompose(const Ctx* c, const u64* cin, int l, u64* x, u64* E, cudaStream_t
     decompose_from(c, cin, x, l, E, s);
 }
 // same, given both forms of the polynomial: cin (NTT) and x (coefficients)
-void decompose_from(const Ctx* c, const u64* cin, const u64* x, int l, u64* E, cudaStream_t s) {
+void decompose_from(const Ctx* c, const u64* cin, const u64* x, int l, u64* E, cudaStream_t s, bool transform) {
     const int N = c->N, P = c->P, rows = l + P, beta = c->digits(l);
     REQUIRE(P <= MAX_ALPHA, "special_modulus_size > %d not supported", MAX_ALPHA);
     REQUIRE(N % TPB == 0, "N must be a multiple of %d", TPB);
@@ -725,8 +684,22 @@ void decompose_from(const Ctx* c, const u64* cin, const u64* x, int l, u64* E, c
         else if (P == 4) go(k_modup<4>);
         else go(k_modup<MAX_ALPHA>);
     }
-    ntt_forward(c, E, beta * rows, RowMap{rows, l, c->L, 0}, N, s, P, /*split30_out=*/true);
+    if (transform) ntt_forward(c, E, beta * rows, RowMap{rows, l, c->L, 0}, N, s, P, /*split30_out=*/true);
     CUDA_CHECK(cudaGetLastError());
+}
+
+// decompose + key inner product; the forward transform's last pass is fused into the product when it applies
+// (SPEAR_FUSED_KS=0 keeps the two-kernel form, for A/B timing)
+void decompose_ks(const Ctx* c, const u64* cin, const u64* x, int l, u64* E, const u64* key, u64* out, u32 elt,
+                  const u64* addp, int add_rows, int add_pscale, int accumulate, cudaStream_t s) {
+    static const bool fused = [] {
+        const char* e = getenv("SPEAR_FUSED_KS");
+        return !(e && e[0] == '0');
+    }();
+    decompose_from(c, cin, x, l, E, s, /*transform=*/false);
+    if (fused && ntt_ks_fused(c, E, key, out, l, elt, addp, add_rows, add_pscale, accumulate, s)) return;
+    ntt_forward(c, E, c->digits(l) * (l + c->P), RowMap{l + c->P, l, c->L, 0}, c->N, s, c->P, /*split30_out=*/true);
+    ks_inner(c, E, key, out, l, elt, addp, add_rows, add_pscale, accumulate, s);
 }
 
 void ks_inner(const Ctx* c, const u64* E, const u64* key, u64* out, int l, u32 elt, const u64* addp, int add_rows,

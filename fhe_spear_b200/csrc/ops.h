@@ -1,6 +1,22 @@
 // ops.h -- launchers of the RNS kernels in ops.cu / sampler.cu / encoder.cu (internal).
 #pragma once
+#include <cuda.h>   // CUtensorMap
+
 #include "engine.h"
+
+// key-switch inner product:  out[p][r][n] (+)= sum_j E[j][r][src(n)] * key[j][p][limb(r)][n]  (+ addp[r][src(n)] (* P) into p = 0)
+struct KsArgs {
+    const u64* E;      // [beta][rows][N]
+    const u64* key;    // [beta_key][2][K][N]
+    u64* out;          // [2][rows][N]
+    const u64* addp;   // optional polynomial added (after the same permutation) to out poly 0
+    int add_rows;      // rows of addp (l: data limbs only; rows: extended)
+    int add_pscale;    // multiply addp by P mod q first
+    int accumulate;    // out += instead of out =
+    int beta, l, rows, N, logn, L, K;
+    u32 elt;           // 0: identity
+};
+
 
 namespace ops {
 void add(const Ctx* c, const u64* a, const u64* b, u64* out, int polys, int rows, int n, RowMap rm, int b_polys, cudaStream_t s);
@@ -11,11 +27,14 @@ void reduce_inplace(const Ctx* c, u64* x, int polys, int rows, RowMap rm, cudaSt
 void tensor(const Ctx* c, const u64* a, const u64* b, u64* out, int l, cudaStream_t s);
 void galois(const Ctx* c, const u64* in, u64* out, int rows, u32 elt, cudaStream_t s);
 void decompose(const Ctx* c, const u64* cin, int l, u64* x, u64* E, cudaStream_t s);
-void decompose_from(const Ctx* c, const u64* cin, const u64* x, int l, u64* E, cudaStream_t s);
+void decompose_from(const Ctx* c, const u64* cin, const u64* x, int l, u64* E, cudaStream_t s, bool transform = true);
+void decompose_ks(const Ctx* c, const u64* cin, const u64* x, int l, u64* E, const u64* key, u64* out, u32 elt,
+                  const u64* addp, int add_rows, int add_pscale, int accumulate, cudaStream_t s);
 void ks_inner(const Ctx* c, const u64* E, const u64* key, u64* out, int l, u32 elt, const u64* addp, int add_rows,
               int add_pscale, int accumulate, cudaStream_t s);
 bool ks_baby_fused(const Ctx* c, const u64* E, const u64* const* keys, const u32* elts, int nb, u64* out, int l,
                    const u64* c0, cudaStream_t s);
+void encode_key_map(const Ctx* c, const u64* key, int box_n, int beta, CUtensorMap* out);
 void pscale(const Ctx* c, const u64* x, u64* y, int l, cudaStream_t s);
 void moddown(const Ctx* c, u64* in, size_t in_pstride, int polys, int l, u64* tmp, const u64* add, u64* out, cudaStream_t s);
 void mod_raise(const Ctx* c, const u64* in, int polys, int l, u64* x, u64* out, cudaStream_t s);

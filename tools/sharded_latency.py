@@ -44,19 +44,41 @@ def main():
     ref = ph.bsgs_hoisted(ckks.ctx, ct, full, ckks.gk)
     same = bool(np.array_equal(y.to_numpy(), ref.to_numpy()))
     err = float(np.abs(ckks.decrypt_vec(y, D) - W @ x).max())
-    for _ in range(3):
-        mv(ct)
-    ckks.ctx.synchronize()
-    dist.barrier()
-    torch.cuda.synchronize()
     steps = 10
     import time
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        mv(ct)
-    ckks.ctx.synchronize()
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / steps * 1e3
+    from fhe_spear_b200.sharding import PeerExchange
+
+    def latency():
+        for _ in range(3):
+            mv(ct)
+        ckks.ctx.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            mv(ct)
+        ckks.ctx.synchronize()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / steps * 1e3
+    peer_on = PeerExchange.get(ckks.ctx) is not None
+    dt = latency()                                      # fused peer-memory exchange (csrc/peer.cu) when available
+    os.environ["SPEAR_PEER"] = "0"
+    dt_nccl = latency()                                 # int64 NCCL all-reduce + Barrett pass
+    same_nccl = bool(np.array_equal(mv(ct).to_numpy(), ref.to_numpy()))
+    os.environ["SPEAR_PEER"] = "1"
+    # the exchange alone, on the engine stream (CUDA events), accumulators already computed
+    ex_ms = float("nan")
+    if peer_on:
+        acc = ph.bsgs_hoisted_partial(ckks.ctx, ct, mv.shard, ckks.gk)
+        ex = PeerExchange.get(ckks.ctx)
+        for _ in range(3):
+            ex.allreduce(acc)
+        ckks.ctx.synchronize()
+        dist.barrier()
+        ckks.ctx.timer_start()
+        for _ in range(steps):
+            ex.allreduce(acc)
+        ex_ms = ckks.ctx.timer_stop() / steps
     # phase breakdown (host clock, synchronised after every phase)
     from fhe_spear_b200.sharding import _DevView, allreduce_residues
     ctx = ckks.ctx
@@ -82,13 +104,16 @@ def main():
         ph_ms["reduce_finish"] += (t4 - t3) * 1e3 / steps
     pt = torch.tensor([ph_ms["partial"], ph_ms["allreduce"], ph_ms["reduce_finish"]], dtype=torch.float64, device="cuda")
     dist.all_reduce(pt, op=dist.ReduceOp.MAX)
-    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dt, dt_nccl, ex_ms], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ok = torch.tensor([1.0 if same else 0.0], device="cuda")
+    ok = torch.tensor([1.0 if same and same_nccl else 0.0], device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps({"what": "giant-step-sharded single mat-vec latency", "config": cfg, "n_gpus": world,
-                          "split": f"G={G} B={B}", "ms_per_matvec": float(t.item()),
+                          "split": f"G={G} B={B}", "ms_per_matvec": float(t[0].item()),
+                          "exchange": "fused peer-memory kernel (csrc/peer.cu)" if peer_on else "NCCL int64 all-reduce",
+                          "ms_per_matvec_nccl_allreduce_path": float(t[1].item()),
+                          "peer_exchange_ms_alone": float(t[2].item()),
                           "phase_ms_max_over_ranks": dict(zip(("partial", "allreduce", "reduce_finish"), [float(v) for v in pt.tolist()])), "bit_identical_to_unsharded_on_all_ranks": bool(ok.item() > 0.5),
                           "max_abs_err_vs_float64": err, "shard_diag_bytes": mv.shard.info()["bytes"]}))
     dist.destroy_process_group()
