@@ -384,6 +384,9 @@ def run_ours(args):
         "share_of_step": {k: v["ms"] / args.steps / step_ms for k, v in prof.items()},
     }
     roofline["matvec"]["frac"] = roofline["matvec"]["achieved_gbs"] / peak
+    ipath = os.path.join(ROOT, "profiles", "integer_pipe_counters.json")
+    if args.config == "c3" and os.path.exists(ipath):   # ncu counters of the integer-bound kernels (static, from profiles/)
+        roofline["integer_pipe"] = json.load(open(ipath))
 
     cpu = None
     if not args.no_cpu_baseline:

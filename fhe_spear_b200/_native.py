@@ -78,6 +78,8 @@ _SIG = {
     "spear_apply_galois": (C.c_int, [vp, vp, C.c_uint32, vp, vpp]),
     "spear_hoisted_rotations": (C.c_int, [vp, vp, u32p, C.c_int, vp, vpp]),
     "spear_bsgs_multiply_accumulate": (C.c_int, [vp, vpp, C.c_int, vpp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vpp]),
+    "spear_bsgs_from_host": (C.c_int, [vp, vpp, C.c_int, vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp, vpp]),
+    "spear_objs_export": (C.c_int, [vp, vpp, C.c_int, vp, C.c_size_t]),
     "spear_diagset_encode": (C.c_int, [vp, f64p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, vpp]),
     "spear_diagset_encode_matrix": (C.c_int, [vp, f64p, f64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                                C.c_int, C.c_int, vpp]),

@@ -19,6 +19,8 @@ void relinearize(const Ctx* c, const u64* ct3, int l, const u64* rlk, u64* out, 
 void rescale(const Ctx* c, const u64* in, int polys, int l, u64* out, cudaStream_t s);
 void bsgs_exact(const Ctx* c, const u64* const* baby, const u64* const* pts, int G, int B, int D, int l,
                 const u32* gelt, const u64* const* gkey, u64* out, cudaStream_t s);
+void bsgs_exact_from_host(const Ctx* c, const u64* const* baby, const u64* host_pts, int pt_limbs, int G, int B, int D,
+                          int l, const u32* gelt, const u64* const* gkey, u64* out, cudaStream_t s);
 void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, int rshift, int G, int n_groups,
                           int n_diags, int g_first, int g_stride, const u32* belt, const u64* const* bkey,
                           const u32* gelt, const u64* const* gkey, u64* R, cudaStream_t s);
@@ -711,6 +713,53 @@ int spear_bsgs_multiply_accumulate(spear_context* ctx, spear_obj* const* ct_baby
     std::unique_ptr<Obj> o(new_obj(c, 2, l - 1, false, c->N, scale));
     eng::bsgs_exact(c, baby.data(), pt.data(), G, B, D, l, gelt.data(), gkey.data(), o->d, c->stream);
     *out = H_(o.release());
+    API_END
+}
+
+int spear_bsgs_from_host(spear_context* ctx, spear_obj* const* ct_baby, int n_baby, const uint64_t* host_pts, int n_pts,
+                         int pt_limbs, double pt_scale, int G, int B, int D, const spear_galois_keys* gk_, spear_obj** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    REQUIRE(G >= 1 && B >= 1 && D >= 1 && n_baby >= std::min(G, D) && n_pts >= D && (size_t)G * B >= (size_t)D && host_pts,
+            "bsgs: need G baby ciphertexts, D plaintexts and G*B >= D");
+    const GaloisKeys* gk = reinterpret_cast<const GaloisKeys*>(gk_);
+    const Obj* b0 = O_(ct_baby[0]);
+    check_ct(b0, "bsgs");
+    const int l = b0->l;
+    REQUIRE(pt_limbs >= l && pt_limbs <= c->L, "bsgs: plaintexts have %d limbs, the ciphertext %d", pt_limbs, l);
+    REQUIRE(l >= 2, "bsgs: no level left for the final rescale");
+    std::vector<const u64*> baby(G, nullptr);
+    for (int b = 0; b < std::min(G, n_baby); b++) {
+        const Obj* o = O_(ct_baby[b]);
+        check_ct(o, "bsgs");
+        REQUIRE(o->size == 2 && o->l == l, "bsgs: baby ciphertext %d has a different level", b);
+        baby[b] = o->d;
+    }
+    std::vector<u32> gelt(B, 0);
+    std::vector<const u64*> gkey(B, nullptr);
+    for (int g = 1; g < B && g * G < D; g++) {
+        gelt[g] = (u32)elt_from_step(g * G, c->N);
+        gkey[g] = find_key(gk, gelt[g])->d;
+    }
+    std::unique_ptr<Obj> o(new_obj(c, 2, l - 1, false, c->N, b0->scale * pt_scale / (double)c->q[l - 1]));
+    eng::bsgs_exact_from_host(c, baby.data(), host_pts, pt_limbs, G, B, D, l, gelt.data(), gkey.data(), o->d, c->stream);
+    // the ring is recycled by the pool once the stream has passed it; the host buffer must stay untouched until then
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    *out = H_(o.release());
+    API_END
+}
+// count objects of one shape -> one host buffer [count][words_each]; one synchronisation for the whole batch
+int spear_objs_export(spear_context* ctx, spear_obj* const* objs, int count, uint64_t* host, size_t words_each) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    for (int i = 0; i < count; i++) {
+        const Obj* o = O_(objs[i]);
+        REQUIRE(o && o->words() == words_each, "export: object %d has %zu words, expected %zu", i, o ? o->words() : 0, words_each);
+        CUDA_CHECK(cudaMemcpyAsync(host + (size_t)i * words_each, o->d, sizeof(u64) * words_each, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
     API_END
 }
 

@@ -105,6 +105,55 @@ void bsgs_exact(const Ctx* c, const u64* const* baby, const u64* const* pts, int
     rescale(c, res, 2, l, out, s);
 }
 
+// The same contraction with the D plaintexts in HOST memory ([D][pt_limbs][N], the reference's offload format,
+// scripts/bootstrap_generation.py:336-358, 449): the diagonals of giant group g+1 cross PCIe into a two-slot device
+// ring on a copy stream while group g is multiplied and rotated, so device memory holds 2 G plaintexts instead of D and
+// the transfer overlaps the arithmetic (truly asynchronous when the host buffer is page-locked -- what
+// pyPhantom.offload_plaintexts hands out -- and merely correct when it is pageable).  Same op order as bsgs_exact.
+void bsgs_exact_from_host(const Ctx* c, const u64* const* baby, const u64* host_pts, int pt_limbs, int G, int B, int D,
+                          int l, const u32* gelt, const u64* const* gkey, u64* out, cudaStream_t s) {
+    const size_t N = c->N, ctw = 2 * l * N, ptw = (size_t)pt_limbs * N, slot_words = (size_t)G * ptw;
+    Scratch sc(c, s);
+    u64* inner = sc.get(ctw);
+    u64* rot = sc.get(ctw);
+    u64* res = sc.get(ctw);
+    u64* ring = sc.get(2 * slot_words);
+    cudaStream_t copy = c->aux[0];
+    cudaEvent_t ready[2], freed[2], born;
+    for (int i = 0; i < 2; i++) {
+        CUDA_CHECK(cudaEventCreateWithFlags(&ready[i], cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&freed[i], cudaEventDisableTiming));
+    }
+    CUDA_CHECK(cudaEventCreateWithFlags(&born, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventRecord(born, s));            // the ring exists (stream-ordered allocation) before the copy stream touches it
+    CUDA_CHECK(cudaStreamWaitEvent(copy, born, 0));
+    bool have = false;
+    std::vector<const u64*> pt(G);
+    for (int g = 0; g < B; g++) {
+        const int nb = std::min(G, D - g * G), slot = g & 1;
+        if (nb <= 0) break;
+        u64* dst_slot = ring + (size_t)slot * slot_words;
+        if (g >= 2) CUDA_CHECK(cudaStreamWaitEvent(copy, freed[slot], 0));   // group g-2 is done with this slot
+        CUDA_CHECK(cudaMemcpyAsync(dst_slot, host_pts + (size_t)g * G * ptw, sizeof(u64) * nb * ptw, cudaMemcpyHostToDevice, copy));
+        CUDA_CHECK(cudaEventRecord(ready[slot], copy));
+        CUDA_CHECK(cudaStreamWaitEvent(s, ready[slot], 0));
+        for (int k = 0; k < nb; k++) pt[k] = dst_slot + (size_t)k * ptw;
+        u64* dst = (g == 0) ? res : inner;
+        ops::pmac_list(c, baby, pt.data(), nb, dst, l, s);
+        CUDA_CHECK(cudaEventRecord(freed[slot], s));
+        if (g == 0) {
+            have = true;
+            continue;
+        }
+        apply_galois(c, inner, l, gelt[g], gkey[g], rot, s);
+        ops::add(c, res, rot, res, 2, l, (int)N, RowMap{l, l, c->L, 0}, 2, s);
+    }
+    for (int i = 0; i < 2; i++) cudaEventDestroy(ready[i]), cudaEventDestroy(freed[i]);
+    cudaEventDestroy(born);
+    REQUIRE(have, "bsgs: empty diagonal set");
+    rescale(c, res, 2, l, out, s);
+}
+
 // ct [2][l][N]; diag [n_diags][l+P][N >> rshift] holds the giant groups g_first + k*g_stride (k < n_groups);
 // bkey[b] (1 <= b < G); gelt/gkey indexed by LOCAL group k (unused where the global group is 0).
 // R [2][l+P][N]: this shard's accumulator in basis Q_l*P (sum over shards, mod q, = the full accumulator).

@@ -240,17 +240,15 @@ class _obj:
 
 
 def pinned_empty(shape, dtype=np.uint64):
-    """numpy array over page-locked host memory (host legs of the end-to-end path)."""
-    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    """numpy array over page-locked host memory (host legs of the end-to-end path, offloaded plaintexts); the memory is
+    released when the last view of the array is garbage-collected."""
+    import weakref
+    nbytes = max(1, int(np.prod(shape)) * np.dtype(dtype).itemsize)
     p = C.c_void_p()
     _check(_lib.spear_pinned_alloc(nbytes, C.byref(p)))
     buf = (C.c_char * nbytes).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
-    _pinned_keepalive.append((p, buf))
-    return arr
-
-
-_pinned_keepalive = []
+    weakref.finalize(buf, _lib.spear_pinned_free, p)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
 class plaintext(_obj):
@@ -562,11 +560,14 @@ def bsgs_multiply_accumulate(ctx, ct_baby, pts, G, B, D, gk):
 
 
 def offload_plaintexts(pts):
-    """list[plaintext] -> (data, chain_index, scale, coeff_modulus_size, poly_modulus_degree)."""
+    """list[plaintext] -> (data, chain_index, scale, coeff_modulus_size, poly_modulus_degree)
+    [ref: fork-only, scripts/bootstrap_generation.py:339].  `data` lives in page-locked host memory, so the way back
+    (upload_plaintexts, bsgs_from_cpu) runs at PCIe speed and asynchronously; one synchronisation for the whole batch."""
     size, limbs, ext, ring, scale, ci = pts[0]._info()
-    data = np.empty((len(pts), limbs, ring), dtype=np.uint64)
-    for k, p in enumerate(pts):
-        p.to_numpy(out=data[k:k + 1])
+    n = len(pts)
+    data = pinned_empty((n, limbs, ring))
+    _check(_lib.spear_objs_export(pts[0]._ctx._h, (C.c_void_p * n)(*[p._h for p in pts]), n,
+                                  data.ctypes.data_as(C.c_void_p), limbs * ring))
     return data, ci, scale, limbs, ring
 
 
@@ -577,8 +578,13 @@ def upload_plaintexts(data, chain_index, scale, coeff_modulus_size, poly_modulus
 
 
 def bsgs_from_cpu(ctx, ct_baby, data, ci, sc, cms, pmd, G, B, D, gk):
-    pts = upload_plaintexts(data, ci, sc, cms, pmd, ctx=ctx)
-    return bsgs_multiply_accumulate(ctx, ct_baby, pts, G, B, D, gk)
+    """BSGS over offloaded plaintexts [ref: fork-only, scripts/bootstrap_generation.py:449]: the diagonals stream from
+    host memory through a two-slot device ring, overlapped with the arithmetic (spear_bsgs_from_host)."""
+    data = np.ascontiguousarray(np.asarray(data, dtype=np.uint64).reshape(-1, cms, pmd))
+    nb = len(ct_baby)
+    cb = (C.c_void_p * nb)(*[c._h for c in ct_baby])
+    return _new(ciphertext, ctx, _lib.spear_bsgs_from_host, cb, nb, data.ctypes.data_as(C.c_void_p), int(data.shape[0]),
+                int(cms), float(sc), int(G), int(B), int(D), gk._h)
 
 
 def bsgs_complete_from_cpu(ctx, ct_x, data, ci, sc, cms, pmd, G, B, D, gk):

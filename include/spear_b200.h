@@ -148,6 +148,14 @@ int spear_hoisted_rotations(spear_context* ctx, const spear_obj* ct, const uint3
  *  executable spec = the Python loop :464-484]  exact mode: reference op order, result rescaled. */
 int spear_bsgs_multiply_accumulate(spear_context* ctx, spear_obj* const* ct_baby, int n_baby, spear_obj* const* pts,
                                    int n_pts, int G, int B, int D, const spear_galois_keys* gk, spear_obj** out);
+/* [ref: fork-only ph.bsgs_from_cpu(ctx, ct_baby, data, ci, sc, cms, pmd, G, B, D, gk), bootstrap_generation.py:449, over the
+ *  offload format of ph.offload_plaintexts, :336-358]  host_pts: [n_pts][pt_limbs][N] NTT-form plaintext residues in host
+ *  memory.  Same result as spear_bsgs_multiply_accumulate; the diagonals stream through a two-slot device ring, the copy of
+ *  giant group g+1 overlapping the arithmetic of group g (page-locked host memory makes the copies asynchronous). */
+int spear_bsgs_from_host(spear_context* ctx, spear_obj* const* ct_baby, int n_baby, const uint64_t* host_pts, int n_pts,
+                         int pt_limbs, double pt_scale, int G, int B, int D, const spear_galois_keys* gk, spear_obj** out);
+/* [ref: fork-only ph.offload_plaintexts(list[pt]), :339]  count objects of one shape -> host [count][words_each] */
+int spear_objs_export(spear_context* ctx, spear_obj* const* objs, int count, uint64_t* host, size_t words_each);
 /* [ref: pre_encode_real_diags / pre_encode_complex_diags, bootstrap_generation.py:252-262, 361-432]
  *  diags: D period-D complex vectors (already pre-rotated by +gG per giant group, :365-369), interleaved
  *  (re, im).  compress != 0 stores the sub-ring form (ring 2D, N/(2D)-fold smaller). */

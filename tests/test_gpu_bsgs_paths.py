@@ -51,6 +51,11 @@ def test_reference_python_loop_golden_limbs():
     assert np.array_equal(y2.to_numpy(), g["ct_y_real"])
     y3 = ph.bsgs_complete_from_cpu(ctx, ct, data, ci, sc, cms, pmd, G, B, D, gk)
     assert np.array_equal(y3.to_numpy(), g["ct_y_real"])
+    pageable = np.array(data)                                        # the same stream from ordinary host memory
+    assert np.array_equal(ph.bsgs_from_cpu(ctx, baby, pageable, ci, sc, cms, pmd, G, B, D, gk).to_numpy(), g["ct_y_real"])
+    back = ph.upload_plaintexts(data, ci, sc, cms, pmd)
+    assert len(back) == D and all(np.array_equal(a.to_numpy(), b.to_numpy()) for a, b in zip(back[:3], pts[:3]))
+    del data, pageable
 
 
 @pytest.mark.parametrize("D,world", [(64, 2), (64, 3), (20, 2)])
@@ -317,11 +322,13 @@ def test_retrieval_wrapper_flow():
     assert int(np.argmax(scores_pt)) == int(np.argmax(truth)) == int(np.argmax(scores_ct))
 
 
-@pytest.mark.parametrize("L0,P", [(12, 1), (20, 2), (9, 4)])
-def test_many_digit_parameter_sets_match_oracle(L0, P):
+@pytest.mark.parametrize("L0,P,N", [(12, 1, 1024), (20, 2, 1024), (9, 4, 1024), (12, 1, 2048), (9, 4, 2048), (36, 3, 2048)])
+def test_many_digit_parameter_sets_match_oracle(L0, P, N):
     """More than 8 key-switch digits (config C5 has beta = 12) takes the generic, non-unrolled kernel paths;
-    P = 4 exercises a wider digit.  Rotation, exact BSGS and hoisted BSGS must stay bit-exact with the oracle."""
-    S = Setup(N=1024, bits=(59,) * (L0 + P), P=P)
+    P = 4 exercises a wider digit.  N = 2048 runs the key product fused into the forward transform's last pass
+    (k_ntt_b_ks) with more digits than warps, N = 1024 the stand-alone kernels.  Rotation, exact BSGS and hoisted BSGS
+    must stay bit-exact with the oracle."""
+    S = Setup(N=N, bits=(59,) * (L0 + P), P=P)
     D = 16
     G, B = bsgs_params(D)
     steps = list(range(1, G)) + [g * G for g in range(1, B)]

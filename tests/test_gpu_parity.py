@@ -315,3 +315,24 @@ def test_mixed_prime_sizes_public_key_path():
     sq = ph.rescale_to_next(ctx, ph.relinearize(ctx, ph.multiply(ctx, prod, prod), rlk))
     got = np.array(enc.decode_double_vector(ctx, sk.decrypt(ctx, sq)))
     assert np.abs(got - (z * w) ** 2).max() < 1e-4
+
+
+def test_wide_primes_take_the_exact_fused_path():
+    """60-bit primes (fhe_rwkv_inference.py:29-35 style) at N = 2048: the fused transform + key product kernel runs its
+    non-lazy butterflies, folds every 8 digits and reduces with the full Barrett step.  Rotation and relinearisation
+    must equal the oracle limb for limb."""
+    s = Setup(N=2048, bits=(60, 59, 60, 40, 40, 60), P=1)   # the rescale drops a 40-bit prime: scale stays 2^40
+    ph, ctx, sk = s.gpu([1, 5])
+    enc = ph.ckks_encoder(ctx)
+    rlk, gk = sk.gen_relinkey(ctx), sk.create_galois_keys(ctx)
+    rng = np.random.default_rng(18)
+    z = rng.standard_normal(s.N // 2)
+    ct = sk.encrypt_symmetric(ctx, enc.encode_double_vector(ctx, z, 2.0 ** 40), enc_id=9)
+    cto = ct.to_numpy()
+    for step in (1, 5):
+        elt = s.o.elt_from_step(step)
+        assert np.array_equal(ph.rotate(ctx, ct, step, gk).to_numpy(), s.o.apply_galois(cto, elt, s.key(elt)))
+    sq = ph.relinearize(ctx, ph.multiply(ctx, ct, ct), rlk)
+    assert np.array_equal(sq.to_numpy(), s.o.relinearize(s.o.multiply(cto, cto), s.o.gen_relin_key(s.seed, s.sk)))
+    got = np.array(enc.decode_double_vector(ctx, sk.decrypt(ctx, ph.rescale_to_next(ctx, sq))))
+    assert np.abs(got - z * z).max() < 1e-4
