@@ -127,14 +127,21 @@ class CKKSBootstrapContext:
         rep = _replicate_to_slots(np.asarray(vec_real) + 1j * np.asarray(vec_imag), self.slots)
         return self.sk.encrypt_symmetric(self.ctx, self.encoder.encode_complex_vector(self.ctx, rep, self.scale))
 
+    def _decode(self, pt, dim):
+        """first `dim` slots as a complex array; list-returning decode of a reference-style encoder as the fallback"""
+        fast = getattr(self.encoder, "decode_array", None)
+        if fast is not None:
+            return fast(self.ctx, pt)[:dim].copy()
+        return np.array(self.encoder.decode_complex_vector(self.ctx, pt)[:dim])
+
     def decrypt_vec(self, ct, dim):
-        return np.array(self.encoder.decode_double_vector(self.ctx, self.sk.decrypt(self.ctx, ct))[:dim])
+        return self._decode(self.sk.decrypt(self.ctx, ct), dim).real.copy()
 
     def decrypt_vec_complex(self, ct, dim):
-        return np.array(self.encoder.decode_complex_vector(self.ctx, self.sk.decrypt(self.ctx, ct))[:dim])
+        return self._decode(self.sk.decrypt(self.ctx, ct), dim)
 
     def decrypt_slot0(self, ct):
-        return self.encoder.decode_double_vector(self.ctx, self.sk.decrypt(self.ctx, ct))[0]
+        return float(self._decode(self.sk.decrypt(self.ctx, ct), 1).real[0])
 
     def bootstrap(self, ct):
         """[ref: :149-154] mod-switch down to two limbs, then ckks_bootstrapper.bootstrap"""

@@ -88,8 +88,10 @@ class PeerExchange:
         import torch.distributed as dist
         if os.environ.get("SPEAR_PEER", "1") == "0" or not dist.is_initialized() or dist.get_world_size(group) < 2:
             return None
+        import weakref
         key = (id(ctx), id(group) if group is not None else 0)
-        if key not in cls._cache:
+        hit = cls._cache.get(key)
+        if hit is None or hit[0]() is not ctx:   # ids are recycled: the entry must belong to this very context
             try:
                 ok, ex = 1, cls(ctx, group)
             except RuntimeError as e:   # every rank must take the same path: agree on the outcome below
@@ -97,8 +99,8 @@ class PeerExchange:
                 print(f"[spear] peer windows unavailable on rank {dist.get_rank()}: {e}; using the NCCL all-reduce")
             flags = [None] * dist.get_world_size(group)
             dist.all_gather_object(flags, ok, group=group)
-            cls._cache[key] = ex if all(flags) else None
-        return cls._cache[key]
+            hit = cls._cache[key] = (weakref.ref(ctx), ex if all(flags) else None)
+        return hit[1]
 
     def allreduce(self, acc, slot=0):
         self.window.allreduce(acc, slot % self.slots)
