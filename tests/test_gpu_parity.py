@@ -336,3 +336,21 @@ def test_wide_primes_take_the_exact_fused_path():
     assert np.array_equal(sq.to_numpy(), s.o.relinearize(s.o.multiply(cto, cto), s.o.gen_relin_key(s.seed, s.sk)))
     got = np.array(enc.decode_double_vector(ctx, sk.decrypt(ctx, ph.rescale_to_next(ctx, sq))))
     assert np.abs(got - z * z).max() < 1e-4
+
+
+@pytest.mark.parametrize("N", [8192, 65536])
+def test_rotation_at_large_ring_sizes(N):
+    """A full rotate (permute, decompose, transform fused with the key product, ModDown) at N = 8192 and at the
+    largest ring the engine supports (N = 65536: pass A of eight stages in front of the fused pass) vs the oracle."""
+    s = Setup(N=N, bits=(59,) * 5, P=2)
+    ph, ctx, sk = s.gpu([7])
+    enc = ph.ckks_encoder(ctx)
+    gk = sk.create_galois_keys(ctx)
+    rng = np.random.default_rng(N)
+    z = rng.standard_normal(64)
+    ct = sk.encrypt_symmetric(ctx, enc.encode_double_vector(ctx, z, s.scale), enc_id=4)
+    elt = s.o.elt_from_step(7)
+    rot = ph.rotate(ctx, ct, 7, gk)
+    assert np.array_equal(rot.to_numpy(), s.o.apply_galois(ct.to_numpy(), elt, s.key(elt)))
+    got = np.array(enc.decode_double_vector(ctx, sk.decrypt(ctx, rot)))[:57]
+    assert np.abs(got - z[7:]).max() < 1e-9
