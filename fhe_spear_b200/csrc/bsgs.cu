@@ -8,6 +8,8 @@
 //                   that basis, one ModDown of the c1 part per giant step, giant key switches accumulated
 //                   in basis Q_l*P, one final ModDown, one rescale.
 // Both are restated step for step by the oracle (orc_bsgs_exact / orc_bsgs_hoisted).
+#include <cstdlib>
+
 #include "engine.h"
 #include "ops.h"
 
@@ -164,7 +166,15 @@ void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, i
     const int beta = c->digits(l);
     const int k0 = (g_first == 0) ? 1 : 0;          // group 0 (if owned) needs no rotation
     const int nrot = n_groups > k0 ? n_groups - k0 : 0;
-    Arena sc(c, s, l * N + beta * pw + (size_t)G * 2 * pw + (size_t)n_groups * 2 * pw + 3 * (size_t)nrot * l * N + 32 * 8);
+    // all giant-step decompositions at once when the digits fit a modest slice of HBM (SPEAR_BATCH_GIANT=0: one at a time)
+    static const bool batch_env = [] {
+        const char* e = getenv("SPEAR_BATCH_GIANT");
+        return !(e && e[0] == '0');
+    }();
+    const bool batch_e = batch_env && nrot >= 2 && ntt_ks_fused_applies(c, l) && (size_t)nrot * beta * rows <= 65535 &&
+                         (size_t)nrot * beta * pw * sizeof(u64) <= ((size_t)6 << 30);
+    Arena sc(c, s, l * N + beta * pw + (size_t)G * 2 * pw + (size_t)n_groups * 2 * pw + 3 * (size_t)nrot * l * N + 32 * 8 +
+                       (batch_e ? (size_t)nrot * beta * pw + 32 : 0));
     u64* x = sc.get(l * N);
     u64* E = sc.get(beta * pw);
     u64* Y = sc.get((size_t)G * 2 * pw);
@@ -195,11 +205,25 @@ void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, i
         ops::moddown(c, A + (size_t)k0 * 2 * pw + pw, 2 * pw, nrot, l, tmp, nullptr, t_all, s);
         CUDA_CHECK(cudaMemcpyAsync(x_all, t_all, sizeof(u64) * nrot * l * N, cudaMemcpyDeviceToDevice, s));
         ntt_inverse(c, x_all, nrot * l, RowMap{l, l, c->L, 0}, (int)N, s);
-        for (int k = k0; k < n_groups; k++) {
-            u64* Ak = A + (size_t)k * 2 * pw;
-            const size_t o = (size_t)(k - k0) * l * N;
-            ops::decompose_ks(c, t_all + o, x_all + o, l, E, gkey[k], R, gelt[k], Ak, (int)rows, 0, have ? 1 : 0, s);
-            have = true;
+        if (batch_e) {
+            // ModUp and the first transform pass of ALL giant groups in one launch each (every launch pays ~10 us of
+            // ramp-up and tail; 2 x 44 of them at C3), then the fused pass + key product per group
+            u64* E_all = sc.get((size_t)nrot * beta * pw);
+            ops::decompose_from(c, t_all, x_all, l, E_all, s, /*transform=*/false, nrot);
+            ntt_pass_a_batch(c, E_all, nrot, l, s);
+            for (int k = k0; k < n_groups; k++) {
+                u64* Ak = A + (size_t)k * 2 * pw;
+                ntt_ks_fused(c, E_all + (size_t)(k - k0) * beta * pw, gkey[k], R, l, gelt[k], Ak, (int)rows, 0, have ? 1 : 0, s,
+                             /*pass_a_done=*/true);
+                have = true;
+            }
+        } else {
+            for (int k = k0; k < n_groups; k++) {
+                u64* Ak = A + (size_t)k * 2 * pw;
+                const size_t o = (size_t)(k - k0) * l * N;
+                ops::decompose_ks(c, t_all + o, x_all + o, l, E, gkey[k], R, gelt[k], Ak, (int)rows, 0, have ? 1 : 0, s);
+                have = true;
+            }
         }
     }
     if (!have) CUDA_CHECK(cudaMemsetAsync(R, 0, sizeof(u64) * 2 * pw, s));

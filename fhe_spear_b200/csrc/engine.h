@@ -161,9 +161,12 @@ struct ProfScope {   // brackets the launches of one kernel class with an event 
 // rows x n in-place transforms; `n` may be a power-of-two prefix size (sub-ring) <= N
 void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s, int skip_digit_alpha = 0,
                  bool split30_out = false, bool pass_a_only = false);
-// forward transform of freshly ModUp'd digits fused with the key inner product (ntt.cu); false: not applicable
+// forward transform of freshly ModUp'd digits fused with the key inner product (ntt.cu); false: not applicable.
+// pass_a_done: the first pass already ran (ntt_pass_a_batch over several decompositions at once)
+bool ntt_ks_fused_applies(const Ctx* c, int l);
+void ntt_pass_a_batch(const Ctx* c, u64* E, int groups, int l, cudaStream_t s);
 bool ntt_ks_fused(const Ctx* c, u64* E, const u64* key, u64* out, int l, u32 elt, const u64* addp, int add_rows,
-                  int add_pscale, int accumulate, cudaStream_t s);
+                  int add_pscale, int accumulate, cudaStream_t s, bool pass_a_done = false);
 void ntt_inverse(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s);
 
 // ---- stream ids shared with the oracle ------------------------------------------------------

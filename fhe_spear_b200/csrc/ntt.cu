@@ -20,6 +20,17 @@ constexpr int TPB = 256;
 constexpr int COLS = 16;        // pass A tile width
 constexpr int B_ELEMS = 2048;   // pass B elements per CTA
 
+// Rows that ModUp already delivered in NTT form (the data limbs of a digit inside that digit's own block of rows) are
+// skipped.  skip = alpha | (beta << 16): digit width, and -- for batches holding several decompositions back to back
+// ([group][digit][row]) -- the digits per decomposition (0: the batch is a single decomposition).
+__device__ __forceinline__ bool own_digit_row(int skip, int limb, int row, const RowMap& rm) {
+    const int alpha = skip & 0xFFFF, beta = skip >> 16;
+    if (!alpha || limb >= rm.L) return false;
+    int digit = row / rm.rpp;
+    if (beta) digit %= beta;
+    return limb / alpha == digit;
+}
+
 __device__ __forceinline__ void ct_butterfly(u64& x, u64& y, ulonglong2 w, u64 q, u64 q2) {
     // x, y in [0,4q) -> x + w*y, x - w*y in [0,4q)
     u64 u = x >= q2 ? x - q2 : x;
@@ -113,7 +124,7 @@ __global__ void __launch_bounds__(TPB) ntt_fwd_a(u64* __restrict__ data, RowMap 
     extern __shared__ u64 sm[];
     const int row = blockIdx.y;
     const int limb = rm.limb(row);
-    if (skip_alpha && limb < rm.L && limb / skip_alpha == row / rm.rpp) return;
+    if (own_digit_row(skip_alpha, limb, row, rm)) return;
     const u64 q = tb.q[limb], q2 = q << 1;
     const ulonglong2* __restrict__ tw = tb.psi + (size_t)limb * N;
     u64* base = data + rm.offset(row, n);
@@ -142,7 +153,7 @@ __global__ void __launch_bounds__(TPB) ntt_fwd_b(u64* __restrict__ data, RowMap 
     extern __shared__ u64 sm[];
     const int row = blockIdx.y;
     const int limb = rm.limb(row);
-    if (skip_alpha && limb < rm.L && limb / skip_alpha == row / rm.rpp) return;
+    if (own_digit_row(skip_alpha, limb, row, rm)) return;
     const u64 q = tb.q[limb], q2 = q << 1;
     const ulonglong2* __restrict__ tw = tb.psi + (size_t)limb * N;
     const int M = 1 << sB;
@@ -341,7 +352,7 @@ __global__ void __launch_bounds__(WB * 32) ntt_fwd_b2(u64* __restrict__ data, Ro
     __shared__ u64 smem[WB][256];
     const int row = blockIdx.y;
     const int limb = rm.limb(row);
-    if (skip_alpha && limb < rm.L && limb / skip_alpha == row / rm.rpp) return;
+    if (own_digit_row(skip_alpha, limb, row, rm)) return;
     const u64 q = tb.q[limb];
     const ulonglong2* __restrict__ tw = tb.psi + (size_t)limb * N;
     const int warp = threadIdx.x >> 5, j = threadIdx.x & 31;
@@ -484,7 +495,7 @@ __global__ void __launch_bounds__(2 << SA) ntt_fwd_a2(u64* __restrict__ data, Ro
     __shared__ u64 sm[R * COLS];
     const int row = blockIdx.y;
     const int limb = rm.limb(row);
-    if (skip_alpha && limb < rm.L && limb / skip_alpha == row / rm.rpp) return;
+    if (own_digit_row(skip_alpha, limb, row, rm)) return;
     const u64 q = tb.q[limb];
     const ulonglong2* __restrict__ tw = tb.psi + (size_t)limb * N;
     const int c = threadIdx.x & (COLS - 1), g = threadIdx.x >> 4;
@@ -679,7 +690,7 @@ void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream
     if (rows == 0) return;
     if (rows > 65535) {
         const int step = max_rows_per_launch(rm);
-        REQUIRE(step > 0 && !skip_alpha, "ntt: %d rows per polynomial do not fit one launch", rm.rpp);
+        REQUIRE(step > 0 && !skip_alpha, "ntt: %d rows per polynomial do not fit one launch", rm.rpp);   // callers keep skip batches below 65536 rows
         for (int r0 = 0; r0 < rows; r0 += step)
             ntt_forward(c, data + rm.offset(r0, n), std::min(step, rows - r0), rm, n, s, skip_alpha, split30_out,
                         pass_a_only);
@@ -717,14 +728,24 @@ void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream
 // E: [beta][l+P][N] as ModUp leaves it (own-digit rows in NTT split-30 form, the others in coefficient form).
 // Runs the forward transform of the other rows and the key inner product (KsArgs semantics of ops::ks_inner) with
 // the last eight stages fused into the product.  Returns false when the fused path does not apply (N < 2048).
+bool ntt_ks_fused_applies(const Ctx* c, int l) {
+    int sA, sB;
+    split(c->logn, sA, sB);
+    return sA >= 3 && (size_t)3 * c->digits(l) * FK_CHUNK * sizeof(u64) + 64 <= 200 * 1024;
+}
+// pass A of `groups` decompositions stored back to back ([group][beta][l+P][N]) in one launch
+void ntt_pass_a_batch(const Ctx* c, u64* E, int groups, int l, cudaStream_t s) {
+    const int beta = c->digits(l), rows = l + c->P;
+    ntt_forward(c, E, groups * beta * rows, RowMap{rows, l, c->L, 0}, c->N, s, c->P | (beta << 16), true, /*pass_a_only=*/true);
+}
 bool ntt_ks_fused(const Ctx* c, u64* E, const u64* key, u64* out, int l, u32 elt, const u64* addp, int add_rows,
-                  int add_pscale, int accumulate, cudaStream_t s) {
+                  int add_pscale, int accumulate, cudaStream_t s, bool pass_a_done) {
     const int beta = c->digits(l), rows = l + c->P;
     const size_t smem = (size_t)3 * beta * FK_CHUNK * sizeof(u64) + 64;
     int sA, sB;
     split(c->logn, sA, sB);
     if (sA < 3 || smem > 200 * 1024) return false;
-    ntt_forward(c, E, beta * rows, RowMap{rows, l, c->L, 0}, c->N, s, c->P, true, /*pass_a_only=*/true);
+    if (!pass_a_done) ntt_forward(c, E, beta * rows, RowMap{rows, l, c->L, 0}, c->N, s, c->P, true, /*pass_a_only=*/true);
     KsArgs a;
     a.E = E, a.key = key, a.out = out, a.addp = addp, a.add_rows = add_rows, a.add_pscale = add_pscale;
     a.accumulate = accumulate, a.beta = beta, a.l = l, a.rows = rows, a.N = c->N, a.logn = c->logn;

@@ -95,6 +95,8 @@ __global__ void __launch_bounds__(TPB) k_modup(const u64* __restrict__ x, const 
     extern __shared__ u64 tab[];   // [rows][A + 2]
     const int j = blockIdx.y, n = blockIdx.x * TPB + threadIdx.x;
     const int rows = l + P, lo = j * P, hi = min(lo + P, l), a = hi - lo;
+    // blockIdx.z: one of several decompositions laid out back to back (x, cin: [z][l][N]; E: [z][beta][rows][N])
+    x += (size_t)blockIdx.z * l * N, cin += (size_t)blockIdx.z * l * N, E += (size_t)blockIdx.z * gridDim.y * rows * N;
     hatinv += (size_t)j * P;
     hat += (size_t)j * P * K;
     for (int e = threadIdx.x; e < rows * (A + 2); e += TPB) {
@@ -666,7 +668,7 @@ void decompose(const Ctx* c, const u64* cin, int l, u64* x, u64* E, cudaStream_t
     decompose_from(c, cin, x, l, E, s);
 }
 // same, given both forms of the polynomial: cin (NTT) and x (coefficients)
-void decompose_from(const Ctx* c, const u64* cin, const u64* x, int l, u64* E, cudaStream_t s, bool transform) {
+void decompose_from(const Ctx* c, const u64* cin, const u64* x, int l, u64* E, cudaStream_t s, bool transform, int count) {
     const int N = c->N, P = c->P, rows = l + P, beta = c->digits(l);
     REQUIRE(P <= MAX_ALPHA, "special_modulus_size > %d not supported", MAX_ALPHA);
     REQUIRE(N % TPB == 0, "N must be a multiple of %d", TPB);
@@ -674,7 +676,7 @@ void decompose_from(const Ctx* c, const u64* cin, const u64* x, int l, u64* E, c
         ProfScope ps(c, PROF_MODUP, s);
         const size_t tab_bytes = sizeof(u64) * rows * ((P <= 4 ? P : MAX_ALPHA) + 2);
         auto go = [&](auto kern) {
-            LAUNCH(kern, dim3(N / TPB, beta), TPB, tab_bytes, s)(x, cin, E, l, N, c->L, P, c->K, c->modtab(),
+            LAUNCH(kern, dim3(N / TPB, beta, count), TPB, tab_bytes, s)(x, cin, E, l, N, c->L, P, c->K, c->modtab(),
                                                                  c->d_up_hatinv + (size_t)l * c->beta * P,
                                                                  c->d_up_hat + (size_t)l * c->beta * P * c->K, c->sbits);
         };
@@ -684,6 +686,7 @@ void decompose_from(const Ctx* c, const u64* cin, const u64* x, int l, u64* E, c
         else if (P == 4) go(k_modup<4>);
         else go(k_modup<MAX_ALPHA>);
     }
+    REQUIRE(count >= 1 && (count == 1 || !transform) && count <= 65535, "modup: bad batch");
     if (transform) ntt_forward(c, E, beta * rows, RowMap{rows, l, c->L, 0}, N, s, P, /*split30_out=*/true);
     CUDA_CHECK(cudaGetLastError());
 }

@@ -27,7 +27,9 @@ void reduce_inplace(const Ctx* c, u64* x, int polys, int rows, RowMap rm, cudaSt
 void tensor(const Ctx* c, const u64* a, const u64* b, u64* out, int l, cudaStream_t s);
 void galois(const Ctx* c, const u64* in, u64* out, int rows, u32 elt, cudaStream_t s);
 void decompose(const Ctx* c, const u64* cin, int l, u64* x, u64* E, cudaStream_t s);
-void decompose_from(const Ctx* c, const u64* cin, const u64* x, int l, u64* E, cudaStream_t s, bool transform = true);
+// count > 1: `count` polynomials back to back (cin, x: [count][l][N]) -> E [count][beta][l+P][N], ModUp only (transform = false)
+void decompose_from(const Ctx* c, const u64* cin, const u64* x, int l, u64* E, cudaStream_t s, bool transform = true,
+                    int count = 1);
 void decompose_ks(const Ctx* c, const u64* cin, const u64* x, int l, u64* E, const u64* key, u64* out, u32 elt,
                   const u64* addp, int add_rows, int add_pscale, int accumulate, cudaStream_t s);
 void ks_inner(const Ctx* c, const u64* E, const u64* key, u64* out, int l, u32 elt, const u64* addp, int add_rows,
