@@ -174,7 +174,7 @@ void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, i
     const bool batch_e = batch_env && nrot >= 2 && ntt_ks_fused_applies(c, l) && (size_t)nrot * beta * rows <= 65535 &&
                          (size_t)nrot * beta * pw * sizeof(u64) <= ((size_t)6 << 30);
     Arena sc(c, s, l * N + beta * pw + (size_t)G * 2 * pw + (size_t)n_groups * 2 * pw + 3 * (size_t)nrot * l * N + 32 * 8 +
-                       (batch_e ? (size_t)nrot * beta * pw + 32 : 0));
+                       (batch_e ? (size_t)nrot * (beta + 2) * pw + 64 : 0));
     u64* x = sc.get(l * N);
     u64* E = sc.get(beta * pw);
     u64* Y = sc.get((size_t)G * 2 * pw);
@@ -211,11 +211,17 @@ void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, i
             u64* E_all = sc.get((size_t)nrot * beta * pw);
             ops::decompose_from(c, t_all, x_all, l, E_all, s, /*transform=*/false, nrot);
             ntt_pass_a_batch(c, E_all, nrot, l, s);
-            for (int k = k0; k < n_groups; k++) {
-                u64* Ak = A + (size_t)k * 2 * pw;
-                ntt_ks_fused(c, E_all + (size_t)(k - k0) * beta * pw, gkey[k], R, l, gelt[k], Ak, (int)rows, 0, have ? 1 : 0, s,
-                             /*pass_a_done=*/true);
+            u64* Rk = sc.get((size_t)nrot * 2 * pw);   // one partial result per giant group, summed below
+            if (ntt_ks_fused_all(c, E_all, gkey + k0, gelt + k0, nrot, Rk, l, A + (size_t)k0 * 2 * pw, 2 * pw, (int)rows, s)) {
+                ops::sum_groups(c, Rk, nrot, have ? R : nullptr, R, l, s);
                 have = true;
+            } else {
+                for (int k = k0; k < n_groups; k++) {
+                    u64* Ak = A + (size_t)k * 2 * pw;
+                    ntt_ks_fused(c, E_all + (size_t)(k - k0) * beta * pw, gkey[k], R, l, gelt[k], Ak, (int)rows, 0, have ? 1 : 0,
+                                 s, /*pass_a_done=*/true);
+                    have = true;
+                }
             }
         } else {
             for (int k = k0; k < n_groups; k++) {

@@ -167,6 +167,9 @@ bool ntt_ks_fused_applies(const Ctx* c, int l);
 void ntt_pass_a_batch(const Ctx* c, u64* E, int groups, int l, cudaStream_t s);
 bool ntt_ks_fused(const Ctx* c, u64* E, const u64* key, u64* out, int l, u32 elt, const u64* addp, int add_rows,
                   int add_pscale, int accumulate, cudaStream_t s, bool pass_a_done = false);
+// the fused pass + key product of `groups` decompositions (pass A done) in one launch, one partial result per group
+bool ntt_ks_fused_all(const Ctx* c, const u64* E, const u64* const* keys, const u32* elts, int groups, u64* out, int l,
+                      const u64* addp, size_t add_stride, int add_rows, cudaStream_t s);
 void ntt_inverse(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s);
 
 // ---- stream ids shared with the oracle ------------------------------------------------------

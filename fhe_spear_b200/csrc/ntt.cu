@@ -569,9 +569,8 @@ __global__ void __launch_bounds__(2 << SA) ntt_inv_a2(u64* __restrict__ data, Ro
 constexpr int FK_CHUNK = 256, FK_MAXW = 8;
 
 template <int FOLD>
-__global__ void __launch_bounds__(FK_MAXW * 32, 4) k_ntt_b_ks(const __grid_constant__ CUtensorMap kmap, KsArgs a, ModTab mt,
-                                                            NttTab tb, const ulonglong2* __restrict__ pmod, int sA,
-                                                            int alpha, int wide_ok) {
+__device__ __forceinline__ void fk_body(const CUtensorMap* kmap_p, const KsArgs& a, const ModTab& mt, const NttTab& tb,
+                                        const ulonglong2* __restrict__ pmod, int sA, int alpha, int wide_ok) {
     extern __shared__ __align__(128) unsigned char smraw[];
     const int beta = a.beta;
     u64* ksm = reinterpret_cast<u64*>(smraw);                     // [2*beta][256]  key box (TMA destination)
@@ -583,7 +582,7 @@ __global__ void __launch_bounds__(FK_MAXW * 32, 4) k_ntt_b_ks(const __grid_const
         mbar_init(full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(full, (u32)(2 * beta * FK_CHUNK * sizeof(u64)));
-        tma_load_3d_hint(ksm, &kmap, (int)n0, t, 0, full, evict_first_policy());
+        tma_load_3d_hint(ksm, kmap_p, (int)n0, t, 0, full, evict_first_policy());
     }
     const u32 csrc = (a.elt ? galois_src(n0, a.elt, a.logn) : n0) / FK_CHUNK;   // chunk the output chunk is gathered from
     const bool has_add = a.addp && r < a.add_rows;
@@ -659,6 +658,31 @@ __global__ void __launch_bounds__(FK_MAXW * 32, 4) k_ntt_b_ks(const __grid_const
         *o0 = v0;
         *o1 = v1;
     }
+}
+
+template <int FOLD>
+__global__ void __launch_bounds__(FK_MAXW * 32, 4) k_ntt_b_ks(const __grid_constant__ CUtensorMap kmap, KsArgs a, ModTab mt,
+                                                            NttTab tb, const ulonglong2* __restrict__ pmod, int sA,
+                                                            int alpha, int wide_ok) {
+    fk_body<FOLD>(&kmap, a, mt, tb, pmod, sA, alpha, wide_ok);
+}
+
+// All giant steps of a mat-vec in ONE launch (blockIdx.z = giant group): group z reads its own digits and rotation key,
+// adds its own permuted c0 part and writes its own partial result; ops::sum_groups adds the partial results up.
+constexpr int FK_MAX_GROUPS = 224;   // 224 x (128 B tensor map + element) = 29.6 KB of the 32 KB parameter space
+struct GiantTab {
+    CUtensorMap map[FK_MAX_GROUPS];
+    u32 elt[FK_MAX_GROUPS];
+};
+template <int FOLD>
+__global__ void __launch_bounds__(FK_MAXW * 32, 4) k_ntt_b_ks_all(const __grid_constant__ GiantTab tab, KsArgs a, ModTab mt,
+                                                                NttTab tb, const ulonglong2* __restrict__ pmod, int sA,
+                                                                int alpha, int wide_ok, size_t e_stride, size_t out_stride,
+                                                                size_t add_stride) {
+    const int z = blockIdx.z;
+    a.E += (size_t)z * e_stride, a.out += (size_t)z * out_stride, a.elt = tab.elt[z];
+    if (a.addp) a.addp += (size_t)z * add_stride;
+    fk_body<FOLD>(&tab.map[z], a, mt, tb, pmod, sA, alpha, wide_ok);
 }
 
 template <int SA>
@@ -763,6 +787,40 @@ bool ntt_ks_fused(const Ctx* c, u64* E, const u64* key, u64* out, int l, u32 elt
     };
     if (small) go(k_ntt_b_ks<16>);
     else go(k_ntt_b_ks<8>);
+    CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+// groups decompositions E [groups][beta][l+P][N] (pass A done) against keys[g] / elts[g]:
+// out[g] = (pi_g(addp[g]) + <pi_g(E[g]), k0_g>, <pi_g(E[g]), k1_g>)   (out: [groups][2][l+P][N], addp stride add_stride words)
+bool ntt_ks_fused_all(const Ctx* c, const u64* E, const u64* const* keys, const u32* elts, int groups, u64* out, int l,
+                      const u64* addp, size_t add_stride, int add_rows, cudaStream_t s) {
+    const int beta = c->digits(l), rows = l + c->P;
+    const size_t smem = (size_t)3 * beta * FK_CHUNK * sizeof(u64) + 64;
+    int sA, sB;
+    split(c->logn, sA, sB);
+    if (!ntt_ks_fused_applies(c, l) || groups < 1 || groups > FK_MAX_GROUPS) return false;
+    static thread_local GiantTab tab;
+    for (int g = 0; g < groups; g++) {
+        ops::encode_key_map(c, keys[g], FK_CHUNK, beta, &tab.map[g]);
+        tab.elt[g] = elts[g];
+    }
+    KsArgs a;
+    a.E = E, a.key = nullptr, a.out = out, a.addp = addp, a.add_rows = add_rows, a.add_pscale = 0, a.accumulate = 0;
+    a.beta = beta, a.l = l, a.rows = rows, a.N = c->N, a.logn = c->logn, a.L = c->L, a.K = c->K, a.elt = 0;
+    bool small = true;
+    for (u64 qq : c->q) small = small && qq < (1ull << 59);
+    const int threads = 32 * std::min(beta, FK_MAXW);
+    const size_t pw = (size_t)rows * c->N;
+    ProfScope ps(c, PROF_NTT_KS, s);
+    auto go = [&](auto kern) {
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        LAUNCH(kern, dim3(c->N / FK_CHUNK, rows, groups), threads, smem, s)(tab, a, c->modtab(), c->ntttab(), c->d_pmod, sA, c->P,
+                                                                           small && beta <= 8 ? 1 : 0, (size_t)beta * pw, 2 * pw,
+                                                                           add_stride);
+    };
+    if (small) go(k_ntt_b_ks_all<16>);
+    else go(k_ntt_b_ks_all<8>);
     CUDA_CHECK(cudaGetLastError());
     return true;
 }

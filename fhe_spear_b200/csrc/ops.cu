@@ -55,6 +55,17 @@ __global__ void k_reduce(u64* __restrict__ x, int polys, int rows, int n, RowMap
     }
 }
 
+// out[e] = (first ? first[e] : 0) + sum_k parts[k][e]  (mod q of the row): the partial results of the giant steps
+__global__ void k_sum_groups(const u64* __restrict__ parts, int nparts, size_t part_words, const u64* __restrict__ first,
+                             u64* __restrict__ out, int rows, int n, RowMap rm, ModTab mt) {
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < part_words; e += (size_t)gridDim.x * blockDim.x) {
+        const u64 q = mt.q[rm.limb((int)((e / n) % rows))];
+        u64 acc = first ? first[e] : 0;
+        for (int k = 0; k < nparts; k++) acc = add_mod(acc, parts[(size_t)k * part_words + e], q);
+        out[e] = acc;
+    }
+}
+
 // tensor product of two size-2 ciphertexts -> size 3
 __global__ void k_tensor(const u64* __restrict__ a, const u64* __restrict__ b, u64* __restrict__ out, int l, int n,
                          ModTab mt) {
@@ -652,6 +663,13 @@ void mul(const Ctx* c, const u64* a, const u64* b, u64* out, int polys, int rows
 }
 void reduce_inplace(const Ctx* c, u64* x, int polys, int rows, RowMap rm, cudaStream_t s) {
     LAUNCH(k_reduce, grid_for(c, (size_t)polys * rows * c->N), TPB, 0, s)(x, polys, rows, c->N, rm, c->modtab());
+    CUDA_CHECK(cudaGetLastError());
+}
+void sum_groups(const Ctx* c, const u64* parts, int nparts, const u64* first, u64* out, int l, cudaStream_t s) {
+    const int rows = l + c->P;
+    const size_t words = (size_t)2 * rows * c->N;
+    LAUNCH(k_sum_groups, grid_for(c, words), TPB, 0, s)(parts, nparts, words, first, out, rows, c->N, RowMap{rows, l, c->L, 0},
+                                                        c->modtab());
     CUDA_CHECK(cudaGetLastError());
 }
 void tensor(const Ctx* c, const u64* a, const u64* b, u64* out, int l, cudaStream_t s) {

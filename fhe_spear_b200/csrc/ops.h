@@ -24,6 +24,8 @@ void sub(const Ctx* c, const u64* a, const u64* b, u64* out, int polys, int rows
 void neg(const Ctx* c, const u64* a, u64* out, int polys, int rows, int n, RowMap rm, cudaStream_t s);
 void mul(const Ctx* c, const u64* a, const u64* b, u64* out, int polys, int rows, int n, RowMap rm, int b_polys, cudaStream_t s);
 void reduce_inplace(const Ctx* c, u64* x, int polys, int rows, RowMap rm, cudaStream_t s);
+// out = first (optional) + sum of nparts accumulators [2][l+P][N], mod q
+void sum_groups(const Ctx* c, const u64* parts, int nparts, const u64* first, u64* out, int l, cudaStream_t s);
 void tensor(const Ctx* c, const u64* a, const u64* b, u64* out, int l, cudaStream_t s);
 void galois(const Ctx* c, const u64* in, u64* out, int rows, u32 elt, cudaStream_t s);
 void decompose(const Ctx* c, const u64* cin, int l, u64* x, u64* E, cudaStream_t s);
