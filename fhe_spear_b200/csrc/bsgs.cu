@@ -166,12 +166,16 @@ void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, i
     const int beta = c->digits(l);
     const int k0 = (g_first == 0) ? 1 : 0;          // group 0 (if owned) needs no rotation
     const int nrot = n_groups > k0 ? n_groups - k0 : 0;
-    // all giant-step decompositions at once when the digits fit a modest slice of HBM (SPEAR_BATCH_GIANT=0: one at a time)
-    static const bool batch_env = [] {
-        const char* e = getenv("SPEAR_BATCH_GIANT");
-        return !(e && e[0] == '0');
-    }();
-    const bool batch_e = batch_env && nrot >= 2 && ntt_ks_fused_applies(c, l) && (size_t)nrot * beta * rows <= 65535 &&
+    // Giant-step launches.  A mat-vec running alone on the engine stream takes everything in single launches over all
+    // giant groups (mode 1: ModUp, first transform pass, fused pass + key product; each small launch pays ~10 us of ramp-up
+    // and tail: 11.6 -> 10.8 ms at C3).  Mat-vecs sharing the GPU on the auxiliary streams (spear_bsgs_hoisted_batch) keep
+    // one launch per group and stage (mode 0): the streams fill each other's gaps anyway (94.7 / 94.9 / 94.1 mat-vecs/s
+    // for modes 0 / 2 / 1 on one box), so they keep the small workspace (mode 1 adds 3.7 GB per stream at C3).
+    // Mode 2 = ModUp and first pass batched, product per group.  SPEAR_BATCH_GIANT / SPEAR_BATCH_GIANT_MULTI override.
+    static const int mode_single = getenv("SPEAR_BATCH_GIANT") ? atoi(getenv("SPEAR_BATCH_GIANT")) : 1;
+    static const int mode_multi = getenv("SPEAR_BATCH_GIANT_MULTI") ? atoi(getenv("SPEAR_BATCH_GIANT_MULTI")) : 0;
+    const int mode = s == c->stream ? mode_single : mode_multi;
+    const bool batch_e = mode != 0 && nrot >= 2 && ntt_ks_fused_applies(c, l) && (size_t)nrot * beta * rows <= 65535 &&
                          (size_t)nrot * beta * pw * sizeof(u64) <= ((size_t)6 << 30);
     Arena sc(c, s, l * N + beta * pw + (size_t)G * 2 * pw + (size_t)n_groups * 2 * pw + 3 * (size_t)nrot * l * N + 32 * 8 +
                        (batch_e ? (size_t)nrot * (beta + 2) * pw + 64 : 0));
@@ -212,7 +216,8 @@ void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, i
             ops::decompose_from(c, t_all, x_all, l, E_all, s, /*transform=*/false, nrot);
             ntt_pass_a_batch(c, E_all, nrot, l, s);
             u64* Rk = sc.get((size_t)nrot * 2 * pw);   // one partial result per giant group, summed below
-            if (ntt_ks_fused_all(c, E_all, gkey + k0, gelt + k0, nrot, Rk, l, A + (size_t)k0 * 2 * pw, 2 * pw, (int)rows, s)) {
+            if (mode == 1 &&
+                ntt_ks_fused_all(c, E_all, gkey + k0, gelt + k0, nrot, Rk, l, A + (size_t)k0 * 2 * pw, 2 * pw, (int)rows, s)) {
                 ops::sum_groups(c, Rk, nrot, have ? R : nullptr, R, l, s);
                 have = true;
             } else {
