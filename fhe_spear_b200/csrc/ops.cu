@@ -56,8 +56,8 @@ __global__ void k_reduce(u64* __restrict__ x, int polys, int rows, int n, RowMap
 }
 
 // out[e] = (first ? first[e] : 0) + sum_k parts[k][e]  (mod q of the row): the partial results of the giant steps
-__global__ void k_sum_groups(const u64* __restrict__ parts, int nparts, size_t part_words, const u64* __restrict__ first,
-                             u64* __restrict__ out, int rows, int n, RowMap rm, ModTab mt) {
+__global__ void k_sum_groups(const u64* __restrict__ parts, int nparts, size_t part_words, const u64* first, u64* out,
+                             int rows, int n, RowMap rm, ModTab mt) {   // first may alias out (element-wise in place)
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < part_words; e += (size_t)gridDim.x * blockDim.x) {
         const u64 q = mt.q[rm.limb((int)((e / n) % rows))];
         u64 acc = first ? first[e] : 0;
