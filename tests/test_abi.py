@@ -26,6 +26,37 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_native.EXPORTED) == names, "ctypes signature table and header disagree"
 
 
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of include/spear_b200.h has as many parameters as its ctypes signature, and integer / pointer /
+    double parameters sit in the same positions (a drifted binding would pass garbage across the C ABI)."""
+    from fhe_spear_b200 import _native
+    src = open(os.path.join(ROOT, "include", "spear_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = dict(re.findall(r"\b(spear_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src))
+    assert set(protos) == set(_native.EXPORTED)
+
+    def kind_of_c(param):
+        param = param.strip()
+        if "*" in param or "[" in param:
+            return "ptr"
+        if re.match(r"(const\s+)?double\b", param):
+            return "f64"
+        return "int"
+
+    def kind_of_ctypes(t):
+        if t in (C.c_double, C.c_float):
+            return "f64"
+        if t in (C.c_int, C.c_uint32, C.c_uint64, C.c_size_t, C.c_int64):
+            return "int"
+        return "ptr"
+    for name, params in protos.items():
+        plist = [] if params.strip() in ("", "void") else [p for p in params.split(",")]
+        argtypes = getattr(_native.lib, name).argtypes or []
+        assert len(plist) == len(argtypes), f"{name}: header has {len(plist)} parameters, ctypes {len(argtypes)}"
+        for i, (cp, ct) in enumerate(zip(plist, argtypes)):
+            assert kind_of_c(cp) == kind_of_ctypes(ct), f"{name}: parameter {i} ({cp.strip()}) bound as {ct}"
+
+
 def test_host_only_entry_points():
     from fhe_spear_b200 import pyPhantom as ph
     from oracle.oracle import Oracle
