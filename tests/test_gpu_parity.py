@@ -354,3 +354,43 @@ def test_rotation_at_large_ring_sizes(N):
     assert np.array_equal(rot.to_numpy(), s.o.apply_galois(ct.to_numpy(), elt, s.key(elt)))
     got = np.array(enc.decode_double_vector(ctx, sk.decrypt(ctx, rot)))[:57]
     assert np.abs(got - z[7:]).max() < 1e-9
+
+
+def test_reference_inference_primitives_golden_limbs():
+    """The call sequences of the reference's fhe_rwkv_inference.py (CKKSContext.encrypt :46-50, ct_pt_dot :66-76,
+    ct_pt_weighted_sum :79-94, ct_ct_square :97-101, ct_ct_multiply :104-108) through pyPhantom on the GPU must
+    reproduce the limbs recorded when the reference's own functions ran over the oracle
+    (tests/golden/inference_primitives.npz, generator tests/golden/make_golden_inference.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "inference_primitives.npz"))
+    N, dim = int(g["N"]), int(g["dim"])
+    s = Setup(N=N, bits=tuple(int(b) for b in g["bits"]), P=int(g["P"]), seed=bytes(g["seed"]))
+    ph, ctx, sk = s.gpu([1, 2, 4])
+    enc = ph.ckks_encoder(ctx)
+    pk, rlk, gk = sk.gen_publickey(ctx), sk.gen_relinkey(ctx), sk.create_galois_keys(ctx)
+    scale, slots = float(g["scale"]), enc.slot_count()
+    pad = lambda v: list(v) + [0.0] * (slots - len(v))
+    ct = pk.encrypt_asymmetric(ctx, enc.encode_double_vector(ctx, pad(g["x"]), scale), enc_id=1)
+    assert np.array_equal(ct.to_numpy(), g["ct"])
+
+    def ct_pt_dot(w):
+        prod = ph.rescale_to_next(ctx, ph.multiply_plain(ctx, ct, enc.encode_double_vector(ctx, pad(w), scale)))
+        step = 1
+        while step < dim:
+            prod = ph.add(ctx, prod, ph.rotate(ctx, prod, step, gk))
+            step *= 2
+        return prod
+    d1, d2 = ct_pt_dot(g["w1"]), ct_pt_dot(g["w2"])
+    assert np.array_equal(d1.to_numpy(), g["d1"]) and np.array_equal(d2.to_numpy(), g["d2"])
+    assert d1.chain_index() == 2
+    terms = []
+    for d, w in zip((d1, d2), g["mix"]):
+        w_pt = ph.mod_switch_to(ctx, enc.encode_double_vector(ctx, [float(w)] * slots, scale), 2)
+        terms.append(ph.rescale_to_next(ctx, ph.multiply_plain(ctx, d, w_pt)))
+    ws = ph.add(ctx, terms[0], terms[1])
+    assert np.array_equal(ws.to_numpy(), g["ws"])
+    sq = ph.rescale_to_next(ctx, ph.relinearize(ctx, ph.multiply(ctx, ws, ws), rlk))
+    pr = ph.rescale_to_next(ctx, ph.relinearize(ctx, ph.multiply(ctx, d1, d2), rlk))
+    assert np.array_equal(sq.to_numpy(), g["sq"]) and np.array_equal(pr.to_numpy(), g["pr"])
+    got = [enc.decode_double_vector(ctx, sk.decrypt(ctx, c))[0] for c in (d1, d2, ws, sq, pr)]
+    assert np.abs(np.array(got) - g["slot0"]).max() < 1e-9 and np.abs(np.array(got) - g["slot0_float64"]).max() < 1e-4

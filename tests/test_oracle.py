@@ -190,3 +190,39 @@ def test_oracle_bsgs_equals_reference_python_loop():
     sc = scale * scale / float(o.q[L0 - 1])
     assert np.array_equal(o.decode(o.decrypt(sk, g["ct_y_real"]), sc)[:D].real, g["y_real_dec"])
     assert np.abs(g["y_real_dec"] - g["W"] @ g["x"]).max() < 1e-9
+
+
+def test_inference_primitives_golden_replay():
+    """tests/golden/inference_primitives.npz was produced by the reference's own fhe_rwkv_inference.py functions
+    (CKKSContext, ct_pt_dot, ct_pt_weighted_sum, ct_ct_square, ct_ct_multiply, :29-108) running over oracle primitives
+    (tests/golden/make_golden_inference.py).  Replaying those call sequences directly on the oracle must give the
+    same limbs: pins the oracle's public-key encryption, plaintext multiply, rescale, rotate, mod-switch, tensor
+    product and relinearisation at the reference's [60] + [40]*d + [60], P = 1 parameter style."""
+    g = np.load(os.path.join(GOLD, "inference_primitives.npz"))
+    S = Setup(N=int(g["N"]), bits=tuple(int(b) for b in g["bits"]), P=int(g["P"]), seed=bytes(g["seed"]))
+    o, scale, dim, slots = S.o, float(g["scale"]), int(g["dim"]), int(g["N"]) // 2
+    pk, rlk = o.gen_public_key(S.seed, S.sk), o.gen_relin_key(S.seed, S.sk)
+    pad = lambda v: np.concatenate([np.asarray(v, dtype=np.float64), np.zeros(slots - len(v))])
+    ct = o.encrypt_asymmetric(S.seed, 1, pk, o.encode(pad(g["x"]), scale, S.L))
+    assert np.array_equal(ct, g["ct"])
+
+    def dot(w):                                   # fhe_rwkv_inference.py:66-76
+        prod = o.rescale(o.multiply_plain(ct, o.encode(pad(w), scale, S.L)))
+        step = 1
+        while step < dim:
+            elt = o.elt_from_step(step)
+            prod = o.add(prod, o.apply_galois(prod, elt, S.key(elt)))
+            step *= 2
+        return prod
+    d1, d2 = dot(g["w1"]), dot(g["w2"])
+    assert np.array_equal(d1, g["d1"]) and np.array_equal(d2, g["d2"])
+    terms = [o.rescale(o.multiply_plain(d, o.encode(np.full(slots, w), scale, S.L)[:d.shape[1]]))   # :79-94, level 2
+             for d, w in zip((d1, d2), g["mix"])]
+    ws = o.add(terms[0], terms[1])
+    assert np.array_equal(ws, g["ws"])
+    sq = o.rescale(o.relinearize(o.multiply(ws, ws), rlk))       # :97-101
+    pr = o.rescale(o.relinearize(o.multiply(d1, d2), rlk))       # :104-108
+    assert np.array_equal(sq, g["sq"]) and np.array_equal(pr, g["pr"])
+    for name, arr, sc in (("d1", d1, scale ** 2 / float(S.q[S.L - 1])), ):
+        val = o.decode(o.decrypt(S.sk, arr), sc)[0].real
+        assert abs(val - float(g["slot0_float64"][0])) < 1e-6
