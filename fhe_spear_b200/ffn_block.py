@@ -4,7 +4,9 @@ rescale, BSGS mat-vecs for the value chunks, level alignment, residual add.  Thr
 
 The mat-vecs go through the hoisted path of this build (`fhe_matmul_bsgs` without baby ciphertexts: diagonals are
 encoded at the ciphertext's level and consumed by `spear_bsgs_hoisted`), so the separately rotated baby ciphertexts
-of the reference loop are not materialised."""
+of the reference loop are not materialised.  `reference_order=True` runs the reference's own op order instead
+(separately rotated baby ciphertexts, plaintext diagonals, `bsgs_multiply_accumulate`): its output ciphertext equals
+the one the reference's function produces limb for limb (tests/golden/ffn_block.npz)."""
 import time
 
 import numpy as np
@@ -27,9 +29,16 @@ def _align(ctx, a, b):
     return a, b
 
 
-def _matvecs(ckks, cts, mats, D, G, B, shard):
+def _matvecs(ckks, cts, mats, D, G, B, shard, reference_order=False):
     """The independent mat-vecs of one phase: diagonals encoded at the ciphertexts' level, then one batched call
     (giant-step sharded over the ranks when shard = (rank, world) with world > 1)."""
+    if reference_order:   # [ref: :36-49, :67-79] baby rotations per distinct input, one reference-order mat-vec per chunk
+        outs, baby, last = [], None, None
+        for ct, M in zip(cts, mats):
+            if ct is not last:
+                baby, last = hb._compute_baby_rotations(ckks, ct, G), ct
+            outs.append(hb.fhe_matmul_bsgs(ckks, ct, M, D, G, B, baby))
+        return outs
     level = cts[0].chain_index()
     sets = [hb.pre_encode_real_diags(ckks, M, D, G, B, level, shard=shard) for M in mats]
     if shard[1] > 1:
@@ -38,7 +47,8 @@ def _matvecs(ckks, cts, mats, D, G, B, shard):
     return ph.bsgs_hoisted_batch(ckks.ctx, cts, sets, ckks.gk)
 
 
-def fully_encrypted_ffn_block(ckks, ct_x_rep, W_key, W_val, D, F, block_idx=0, split=None, shard=(0, 1), verbose=False):
+def fully_encrypted_ffn_block(ckks, ct_x_rep, W_key, W_val, D, F, block_idx=0, split=None, shard=(0, 1), verbose=False,
+                              reference_order=False):
     """Enc(x replicated) -> (Enc(x + ((x W_key)^2) W_val), levels used)  [ref: :26-118]"""
     t0 = time.perf_counter()
     G, B = split if split else hb.compute_bsgs_params(D)
@@ -51,7 +61,7 @@ def fully_encrypted_ffn_block(ckks, ct_x_rep, W_key, W_val, D, F, block_idx=0, s
         M[:hi - lo, :] = W_key[:, lo:hi].T
         mats.append(M)
     ct_sq = [ph.rescale_to_next(ckks.ctx, ph.relinearize(ckks.ctx, ph.multiply(ckks.ctx, fk, fk), ckks.rlk))
-             for fk in _matvecs(ckks, [ct_x_rep] * n_chunks, mats, D, G, B, shard)]
+             for fk in _matvecs(ckks, [ct_x_rep] * n_chunks, mats, D, G, B, shard, reference_order)]
     mats = []
     for c in range(n_chunks):                                   # FFN value: chunk partials summed homomorphically
         lo, hi = c * D, min((c + 1) * D, F)
@@ -59,7 +69,7 @@ def fully_encrypted_ffn_block(ckks, ct_x_rep, W_key, W_val, D, F, block_idx=0, s
         M[:, :hi - lo] = W_val[lo:hi, :].T
         mats.append(M)
     acc = None
-    for part in _matvecs(ckks, ct_sq, mats, D, G, B, shard):
+    for part in _matvecs(ckks, ct_sq, mats, D, G, B, shard, reference_order):
         if acc is None:
             acc = part
         else:

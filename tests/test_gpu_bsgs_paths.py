@@ -353,3 +353,28 @@ def test_many_digit_parameter_sets_match_oracle(L0, P, N):
     ye = ph.bsgs_multiply_accumulate(ctx, baby, pts, G, B, D, gk)
     assert np.array_equal(ye.to_numpy(), S.o.bsgs_exact(np.stack([c.to_numpy() for c in baby]),
                                                          np.stack([p.to_numpy()[0] for p in pts]), G, B, D, keys))
+
+
+def test_reference_ffn_block_golden_limbs():
+    """tests/golden/ffn_block.npz holds the output ciphertext of the reference's own fully_encrypted_ffn_block
+    (test_fully_enc_bsgs.py:26-118) run over oracle primitives (tests/golden/make_golden_ffn.py).  The mirror in its
+    reference-order mode on the CUDA library must reproduce it limb for limb; the default hoisted mode must decrypt to
+    the same values."""
+    import os
+    from fhe_spear_b200 import bsgs as hb
+    from fhe_spear_b200 import ffn_block as fb
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ffn_block.npz"))
+    N, L0, P, D, F = (int(g[k]) for k in ("N", "L0", "P", "D", "F"))
+    ckks = hb.CKKSBootstrapContext(poly_degree=N, L0=L0, prime_bits=59, special_mod_size=P, max_rot_dim=D, bsgs_dim=[D],
+                                   skip_bootstrap=True, seed=bytes(g["seed"]), verbose=False)
+    rep = hb._replicate_to_slots(np.asarray(g["x"], dtype=np.float64), ckks.slots)
+    ct_x = ckks.sk.encrypt_symmetric(ckks.ctx, ckks.encoder.encode_double_vector(ckks.ctx, rep, ckks.scale),
+                                     enc_id=int(g["enc_id_x"]))
+    assert np.array_equal(ct_x.to_numpy(), g["ct_x"])
+    out, used = fb.fully_encrypted_ffn_block(ckks, ct_x, g["W_key"], g["W_val"], D, F, reference_order=True)
+    assert used == int(g["levels_used"]) == 3
+    assert np.array_equal(out.to_numpy(), g["ct_out"])
+    assert out.scale() == float(g["out_scale"])
+    assert np.array_equal(ckks.decrypt_vec(out, D), g["dec"])
+    fast, used2 = fb.fully_encrypted_ffn_block(ckks, ct_x, g["W_key"], g["W_val"], D, F)      # hoisted mat-vecs
+    assert used2 == 3 and np.abs(ckks.decrypt_vec(fast, D) - g["plaintext"]).max() < 1e-6
