@@ -156,7 +156,8 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    res = cpu_matvec_rate(args.config, max(1, args.steps + args.warmup))
+    # a step = a bounded sample of the workload: 8 x (one rotation, 8 plaintext MACs, one rescale at full size), ~0.8 s
+    res = cpu_matvec_rate(args.config, 8 * max(1, args.steps + args.warmup))
     wall = time.perf_counter() - t0
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -434,7 +435,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tuned", action="store_true", help="skip the secondary hoisting-aware-split measurement")
     ap.add_argument("--tuned-weight", type=float, default=8.0, help="secondary split: G = ceil(sqrt(weight * D))")
-    ap.add_argument("--cpu-reps", type=int, default=3)
+    ap.add_argument("--cpu-reps", type=int, default=100, help="samples of the CPU baseline (~0.1 s each on 16 cores)")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--count-only", action="store_true",
                     help="print the number of kernel launches that precede the first timed region and exit "
