@@ -100,6 +100,7 @@ _SIG = {
     "spear_peer_allreduce": (C.c_int, [vp, vp, C.c_int, vp]),
     "spear_peer_window_status": (C.c_int, [vp]),
     "spear_peer_window_destroy": (None, [vp]),
+    "spear_peer_selftest": (C.c_int, [vp, vpp, C.c_int]),
     "spear_ntt_host": (C.c_int, [vp, vp, C.c_int, ip, C.c_int, C.c_int]),
 }
 

@@ -56,6 +56,28 @@ Obj* new_obj(Ctx* c, int size, int l, bool ext, int n, double scale, cudaStream_
 }
 void use(Ctx* c) { CUDA_CHECK(cudaSetDevice(c->device)); }
 
+// ChaCha20 block function on the host (same stream layout as sampler.cu / the oracle: key = seed, nonce = stream id,
+// 64-bit block counter).  Only used to derive seeds from seeds, never on a data path.
+void host_chacha_block(const u32 key[8], u64 nonce, u64 counter, u32 out[16]) {
+    auto rotl = [](u32 v, int n) { return (v << n) | (v >> (32 - n)); };
+    u32 in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};
+    for (int i = 0; i < 8; i++) in[4 + i] = key[i];
+    in[12] = (u32)counter, in[13] = (u32)(counter >> 32), in[14] = (u32)nonce, in[15] = (u32)(nonce >> 32);
+    u32 x[16];
+    memcpy(x, in, sizeof x);
+    auto quarter = [&](int a, int b, int c, int d) {
+        x[a] += x[b], x[d] = rotl(x[d] ^ x[a], 16);
+        x[c] += x[d], x[b] = rotl(x[b] ^ x[c], 12);
+        x[a] += x[b], x[d] = rotl(x[d] ^ x[a], 8);
+        x[c] += x[d], x[b] = rotl(x[b] ^ x[c], 7);
+    };
+    for (int round = 0; round < 10; round++) {
+        quarter(0, 4, 8, 12), quarter(1, 5, 9, 13), quarter(2, 6, 10, 14), quarter(3, 7, 11, 15);
+        quarter(0, 5, 10, 15), quarter(1, 6, 11, 12), quarter(2, 7, 8, 13), quarter(3, 4, 9, 14);
+    }
+    for (int i = 0; i < 16; i++) out[i] = x[i] + in[i];
+}
+
 void check_ct(const Obj* o, const char* what) {
     REQUIRE(o && o->size >= 2 && !o->ext && o->n == o->ctx->N, "%s: expected a ciphertext", what);
 }
@@ -245,7 +267,14 @@ int spear_gen_public_key(spear_context* ctx, const spear_secret_key* sk_, spear_
     const size_t KN = (size_t)c->K * c->N;
     std::unique_ptr<PublicKey> pk(new PublicKey);
     pk->bind(c);
-    memcpy(pk->seed, sk->seed, 32);
+    // The public key carries its OWN seed for the encryption randomness (u, e0, e1): the first 32 bytes of the secret
+    // seed's ChaCha stream DOM_PK_SEED.  One-way: whoever holds the public key cannot get back to the secret seed
+    // (and through it to the secret key, which is ternary(seed, DOM_SK)).
+    {
+        u32 blk[16];
+        host_chacha_block(sk->seed, stream_id(DOM_PK_SEED, 0), 0, blk);
+        memcpy(pk->seed, blk, 32);
+    }
     pk->d = c->alloc(2 * KN);
     u64* e = c->alloc(KN);
     RowMap all{c->K, c->L, c->L, 0};
@@ -929,6 +958,18 @@ static Obj* bsgs_finish(Ctx* c, Obj* R, cudaStream_t s = nullptr) {
     return o.release();
 }
 
+// Joins the auxiliary streams back into the main stream when it goes out of scope -- also when an item of a batch
+// throws: the accumulators of the earlier items are then released on the main stream only after the kernels still
+// running on the auxiliary streams are ordered before it.  Declare it AFTER the objects it protects.
+struct AuxJoin {
+    Ctx* c;
+    int used;
+    ~AuxJoin() {
+        for (int k = 0; k < used; k++)
+            if (cudaEventRecord(c->ev_aux[k], c->aux[k]) == cudaSuccess) cudaStreamWaitEvent(c->stream, c->ev_aux[k], 0);
+    }
+};
+
 int spear_bsgs_hoisted(spear_context* ctx, const spear_obj* ct_, const spear_diagset* ds_, const spear_galois_keys* gk_,
                        spear_obj** out) {
     API_BEGIN
@@ -948,23 +989,25 @@ int spear_bsgs_hoisted_batch(spear_context* ctx, spear_obj* const* cts, spear_di
     use(c);
     REQUIRE(count >= 1, "bsgs_hoisted_batch: empty batch");
     const GaloisKeys* gk = reinterpret_cast<const GaloisKeys*>(gk_);
+    for (int i = 0; i < count; i++) {   // validate everything before anything is queued
+        const DiagSet* ds = reinterpret_cast<const DiagSet*>(dss[i]);
+        REQUIRE(ds && cts[i], "bsgs_hoisted_batch: null item %d", i);
+        REQUIRE(ds->g_first == 0 && ds->g_stride == 1, "bsgs_hoisted_batch: sharded diagonal set");
+        REQUIRE(O_(cts[i])->l >= 2, "bsgs_hoisted_batch: no level left for the final rescale");
+    }
     std::vector<std::unique_ptr<Obj>> acc(count), res(count);
     // independent mat-vecs on the auxiliary streams: the HBM-bound key streams of one overlap the
     // integer-bound NTT / MAC phases of the others
     CUDA_CHECK(cudaEventRecord(c->ev_main, c->stream));
-    for (int i = 0; i < count; i++) {
-        const DiagSet* ds = reinterpret_cast<const DiagSet*>(dss[i]);
-        REQUIRE(ds->g_first == 0 && ds->g_stride == 1, "bsgs_hoisted_batch: sharded diagonal set");
-        cudaStream_t s = count == 1 ? c->stream : c->aux[i % 3];
-        if (count > 1 && i < 3) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_main, 0));
-        acc[i].reset(bsgs_partial(c, O_(cts[i]), ds, gk, s));
-        res[i].reset(bsgs_finish(c, acc[i].get(), s));
-    }
-    if (count > 1)
-        for (int k = 0; k < 3 && k < count; k++) {
-            CUDA_CHECK(cudaEventRecord(c->ev_aux[k], c->aux[k]));
-            CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_aux[k], 0));
+    {
+        AuxJoin join{c, count > 1 ? std::min(count, 3) : 0};
+        for (int i = 0; i < count; i++) {
+            cudaStream_t s = count == 1 ? c->stream : c->aux[i % 3];
+            if (count > 1 && i < 3) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_main, 0));
+            acc[i].reset(bsgs_partial(c, O_(cts[i]), reinterpret_cast<const DiagSet*>(dss[i]), gk, s));
+            res[i].reset(bsgs_finish(c, acc[i].get(), s));
         }
+    }
     for (int i = 0; i < count; i++) outs[i] = H_(res[i].release());
     API_END
 }
@@ -983,18 +1026,17 @@ int spear_bsgs_hoisted_partial_batch(spear_context* ctx, spear_obj* const* cts, 
     use(c);
     REQUIRE(count >= 1, "bsgs_hoisted_partial_batch: empty batch");
     const GaloisKeys* gk = reinterpret_cast<const GaloisKeys*>(gk_);
+    for (int i = 0; i < count; i++) REQUIRE(dss[i] && cts[i], "bsgs_hoisted_partial_batch: null item %d", i);
     std::vector<std::unique_ptr<Obj>> acc(count);
     CUDA_CHECK(cudaEventRecord(c->ev_main, c->stream));
-    for (int i = 0; i < count; i++) {
-        cudaStream_t s = count == 1 ? c->stream : c->aux[i % 3];
-        if (count > 1 && i < 3) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_main, 0));
-        acc[i].reset(bsgs_partial(c, O_(cts[i]), reinterpret_cast<const DiagSet*>(dss[i]), gk, s));
-    }
-    if (count > 1)
-        for (int k = 0; k < 3 && k < count; k++) {
-            CUDA_CHECK(cudaEventRecord(c->ev_aux[k], c->aux[k]));
-            CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_aux[k], 0));
+    {
+        AuxJoin join{c, count > 1 ? std::min(count, 3) : 0};
+        for (int i = 0; i < count; i++) {
+            cudaStream_t s = count == 1 ? c->stream : c->aux[i % 3];
+            if (count > 1 && i < 3) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_main, 0));
+            acc[i].reset(bsgs_partial(c, O_(cts[i]), reinterpret_cast<const DiagSet*>(dss[i]), gk, s));
         }
+    }
     for (int i = 0; i < count; i++) outs[i] = H_(acc[i].release());
     API_END
 }

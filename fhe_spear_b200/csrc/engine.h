@@ -174,5 +174,5 @@ void ntt_inverse(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream
 
 // ---- stream ids shared with the oracle ------------------------------------------------------
 enum { DOM_SK = 1, DOM_PK_A = 2, DOM_PK_E = 3, DOM_KSK_A = 4, DOM_KSK_E = 5,
-       DOM_ENC_A = 6, DOM_ENC_E = 7, DOM_ASYM_U = 8, DOM_ASYM_E0 = 9, DOM_ASYM_E1 = 10 };
+       DOM_ENC_A = 6, DOM_ENC_E = 7, DOM_ASYM_U = 8, DOM_ASYM_E0 = 9, DOM_ASYM_E1 = 10, DOM_PK_SEED = 11 };
 static inline u64 stream_id(int dom, u64 id) { return ((u64)dom << 56) | (id & 0x00FFFFFFFFFFFFFFull); }

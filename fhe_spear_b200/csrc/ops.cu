@@ -919,12 +919,7 @@ void pmac_hoisted(const Ctx* c, const u64* Y, const u64* diag, u64* A, int G, in
     }
     size_t smem = sizeof(u64) * (size_t)G * 2 * PM_TILE;
     REQUIRE(smem <= 227 * 1024, "too many baby steps (%d) for the shared-memory tile", G);
-    static bool attr_set = false;
-
-    if (!attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(k_pmac_hoisted, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    CUDA_CHECK(cudaFuncSetAttribute(k_pmac_hoisted, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per device
     LAUNCH(k_pmac_hoisted, dim3(c->N / PM_TILE, rows), PM_TILE, smem, s)(Y, diag, A, G, B, D, l, rows, c->N, c->L, rshift,
                                                                      c->modtab());
     CUDA_CHECK(cudaGetLastError());

@@ -104,7 +104,9 @@ __global__ void k_peer_sync(PeerPtrs pp, int world, int me, int slot, int kind, 
 // slice [lo, hi) (in pairs of words) of the accumulator: sum over the R windows, mod q, written back to every window
 template <int R>
 __global__ void __launch_bounds__(256) k_peer_reduce(PeerPtrs pp, size_t data_off, size_t lo, size_t hi, int rows,
-                                                     int logn, RowMap rm, ModTab mt, int me, int slot, u64 epoch) {
+                                                     int logn, RowMap rm, ModTab mt, int me, int slot, u64 epoch,
+                                                     const int* status) {
+    if (*(volatile const int*)status) return;   // a peer never arrived: its window holds stale data, touch nothing
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t v = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < hi; v += stride) {
         const size_t e = data_off + 2 * v;
@@ -133,6 +135,14 @@ __global__ void __launch_bounds__(256) k_peer_reduce(PeerPtrs pp, size_t data_of
             for (int r = 0; r < R; r++) st_release_sys(pp.w[r] + flag_index(slot, 1, me), epoch);
         }
     }
+}
+
+// window -> accumulator, or -- when a wait timed out -- an accumulator of all-ones words (no valid residue: q < 2^61),
+// so that a failed exchange can never pass for a ciphertext downstream
+__global__ void k_peer_collect(const u64* __restrict__ win, u64* __restrict__ acc, size_t words, const int* status) {
+    const bool failed = *(volatile const int*)status != 0;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < words; e += (size_t)gridDim.x * blockDim.x)
+        acc[e] = failed ? ~0ull : win[e];
 }
 
 inline PeerWindow* W_(spear_peer_window* w) { return reinterpret_cast<PeerWindow*>(w); }
@@ -230,7 +240,8 @@ int spear_peer_allreduce(spear_context* ctx, spear_peer_window* win, int slot, s
     const int grid = (int)std::max<size_t>(1, std::min<size_t>((hi - lo + 255) / 256, (size_t)c->sm_count * 8));
     const RowMap rm{acc->rows(), acc->l, c->L, 0};
     auto go = [&](auto kern) {
-        LAUNCH(kern, grid, 256, 0, s)(pp, data_off, lo, hi, acc->rows(), c->logn, rm, c->modtab(), w->rank, slot, epoch);
+        LAUNCH(kern, grid, 256, 0, s)(pp, data_off, lo, hi, acc->rows(), c->logn, rm, c->modtab(), w->rank, slot, epoch,
+                                      w->d_status);
     };
     switch (w->world) {
         case 2: go(k_peer_reduce<2>); break;
@@ -242,7 +253,61 @@ int spear_peer_allreduce(spear_context* ctx, spear_peer_window* win, int slot, s
         default: go(k_peer_reduce<8>); break;
     }
     LAUNCH(k_peer_sync, 1, 32, 0, s)(pp, w->world, w->rank, slot, 1, 0, epoch, w->d_status);
-    CUDA_CHECK(cudaMemcpyAsync(acc->d, w->base + data_off, bytes, cudaMemcpyDeviceToDevice, s));
+    LAUNCH(k_peer_collect, (int)std::min<size_t>((acc->words() + 255) / 256, (size_t)c->sm_count * 8), 256, 0, s)(
+        w->base + data_off, acc->d, acc->words(), w->d_status);
+    CUDA_CHECK(cudaGetLastError());
+    PEER_END
+}
+
+// Test hook (one GPU, one process): the reduce kernels of all `world` ranks run one after the other over `world`
+// local windows holding accs[0..world), without the epoch waits -- kernels that wait on one another must not share a
+// GPU as separate launches.  Every accs[r] ends as the sum of all of them mod q, exactly as after a real exchange.
+int spear_peer_selftest(spear_context* ctx, spear_obj* const* accs_, int world) {
+    PEER_BEGIN
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    REQUIRE(world >= 2 && world <= MAX_PEERS, "peer selftest: 2..%d ranks", MAX_PEERS);
+    CUDA_CHECK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    Obj* const* accs = reinterpret_cast<Obj* const*>(accs_);
+    const size_t words = accs[0]->words();
+    for (int r = 0; r < world; r++)
+        REQUIRE(accs[r] && accs[r]->words() == words && accs[r]->n == c->N && words % 2 == 0, "peer selftest: bad operand");
+    PeerPtrs pp;
+    u64* win[MAX_PEERS] = {};
+    int* d_status = (int*)c->alloc(8, s);
+    CUDA_CHECK(cudaMemsetAsync(d_status, 0, 8, s));
+    for (int r = 0; r < world; r++) {
+        win[r] = c->alloc(DATA_OFFSET_WORDS + words, s);
+        CUDA_CHECK(cudaMemsetAsync(win[r], 0, DATA_OFFSET_WORDS * sizeof(u64), s));
+        CUDA_CHECK(cudaMemcpyAsync(win[r] + DATA_OFFSET_WORDS, accs[r]->d, words * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+    }
+    for (int r = 0; r < MAX_PEERS; r++) pp.w[r] = win[r < world ? r : 0];
+    const Obj* a0 = accs[0];
+    const RowMap rm{a0->rows(), a0->l, c->L, 0};
+    const size_t pairs = words / 2, per = (pairs + world - 1) / world;
+    for (int me = 0; me < world; me++) {
+        const size_t lo = std::min(pairs, per * me), hi = std::min(pairs, lo + per);
+        const int grid = (int)std::max<size_t>(1, std::min<size_t>((hi - lo + 255) / 256, (size_t)c->sm_count * 8));
+        auto go = [&](auto kern) {
+            LAUNCH(kern, grid, 256, 0, s)(pp, (size_t)DATA_OFFSET_WORDS, lo, hi, a0->rows(), c->logn, rm, c->modtab(), me, 0,
+                                          (u64)1, d_status);
+        };
+        switch (world) {
+            case 2: go(k_peer_reduce<2>); break;
+            case 3: go(k_peer_reduce<3>); break;
+            case 4: go(k_peer_reduce<4>); break;
+            case 5: go(k_peer_reduce<5>); break;
+            case 6: go(k_peer_reduce<6>); break;
+            case 7: go(k_peer_reduce<7>); break;
+            default: go(k_peer_reduce<8>); break;
+        }
+    }
+    for (int r = 0; r < world; r++) {
+        LAUNCH(k_peer_collect, (int)std::min<size_t>((words + 255) / 256, (size_t)c->sm_count * 8), 256, 0, s)(
+            win[r] + DATA_OFFSET_WORDS, accs[r]->d, words, d_status);
+        c->free(win[r], s);
+    }
+    c->free(d_status, s);
     CUDA_CHECK(cudaGetLastError());
     PEER_END
 }

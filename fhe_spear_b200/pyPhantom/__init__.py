@@ -328,7 +328,13 @@ class public_key:
 class secret_key:
     def __init__(self, ctx, seed=None):
         if seed is None:
+            # SPEAR_SEED is for reproducible TESTS only: a fixed seed with the per-process counter below restarting at 0
+            # reuses (seed, nonce) pairs across runs, which breaks semantic security.  Production keys use os.urandom.
             env = os.environ.get("SPEAR_SEED")
+            if env:
+                import warnings
+                warnings.warn("SPEAR_SEED fixes the secret seed: encryption randomness repeats across runs (tests only)",
+                              RuntimeWarning, stacklevel=2)
             seed = bytes.fromhex(env).ljust(32, b"\0")[:32] if env else os.urandom(32)
         if isinstance(seed, int):
             seed = seed.to_bytes(32, "little")
@@ -364,9 +370,16 @@ class secret_key:
         arr = (C.c_uint32 * len(elts))(*elts)
         _check(_lib.spear_galois_keys_add(ctx._h, self._h, gk._h, arr, len(elts)))
 
+    def reserve_enc_ids(self, count=1):
+        """`count` fresh encryption ids from the key's ONE monotonic counter (the nonce of the randomness streams of
+        encrypt_symmetric).  Callers that pass enc_id explicitly -- e.g. the ranks of a sharded block, which must all
+        form the same ciphertext -- draw their ids here, so no id is ever handed out twice under one key."""
+        base, self._enc = self._enc, self._enc + int(count)
+        return base
+
     def encrypt_symmetric(self, ctx, pt, enc_id=None):
         if enc_id is None:
-            enc_id, self._enc = self._enc, self._enc + 1
+            enc_id = self.reserve_enc_ids(1)
         return _new(ciphertext, ctx, _lib.spear_encrypt_symmetric, self._h, pt._h, int(enc_id))
 
     def decrypt(self, ctx, ct):
@@ -749,6 +762,12 @@ class peer_window:
         h, self._h = getattr(self, "_h", None), None
         if h:
             _lib.spear_peer_window_destroy(h)
+
+
+def peer_selftest(ctx, accs):
+    """One-GPU emulation of the peer exchange over len(accs) ranks (test hook): every acc becomes the sum mod q."""
+    arr = (C.c_void_p * len(accs))(*[a._h for a in accs])
+    _check(_lib.spear_peer_selftest(ctx._h, arr, len(accs)))
 
 
 def bsgs_hoisted(ctx, ct, diags, gk):

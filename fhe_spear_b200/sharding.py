@@ -70,16 +70,33 @@ class PeerExchange:
     _cache = {}
 
     def __init__(self, ctx, group=None, slots=3):
+        """Every rank runs the SAME collective sequence whether or not a local step fails (handle all-gather, outcome
+        all-gather after mapping), so a failure on one rank degrades the whole group to the NCCL path instead of
+        leaving the others in a mismatched collective.  `self.ok` is the agreed outcome."""
         import torch.distributed as dist
         from . import pyPhantom as ph
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.slots, self.window, err = slots, None, None
         slot_bytes = 2 * (ctx.L + ctx.P) * ctx.N * 8            # an accumulator at the top level
-        self.window = ph.peer_window(ctx, self.rank, self.world, slot_bytes, slots)
+        try:
+            self.window = ph.peer_window(ctx, self.rank, self.world, slot_bytes, slots)
+        except RuntimeError as e:
+            err = e
         handles = [None] * self.world
-        dist.all_gather_object(handles, self.window.handle, group=group)
-        self.window.connect(handles)
-        dist.barrier(group=group)                               # every window is mapped before anyone posts to it
-        self.slots = slots
+        dist.all_gather_object(handles, self.window.handle if self.window is not None else None, group=group)
+        if err is None and all(h is not None for h in handles):
+            try:
+                self.window.connect(handles)
+            except RuntimeError as e:
+                err = e
+        elif err is None:
+            err = RuntimeError("a peer could not create its window")
+        flags = [None] * self.world
+        dist.all_gather_object(flags, err is None, group=group)   # doubles as the barrier: every window is mapped before anyone posts
+        self.ok = all(flags)
+        if not self.ok:
+            print(f"[spear] peer windows unavailable on rank {dist.get_rank()}: {err or 'a peer failed'}; using the NCCL all-reduce")
+            self.window = None
 
     @classmethod
     def get(cls, ctx, group=None):
@@ -92,18 +109,21 @@ class PeerExchange:
         key = (id(ctx), id(group) if group is not None else 0)
         hit = cls._cache.get(key)
         if hit is None or hit[0]() is not ctx:   # ids are recycled: the entry must belong to this very context
-            try:
-                ok, ex = 1, cls(ctx, group)
-            except RuntimeError as e:   # every rank must take the same path: agree on the outcome below
-                ok, ex = 0, None
-                print(f"[spear] peer windows unavailable on rank {dist.get_rank()}: {e}; using the NCCL all-reduce")
-            flags = [None] * dist.get_world_size(group)
-            dist.all_gather_object(flags, ok, group=group)
-            hit = cls._cache[key] = (weakref.ref(ctx), ex if all(flags) else None)
+            ex = cls(ctx, group)
+            hit = cls._cache[key] = (weakref.ref(ctx), ex if ex.ok else None)
         return hit[1]
 
     def allreduce(self, acc, slot=0):
         self.window.allreduce(acc, slot % self.slots)
+
+    def check(self, ctx):
+        """Raise if a peer never arrived.  The exchange is asynchronous, so the status word is only meaningful after a
+        synchronisation: called by sharded_matvec* before a result leaves (the decrypt that follows synchronises anyway)."""
+        ctx.synchronize()
+        st = self.window.status()
+        if st != 0:
+            raise RuntimeError(f"peer exchange failed: rank {st - 1} of the group never arrived (CUDA peer window timed out); "
+                               "the accumulator was poisoned")
 
 
 def sharded_matvec(ckks, ct, shard_set, group=None):
@@ -126,7 +146,10 @@ def sharded_matvec(ckks, ct, shard_set, group=None):
         allreduce_residues(t, group)
         torch.cuda.synchronize(ctx.device)
         ph.reduce_inplace(ctx, acc)
-    return ph.bsgs_finish(ctx, acc)
+    out = ph.bsgs_finish(ctx, acc)
+    if ex is not None:
+        ex.check(ctx)
+    return out
 
 
 def sharded_matvec_batch(ckks, cts, shard_sets, group=None):
@@ -154,7 +177,10 @@ def sharded_matvec_batch(ckks, cts, shard_sets, group=None):
         torch.cuda.synchronize(ctx.device)
         for acc in accs:
             ph.reduce_inplace(ctx, acc)
-    return [ph.bsgs_finish(ctx, acc) for acc in accs]
+    outs = [ph.bsgs_finish(ctx, acc) for acc in accs]
+    if ex is not None:
+        ex.check(ctx)
+    return outs
 
 
 class ShardedMatvec:
@@ -228,7 +254,6 @@ class HybridBlock:
         self.ckks, self.D, self.F, self.rank, self.world = ckks, D, F, rank, world
         self.plan = self.plans(world, D, F)
         self.pairs = hb._chunk_pairs(F, D)
-        self.seq = 1 << 20                                   # encryption counter shared by all ranks
         level = ckks.encrypt_replicated(np.zeros(1)).chain_index()
         # one process group per distinct rank group (every rank creates all of them, in the same order)
         self.pg = {}
@@ -251,20 +276,29 @@ class HybridBlock:
                     enc = hb.pre_encode_real_diags if m[0] == "real" else hb.pre_encode_complex_diags
                     self.sets[(phase, j)] = enc(ckks, *m[1:], D, G, B, level, shard=(ranks.index(rank), len(ranks)))
 
+    def _encrypt_inputs(self, inputs, js, base):
+        """Enc(inputs[j] replicated) with encryption id base + j for j in js: identical on every rank of the group"""
+        ckks, D = self.ckks, self.D
+        cts = []
+        for j in js:
+            rep = np.asarray(inputs[j], dtype=np.complex128)
+            rep = np.concatenate([np.tile(rep, ckks.slots // D), rep[:ckks.slots % D]])
+            cts.append(ckks.sk.encrypt_symmetric(ckks.ctx, ckks.encoder.encode_complex_vector(ckks.ctx, rep, ckks.scale),
+                                                 enc_id=base + j))
+        return cts
+
     def _serve(self, phase, inputs):
         """inputs: k complex (or real) vectors of length D -> k complex result vectors, identical on every rank"""
         import torch
         import torch.distributed as dist
         ckks, D, plan = self.ckks, self.D, self.plan[phase]
-        base, self.seq = self.seq, self.seq + plan.k
+        # Encryption ids come from the secret key's one monotonic counter: every rank runs the same client code in the
+        # same order, so all ranks reserve the same range (the ranks of a group form identical ciphertexts) and no
+        # (seed, nonce) pair is ever used twice -- neither across blocks, tokens, nor against plain encrypt calls.
+        base = ckks.sk.reserve_enc_ids(plan.k)
         res = np.zeros((plan.k, D), dtype=np.complex128)
         for ranks, js in plan.mine(self.rank):
-            cts = []
-            for j in js:
-                rep = np.asarray(inputs[j], dtype=np.complex128)
-                rep = np.concatenate([np.tile(rep, ckks.slots // D), rep[:ckks.slots % D]])
-                cts.append(ckks.sk.encrypt_symmetric(ckks.ctx, ckks.encoder.encode_complex_vector(ckks.ctx, rep, ckks.scale),
-                                                     enc_id=base + j))   # identical ciphertext on every rank of the group
+            cts = self._encrypt_inputs(inputs, js, base)
             outs = sharded_matvec_batch(ckks, cts, [self.sets[(phase, j)] for j in js], group=self.pg.get(ranks))
             for j, ct_y in zip(js, outs):
                 res[j] = ckks.decrypt_vec_complex(ct_y, D)

@@ -205,7 +205,9 @@ void* spear_obj_device_ptr(spear_obj* o);                                     /*
  * replaces acc (size 2, basis Q_l*P, same shape on every rank) by the sum over ranks mod q, in place, with one fused
  * reduce-scatter + Barrett + all-gather kernel over NVLink, ordered on the context's stream (no host sync).
  * Every rank of the group must call it with the same slot in the same order.  A peer that does not arrive within
- * 20 s raises the window status (non-zero) instead of hanging; later calls on the window then fail. */
+ * 20 s raises the window status (non-zero) instead of hanging: the reduce step is skipped, acc is filled with all-ones
+ * words (no valid residue), and later calls on the window fail.  Check spear_peer_window_status after the next
+ * synchronisation (fhe_spear_b200.sharding does, before it hands a result out). */
 typedef struct spear_peer_window spear_peer_window;
 #define SPEAR_IPC_HANDLE_BYTES 64
 int spear_peer_window_create(spear_context* ctx, int rank, int world, uint64_t slot_bytes, int slots,
@@ -213,6 +215,10 @@ int spear_peer_window_create(spear_context* ctx, int rank, int world, uint64_t s
 int spear_peer_window_connect(spear_context* ctx, spear_peer_window* w, const uint8_t* handles /* [world][64] */);
 int spear_peer_allreduce(spear_context* ctx, spear_peer_window* w, int slot, spear_obj* acc);
 int spear_peer_window_status(const spear_peer_window* w);   /* 0 = healthy; 1 + r = peer r timed out */
+/* Test hook for one-GPU boxes: runs the reduce kernels of all `world` ranks one after the other over local windows
+ * holding accs[0..world) (no epoch waits: kernels that wait on one another must not share a GPU); afterwards every
+ * accs[r] holds the sum of all of them mod q, as after a real exchange. */
+int spear_peer_selftest(spear_context* ctx, spear_obj* const* accs, int world);
 void spear_peer_window_destroy(spear_peer_window* w);
 
 /* ---- raw transforms (tests / profiling) ------------------------------------------------------------- */

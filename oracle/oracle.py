@@ -161,6 +161,12 @@ class Oracle:
         self.lib.orc_gen_public_key(self.ctx, _p(self.seed_words(seed), u32p), _p(sk), _p(pk))
         return pk
 
+    def public_key_seed(self, seed):
+        """Seed carried by the public key of secret seed `seed` (the `seed` argument of encrypt_asymmetric)."""
+        out = np.empty(8, dtype=np.uint32)
+        self.lib.orc_public_key_seed(_p(self.seed_words(seed), u32p), _p(out, u32p))
+        return out.tobytes()
+
     # ---- encryption -------------------------------------------------
     def encrypt_symmetric(self, seed, enc_id, sk, pt):
         pt = _u64(pt)
@@ -171,6 +177,7 @@ class Oracle:
         return ct
 
     def encrypt_asymmetric(self, seed, enc_id, pk, pt):
+        """`seed` is the public key's own seed (public_key_seed of the secret seed), not the secret seed."""
         pt = _u64(pt)
         l = pt.shape[0]
         ct = np.empty((2, l, self.N), dtype=np.uint64)

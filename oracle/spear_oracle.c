@@ -245,8 +245,14 @@ void orc_prng_words(const u32 *key, u64 nonce, u64 first, u64 count, u64 *out) {
 
 /* stream ids: (domain << 56) | id  -- shared verbatim with the CUDA library */
 enum { DOM_SK = 1, DOM_PK_A = 2, DOM_PK_E = 3, DOM_KSK_A = 4, DOM_KSK_E = 5,
-       DOM_ENC_A = 6, DOM_ENC_E = 7, DOM_ASYM_U = 8, DOM_ASYM_E0 = 9, DOM_ASYM_E1 = 10 };
+       DOM_ENC_A = 6, DOM_ENC_E = 7, DOM_ASYM_U = 8, DOM_ASYM_E0 = 9, DOM_ASYM_E1 = 10, DOM_PK_SEED = 11 };
 static inline u64 stream_id(int dom, u64 id) { return ((u64)dom << 56) | (id & 0x00FFFFFFFFFFFFFFull); }
+/* the seed a public key carries for its encryption randomness: the first 32 bytes of the secret seed's stream
+ * DOM_PK_SEED (one-way, so the public key does not reveal the secret seed) */
+void orc_public_key_seed(const u32 *seed, u32 out[8]) {
+    u64 blk[8]; chacha_block(seed, stream_id(DOM_PK_SEED, 0), 0, blk);
+    memcpy(out, blk, 32);
+}
 
 /* uniform residue for (limb id, coefficient j): words 2*(limb*N+j), +1 -> 128 bit mod q */
 static void sample_uniform_row(const orc_ctx *c, const u32 *key, u64 nonce, int limb, u64 *out) {
@@ -271,6 +277,7 @@ static inline int sample_cbd(const u32 *key, u64 nonce, u64 j) {
 }
 static void small_poly_rows(const orc_ctx *c, const int *vals, int l, int ext, u64 *out /*[rows][N]*/) {
     int rows = l + (ext ? c->P : 0);
+    #pragma omp parallel for schedule(static)
     for (int r = 0; r < rows; r++) {
         int limb = row_limb(c, l, r); u64 q = c->q[limb];
         u64 *o = out + (u64)r * c->N;
@@ -493,6 +500,7 @@ void orc_gen_switch_key(const orc_ctx *c, const u32 *seed, u64 tag, const u64 *s
         for (u64 n = 0; n < N; n++) ev[n] = sample_cbd(seed, ne, n);
         small_poly_rows(c, ev, c->L, 1, e);
         u64 *k0 = key + ((u64)j * 2 + 0) * K * N, *k1 = key + ((u64)j * 2 + 1) * K * N;
+        #pragma omp parallel for schedule(static)
         for (int i = 0; i < K; i++) {
             u64 q = c->q[i];
             sample_uniform_row(c, seed, na, i, k1 + (u64)i * N);

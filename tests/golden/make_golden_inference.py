@@ -80,7 +80,7 @@ def shim():
 
         def encrypt_asymmetric(self, ctx, pt):
             ST.enc_counter += 1
-            return Obj(ST.o.encrypt_asymmetric(SEED, ST.enc_counter, self.pk, pt.a[0]), pt._scale)
+            return Obj(ST.o.encrypt_asymmetric(ST.o.public_key_seed(SEED), ST.enc_counter, self.pk, pt.a[0]), pt._scale)
 
     class secret_key:
         def __init__(self, ctx):

@@ -265,6 +265,48 @@ def test_client_aided_rwkv_block_matches_plaintext_block():
         assert np.corrcoef(xf, xp)[0, 1] > 0.999999
 
 
+def test_hybrid_block_single_rank_and_encryption_ids():
+    """sharding.HybridBlock (the multi-GPU server of a block, here with one rank): same block output as
+    plaintext_block through client_aided_block, and -- ADVICE round 1 -- encryption ids come from the secret key's
+    one monotonic counter: two HybridBlocks on one context never reuse a (seed, nonce) pair, so no two of their
+    ciphertexts share the c1 polynomial (equal c1 would leak m_i - m_j)."""
+    from fhe_spear_b200 import bsgs as hb
+    from fhe_spear_b200.rwkv_block import RWKVBlockWeights, client_aided_block, plaintext_block
+    from fhe_spear_b200.sharding import HybridBlock, PhasePlan
+    D, F, H, S = 16, 64, 2, 8
+    ckks = hb.CKKSBootstrapContext(poly_degree=2048, L0=3, prime_bits=59, special_mod_size=1, max_rot_dim=1,
+                                   bsgs_dim=[D], skip_bootstrap=True, seed=SEED, verbose=False,
+                                   baby_weights=HybridBlock.required_weights(1, D, F))
+    blocks = [RWKVBlockWeights.random(D, F, H, S, block_idx=i, seed=30 + i) for i in range(2)]
+    servers = [HybridBlock(ckks, b, D, F) for b in blocks]
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal(D)
+    xf, xp = x.copy(), x.copy()
+    st_f = st_p = np.zeros((H, S, S))
+    pa_f = pa_p = pf_f = pf_p = np.zeros(D)
+    vf_f = vf_p = None
+    for blk, srv in zip(blocks, servers):
+        xf, pa_f, pf_f, st_f, vf_f, tm = client_aided_block(ckks, blk, xf, pa_f, pf_f, st_f, vf_f, preencoded_block=srv)
+        xp, pa_p, pf_p, st_p, vf_p = plaintext_block(blk, xp, pa_p, pf_p, st_p, vf_p)
+        assert np.abs(xf - xp).max() < 1e-7 and np.abs(st_f - st_p).max() < 1e-7
+    # the same phase of two blocks (two layers of a model) and a plain encrypt call in between: all c1 differ
+    ins = [rng.standard_normal(D) for _ in range(3)]
+    c1s = []
+    for srv in servers:
+        base = ckks.sk.reserve_enc_ids(3)
+        c1s += [ct.to_numpy()[1] for ct in srv._encrypt_inputs(ins, [0, 1, 2], base)]
+        c1s.append(ckks.encrypt_replicated(ins[0]).to_numpy()[1])
+    for i in range(len(c1s)):
+        for j in range(i + 1, len(c1s)):
+            assert not np.array_equal(c1s[i], c1s[j]), (i, j)
+    # plans: every mat-vec of a phase has exactly one leader, every rank carries work
+    for world in (2, 4, 8):
+        for k in (1, 2, 3):
+            plan = PhasePlan(k, world)
+            assert sorted(j for j, _ in plan.assign) == list(range(k))
+            assert all(plan.mine(r) for r in range(world))
+
+
 def test_retrieval_wrapper_flow():
     """The call sequence of the reference's PhantomFHE retrieval wrapper (fhe_common.py:83-194; BASELINE config 1
     uses the same primitives): N=8192, primes [60, 40, 40, 60], P=1, asymmetric encryption, complex-packed

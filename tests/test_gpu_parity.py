@@ -126,7 +126,7 @@ def test_encrypt_decrypt_match_oracle(S, G_):
     # asymmetric
     pk = sk.gen_publickey(ctx)
     ca = pk.encrypt_asymmetric(ctx, pt, enc_id=5)
-    assert np.array_equal(ca.to_numpy(), S.o.encrypt_asymmetric(SEED, 5, S.o.gen_public_key(SEED, S.sk), pt_o))
+    assert np.array_equal(ca.to_numpy(), S.o.encrypt_asymmetric(S.o.public_key_seed(SEED), 5, S.o.gen_public_key(SEED, S.sk), pt_o))
     assert np.abs(np.array(enc.decode_double_vector(ctx, sk.decrypt(ctx, ca))) - z).max() < 1e-9
 
 

@@ -1,8 +1,11 @@
-"""The fused NVLink peer-memory exchange of shard accumulators (csrc/peer.cu), driven the way
-fhe_spear_b200.sharding drives it: one process per rank, windows mapped through CUDA IPC, handles swapped over
-torch.distributed (gloo here: host plumbing only).  On a one-GPU box both ranks share cuda:0 -- IPC mapping, the
-epoch flags and the reduce kernel are the same code that runs across NVLink; `tools/sharded_latency.py` is the
-multi-GPU run of it."""
+"""The fused NVLink peer-memory exchange of shard accumulators (csrc/peer.cu).
+
+  * one GPU: `ph.peer_selftest` runs the reduce kernels of all ranks one after the other over local windows (no epoch
+    waits -- kernels that wait on one another must not share a GPU as separate launches, B200_PROFILING.md) and the
+    result is compared with plain integer arithmetic for every group size 2..8, and with the unsharded mat-vec;
+  * two or more GPUs (`gpurun --gpus 2`): the real thing, driven the way fhe_spear_b200.sharding drives it -- one
+    process per GPU, windows mapped through CUDA IPC, handles swapped over torch.distributed (gloo: host plumbing
+    only), epoch flags across NVLink."""
 import os
 import socket
 
@@ -18,7 +21,7 @@ pytestmark = pytest.mark.gpu
 
 def _worker(rank, world, port, D, out):
     try:
-        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SPEAR_DEVICE="0")
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SPEAR_DEVICE=str(rank))   # one GPU per rank
         os.environ.pop("LOCAL_RANK", None)
         dist.init_process_group("gloo", rank=rank, world_size=world)
         from fhe_spear_b200 import sharding as sh
@@ -64,6 +67,53 @@ def _worker(rank, world, port, D, out):
         raise
 
 
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 5, 6, 7, 8])
+def test_peer_reduce_kernels_emulated_on_one_gpu(world):
+    """every rank's slice of the fused reduce-scatter + Barrett + all-gather, for every group size"""
+    S = Setup(N=2048, bits=(59,) * 5, P=2)
+    ph, ctx, sk = S.gpu([1])
+    rng = np.random.default_rng(world)
+    q = np.array([int(v) for v in S.q], dtype=object)
+    raws = [np.stack([np.stack([rng.integers(0, int(S.q[i]), S.N, dtype=np.uint64) for i in range(S.L + S.P)])
+                      for _ in range(2)]) for _ in range(world)]
+    accs = [ph.ciphertext.from_numpy(ctx, r, 1.0, ext=True) for r in raws]
+    ph.peer_selftest(ctx, accs)
+    exp = (sum(r.astype(object) for r in raws) % q[None, :, None]).astype(np.uint64)
+    for a in accs:
+        assert np.array_equal(a.to_numpy(), exp)
+
+
+@pytest.mark.parametrize("D,world", [(64, 2), (20, 3), (64, 8)])
+def test_emulated_exchange_of_shard_accumulators_matches_unsharded(D, world):
+    """shard accumulators of all ranks (computed one after the other on this GPU) -> emulated exchange -> finish
+    == the unsharded hoisted mat-vec, bit for bit"""
+    S = Setup(N=2048, bits=(59,) * 6, P=2)
+    G, B = bsgs_params(D)
+    steps = list(range(1, G)) + [g * G for g in range(1, B)]
+    ph, ctx, sk = S.gpu(steps)
+    gk = sk.create_galois_keys(ctx)
+    enc = ph.ckks_encoder(ctx)
+    rng = np.random.default_rng(D)
+    W, x = rng.standard_normal((D, D)) * 0.1, rng.standard_normal(D)
+    rolled = rolled_diagonals(W, D, G, B)
+    ct = sk.encrypt_symmetric(ctx, enc.encode_double_vector(ctx, tile(x, S.N // 2), S.scale), enc_id=3)
+    ref = ph.bsgs_hoisted(ctx, ct, ph.diagonal_set(ctx, rolled, G, B, S.scale), gk).to_numpy()
+    accs = [ph.bsgs_hoisted_partial(ctx, ct, ph.diagonal_set(ctx, rolled, G, B, S.scale, shard=(r, world)), gk)
+            for r in range(world)]
+    ph.peer_selftest(ctx, accs)
+    for a in accs:
+        assert np.array_equal(ph.bsgs_finish(ctx, a).to_numpy(), ref)
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs (kernels that wait on one another must not share one)")
 @pytest.mark.parametrize("D", [64, 20])
 def test_two_process_peer_exchange_matches_unsharded(D):
     with socket.socket() as s:

@@ -85,7 +85,7 @@ def test_encrypt_rotate_multiply_decrypt(S):
     sq = o.rescale(o.relinearize(o.multiply(ct, ct), rlk))
     assert np.abs(o.decode(o.decrypt(S.sk, sq), S.scale ** 2 / float(S.q[S.L - 1])) - z * z).max() < 1e-9
     pk = o.gen_public_key(SEED, S.sk)
-    ca = o.encrypt_asymmetric(SEED, 3, pk, pt)
+    ca = o.encrypt_asymmetric(o.public_key_seed(SEED), 3, pk, pt)
     assert np.abs(o.decode(o.decrypt(S.sk, ca), S.scale) - z).max() < 1e-9
 
 
@@ -203,7 +203,7 @@ def test_inference_primitives_golden_replay():
     o, scale, dim, slots = S.o, float(g["scale"]), int(g["dim"]), int(g["N"]) // 2
     pk, rlk = o.gen_public_key(S.seed, S.sk), o.gen_relin_key(S.seed, S.sk)
     pad = lambda v: np.concatenate([np.asarray(v, dtype=np.float64), np.zeros(slots - len(v))])
-    ct = o.encrypt_asymmetric(S.seed, 1, pk, o.encode(pad(g["x"]), scale, S.L))
+    ct = o.encrypt_asymmetric(o.public_key_seed(S.seed), 1, pk, o.encode(pad(g["x"]), scale, S.L))
     assert np.array_equal(ct, g["ct"])
 
     def dot(w):                                   # fhe_rwkv_inference.py:66-76
