@@ -51,8 +51,6 @@ void keyswitch(const Ctx* c, const u64* cin, int l, const u64* key, const u64* a
     u64* E = sc.get(c->digits(l) * rows * N);
     u64* acc = sc.get(2 * rows * N);
     u64* tmp = sc.get(2 * l * N);
-    CUDA_CHECK(cudaMemcpyAsync(x, cin, sizeof(u64) * l * N, cudaMemcpyDeviceToDevice, s));
-    ntt_inverse(c, x, l, RowMap{l, l, c->L, 0}, (int)N, s);
     ops::decompose_ks(c, cin, x, l, E, key, acc, 0, nullptr, 0, 0, 0, s);
     ops::moddown(c, acc, rows * N, 2, l, tmp, nullptr, out, s);
     if (add0) ops::add(c, out, add0, out, 1, l, (int)N, RowMap{l, l, c->L, 0}, 1, s);
@@ -173,7 +171,7 @@ void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, i
     // for modes 0 / 2 / 1 on one box), so they keep the small workspace (mode 1 adds 3.7 GB per stream at C3).
     // Mode 2 = ModUp and first pass batched, product per group.  SPEAR_BATCH_GIANT / SPEAR_BATCH_GIANT_MULTI override.
     static const int mode_single = getenv("SPEAR_BATCH_GIANT") ? atoi(getenv("SPEAR_BATCH_GIANT")) : 1;
-    static const int mode_multi = getenv("SPEAR_BATCH_GIANT_MULTI") ? atoi(getenv("SPEAR_BATCH_GIANT_MULTI")) : 0;
+    static const int mode_multi = getenv("SPEAR_BATCH_GIANT_MULTI") ? atoi(getenv("SPEAR_BATCH_GIANT_MULTI")) : 1;
     const int mode = s == c->stream ? mode_single : mode_multi;
     const bool batch_e = mode != 0 && nrot >= 2 && ntt_ks_fused_applies(c, l) && (size_t)nrot * beta * rows <= 65535 &&
                          (size_t)nrot * beta * pw * sizeof(u64) <= ((size_t)6 << 30);
@@ -204,17 +202,19 @@ void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, i
     }
     if (nrot > 0) {
         u64* t_all = sc.get((size_t)nrot * l * N);      // ModDown(A_k.1), NTT form
-        u64* x_all = sc.get((size_t)nrot * l * N);      // the same, coefficient form
+        u64* x_all = sc.get((size_t)nrot * l * N);      // scratch: the same on its way to coefficient form
         u64* tmp = sc.get((size_t)nrot * l * N);
         ops::moddown(c, A + (size_t)k0 * 2 * pw + pw, 2 * pw, nrot, l, tmp, nullptr, t_all, s);
-        CUDA_CHECK(cudaMemcpyAsync(x_all, t_all, sizeof(u64) * nrot * l * N, cudaMemcpyDeviceToDevice, s));
-        ntt_inverse(c, x_all, nrot * l, RowMap{l, l, c->L, 0}, (int)N, s);
         if (batch_e) {
-            // ModUp and the first transform pass of ALL giant groups in one launch each (every launch pays ~10 us of
-            // ramp-up and tail; 2 x 44 of them at C3), then the fused pass + key product per group
+            // The decomposition front end of ALL giant groups in one launch (inverse pass A + ModUp + forward pass A
+            // fused: the coefficient-form digits are never written), then the fused pass B + key product
             u64* E_all = sc.get((size_t)nrot * beta * pw);
-            ops::decompose_from(c, t_all, x_all, l, E_all, s, /*transform=*/false, nrot);
-            ntt_pass_a_batch(c, E_all, nrot, l, s);
+            if (!ntt_decompose_a(c, t_all, l, x_all, E_all, nrot, s)) {
+                CUDA_CHECK(cudaMemcpyAsync(x_all, t_all, sizeof(u64) * nrot * l * N, cudaMemcpyDeviceToDevice, s));
+                ntt_inverse(c, x_all, nrot * l, RowMap{l, l, c->L, 0}, (int)N, s);
+                ops::decompose_from(c, t_all, x_all, l, E_all, s, /*transform=*/false, nrot);
+                ntt_pass_a_batch(c, E_all, nrot, l, s);
+            }
             u64* Rk = sc.get((size_t)nrot * 2 * pw);   // one partial result per giant group, summed below
             if (mode == 1 &&
                 ntt_ks_fused_all(c, E_all, gkey + k0, gelt + k0, nrot, Rk, l, A + (size_t)k0 * 2 * pw, 2 * pw, (int)rows, s)) {

@@ -205,6 +205,7 @@ Ctx* ctx_create(u64 N, const u64* moduli, int K, int P, int device) {
 
     // ModUp: level l in 1..L, digit j: limbs [jP, min((j+1)P, l))
     std::vector<ulonglong2> up_hatinv((size_t)(L + 1) * beta * P, make_ulonglong2(0, 0));
+    std::vector<ulonglong2> up_hatinv_n((size_t)(L + 1) * beta * P, make_ulonglong2(0, 0));
     std::vector<u64> up_hat((size_t)(L + 1) * beta * P * K, 0);
     for (int l = 1; l <= L; l++)
         for (int j = 0; j < c->digits(l); j++) {
@@ -215,6 +216,7 @@ Ctx* ctx_create(u64 N, const u64* moduli, int K, int P, int device) {
                 for (int b = lo; b < hi; b++)
                     if (b != a) h = mulm(h, c->q[b] % qa, qa);
                 up_hatinv[e] = with_shoup(invm(h, qa), qa);
+                up_hatinv_n[e] = with_shoup(mulm(invm(h, qa), invm(N % qa, qa), qa), qa);
                 for (int t = 0; t < K; t++) {
                     u64 qt = c->q[t], ht = 1;
                     for (int b = lo; b < hi; b++)
@@ -223,7 +225,7 @@ Ctx* ctx_create(u64 N, const u64* moduli, int K, int P, int device) {
                 }
             }
         }
-    c->d_up_hatinv = upload(up_hatinv), c->d_up_hat = upload(up_hat);
+    c->d_up_hatinv = upload(up_hatinv), c->d_up_hat = upload(up_hat), c->d_up_hatinv_n = upload(up_hatinv_n);
 
     // ModDown: from the special primes to every data limb, with the rounding constant floor(P/2)
     auto half_mod = [&](u64 m) {   // ((P mod 2m) - 1) / 2 mod m, P = prod of special primes (odd)
@@ -282,7 +284,7 @@ void ctx_destroy(Ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (void* p : {(void*)c->d_q, (void*)c->d_ratio0, (void*)c->d_ratio1, (void*)c->d_rwide, (void*)c->d_psi, (void*)c->d_ipsi,
-                    (void*)c->d_invn, (void*)c->d_pmod, (void*)c->d_pinv, (void*)c->d_up_hatinv, (void*)c->d_up_hat,
+                    (void*)c->d_invn, (void*)c->d_pmod, (void*)c->d_pinv, (void*)c->d_up_hatinv, (void*)c->d_up_hat, (void*)c->d_up_hatinv_n,
                     (void*)c->d_dn_hatinv, (void*)c->d_dn_half, (void*)c->d_dn_hat, (void*)c->d_rs_inv,
                     (void*)c->d_garner, (void*)c->d_zeta})
         cudaFree(p);

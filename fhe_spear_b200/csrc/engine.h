@@ -32,6 +32,7 @@ struct Ctx {
     // ModUp tables, for level l (1..L) and digit j: hatinv[(l*beta + j)*P + a] (value, shoup),
     // hat[((l*beta + j)*P + a)*K + t] = (Q_j / q_a) mod q_t
     ulonglong2* d_up_hatinv = nullptr;
+    ulonglong2* d_up_hatinv_n = nullptr;   // the same times N^-1: the fused decomposition kernel folds the INTT's scaling in
     u64* d_up_hat = nullptr;
     // ModDown tables: special prime k: (hatinv, shoup), half mod p_k ; data limb i: hat[k*K+i], half mod q_i
     ulonglong2* d_dn_hatinv = nullptr;
@@ -138,8 +139,10 @@ struct DiagSet : CtxRef {
     }
 };
 
-enum { PROF_KS_INNER = 0, PROF_PMAC = 1, PROF_NTT = 2, PROF_MODUP = 3, PROF_MODDOWN = 4, PROF_RESCALE = 5,
-       PROF_KS_BABY = 6, PROF_NTT_KS = 7, PROF_CLASSES = 8 };
+// one class per kernel of the mat-vec path (bench.py picks the dominant one for its roofline line live)
+enum { PROF_KS_INNER = 0, PROF_PMAC = 1, PROF_NTT_FWD_A = 2, PROF_MODUP = 3, PROF_MODDOWN = 4, PROF_RESCALE = 5,
+       PROF_KS_BABY = 6, PROF_NTT_KS = 7, PROF_NTT_FWD_B = 8, PROF_NTT_INV_A = 9, PROF_NTT_INV_B = 10,
+       PROF_SUM_GROUPS = 11, PROF_CLASSES = 12 };
 struct ProfScope {   // brackets the launches of one kernel class with an event pair when profiling is on
     const Ctx* c;
     cudaStream_t s;
@@ -160,7 +163,10 @@ struct ProfScope {   // brackets the launches of one kernel class with an event 
 // ---- launchers (ntt.cu) --------------------------------------------------------------------
 // rows x n in-place transforms; `n` may be a power-of-two prefix size (sub-ring) <= N
 void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s, int skip_digit_alpha = 0,
-                 bool split30_out = false, bool pass_a_only = false);
+                 bool split30_out = false, bool pass_a_only = false, bool pass_b_only = false);
+// decomposition front end in one kernel (inverse pass A + n^-1 * hatinv + ModUp + forward pass A); false: not applicable
+bool ntt_decompose_a_applies(const Ctx* c, int l);
+bool ntt_decompose_a(const Ctx* c, const u64* cin, int l, u64* x, u64* E, int count, cudaStream_t s);
 // forward transform of freshly ModUp'd digits fused with the key inner product (ntt.cu); false: not applicable.
 // pass_a_done: the first pass already ran (ntt_pass_a_batch over several decompositions at once)
 bool ntt_ks_fused_applies(const Ctx* c, int l);
@@ -170,7 +176,7 @@ bool ntt_ks_fused(const Ctx* c, u64* E, const u64* key, u64* out, int l, u32 elt
 // the fused pass + key product of `groups` decompositions (pass A done) in one launch, one partial result per group
 bool ntt_ks_fused_all(const Ctx* c, const u64* E, const u64* const* keys, const u32* elts, int groups, u64* out, int l,
                       const u64* addp, size_t add_stride, int add_rows, cudaStream_t s);
-void ntt_inverse(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s);
+void ntt_inverse(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s, bool pass_b_only = false);
 
 // ---- stream ids shared with the oracle ------------------------------------------------------
 enum { DOM_SK = 1, DOM_PK_A = 2, DOM_PK_E = 3, DOM_KSK_A = 4, DOM_KSK_E = 5,

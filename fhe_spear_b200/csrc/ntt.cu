@@ -10,6 +10,8 @@
 // coalesced); the last sB = min(logn, 8) stages act on contiguous 2^sB-element chunks (pass B,
 // 2048 elements per CTA).  Each element crosses L2 twice per transform; twiddles are (w, shoup(w))
 // pairs fetched with one 16-byte load.
+#include <cstdlib>
+
 #include "engine.h"
 #include "ops.h"
 #include "tma.cuh"
@@ -439,20 +441,24 @@ __global__ void __launch_bounds__(WB * 32) ntt_inv_b2(u64* __restrict__ data, Ro
 }
 
 // pass A, forward: SA stages on a [R = 2^SA][16] tile, 2R threads, thread = (column c, row group g)
-template <int SA, bool LAZY>
+// PRELOADED: v already holds the thread's eight first-round values (rows g % gbot + (g / gbot) * 8 gbot + k * gbot,
+// gbot = R >> min(3, SA)) -- the fused ModUp kernel computes them in place instead of loading them.
+template <int SA, bool LAZY, bool PRELOADED = false>
 __device__ __forceinline__ void fwd_a2_body(u64* __restrict__ base, u64* __restrict__ sm,
-                                            const ulonglong2* __restrict__ tw, u64 q, int S, int c, int g) {
+                                            const ulonglong2* __restrict__ tw, u64 q, int S, int c, int g,
+                                            u64 (&v)[8]) {
     constexpr int R = 1 << SA;
     const u64 q2 = q << 1, q4 = q << 2;
-    u64 v[8];
 #pragma unroll
     for (int s0 = 0; s0 < SA; s0 += 3) {
         const int ns = (SA - s0) < 3 ? (SA - s0) : 3;
         const int gbot = R >> (s0 + ns);                 // smallest row gap of this round
         const int rowbase = (g / gbot) * (8 * gbot) + (g % gbot);
         if (s0 == 0) {
+            if (!PRELOADED) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) v[k] = base[(size_t)(rowbase + k * gbot) * S];
+                for (int k = 0; k < 8; k++) v[k] = base[(size_t)(rowbase + k * gbot) * S];
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < 8; k++) v[k] = sm[(rowbase + k * gbot) * COLS + c];
@@ -500,27 +506,23 @@ __global__ void __launch_bounds__(2 << SA) ntt_fwd_a2(u64* __restrict__ data, Ro
     const ulonglong2* __restrict__ tw = tb.psi + (size_t)limb * N;
     const int c = threadIdx.x & (COLS - 1), g = threadIdx.x >> 4;
     u64* base = data + rm.offset(row, n) + blockIdx.x * COLS + c;
-    if (q < (1ull << 59) && q > (1ull << 33)) fwd_a2_body<SA, true>(base, sm, tw, q, n >> SA, c, g);
-    else fwd_a2_body<SA, false>(base, sm, tw, q, n >> SA, c, g);
+    u64 v[8];
+    if (q < (1ull << 59) && q > (1ull << 33)) fwd_a2_body<SA, true>(base, sm, tw, q, n >> SA, c, g, v);
+    else fwd_a2_body<SA, false>(base, sm, tw, q, n >> SA, c, g, v);
 }
 
 // pass A, inverse: row gaps 1, 2, ..., R/2, then n^-1
+// The SA remaining stages of the inverse transform on a [R][16] column tile.  Returns with the thread's eight values of
+// the LAST round in v (in [0, 2q), n^-1 not applied yet): rows rowbase + k * gs with gs = 2^(SA-3) -- the very rows the
+// forward pass's first round starts from (gbot = R >> 3), which is what lets the fused ModUp kernel go straight on.
 template <int SA>
-__global__ void __launch_bounds__(2 << SA) ntt_inv_a2(u64* __restrict__ data, RowMap rm, NttTab tb, int N, int n,
-                                                       int logn) {
+__device__ __forceinline__ int inv_a2_rounds(const u64* __restrict__ base, u64* __restrict__ sm,
+                                             const ulonglong2* __restrict__ tw, u64 q, int S, int c, int g, u64 (&v)[8]) {
     constexpr int R = 1 << SA;
-    __shared__ u64 sm[R * COLS];
-    const int row = blockIdx.y;
-    const int limb = rm.limb(row);
-    const u64 q = tb.q[limb], q2 = q << 1;
-    const ulonglong2* __restrict__ tw = tb.ipsi + (size_t)limb * N;
-    const int c = threadIdx.x & (COLS - 1), g = threadIdx.x >> 4;
-    const int S = n >> SA;
-    u64* base = data + rm.offset(row, n) + blockIdx.x * COLS + c;
-    const ulonglong2 ninv = tb.invn[limb * 17 + logn];
-    u64 v[8];
+    const u64 q2 = q << 1;
     // a partial round (SA % 3 stages) comes first, where the 8 rows of a thread are contiguous
     constexpr int NS0 = (SA % 3) ? (SA % 3) : 3;
+    int last_rowbase = 0;
 #pragma unroll
     for (int u0 = 0; u0 < SA; u0 += (u0 == 0 ? NS0 : 3)) {
         const int ns = u0 == 0 ? NS0 : 3;
@@ -547,14 +549,126 @@ __global__ void __launch_bounds__(2 << SA) ntt_inv_a2(u64* __restrict__ data, Ro
             }
         }
         if (u0 + ns >= SA) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) base[(size_t)(rowbase + k * gs) * S] = mul_shoup(v[k], ninv.x, ninv.y, q);
+            last_rowbase = rowbase;
         } else {
 #pragma unroll
             for (int k = 0; k < 8; k++) sm[(rowbase + k * gs) * COLS + c] = v[k];
             __syncthreads();
         }
     }
+    return last_rowbase;
+}
+
+template <int SA>
+__global__ void __launch_bounds__(2 << SA) ntt_inv_a2(u64* __restrict__ data, RowMap rm, NttTab tb, int N, int n,
+                                                       int logn) {
+    constexpr int R = 1 << SA;
+    __shared__ u64 sm[R * COLS];
+    const int row = blockIdx.y;
+    const int limb = rm.limb(row);
+    const u64 q = tb.q[limb];
+    const ulonglong2* __restrict__ tw = tb.ipsi + (size_t)limb * N;
+    const int c = threadIdx.x & (COLS - 1), g = threadIdx.x >> 4;
+    const int S = n >> SA;
+    u64* base = data + rm.offset(row, n) + blockIdx.x * COLS + c;
+    const ulonglong2 ninv = tb.invn[limb * 17 + logn];
+    u64 v[8];
+    const int rowbase = inv_a2_rounds<SA>(base, sm, tw, q, S, c, g, v);
+    constexpr int GS = SA >= 3 ? (1 << (SA - 3)) : 1;
+#pragma unroll
+    for (int k = 0; k < 8; k++) base[(size_t)(rowbase + k * GS) * S] = mul_shoup(v[k], ninv.x, ninv.y, q);
+}
+
+// =============================================================================================
+// Decomposition front end in ONE kernel: the last SA stages of the inverse transform of the alpha source limbs of a
+// digit, the scaling by n^-1 * hatinv (one merged Shoup constant), ModUp to every other limb (fast base conversion,
+// split-30 Karatsuba sums exactly as ops.cu k_modup) and the first SA stages of the forward transform of each ModUp'd
+// row.  A CTA owns (decomposition z, digit j, a tile of 16 columns) and walks its share of the l + P - alpha target rows.
+// The coefficient-form digits never exist in memory: per decomposition this removes a write and a read of
+// beta * (l+P) * N words (57 MB at C3) and two launches ("cut the giant-step chain").
+//   x   [count][l][N]  rows after inverse pass B (n^-1 pending)      cin [count][l][N]  the same polynomials, NTT form
+//   E   [count][beta][l+P][N]: own-digit rows = split30(cin), the others = forward pass A done, canonical residues
+// =============================================================================================
+template <int SA, int A>
+__global__ void __launch_bounds__(2 << SA) k_intt_modup_fwd_a(const u64* __restrict__ x, const u64* __restrict__ cin,
+                                                               u64* __restrict__ E, int l, int N, int L, int P, int K,
+                                                               NttTab tb, ModTab mt,
+                                                               const ulonglong2* __restrict__ hatinv_n,
+                                                               const u64* __restrict__ hat, int sbits, int rsplit) {
+    constexpr int R = 1 << SA, T = 2 << SA;
+    extern __shared__ __align__(16) u64 dyn[];
+    u64* sm = dyn;                                   // [R][COLS]      exchange tile of the transforms
+    u64* ysm = sm + R * COLS;                        // [A][8][T]      scaled source values, split-30, thread-private slots
+    u64* tab = ysm + (size_t)A * 8 * T;              // [rows][A + 2]  hat_0..hat_{A-1}, q, floor(2^(s+64)/q) per target row
+    const int rows = l + P, beta = gridDim.y / rsplit;
+    const int j = blockIdx.y / rsplit, part = blockIdx.y % rsplit, z = blockIdx.z;
+    const int lo = j * P, hi = min(lo + P, l), a = hi - lo;
+    const int c = threadIdx.x & (COLS - 1), g = threadIdx.x >> 4, S = N >> SA;
+    x += (size_t)z * l * N, cin += (size_t)z * l * N;
+    u64* Ej = E + ((size_t)z * beta + j) * rows * N;
+    hatinv_n += (size_t)j * P;
+    hat += (size_t)j * P * K;
+    for (int e = threadIdx.x; e < rows * (A + 2); e += T) {
+        const int r = e / (A + 2), cc = e % (A + 2), t = r < l ? r : L + (r - l);
+        tab[e] = cc < A ? (cc < a ? hat[(size_t)cc * K + t] : 0) : cc == A ? mt.q[t] : mt.rwide[t];
+    }
+    constexpr int GS = 1 << (SA - 3);                // row gap of the values a thread ends / starts with
+    const int rowbase = (g / GS) * (8 * GS) + (g % GS);
+    const size_t col = (size_t)blockIdx.x * COLS + c;
+    u64 v[8];
+    // 1. inverse pass A of the digit's source limbs, scaled by n^-1 * hatinv
+#pragma unroll
+    for (int i = 0; i < A; i++) {
+        if (i < a) {
+            const int limb = lo + i;
+            const u64 q = tb.q[limb];
+            inv_a2_rounds<SA>(x + (size_t)limb * N + col, sm, tb.ipsi + (size_t)limb * N, q, S, c, g, v);
+            const ulonglong2 h = hatinv_n[i];
+#pragma unroll
+            for (int k = 0; k < 8; k++) ysm[((size_t)i * 8 + k) * T + threadIdx.x] = split30(mul_shoup(v[k], h.x, h.y, q));
+            __syncthreads();                         // the exchange tile is free again
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) ysm[((size_t)i * 8 + k) * T + threadIdx.x] = 0;
+        }
+    }
+    __syncthreads();                                 // tab complete (also when the digit is empty of work above)
+    // 2. every target row of this CTA: ModUp in registers, then forward pass A
+    int idx = 0;
+    for (int r = 0; r < rows; r++) {
+        const int t = r < l ? r : L + (r - l);
+        if (t >= lo && t < hi) continue;             // own-digit rows: step 3
+        if (idx++ % rsplit != part) continue;
+        const u64* tr = tab + r * (A + 2);
+        const u64 q = tr[A], rw = tr[A + 1];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            Acc3 acc = {0, 0, 0};
+#pragma unroll
+            for (int i = 0; i < A; i++) {
+                const u64 y = ysm[((size_t)i * 8 + k) * T + threadIdx.x];
+                mac_split(acc, y, (u32)y + (u32)(y >> 32), tr[i]);   // rows i >= a hold zeros
+            }
+            u64 alo = 0, ahi = 0;
+            fold_split(alo, ahi, acc);
+            v[k] = sbits > 0 ? reduce_wide_s(alo, ahi, q, rw, sbits) : reduce_wide(alo, ahi, q, rw);
+        }
+        u64* base = Ej + (size_t)r * N + col;
+        const ulonglong2* __restrict__ tw = tb.psi + (size_t)t * N;
+        if (q < (1ull << 59) && q > (1ull << 33)) fwd_a2_body<SA, true, true>(base, sm, tw, q, S, c, g, v);
+        else fwd_a2_body<SA, false, true>(base, sm, tw, q, S, c, g, v);
+        __syncthreads();                             // last-round readers of the exchange tile are done
+    }
+    // 3. own-digit rows arrive in NTT form already: the consumers want them split-30
+    if (part == 0)
+        for (int i = 0; i < a; i++) {
+            const size_t off = (size_t)(lo + i) * N + col;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const size_t e = off + (size_t)(rowbase + k * GS) * S;
+                Ej[e] = split30(cin[e]);
+            }
+        }
 }
 
 // =============================================================================================
@@ -707,7 +821,7 @@ inline void split(int logn, int& sA, int& sB) {
 static int max_rows_per_launch(const RowMap& rm) { return 65535 / rm.rpp * rm.rpp; }
 
 void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s, int skip_alpha, bool split30_out,
-                 bool pass_a_only) {
+                 bool pass_a_only, bool pass_b_only) {
     int logn = 0;
     while ((1 << logn) < n) logn++;
     REQUIRE((1 << logn) == n && n <= c->N && logn <= 16 && n >= 2, "ntt: bad size %d", n);
@@ -717,28 +831,33 @@ void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream
         REQUIRE(step > 0 && !skip_alpha, "ntt: %d rows per polynomial do not fit one launch", rm.rpp);   // callers keep skip batches below 65536 rows
         for (int r0 = 0; r0 < rows; r0 += step)
             ntt_forward(c, data + rm.offset(r0, n), std::min(step, rows - r0), rm, n, s, skip_alpha, split30_out,
-                        pass_a_only);
+                        pass_a_only, pass_b_only);
         return;
     }
     int sA, sB;
     split(logn, sA, sB);
     NttTab tb = c->ntttab();
-    REQUIRE(!pass_a_only || sA >= 3, "ntt: pass A alone needs n >= 2048");
-    ProfScope ps(c, PROF_NTT, s);
+    REQUIRE(!(pass_a_only || pass_b_only) || sA >= 3, "ntt: a single pass needs n >= 2048");
     if (sA >= 3) {   // n >= 2048: register-tiled kernels
-        switch (sA) {
-            case 3: launch_fwd_a2<3>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
-            case 4: launch_fwd_a2<4>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
-            case 5: launch_fwd_a2<5>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
-            case 6: launch_fwd_a2<6>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
-            case 7: launch_fwd_a2<7>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
-            default: launch_fwd_a2<8>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
+        if (!pass_b_only) {
+            ProfScope ps(c, PROF_NTT_FWD_A, s);
+            switch (sA) {
+                case 3: launch_fwd_a2<3>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
+                case 4: launch_fwd_a2<4>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
+                case 5: launch_fwd_a2<5>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
+                case 6: launch_fwd_a2<6>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
+                case 7: launch_fwd_a2<7>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
+                default: launch_fwd_a2<8>(data, rows, rm, tb, c->N, n, skip_alpha, s); break;
+            }
         }
-        if (!pass_a_only)
+        if (!pass_a_only) {
+            ProfScope ps(c, PROF_NTT_FWD_B, s);
             LAUNCH(ntt_fwd_b2, dim3(n / (256 * WB), rows), WB * 32, 0, s)(data, rm, tb, c->N, n, sA, skip_alpha, split30_out ? 1 : 0);
+        }
         CUDA_CHECK(cudaGetLastError());
         return;
     }
+    ProfScope ps(c, PROF_NTT_FWD_A, s);
     if (sA > 0) {
         dim3 grid((n >> sA) / COLS, rows);
         LAUNCH(ntt_fwd_a, grid, TPB, sizeof(u64) * COLS << sA, s)(data, rm, tb, c->N, n, sA, skip_alpha);
@@ -747,6 +866,55 @@ void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream
     dim3 grid(n / elems, rows);
     LAUNCH(ntt_fwd_b, grid, TPB, sizeof(u64) * elems, s)(data, rm, tb, c->N, n, sA, sB, skip_alpha, split30_out ? 1 : 0);
     CUDA_CHECK(cudaGetLastError());
+}
+
+// cin [count][l][N] (NTT form) -> E [count][beta][l+P][N]: own-digit rows split-30, the other rows ModUp'd with the
+// forward transform's first pass done (pass B pending: ntt_ks_fused*(pass_a_done) or ntt_forward(pass_b_only)).
+// x: scratch [count][l][N].  false: the fused front end does not apply (N < 2048, P > 4, or the tile does not fit).
+static size_t decompose_a_smem(const Ctx* c, int l, int sA, int A) {
+    return sizeof(u64) * (((size_t)COLS << sA) + (size_t)A * 8 * (2 << sA) + (size_t)(l + c->P) * (A + 2));
+}
+bool ntt_decompose_a_applies(const Ctx* c, int l) {
+    static const bool enabled = [] {
+        const char* e = getenv("SPEAR_FUSED_MODUP");
+        return !(e && e[0] == '0');
+    }();
+    int sA, sB;
+    split(c->logn, sA, sB);
+    return enabled && sA >= 3 && c->P <= 4 && decompose_a_smem(c, l, sA, c->P) <= 200 * 1024;
+}
+bool ntt_decompose_a(const Ctx* c, const u64* cin, int l, u64* x, u64* E, int count, cudaStream_t s) {
+    if (!ntt_decompose_a_applies(c, l)) return false;
+    const int N = c->N, P = c->P, rows = l + P, beta = c->digits(l);
+    int sA, sB;
+    split(c->logn, sA, sB);
+    REQUIRE(count >= 1 && count <= 65535, "decompose: bad batch");
+    CUDA_CHECK(cudaMemcpyAsync(x, cin, sizeof(u64) * count * l * N, cudaMemcpyDeviceToDevice, s));
+    ntt_inverse(c, x, count * l, RowMap{l, l, c->L, 0}, N, s, /*pass_b_only=*/true);
+    // target rows of a digit are dealt to `rsplit` CTAs so that small batches still fill the GPU (the inverse part is
+    // repeated by each of them: alpha of l + P - alpha row transforms)
+    const int tiles = (N >> sA) / COLS, targets = rows - std::min(P, l);
+    int rsplit = 1;
+    while (rsplit < targets && (size_t)tiles * beta * count * rsplit < (size_t)c->sm_count * 6) rsplit++;
+    const size_t smem = decompose_a_smem(c, l, sA, P);
+    ProfScope ps(c, PROF_MODUP, s);
+    auto go = [&](auto kern) {
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        LAUNCH(kern, dim3(tiles, beta * rsplit, count), 2 << sA, smem, s)(
+            x, cin, E, l, N, c->L, P, c->K, c->ntttab(), c->modtab(), c->d_up_hatinv_n + (size_t)l * c->beta * P,
+            c->d_up_hat + (size_t)l * c->beta * P * c->K, c->sbits, rsplit);
+    };
+#define DA_CASE(SA_)                                              \
+    case SA_:                                                     \
+        if (P == 1) go(k_intt_modup_fwd_a<SA_, 1>);               \
+        else if (P == 2) go(k_intt_modup_fwd_a<SA_, 2>);          \
+        else if (P == 3) go(k_intt_modup_fwd_a<SA_, 3>);          \
+        else go(k_intt_modup_fwd_a<SA_, 4>);                      \
+        break;
+    switch (sA) { DA_CASE(3) DA_CASE(4) DA_CASE(5) DA_CASE(6) DA_CASE(7) default: REQUIRE(sA == 8, "decompose: bad size"); DA_CASE(8) }
+#undef DA_CASE
+    CUDA_CHECK(cudaGetLastError());
+    return true;
 }
 
 // E: [beta][l+P][N] as ModUp leaves it (own-digit rows in NTT split-30 form, the others in coefficient form).
@@ -825,7 +993,7 @@ bool ntt_ks_fused_all(const Ctx* c, const u64* E, const u64* const* keys, const 
     return true;
 }
 
-void ntt_inverse(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s) {
+void ntt_inverse(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s, bool pass_b_only) {
     int logn = 0;
     while ((1 << logn) < n) logn++;
     REQUIRE((1 << logn) == n && n <= c->N && logn <= 16 && n >= 2, "intt: bad size %d", n);
@@ -834,15 +1002,23 @@ void ntt_inverse(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream
         const int step = max_rows_per_launch(rm);
         REQUIRE(step > 0, "intt: %d rows per polynomial do not fit one launch", rm.rpp);
         for (int r0 = 0; r0 < rows; r0 += step)
-            ntt_inverse(c, data + rm.offset(r0, n), std::min(step, rows - r0), rm, n, s);
+            ntt_inverse(c, data + rm.offset(r0, n), std::min(step, rows - r0), rm, n, s, pass_b_only);
         return;
     }
     int sA, sB;
     split(logn, sA, sB);
     NttTab tb = c->ntttab();
-    ProfScope ps(c, PROF_NTT, s);
+    REQUIRE(!pass_b_only || sA >= 3, "intt: a single pass needs n >= 2048");
     if (sA >= 3) {
-        LAUNCH(ntt_inv_b2, dim3(n / (256 * WB), rows), WB * 32, 0, s)(data, rm, tb, c->N, n, sA, logn);
+        {
+            ProfScope ps(c, PROF_NTT_INV_B, s);
+            LAUNCH(ntt_inv_b2, dim3(n / (256 * WB), rows), WB * 32, 0, s)(data, rm, tb, c->N, n, sA, logn);
+        }
+        if (pass_b_only) {
+            CUDA_CHECK(cudaGetLastError());
+            return;
+        }
+        ProfScope ps(c, PROF_NTT_INV_A, s);
         switch (sA) {
             case 3: launch_inv_a2<3>(data, rows, rm, tb, c->N, n, logn, s); break;
             case 4: launch_inv_a2<4>(data, rows, rm, tb, c->N, n, logn, s); break;
@@ -854,6 +1030,7 @@ void ntt_inverse(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream
         CUDA_CHECK(cudaGetLastError());
         return;
     }
+    ProfScope ps(c, PROF_NTT_INV_B, s);
     int elems = n < B_ELEMS ? n : B_ELEMS;
     dim3 grid(n / elems, rows);
     LAUNCH(ntt_inv_b, grid, TPB, sizeof(u64) * elems, s)(data, rm, tb, c->N, n, sA, sB, logn);

@@ -668,6 +668,7 @@ void reduce_inplace(const Ctx* c, u64* x, int polys, int rows, RowMap rm, cudaSt
 void sum_groups(const Ctx* c, const u64* parts, int nparts, const u64* first, u64* out, int l, cudaStream_t s) {
     const int rows = l + c->P;
     const size_t words = (size_t)2 * rows * c->N;
+    ProfScope ps(c, PROF_SUM_GROUPS, s);
     LAUNCH(k_sum_groups, grid_for(c, words), TPB, 0, s)(parts, nparts, words, first, out, rows, c->N, RowMap{rows, l, c->L, 0},
                                                         c->modtab());
     CUDA_CHECK(cudaGetLastError());
@@ -681,6 +682,11 @@ void galois(const Ctx* c, const u64* in, u64* out, int rows, u32 elt, cudaStream
 
 // cin [l][N] NTT form -> E [digits(l)][l+P][N] NTT form (scratch x: [l][N])
 void decompose(const Ctx* c, const u64* cin, int l, u64* x, u64* E, cudaStream_t s) {
+    if (ntt_decompose_a(c, cin, l, x, E, 1, s)) {   // fused front end; the second forward pass completes the digits
+        ntt_forward(c, E, c->digits(l) * (l + c->P), RowMap{l + c->P, l, c->L, 0}, c->N, s, c->P, /*split30_out=*/true,
+                    /*pass_a_only=*/false, /*pass_b_only=*/true);
+        return;
+    }
     CUDA_CHECK(cudaMemcpyAsync(x, cin, sizeof(u64) * l * c->N, cudaMemcpyDeviceToDevice, s));
     ntt_inverse(c, x, l, RowMap{l, l, c->L, 0}, c->N, s);
     decompose_from(c, cin, x, l, E, s);
@@ -711,12 +717,19 @@ void decompose_from(const Ctx* c, const u64* cin, const u64* x, int l, u64* E, c
 
 // decompose + key inner product; the forward transform's last pass is fused into the product when it applies
 // (SPEAR_FUSED_KS=0 keeps the two-kernel form, for A/B timing)
-void decompose_ks(const Ctx* c, const u64* cin, const u64* x, int l, u64* E, const u64* key, u64* out, u32 elt,
+void decompose_ks(const Ctx* c, const u64* cin, u64* x, int l, u64* E, const u64* key, u64* out, u32 elt,
                   const u64* addp, int add_rows, int add_pscale, int accumulate, cudaStream_t s) {
     static const bool fused = [] {
         const char* e = getenv("SPEAR_FUSED_KS");
         return !(e && e[0] == '0');
     }();
+    // x is scratch [l][N].  Fully fused form: one kernel for inverse pass A + ModUp + forward pass A, one for forward
+    // pass B + key product
+    if (fused && ntt_ks_fused_applies(c, l) && ntt_decompose_a(c, cin, l, x, E, 1, s) &&
+        ntt_ks_fused(c, E, key, out, l, elt, addp, add_rows, add_pscale, accumulate, s, /*pass_a_done=*/true))
+        return;
+    CUDA_CHECK(cudaMemcpyAsync(x, cin, sizeof(u64) * l * c->N, cudaMemcpyDeviceToDevice, s));
+    ntt_inverse(c, x, l, RowMap{l, l, c->L, 0}, c->N, s);
     decompose_from(c, cin, x, l, E, s, /*transform=*/false);
     if (fused && ntt_ks_fused(c, E, key, out, l, elt, addp, add_rows, add_pscale, accumulate, s)) return;
     ntt_forward(c, E, c->digits(l) * (l + c->P), RowMap{l + c->P, l, c->L, 0}, c->N, s, c->P, /*split30_out=*/true);

@@ -32,7 +32,8 @@ void decompose(const Ctx* c, const u64* cin, int l, u64* x, u64* E, cudaStream_t
 // count > 1: `count` polynomials back to back (cin, x: [count][l][N]) -> E [count][beta][l+P][N], ModUp only (transform = false)
 void decompose_from(const Ctx* c, const u64* cin, const u64* x, int l, u64* E, cudaStream_t s, bool transform = true,
                     int count = 1);
-void decompose_ks(const Ctx* c, const u64* cin, const u64* x, int l, u64* E, const u64* key, u64* out, u32 elt,
+// x: scratch [l][N] (receives the coefficient form of cin on the way)
+void decompose_ks(const Ctx* c, const u64* cin, u64* x, int l, u64* E, const u64* key, u64* out, u32 elt,
                   const u64* addp, int add_rows, int add_pscale, int accumulate, cudaStream_t s);
 void ks_inner(const Ctx* c, const u64* E, const u64* key, u64* out, int l, u32 elt, const u64* addp, int add_rows,
               int add_pscale, int accumulate, cudaStream_t s);

@@ -165,7 +165,8 @@ class context:
         _check(_lib.spear_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
-    PROFILE_CLASSES = ("ks_inner", "pmac", "ntt", "modup", "moddown", "rescale", "ks_baby_fused", "ntt_ks_fused")
+    PROFILE_CLASSES = ("ks_inner", "pmac", "ntt_fwd_a", "modup", "moddown", "rescale", "ks_baby_fused", "ntt_ks_fused",
+                       "ntt_fwd_b", "ntt_inv_a", "ntt_inv_b", "sum_groups")
 
     def profile(self, on=True):
         """Bracket every launch of each kernel class with a CUDA event pair (bench.py roofline line)."""

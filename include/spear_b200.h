@@ -58,8 +58,10 @@ void* spear_context_stream(spear_context* ctx);   /* cudaStream_t */
 int spear_timer_start(spear_context* ctx);
 int spear_timer_stop(spear_context* ctx, float* elapsed_ms);
 /* per-kernel-class device timing (event pair around every launch of the class) for the roofline line:
- * classes 0 key inner product (one rotation per launch), 1 diagonal MAC, 2 NTT/INTT, 3 ModUp, 4 ModDown, 5 rescale,
- * 6 fused hoisted baby-step key inner product (G-1 rotations per launch) */
+ * classes 0 key inner product (one rotation per launch), 1 diagonal MAC, 2 forward NTT pass A, 3 ModUp (stand-alone, or
+ * the fused inverse pass A + ModUp + forward pass A front end), 4 ModDown, 5 rescale, 6 fused hoisted baby-step key inner
+ * product (G-1 rotations per launch), 7 forward pass B fused with the key product (giant steps), 8 forward pass B,
+ * 9 inverse pass A, 10 inverse pass B, 11 sum of the giant groups' partial results */
 int spear_profile_enable(spear_context* ctx, int on);
 int spear_profile_read(spear_context* ctx, double* ms, uint64_t* launches, int classes);
 /* pinned host buffers for the host<->device legs of the end-to-end path */

@@ -59,6 +59,13 @@ class Oracle:
         except Exception:
             pass
 
+    @staticmethod
+    def set_threads(n):
+        """OpenMP team size of the oracle (explicit: torchrun exports OMP_NUM_THREADS=1); returns the size in effect"""
+        lib = C.CDLL(build())
+        lib.orc_set_threads.restype = C.c_int
+        return int(lib.orc_set_threads(int(n)))
+
     # ---- parameters -------------------------------------------------
     @staticmethod
     def create_coeff_modulus(N, bits):

@@ -32,9 +32,25 @@
 #include <math.h>
 #include <stdio.h>
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
 typedef uint64_t u64;
 typedef uint32_t u32;
 typedef unsigned __int128 u128;
+
+/* OpenMP team size, set explicitly by the timing legs of bench.py: launchers such as torch.distributed.run export
+ * OMP_NUM_THREADS=1, which would silently turn the CPU baseline into a single-core number.  Returns the team size. */
+int orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 #define ORC_MAX_LIMBS 64
 
