@@ -333,8 +333,7 @@ def run_ours(args):
         # strong scaling: the same nb mat-vecs dealt to rank groups, giant steps sharded inside a group; every rank
         # creates every process group in the same order
         plan = sh.PhasePlan(nb, world)
-        pg = {ranks: (dist.group.WORLD if len(ranks) == world else dist.new_group(list(ranks))) for ranks in plan.groups
-              if len(ranks) > 1}
+        pg = {ranks: (dist.group.WORLD if len(ranks) == world else dist.new_group(list(ranks))) for ranks in plan.groups}
         mine = plan.mine(rank)
         dsets = {}
         for ranks, js in mine:
@@ -349,7 +348,7 @@ def run_ours(args):
         def step():
             outs = {}
             for ranks, js in mine:
-                ys_ = sh.sharded_matvec_batch(ckks, [cts[j] for j in js], [dsets[j] for j in js], group=pg.get(ranks))
+                ys_ = sh.sharded_matvec_batch(ckks, [cts[j] for j in js], [dsets[j] for j in js], group=pg[ranks])
                 outs.update(zip(js, ys_))
             return outs
         parallelism = (f"{world} GPUs, strong scaling: mat-vecs dealt to rank groups {plan.groups}, giant steps sharded inside a group, "
@@ -451,7 +450,7 @@ def run_ours(args):
             res = {}
             for ranks, js in mine:
                 res.update(zip(js, sh.sharded_matvec_batch(ckks, [ins[j] for j in js], [dsets[j] for j in js],
-                                                           group=pg.get(ranks))))
+                                                           group=pg[ranks])))
         for j, h in h_out.items():
             res[j].to_numpy(out=h)                                                        # D2H (synchronises)
         ctx.synchronize()

@@ -41,7 +41,8 @@ struct PeerWindow : CtxRef {
     bool connected = false;
     u64 epoch[MAX_SLOTS] = {};
     int* status = nullptr;             // pinned host word, written by the waiting kernels on time-out
-    int* d_status = nullptr;
+    int* d_status = nullptr;           // its device address (zero-copy: only the one-warp sync kernels touch it)
+    int* d_failed = nullptr;           // the same flag in device memory, read by the reduce / collect kernels
     ~PeerWindow() {
         if (!ctx) return;
         cudaSetDevice(ctx->device);
@@ -49,6 +50,7 @@ struct PeerWindow : CtxRef {
         for (int r = 0; r < world; r++)
             if (r != rank && peer[r]) cudaIpcCloseMemHandle(peer[r]);
         if (base) cudaFree(base);
+        if (d_failed) cudaFree(d_failed);
         if (status) cudaFreeHost(status);
     }
 };
@@ -85,7 +87,8 @@ __host__ __device__ __forceinline__ size_t flag_index(int slot, int kind, int wr
 }
 
 // lane r < world:  (post != 0) tell peer r that `me` reached `epoch` of `kind`;  then wait until peer r told us the same
-__global__ void k_peer_sync(PeerPtrs pp, int world, int me, int slot, int kind, int post, u64 epoch, int* status) {
+__global__ void k_peer_sync(PeerPtrs pp, int world, int me, int slot, int kind, int post, u64 epoch, int* status,
+                            int* failed) {
     const int r = threadIdx.x;
     if (r >= world) return;
     if (post) st_release_sys(pp.w[r] + flag_index(slot, kind, me), epoch);
@@ -93,7 +96,8 @@ __global__ void k_peer_sync(PeerPtrs pp, int world, int me, int slot, int kind, 
     const unsigned long long deadline = globaltimer_ns() + SPIN_TIMEOUT_NS;
     while (ld_acquire_sys(mine) < epoch) {
         if (globaltimer_ns() > deadline) {
-            *(volatile int*)status = 1 + r;
+            *(volatile int*)status = 1 + r;   // host-visible (zero-copy)
+            *(volatile int*)failed = 1 + r;   // device copy for the kernels queued behind this one
             __threadfence_system();
             return;
         }
@@ -105,8 +109,8 @@ __global__ void k_peer_sync(PeerPtrs pp, int world, int me, int slot, int kind, 
 template <int R>
 __global__ void __launch_bounds__(256) k_peer_reduce(PeerPtrs pp, size_t data_off, size_t lo, size_t hi, int rows,
                                                      int logn, RowMap rm, ModTab mt, int me, int slot, u64 epoch,
-                                                     const int* status) {
-    if (*(volatile const int*)status) return;   // a peer never arrived: its window holds stale data, touch nothing
+                                                     const int* failed) {
+    if (*(volatile const int*)failed) return;   // a peer never arrived: its window holds stale data, touch nothing
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t v = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < hi; v += stride) {
         const size_t e = data_off + 2 * v;
@@ -139,8 +143,8 @@ __global__ void __launch_bounds__(256) k_peer_reduce(PeerPtrs pp, size_t data_of
 
 // window -> accumulator, or -- when a wait timed out -- an accumulator of all-ones words (no valid residue: q < 2^61),
 // so that a failed exchange can never pass for a ciphertext downstream
-__global__ void k_peer_collect(const u64* __restrict__ win, u64* __restrict__ acc, size_t words, const int* status) {
-    const bool failed = *(volatile const int*)status != 0;
+__global__ void k_peer_collect(const u64* __restrict__ win, u64* __restrict__ acc, size_t words, const int* failed_flag) {
+    const bool failed = *(volatile const int*)failed_flag != 0;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < words; e += (size_t)gridDim.x * blockDim.x)
         acc[e] = failed ? ~0ull : win[e];
 }
@@ -183,6 +187,8 @@ int spear_peer_window_create(spear_context* ctx, int rank, int world, uint64_t s
     CUDA_CHECK(cudaHostAlloc(&w->status, sizeof(int), cudaHostAllocMapped));
     *w->status = 0;
     CUDA_CHECK(cudaHostGetDevicePointer(&w->d_status, w->status, 0));
+    CUDA_CHECK(cudaMalloc(&w->d_failed, sizeof(int)));
+    CUDA_CHECK(cudaMemset(w->d_failed, 0, sizeof(int)));
     w->peer[rank] = w->base;
     cudaIpcMemHandle_t h;
     std::memset(&h, 0, sizeof(h));
@@ -234,14 +240,14 @@ int spear_peer_allreduce(spear_context* ctx, spear_peer_window* win, int slot, s
     PeerPtrs pp;
     for (int r = 0; r < MAX_PEERS; r++) pp.w[r] = w->peer[r < w->world ? r : w->rank];
     CUDA_CHECK(cudaMemcpyAsync(w->base + data_off, acc->d, bytes, cudaMemcpyDeviceToDevice, s));
-    LAUNCH(k_peer_sync, 1, 32, 0, s)(pp, w->world, w->rank, slot, 0, 1, epoch, w->d_status);
+    LAUNCH(k_peer_sync, 1, 32, 0, s)(pp, w->world, w->rank, slot, 0, 1, epoch, w->d_status, w->d_failed);
     const size_t pairs = acc->words() / 2, per = (pairs + w->world - 1) / w->world;
     const size_t lo = std::min(pairs, per * w->rank), hi = std::min(pairs, lo + per);
     const int grid = (int)std::max<size_t>(1, std::min<size_t>((hi - lo + 255) / 256, (size_t)c->sm_count * 8));
     const RowMap rm{acc->rows(), acc->l, c->L, 0};
     auto go = [&](auto kern) {
         LAUNCH(kern, grid, 256, 0, s)(pp, data_off, lo, hi, acc->rows(), c->logn, rm, c->modtab(), w->rank, slot, epoch,
-                                      w->d_status);
+                                      w->d_failed);
     };
     switch (w->world) {
         case 2: go(k_peer_reduce<2>); break;
@@ -252,9 +258,9 @@ int spear_peer_allreduce(spear_context* ctx, spear_peer_window* win, int slot, s
         case 7: go(k_peer_reduce<7>); break;
         default: go(k_peer_reduce<8>); break;
     }
-    LAUNCH(k_peer_sync, 1, 32, 0, s)(pp, w->world, w->rank, slot, 1, 0, epoch, w->d_status);
+    LAUNCH(k_peer_sync, 1, 32, 0, s)(pp, w->world, w->rank, slot, 1, 0, epoch, w->d_status, w->d_failed);
     LAUNCH(k_peer_collect, (int)std::min<size_t>((acc->words() + 255) / 256, (size_t)c->sm_count * 8), 256, 0, s)(
-        w->base + data_off, acc->d, acc->words(), w->d_status);
+        w->base + data_off, acc->d, acc->words(), w->d_failed);
     CUDA_CHECK(cudaGetLastError());
     PEER_END
 }
