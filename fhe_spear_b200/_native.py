@@ -63,6 +63,8 @@ _SIG = {
     "spear_decode": (C.c_int, [vp, vp, f64p]),
     "spear_encrypt_symmetric": (C.c_int, [vp, vp, vp, C.c_uint64, vpp]),
     "spear_encrypt_asymmetric": (C.c_int, [vp, vp, vp, C.c_uint64, vpp]),
+    "spear_encrypt_vector": (C.c_int, [vp, vp, f64p, C.c_int, C.c_int, C.c_double, C.c_uint64, vpp]),
+    "spear_decrypt_decode": (C.c_int, [vp, vp, vp, f64p, C.c_int]),
     "spear_decrypt": (C.c_int, [vp, vp, vp, vpp]),
     "spear_negate": (C.c_int, [vp, vp, vpp]),
     "spear_add": (C.c_int, [vp, vp, vp, vpp]),
@@ -83,6 +85,8 @@ _SIG = {
     "spear_diagset_encode": (C.c_int, [vp, f64p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, vpp]),
     "spear_diagset_encode_matrix": (C.c_int, [vp, f64p, f64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                                C.c_int, C.c_int, vpp]),
+    "spear_diagset_encode_matrix_view": (C.c_int, [vp, f64p, f64p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int,
+                                                    C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, vpp]),
     "spear_diagset_encode_shard": (C.c_int, [vp, f64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                             C.c_int, C.c_int, vpp]),
     "spear_diagset_destroy": (None, [vp]),

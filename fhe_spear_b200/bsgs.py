@@ -114,16 +114,25 @@ class CKKSBootstrapContext:
             say(f"[CKKS] Bootstrap depth={bt_depth}, post-bootstrap levels={L0 - bt_depth - 1}")
         say(f"[CKKS] Slots={self.slots}")
 
+    # The client legs go through the one-call forms of the drop-in (encode + encrypt / decrypt + decode in three launches
+    # each, csrc/client.cu) when the secret key offers them; results are bit-identical to the reference's two-step form
+    # below them [ref: :119-147], which stays as the path for a reference-style pyPhantom.
     def encrypt(self, vec):
+        if hasattr(self.sk, "encrypt_vector"):
+            return self.sk.encrypt_vector(self.ctx, np.asarray(vec, dtype=np.float64), self.scale, replicate=False)
         padded = np.zeros(self.slots)
         padded[:len(vec)] = vec
         return self.sk.encrypt_symmetric(self.ctx, self.encoder.encode_double_vector(self.ctx, padded, self.scale))
 
     def encrypt_replicated(self, vec):
+        if hasattr(self.sk, "encrypt_vector"):
+            return self.sk.encrypt_vector(self.ctx, np.asarray(vec, dtype=np.float64), self.scale, replicate=True)
         rep = _replicate_to_slots(np.asarray(vec, dtype=np.float64), self.slots)
         return self.sk.encrypt_symmetric(self.ctx, self.encoder.encode_double_vector(self.ctx, rep, self.scale))
 
     def encrypt_replicated_complex(self, vec_real, vec_imag):
+        if hasattr(self.sk, "encrypt_vector"):
+            return self.sk.encrypt_vector(self.ctx, np.asarray(vec_real) + 1j * np.asarray(vec_imag), self.scale, replicate=True)
         rep = _replicate_to_slots(np.asarray(vec_real) + 1j * np.asarray(vec_imag), self.slots)
         return self.sk.encrypt_symmetric(self.ctx, self.encoder.encode_complex_vector(self.ctx, rep, self.scale))
 
@@ -134,14 +143,19 @@ class CKKSBootstrapContext:
             return fast(self.ctx, pt)[:dim].copy()
         return np.array(self.encoder.decode_complex_vector(self.ctx, pt)[:dim])
 
-    def decrypt_vec(self, ct, dim):
-        return self._decode(self.sk.decrypt(self.ctx, ct), dim).real.copy()
-
-    def decrypt_vec_complex(self, ct, dim):
+    def _decrypt_decode(self, ct, dim):
+        if hasattr(self.sk, "decrypt_decode"):
+            return self.sk.decrypt_decode(self.ctx, ct, dim)
         return self._decode(self.sk.decrypt(self.ctx, ct), dim)
 
+    def decrypt_vec(self, ct, dim):
+        return self._decrypt_decode(ct, dim).real.copy()
+
+    def decrypt_vec_complex(self, ct, dim):
+        return self._decrypt_decode(ct, dim)
+
     def decrypt_slot0(self, ct):
-        return float(self._decode(self.sk.decrypt(self.ctx, ct), 1).real[0])
+        return float(self._decrypt_decode(ct, 1).real[0])
 
     def bootstrap(self, ct):
         """[ref: :149-154] mod-switch down to two limbs, then ckks_bootstrapper.bootstrap"""
@@ -188,18 +202,29 @@ def pre_encode_real_diags(ckks, W, D, G, B, level, as_plaintexts=False, compress
     """shard = (rank, world): keep only this rank's giant groups (giant-step sharding over GPUs)."""
     W = np.asarray(W, dtype=np.float64)
     if as_plaintexts:
-        return _batch_encode_diags_real(ckks, _extract_diagonals(W, D), D, G, ckks.slots, level)
-    # diagonal extraction and pre-rotation run on the device (the host gather alone took 0.19 s at D = 2048)
+        return _batch_encode_diags_real(ckks, _extract_diagonals(_padded(W, D), D), D, G, ckks.slots, level)
+    # diagonal extraction and pre-rotation run on the device (the host gather alone took 0.19 s at D = 2048); W may be a
+    # view of a larger weight matrix (chunks, transposes) and smaller than D x D: it is read as it lies in host memory
     return ph.diagonal_set.from_matrix(ckks.ctx, W[:D, :D], G, B, ckks.diag_scale, chain_index=level, compress=compress,
-                                       shard=shard)
+                                       shard=shard, D=D)
 
 
 def pre_encode_complex_diags(ckks, W1, W2, D, G, B, level, as_plaintexts=False, compress=True, shard=(0, 1)):
     W1, W2 = np.asarray(W1, dtype=np.float64), np.asarray(W2, dtype=np.float64)
     if as_plaintexts:
-        return _batch_encode_diags_complex(ckks, _extract_diagonals(W1, D), _extract_diagonals(W2, D), D, G, ckks.slots, level)
+        return _batch_encode_diags_complex(ckks, _extract_diagonals(_padded(W1, D), D), _extract_diagonals(_padded(W2, D), D), D, G,
+                                           ckks.slots, level)
     return ph.diagonal_set.from_matrix(ckks.ctx, W1[:D, :D], G, B, ckks.diag_scale, chain_index=level, compress=compress,
-                                       shard=shard, M_imag=W2[:D, :D])
+                                       shard=shard, M_imag=W2[:D, :D], D=D)
+
+
+def _padded(W, D):
+    """W zero-padded to D x D (host copy; only the plaintext-list forms need it)"""
+    if W.shape == (D, D):
+        return W
+    M = np.zeros((D, D))
+    M[:min(D, W.shape[0]), :min(D, W.shape[1])] = W[:D, :D]
+    return M
 
 
 def _chunk_pairs(F, D):
@@ -211,17 +236,13 @@ def _chunk_pairs(F, D):
 def _key_chunk(W, c, D, F):
     """rows = outputs of chunk c of a (D, F) matrix used as x @ W  [ref: :287-291]"""
     lo, hi = c * D, min((c + 1) * D, F)
-    M = np.zeros((D, D))
-    M[:hi - lo, :] = W[:, lo:hi].T
-    return M
+    return W[:, lo:hi].T          # a (hi - lo, D) view: the device reads it in place and zero-pads to D x D
 
 
 def _val_chunk(W, c, D, F, sign=1.0):
     """columns = inputs of chunk c of an (F, D) matrix used as x @ W  [ref: :313-317]"""
     lo, hi = c * D, min((c + 1) * D, F)
-    M = np.zeros((D, D))
-    M[:, :hi - lo] = sign * W[lo:hi, :].T
-    return M
+    return W[lo:hi, :].T if sign == 1.0 else (sign * W[lo:hi, :]).T      # a (D, hi - lo) view (one scaled copy for sign = -1)
 
 
 def pre_encode_block(ckks, block, D, F, G=None, B=None, as_plaintexts=False, shard=(0, 1)):

@@ -1,5 +1,7 @@
 // api.cu -- extern "C" surface declared in include/spear_b200.h.
 // Thin: argument checks, object allocation, and calls into the engine (bsgs.cu / ops.cu / ...).
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <exception>
 #include <string>
@@ -516,6 +518,70 @@ int spear_decrypt(spear_context* ctx, const spear_secret_key* sk_, const spear_o
     API_END
 }
 
+// ---- fused client legs (client.cu) ------------------------------------------------------------------
+int spear_encrypt_vector(spear_context* ctx, const spear_secret_key* sk_, const double* values, int count, int replicate,
+                         double scale, uint64_t enc_id, spear_obj** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const SecretKey* sk = reinterpret_cast<const SecretKey*>(sk_);
+    const int slots = c->N / 2, l = c->L;
+    REQUIRE(values && count >= 1 && count <= slots, "encrypt_vector: 1..%d slot values expected", slots);
+    REQUIRE(scale > 0, "encrypt_vector: scale must be positive");
+    // |coefficient| <= max |z| * scale: the three-launch path needs no device-side overflow flag below 2^125
+    double zmax = 0.0;
+    for (int i = 0; i < 2 * count; i++) zmax = std::max(zmax, std::fabs(values[i]));
+    if (client::fused_applies(c) && zmax * scale < 0x1p125) {
+        std::unique_ptr<Obj> ct(new_obj(c, 2, l, false, c->N, scale));
+        double2* dv = (double2*)c->alloc((size_t)2 * count);
+        double2* W = (double2*)c->alloc((size_t)2 * c->N);
+        CUDA_CHECK(cudaMemcpyAsync(dv, values, sizeof(double2) * count, cudaMemcpyHostToDevice, c->stream));
+        client::encode_encrypt(c, dv, count, replicate != 0, scale, l, sk->seed, enc_id, sk->d, ct->d, W, c->stream);
+        c->free(dv);
+        c->free(W);
+        *out = H_(ct.release());
+        return SPEAR_OK;
+    }
+    // staged form: the full slot vector on the host, encode, encrypt
+    std::vector<double> full((size_t)2 * slots, 0.0);
+    for (int j = 0; j < (replicate ? slots : count); j++) {
+        full[2 * j] = values[2 * (j % count)];
+        full[2 * j + 1] = values[2 * (j % count) + 1];
+    }
+    spear_obj* pt = nullptr;
+    int rc = spear_encode(ctx, full.data(), 1, c->N, scale, 1, 0, &pt);
+    if (rc) return rc;
+    rc = spear_encrypt_symmetric(ctx, sk_, pt, enc_id, out);
+    spear_obj_destroy(pt);
+    return rc;
+    API_END
+}
+int spear_decrypt_decode(spear_context* ctx, const spear_secret_key* sk_, const spear_obj* ct_, double* out, int want) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const SecretKey* sk = reinterpret_cast<const SecretKey*>(sk_);
+    const Obj* ct = O_(ct_);
+    check_ct(ct, "decrypt_decode");
+    REQUIRE(out && want >= 1 && want <= c->N / 2, "decrypt_decode: 1..%d slots", c->N / 2);
+    double2* dv = (double2*)c->alloc((size_t)c->N);
+    if (client::fused_applies(c)) {
+        u64* x = c->alloc((size_t)3 * c->N);
+        double2* W = (double2*)c->alloc((size_t)2 * c->N);
+        client::decrypt_decode(c, ct->d, ct->size, ct->l, ct->scale, sk->d, dv, want, x, W, c->stream);
+        c->free(x);
+        c->free(W);
+    } else {
+        std::unique_ptr<Obj> pt(new_obj(c, 1, ct->l, false, c->N, ct->scale));
+        sampler::dec_combine(c, ct->d, ct->size, ct->l, sk->d, pt->d, c->stream);
+        encoder::decode(c, pt->d, pt->l, pt->scale, dv, c->stream);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(out, dv, sizeof(double2) * want, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->free(dv);
+    API_END
+}
+
 // ---- evaluator ------------------------------------------------------------------------------------
 int spear_negate(spear_context* ctx, const spear_obj* a_, spear_obj** out) {
     API_BEGIN
@@ -823,6 +889,24 @@ static DiagSet* diagset_build(Ctx* c, const double* host, double2* dv_in, int n_
             dv = (double2*)c->alloc((size_t)n_diags * D * 2);
             CUDA_CHECK(cudaMemcpyAsync(dv, host, sizeof(double2) * n_diags * D, cudaMemcpyHostToDevice, c->stream));
         }
+        static const bool fused_enc = [] {
+            const char* e = getenv("SPEAR_FUSED_ENCODE");
+            return !(e && e[0] == '0');
+        }();
+        if (fused_enc && n == 2 * D) {   // sub-ring diagonals: one kernel per set, one synchronisation for the overflow flag
+            int* flag = (int*)c->alloc(1);
+            CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
+            if (encoder::encode_ring_fused(c, dv, n_diags, n, scale, l, true, ds->d, /*split30_out=*/true, flag, c->stream)) {
+                int h_flag = 0;
+                CUDA_CHECK(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                CUDA_CHECK(cudaStreamSynchronize(c->stream));
+                c->free(flag);
+                if (!dv_in) c->free(dv);
+                REQUIRE(!h_flag, "encode: scaled value too large (|coefficient| >= 2^126)");
+                return ds.release();
+            }
+            c->free(flag);
+        }
         const int chunk = std::max(1, std::min(n_diags, (int)((32u << 20) / ((size_t)n))));
         double2* full = n == 2 * D ? nullptr : (double2*)c->alloc((size_t)chunk * slots * 2);
         for (int v0 = 0; v0 < n_diags; v0 += chunk) {
@@ -852,8 +936,12 @@ int spear_diagset_encode_shard(spear_context* ctx, const double* diags, int n_di
 }
 // rows of the shard's giant groups straight from the matrix: row (g, b), k = gG + b:
 //   out[row][t] = M[j][(j + k) mod D],  j = (t - gG) mod D     (diagonal k of y = M x, rolled right by gG)
+// The device copy of the matrix keeps the host layout: element (i, j) of M sits at  i * ld + j  (or  j * ld + i  when
+// `transposed`), and is zero outside [0, rv) x [0, cv) -- so callers hand over views such as W[:, lo:hi].T without a
+// host-side transposed copy (33 MB and ~35 ms per chunk at D = 2048).
 __global__ void k_diag_rows(const double* __restrict__ mre, const double* __restrict__ mim, double2* __restrict__ out,
-                            int n_diags, int D, int G, int B, int g_first, int g_stride) {
+                            int n_diags, int D, int G, int B, int g_first, int g_stride, int ld, int transposed, int rv,
+                            int cv) {
     const size_t total = (size_t)n_diags * D;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const int row = (int)(e / D), t = (int)(e % D);
@@ -861,27 +949,56 @@ __global__ void k_diag_rows(const double* __restrict__ mre, const double* __rest
         const int gi = row / G, b = row % G, g = g_first + gi * g_stride, k = g * G + b;
         int j = t - (g * G) % D;
         if (j < 0) j += D;
-        const size_t at = (size_t)j * D + (j + k) % D;
-        out[e] = make_double2(mre[at], mim ? mim[at] : 0.0);
+        const int col = (j + k) % D;
+        double re = 0.0, im = 0.0;
+        if (j < rv && col < cv) {
+            const size_t at = transposed ? (size_t)col * ld + j : (size_t)j * ld + col;
+            re = mre[at];
+            if (mim) im = mim[at];
+        }
+        out[e] = make_double2(re, im);
     }
 }
 int spear_diagset_encode_matrix(spear_context* ctx, const double* m_re, const double* m_im, int D, int G, int B,
                                 int g_first, int g_stride, double scale, int chain_index, int compress,
                                 spear_diagset** out) {
+    return spear_diagset_encode_matrix_view(ctx, m_re, m_im, D, D, D, (size_t)D, 0, G, B, g_first, g_stride, scale, chain_index,
+                                            compress, out);
+}
+int spear_diagset_encode_matrix_view(spear_context* ctx, const double* m_re, const double* m_im, int D, int rows_valid,
+                                     int cols_valid, size_t pitch, int transposed, int G, int B, int g_first, int g_stride,
+                                     double scale, int chain_index, int compress, spear_diagset** out) {
     API_BEGIN
     Ctx* c = C_(ctx);
     use(c);
     REQUIRE(m_re && D >= 1 && G >= 1 && B >= 1 && g_first >= 0 && g_stride >= 1, "diagset: bad matrix arguments");
+    REQUIRE(rows_valid >= 0 && rows_valid <= D && cols_valid >= 0 && cols_valid <= D, "diagset: view larger than D x D");
+    // host lines: `lines` runs of `run` contiguous doubles, `pitch` doubles apart; compacted on the device (ld = run)
+    const int lines = transposed ? cols_valid : rows_valid, run = transposed ? rows_valid : cols_valid;
+    REQUIRE(pitch >= (size_t)run, "diagset: pitch %zu shorter than a line of %d", pitch, run);
     int n_diags = 0;
     for (int g = g_first; g < B && g * G < D; g += g_stride) n_diags += std::min(G, D - g * G);
-    const size_t mw = (size_t)D * D;
+    const size_t mw = (size_t)std::max(lines, 1) * std::max(run, 1);
     double* dm = (double*)c->alloc(mw * (m_im ? 2 : 1));
-    CUDA_CHECK(cudaMemcpyAsync(dm, m_re, sizeof(double) * mw, cudaMemcpyHostToDevice, c->stream));
-    if (m_im) CUDA_CHECK(cudaMemcpyAsync(dm + mw, m_im, sizeof(double) * mw, cudaMemcpyHostToDevice, c->stream));
+    if (lines > 0 && run > 0) {
+        // pageable caller memory: the lines are packed into the context's page-locked staging buffer (plain memcpy, one
+        // line at a time) and cross the bus in one asynchronous copy
+        const int parts = m_im ? 2 : 1;
+        double* st = (double*)c->staging(sizeof(double) * mw * parts);
+        for (int part = 0; part < parts; part++) {
+            const double* src = part ? m_im : m_re;
+            double* dst = st + (size_t)part * mw;
+            if (pitch == (size_t)run) memcpy(dst, src, sizeof(double) * mw);
+            else
+                for (int i = 0; i < lines; i++) memcpy(dst + (size_t)i * run, src + (size_t)i * pitch, sizeof(double) * run);
+        }
+        CUDA_CHECK(cudaMemcpyAsync(dm, st, sizeof(double) * mw * parts, cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaEventRecord(c->staged, c->stream));
+    }
     double2* dv = (double2*)c->alloc((size_t)std::max(n_diags, 1) * D * 2);
     if (n_diags > 0)
         LAUNCH(k_diag_rows, c->sm_count * 8, 256, 0, c->stream)(dm, m_im ? dm + mw : nullptr, dv, n_diags, D, G, B, g_first,
-                                                              g_stride);
+                                                              g_stride, run, transposed ? 1 : 0, rows_valid, cols_valid);
     DiagSet* ds = nullptr;
     try {
         ds = diagset_build(c, nullptr, dv, n_diags, D, G, B, g_first, g_stride, scale, chain_index, compress);

@@ -102,6 +102,22 @@ __device__ __forceinline__ u64 mul_shoup(u64 a, u64 w, u64 wp, u64 q) {
     u64 r = mul_shoup_lazy(a, w, wp, q);
     return r >= q ? r - q : r;
 }
+// Harvey lazy butterflies shared by the transforms (ntt.cu) and the one-kernel ring encoder (encoder.cu)
+__device__ __forceinline__ void ct_butterfly(u64& x, u64& y, ulonglong2 w, u64 q, u64 q2) {
+    // x, y in [0,4q) -> x + w*y, x - w*y in [0,4q)
+    u64 u = x >= q2 ? x - q2 : x;
+    u64 t = mul_shoup_lazy(y, w.x, w.y, q);
+    x = u + t;
+    y = u - t + q2;
+}
+__device__ __forceinline__ void gs_butterfly(u64& x, u64& y, ulonglong2 w, u64 q, u64 q2) {
+    // x, y in [0,2q) -> x + y, (x - y)*w in [0,2q)
+    u64 s = x + y;
+    u64 d = x - y + q2;
+    x = s >= q2 ? s - q2 : s;
+    y = mul_shoup_lazy(d, w.x, w.y, q);
+}
+
 // x mod q for any x < 2^64; r1 = floor(2^64 / q)
 __device__ __forceinline__ u64 barrett64(u64 x, u64 q, u64 r1) {
     u64 h = __umul64hi(x, r1);

@@ -133,6 +133,17 @@ u64* Ctx::workspace(cudaStream_t s, size_t words) const {
     }
     return ws_base[slot];
 }
+void* Ctx::staging(size_t bytes) const {
+    if (!staged) CUDA_CHECK(cudaEventCreateWithFlags(&staged, cudaEventDisableTiming));
+    else CUDA_CHECK(cudaEventSynchronize(staged));   // the previous upload has left the buffer
+    if (stage_cap < bytes) {
+        if (stage_base) CUDA_CHECK(cudaFreeHost(stage_base));
+        stage_base = nullptr, stage_cap = 0;
+        CUDA_CHECK(cudaMallocHost(&stage_base, bytes));
+        stage_cap = bytes;
+    }
+    return stage_base;
+}
 void Ctx::free(void* p, cudaStream_t s) const {
     if (p) cudaFreeAsync(p, s ? s : stream);
 }
@@ -270,6 +281,18 @@ Ctx* ctx_create(u64 N, const u64* moduli, int K, int P, int device) {
         zeta[brev((u32)k, c->logn)] = make_double2(cos(ang), sin(ang));
     }
     c->d_zeta = upload(zeta);
+    // slot j sits at position bitrev((5^j mod 2N - 1) / 2), its conjugate at bitrev((2N - 5^j mod 2N - 1) / 2)
+    std::vector<u32> pos_slot(N);
+    {
+        const u64 m = 2 * N;
+        u64 pos = 1;
+        for (u64 j = 0; j < N / 2; j++) {
+            pos_slot[brev((u32)((pos - 1) >> 1), c->logn)] = (u32)j;
+            pos_slot[brev((u32)((m - pos - 1) >> 1), c->logn)] = (u32)j | 0x80000000u;
+            pos = pos * 5 % m;
+        }
+    }
+    c->d_pos_slot = upload(pos_slot);
     return c.release();
 }
 
@@ -286,9 +309,11 @@ void ctx_destroy(Ctx* c) {
     for (void* p : {(void*)c->d_q, (void*)c->d_ratio0, (void*)c->d_ratio1, (void*)c->d_rwide, (void*)c->d_psi, (void*)c->d_ipsi,
                     (void*)c->d_invn, (void*)c->d_pmod, (void*)c->d_pinv, (void*)c->d_up_hatinv, (void*)c->d_up_hat, (void*)c->d_up_hatinv_n,
                     (void*)c->d_dn_hatinv, (void*)c->d_dn_half, (void*)c->d_dn_hat, (void*)c->d_rs_inv,
-                    (void*)c->d_garner, (void*)c->d_zeta})
+                    (void*)c->d_garner, (void*)c->d_zeta, (void*)c->d_pos_slot})
         cudaFree(p);
     for (int i = 0; i < 4; i++) cudaFree(c->ws_base[i]);
+    if (c->stage_base) cudaFreeHost(c->stage_base);
+    if (c->staged) cudaEventDestroy(c->staged);
     for (int i = 0; i < 3; i++) {
         cudaStreamDestroy(c->aux[i]);
         cudaEventDestroy(c->ev_aux[i]);

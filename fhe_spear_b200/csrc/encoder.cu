@@ -138,6 +138,94 @@ __global__ void k_dec_gather(const double2* __restrict__ W, double2* __restrict_
     }
 }
 
+// ---- one kernel per encoding for rings that fit shared memory (sub-ring diagonals: n = 2D <= 8192) ----------------
+// A CTA encodes one vector completely: scatter to the embedding order, the n-point inverse embedding (same
+// Gentleman-Sande stages as k_fft_inv_stage, in shared memory), rounding to 128-bit integers, and for every limb the
+// residues and the n-point forward NTT (same butterflies and twiddle prefix as ntt_forward on a ring of n), written out
+// once, already in the split-30 storage form of the diagonal MAC.  Bit-identical to the staged path; it replaces
+// 12 + 2 stage launches over count * n words each, a 2.6 GB round trip at C5 and a host synchronisation per batch
+// (fully encrypted blocks encode four diagonal sets per block on the fly, reference test_fully_enc_bsgs.py:41-79).
+__global__ void __launch_bounds__(256) k_encode_ring_fused(const double2* __restrict__ vals, u64* __restrict__ out, int n,
+                                                           int logn, int rows, RowMap rm, double fix, ModTab mt,
+                                                           NttTab tb, int N, const double2* __restrict__ zeta,
+                                                           int split, int* __restrict__ overflow) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    double2* W = reinterpret_cast<double2*>(smraw);                 // [n]   embedding values, then (lo, hi | sign) integers
+    u64* buf = reinterpret_cast<u64*>(W + n);                       // [n]   one limb's residues
+    const int T = blockDim.x, tid = threadIdx.x, half = n >> 1;
+    const size_t v = blockIdx.x;
+    const u32 m2 = 2u * n;
+    for (int j = tid; j < half; j += T) {
+        const u32 pos = pow5_mod((u32)j, m2 - 1);
+        const double2 z = vals[v * half + j];
+        W[brev_n((pos - 1) >> 1, logn)] = z;
+        W[brev_n((m2 - pos - 1) >> 1, logn)] = make_double2(z.x, -z.y);
+    }
+    __syncthreads();
+    for (int m = n, t = 1; m > 1; m >>= 1, t <<= 1) {               // inverse embedding: gap t doubles, twiddle conj(zeta[h + i])
+        const int h = m >> 1;
+        for (int b = tid; b < half; b += T) {
+            const int i = b / t, kk = b - i * t;
+            double2* a = W + 2 * i * t + kk;
+            const double2 w = zeta[h + i], U = a[0], V = a[t];
+            const double wr = w.x, wi = -w.y;
+            a[0] = make_double2(__dadd_rn(U.x, V.x), __dadd_rn(U.y, V.y));
+            const double dr = __dsub_rn(U.x, V.x), di = __dsub_rn(U.y, V.y);
+            a[t] = make_double2(__dsub_rn(__dmul_rn(dr, wr), __dmul_rn(di, wi)), __dadd_rn(__dmul_rn(dr, wi), __dmul_rn(di, wr)));
+        }
+        __syncthreads();
+    }
+    u64* I = reinterpret_cast<u64*>(W);                             // I[2j] = low word, I[2j+1] = high word | sign << 63
+    for (int j = tid; j < n; j += T) {
+        const double x = rint(__dmul_rn(W[j].x, fix));
+        const bool neg = x < 0.0;
+        double ax = fabs(x);
+        if (!(ax < 0x1p126)) {
+            *overflow = 1;
+            ax = 0.0;
+        }
+        u64 lo = 0, hi = 0;
+        if (ax >= 1.0) {
+            const long long bits = __double_as_longlong(ax);
+            const int ex = (int)(bits >> 52) - 1075;
+            const u64 mant = ((u64)bits & 0xFFFFFFFFFFFFFull) | (1ull << 52);
+            if (ex <= 0) lo = mant >> (-ex);
+            else if (ex < 64) lo = mant << ex, hi = mant >> (64 - ex);
+            else hi = mant << (ex - 64);
+        }
+        I[2 * j] = lo, I[2 * j + 1] = hi | ((u64)neg << 63);      // |coefficient| < 2^126: bit 63 of the high word is free
+    }
+    __syncthreads();
+    for (int r = 0; r < rows; r++) {
+        const int lt = rm.limb(r);
+        const u64 q = mt.q[lt], q2 = q << 1, r0 = mt.ratio0[lt], r1 = mt.ratio1[lt];
+        const ulonglong2* __restrict__ tw = tb.psi + (size_t)lt * N;
+        for (int j = tid; j < n; j += T) {
+            const u64 hi = I[2 * j + 1];
+            const u64 res = barrett128(I[2 * j], hi & ~(1ull << 63), q, r0, r1);
+            buf[j] = (hi >> 63) ? neg_mod(res, q) : res;
+        }
+        __syncthreads();
+        for (int m = 1, t = half; m < n; m <<= 1, t >>= 1) {        // forward NTT on the ring of n: twiddles psi[m + i]
+            for (int b = tid; b < half; b += T) {
+                const int i = b / t, kk = b - i * t, x0 = 2 * i * t + kk;
+                u64 x = buf[x0], y = buf[x0 + t];
+                ct_butterfly(x, y, tw[m + i], q, q2);
+                buf[x0] = x, buf[x0 + t] = y;
+            }
+            __syncthreads();
+        }
+        u64* o = out + (v * rows + r) * n;
+        for (int j = tid; j < n; j += T) {
+            u64 x = buf[j];
+            x = x >= q2 ? x - q2 : x;
+            x = x >= q ? x - q : x;
+            o[j] = split ? split30(x) : x;
+        }
+        __syncthreads();
+    }
+}
+
 int grid_for(const Ctx* c, size_t total) {
     size_t blocks = (total + TPB - 1) / TPB, cap = (size_t)c->sm_count * 16;
     return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
@@ -170,6 +258,26 @@ void encode(const Ctx* c, const double2* vals, int count, int n, double scale, i
     c->free(W);
     c->free(flag);
     REQUIRE(!h_flag, "encode: scaled value too large (|coefficient| >= 2^126)");
+}
+
+// count vectors on a ring of n <= 8192, one kernel; out in split-30 form when `split30_out`.  `overflow`: sticky device
+// flag (the caller checks it once per batch).  false: the ring does not fit shared memory.
+bool encode_ring_fused(const Ctx* c, const double2* vals, int count, int n, double scale, int l, bool ext, u64* out,
+                       bool split30_out, int* overflow, cudaStream_t s) {
+    int logn = 0;
+    while ((1 << logn) < n) logn++;
+    const size_t smem = (size_t)n * (sizeof(double2) + sizeof(u64));
+    if ((1 << logn) != n || n < 4 || n > c->N || smem > 200 * 1024 || count < 1) return false;
+    const int rows = l + (ext ? c->P : 0);
+    CUDA_CHECK(cudaFuncSetAttribute(k_encode_ring_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int v0 = 0; v0 < count; v0 += 65535 * 16) {   // grid.x is wide enough; kept as a loop for clarity of the bound
+        const int nv = std::min(count - v0, 65535 * 16);
+        LAUNCH(k_encode_ring_fused, nv, 256, smem, s)(vals + (size_t)v0 * (n / 2), out + (size_t)v0 * rows * n, n, logn, rows,
+                                                     RowMap{rows, l, c->L, 0}, scale / (double)n, c->modtab(), c->ntttab(), c->N,
+                                                     c->d_zeta, split30_out ? 1 : 0, overflow);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    return true;
 }
 
 void decode(const Ctx* c, const u64* pt, int l, double scale, double2* vals, cudaStream_t s) {

@@ -43,6 +43,8 @@ struct Ctx {
     ulonglong2* d_garner = nullptr;
     // encoder: complex roots zeta^{bitrev(i)}, slot index maps are computed in-kernel
     double2* d_zeta = nullptr;
+    // embedding position p (index into the FFT array) -> slot index, bit 31 set where the position holds the conjugate
+    u32* d_pos_slot = nullptr;
 
     ModTab modtab() const { return ModTab{d_q, d_ratio0, d_ratio1, d_rwide}; }
     NttTab ntttab() const { return NttTab{d_psi, d_ipsi, d_invn, d_q}; }
@@ -61,6 +63,12 @@ struct Ctx {
     u64* workspace(cudaStream_t s, size_t words) const;
     mutable u64* ws_base[4] = {nullptr, nullptr, nullptr, nullptr};
     mutable size_t ws_cap[4] = {0, 0, 0, 0};
+    // grow-only page-locked staging buffer for host -> device uploads of pageable caller memory (diagonal-set matrices):
+    // rows are packed into it by the CPU and leave in ONE asynchronous copy; `staged` guards its reuse
+    void* staging(size_t bytes) const;
+    mutable void* stage_base = nullptr;
+    mutable size_t stage_cap = 0;
+    mutable cudaEvent_t staged = nullptr;
     u64* alloc(size_t n_u64, cudaStream_t s = nullptr) const;   // stream-ordered (default: the main stream)
     void free(void* p, cudaStream_t s = nullptr) const;
 };

@@ -68,6 +68,18 @@ void asym_combine(const Ctx* c, const u64* pk, const u64* u, const u64* e0, cons
 namespace encoder {
 // values: host-resident doubles already on device as (re, im) pairs: [count][n/2]; out: [count][rows][n]
 void encode(const Ctx* c, const double2* vals, int count, int n, double scale, int l, bool ext, u64* out, cudaStream_t s);
+// the same in ONE kernel for rings that fit shared memory (sub-ring diagonals); overflow: sticky device flag
+bool encode_ring_fused(const Ctx* c, const double2* vals, int count, int n, double scale, int l, bool ext, u64* out,
+                       bool split30_out, int* overflow, cudaStream_t s);
 // pt [l][N] -> vals [N/2] (re, im)
 void decode(const Ctx* c, const u64* pt, int l, double scale, double2* vals, cudaStream_t s);
 }  // namespace encoder
+
+namespace client {
+// the client legs of a projection round trip in three launches each (client.cu); false: use the staged path
+bool fused_applies(const Ctx* c);
+void encode_encrypt(const Ctx* c, const double2* vals, int nvals, bool replicate, double scale, int l, const u32* seed,
+                    u64 enc_id, const u64* sk, u64* ct, double2* W, cudaStream_t s);
+void decrypt_decode(const Ctx* c, const u64* ct, int size, int l, double scale, const u64* sk, double2* vals_out, int want,
+                    u64* x, double2* W, cudaStream_t s);
+}  // namespace client

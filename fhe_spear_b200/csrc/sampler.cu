@@ -4,39 +4,13 @@
 // generated here are bit-identical to the oracle's for the same 32-byte seed.
 // Client-side surface replaced: PhantomSecretKey::{gen_*, encrypt_symmetric, decrypt},
 // PhantomPublicKey::encrypt_asymmetric (reference gpu/phantom_binding.cu:100-116).
+#include "chacha.cuh"
 #include "engine.h"
 #include "ops.h"
 
 namespace {
 
 constexpr int TPB = 256;
-
-struct Seed {
-    u32 k[8];
-};
-
-__device__ __forceinline__ u32 rotl(u32 v, int n) { return (v << n) | (v >> (32 - n)); }
-#define QR(a, b, c, d)                                                  \
-    a += b; d ^= a; d = rotl(d, 16); c += d; b ^= c; b = rotl(b, 12);   \
-    a += b; d ^= a; d = rotl(d, 8);  c += d; b ^= c; b = rotl(b, 7);
-
-__device__ void chacha_block(const Seed& key, u64 nonce, u64 counter, u64 out[8]) {
-    u32 s[16], x[16];
-    s[0] = 0x61707865u, s[1] = 0x3320646eu, s[2] = 0x79622d32u, s[3] = 0x6b206574u;
-#pragma unroll
-    for (int i = 0; i < 8; i++) s[4 + i] = key.k[i];
-    s[12] = (u32)counter, s[13] = (u32)(counter >> 32);
-    s[14] = (u32)nonce, s[15] = (u32)(nonce >> 32);
-#pragma unroll
-    for (int i = 0; i < 16; i++) x[i] = s[i];
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-        QR(x[0], x[4], x[8], x[12]) QR(x[1], x[5], x[9], x[13]) QR(x[2], x[6], x[10], x[14]) QR(x[3], x[7], x[11], x[15])
-        QR(x[0], x[5], x[10], x[15]) QR(x[1], x[6], x[11], x[12]) QR(x[2], x[7], x[8], x[13]) QR(x[3], x[4], x[9], x[14])
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++) out[i] = (u64)(x[2 * i] + s[2 * i]) | ((u64)(x[2 * i + 1] + s[2 * i + 1]) << 32);
-}
 
 // 4 coefficients per thread: coefficient j of limb t uses words 2*(t*N + j), +1 as (hi, lo) of a 128-bit value
 __global__ void __launch_bounds__(TPB) k_uniform(Seed seed, u64 nonce, u64* __restrict__ out, int N, RowMap rm, ModTab mt) {
@@ -63,8 +37,7 @@ __global__ void __launch_bounds__(TPB) k_small(Seed seed, u64 nonce, u64* __rest
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         u64 w = blk[k];
-        if (KIND == 0) v[k] = (int)__umul64hi(w, 3ull) - 1;
-        else v[k] = __popcll(w & 0x1FFFFFull) - __popcll((w >> 21) & 0x1FFFFFull);
+        v[k] = KIND == 0 ? ternary_of_word(w) : cbd_of_word(w);
     }
     for (int r = 0; r < nrows; r++) {
         const u64 q = mt.q[rm.limb(r)];
@@ -127,11 +100,7 @@ __global__ void k_asym_combine(const u64* __restrict__ pk, const u64* __restrict
     }
 }
 
-Seed mk(const u32* s) {
-    Seed k;
-    for (int i = 0; i < 8; i++) k.k[i] = s[i];
-    return k;
-}
+Seed mk(const u32* s) { return make_seed(s); }
 int grid_for(const Ctx* c, size_t total) {
     size_t blocks = (total + TPB - 1) / TPB, cap = (size_t)c->sm_count * 16;
     return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);

@@ -15,6 +15,9 @@ from . import bsgs as hb
 from . import pyPhantom as ph
 
 
+PHASES = None   # set to a dict to collect host-clock seconds per phase (synchronising; tools/fully_enc_bench.py --phases)
+
+
 def plaintext_ffn_block(x, W_key, W_val):
     """[ref: :121-125]"""
     return x + ((x @ W_key) ** 2) @ W_val
@@ -40,11 +43,21 @@ def _matvecs(ckks, cts, mats, D, G, B, shard, reference_order=False):
             outs.append(hb.fhe_matmul_bsgs(ckks, ct, M, D, G, B, baby))
         return outs
     level = cts[0].chain_index()
+    t0 = time.perf_counter()
     sets = [hb.pre_encode_real_diags(ckks, M, D, G, B, level, shard=shard) for M in mats]
+    if PHASES is not None:
+        ckks.ctx.synchronize()
+        PHASES["encode_diagonals"] = PHASES.get("encode_diagonals", 0.0) + time.perf_counter() - t0
+        t0 = time.perf_counter()
     if shard[1] > 1:
         from .sharding import sharded_matvec_batch
-        return sharded_matvec_batch(ckks, cts, sets)
-    return ph.bsgs_hoisted_batch(ckks.ctx, cts, sets, ckks.gk)
+        outs = sharded_matvec_batch(ckks, cts, sets)
+    else:
+        outs = ph.bsgs_hoisted_batch(ckks.ctx, cts, sets, ckks.gk)
+    if PHASES is not None:
+        ckks.ctx.synchronize()
+        PHASES["matvecs"] = PHASES.get("matvecs", 0.0) + time.perf_counter() - t0
+    return outs
 
 
 def fully_encrypted_ffn_block(ckks, ct_x_rep, W_key, W_val, D, F, block_idx=0, split=None, shard=(0, 1), verbose=False,
@@ -57,17 +70,13 @@ def fully_encrypted_ffn_block(ckks, ct_x_rep, W_key, W_val, D, F, block_idx=0, s
     mats = []
     for c in range(n_chunks):                                   # FFN key: one mat-vec per chunk of D outputs
         lo, hi = c * D, min((c + 1) * D, F)
-        M = np.zeros((D, D))
-        M[:hi - lo, :] = W_key[:, lo:hi].T
-        mats.append(M)
+        mats.append(W_key[:, lo:hi].T if not reference_order else hb._padded(W_key[:, lo:hi].T, D))   # a view: no host transpose
     ct_sq = [ph.rescale_to_next(ckks.ctx, ph.relinearize(ckks.ctx, ph.multiply(ckks.ctx, fk, fk), ckks.rlk))
              for fk in _matvecs(ckks, [ct_x_rep] * n_chunks, mats, D, G, B, shard, reference_order)]
     mats = []
     for c in range(n_chunks):                                   # FFN value: chunk partials summed homomorphically
         lo, hi = c * D, min((c + 1) * D, F)
-        M = np.zeros((D, D))
-        M[:, :hi - lo] = W_val[lo:hi, :].T
-        mats.append(M)
+        mats.append(W_val[lo:hi, :].T if not reference_order else hb._padded(W_val[lo:hi, :].T, D))
     acc = None
     for part in _matvecs(ckks, ct_sq, mats, D, G, B, shard, reference_order):
         if acc is None:

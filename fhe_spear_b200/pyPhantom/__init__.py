@@ -25,6 +25,16 @@ except ImportError:   # imported as top-level `pyPhantom` (sys.path points at fh
 _lib = _n.lib
 _check = _n.check
 
+
+def _bootstrapper():
+    """fhe_spear_b200.bootstrap.Bootstrapper, whether this module was imported as fhe_spear_b200.pyPhantom or -- the
+    way the reference's scripts do -- as top-level `pyPhantom`"""
+    try:
+        from ..bootstrap import Bootstrapper
+    except ImportError:
+        from fhe_spear_b200.bootstrap import Bootstrapper
+    return Bootstrapper
+
 __version__ = _lib.spear_version().decode()
 
 
@@ -386,6 +396,24 @@ class secret_key:
     def decrypt(self, ctx, ct):
         return _new(plaintext, ctx, _lib.spear_decrypt, self._h, ct._h)
 
+    # ---- the client legs of a projection round trip, three launches each (csrc/client.cu) ----------------------
+    def encrypt_vector(self, ctx, values, scale, replicate=True, enc_id=None):
+        """encode + encrypt_symmetric of `values` (real or complex; tiled over all slots when `replicate`, else
+        zero-padded) in one call: the same fresh ciphertext, limb for limb, as
+        encrypt_symmetric(encode_complex_vector(replicated values)) with the same enc_id."""
+        v = np.ascontiguousarray(np.asarray(values, dtype=np.complex128).ravel())
+        if enc_id is None:
+            enc_id = self.reserve_enc_ids(1)
+        return _new(ciphertext, ctx, _lib.spear_encrypt_vector, self._h, v.view(np.float64).ctypes.data_as(_n.f64p),
+                    int(v.size), int(bool(replicate)), float(scale), int(enc_id))
+
+    def decrypt_decode(self, ctx, ct, count=None):
+        """first `count` slots of decode(decrypt(ct)) as a complex array, in one call (bit-identical to the two steps)"""
+        count = ctx.N // 2 if count is None else int(count)
+        out = np.empty(count, dtype=np.complex128)
+        _check(_lib.spear_decrypt_decode(ctx._h, self._h, ct._h, out.view(np.float64).ctypes.data_as(_n.f64p), count))
+        return out
+
     def to_numpy(self):
         c = self._ctx
         out = np.empty((c.L + c.P, c.N), dtype=np.uint64)
@@ -656,23 +684,51 @@ class diagonal_set:
         self._ctx, self._h = ctx, h
         self.D, self.G, self.B, self.shard, self.rows = D, int(G), int(B), (first, stride), rows
 
+    @staticmethod
+    def _view(M):
+        """(array kept alive, pointer, pitch in doubles, transposed) of a 2-D float64 array WITHOUT copying it when one
+        of its strides is the item size: row-pitched views (W[lo:hi, :], W[:, lo:hi]) and their transposes."""
+        M = np.asarray(M, dtype=np.float64)
+        if M.ndim != 2:
+            raise RuntimeError("diagonal_set.from_matrix expects a 2-D matrix")
+        r, c = M.shape
+        s0, s1 = M.strides
+        if (s1 == 8 or c <= 1) and s0 % 8 == 0 and s0 >= 8 * c:
+            return M, s0 // 8 if r > 1 else max(c, 1), 0
+        if (s0 == 8 or r <= 1) and s1 % 8 == 0 and s1 >= 8 * r:
+            return M, s1 // 8 if c > 1 else max(r, 1), 1
+        M = np.ascontiguousarray(M)
+        return M, max(c, 1), 0
+
     @classmethod
-    def from_matrix(cls, ctx, M, G, B, scale, chain_index=1, compress=True, shard=(0, 1), M_imag=None):
+    def from_matrix(cls, ctx, M, G, B, scale, chain_index=1, compress=True, shard=(0, 1), M_imag=None, D=None):
         """Same set from the matrix of y = M x (optionally M + i M_imag for the complex packing): diagonal extraction,
-        the +gG pre-rotation and the slot tiling run on the device; only D*D doubles cross the bus."""
-        M = np.ascontiguousarray(M, dtype=np.float64)
-        D = M.shape[0]
-        if M.shape != (D, D):
-            raise RuntimeError("diagonal_set.from_matrix expects a (D, D) matrix")
-        Mi = None if M_imag is None else np.ascontiguousarray(M_imag, dtype=np.float64)
-        if Mi is not None and Mi.shape != (D, D):
-            raise RuntimeError("diagonal_set.from_matrix: M_imag must have the shape of M")
+        the +gG pre-rotation and the slot tiling run on the device; only the matrix crosses the bus.  M may be any
+        row- or column-pitched VIEW (a chunk W[:, lo:hi].T of a larger weight matrix is taken as it lies in host memory:
+        no transposed host copy) and may be smaller than D x D (zero-padded)."""
+        M, pitch, tr = cls._view(M)
+        D = int(D) if D is not None else max(M.shape)
+        if M.shape[0] > D or M.shape[1] > D:
+            raise RuntimeError("diagonal_set.from_matrix: matrix larger than D x D")
+        Mi = None
+        if M_imag is not None:
+            Mi, pitch_i, tr_i = cls._view(M_imag)
+            if Mi.shape[0] > D or Mi.shape[1] > D:
+                raise RuntimeError("diagonal_set.from_matrix: M_imag larger than D x D")
+            if Mi.shape != M.shape or (pitch_i, tr_i) != (pitch, tr):   # different shapes / layouts: zero-padded compact copies
+                def pad(A):
+                    out = np.zeros((D, D))
+                    out[:A.shape[0], :A.shape[1]] = A
+                    return out
+                M, Mi = pad(M), pad(Mi)
+                pitch, tr = D, 0
         first, stride = int(shard[0]), int(shard[1])
         compress = bool(compress) and (D & (D - 1)) == 0 and D >= 2
         h = C.c_void_p()
-        _check(_lib.spear_diagset_encode_matrix(ctx._h, M.ctypes.data_as(_n.f64p),
-                                                Mi.ctypes.data_as(_n.f64p) if Mi is not None else None, D, int(G), int(B),
-                                                first, stride, float(scale), int(chain_index), int(compress), C.byref(h)))
+        _check(_lib.spear_diagset_encode_matrix_view(ctx._h, M.ctypes.data_as(_n.f64p),
+                                                     Mi.ctypes.data_as(_n.f64p) if Mi is not None else None, D,
+                                                     int(M.shape[0]), int(M.shape[1]), int(pitch), int(tr), int(G), int(B),
+                                                     first, stride, float(scale), int(chain_index), int(compress), C.byref(h)))
         self = cls.__new__(cls)
         self._ctx, self._h = ctx, h
         self.D, self.G, self.B, self.shard = D, int(G), int(B), (first, stride)
@@ -790,7 +846,7 @@ class ckks_bootstrapper:
     @staticmethod
     def get_galois_elements(poly_degree, slots, level_budget):
         """Galois elements of every rotation the linear transforms need, plus conjugation (slots = 0: all N/2)."""
-        from ..bootstrap import Bootstrapper
+        Bootstrapper = _bootstrapper()
         steps = Bootstrapper.rotation_steps(int(poly_degree), tuple(level_budget or ckks_bootstrapper.DEFAULT_BUDGET))
         return sorted(set(get_elts_from_steps(steps, poly_degree)) | {2 * int(poly_degree) - 1})
 
@@ -798,11 +854,11 @@ class ckks_bootstrapper:
     def get_bootstrap_depth(level_budget, poly_degree=32768):
         """Levels between the raised ciphertext and the bootstrapped one (the reference passes the budget only: the
         default degree is the largest ring of its configurations, smaller rings need at most as many levels)."""
-        from ..bootstrap import Bootstrapper
+        Bootstrapper = _bootstrapper()
         return Bootstrapper.depth_for(int(poly_degree), tuple(level_budget or ckks_bootstrapper.DEFAULT_BUDGET))
 
     def setup(self, ctx, level_budget=None):
-        from ..bootstrap import Bootstrapper
+        Bootstrapper = _bootstrapper()
         import sys
         self.impl = Bootstrapper(sys.modules[__name__], ctx, self.encoder, ctx.N, ctx.moduli, ctx.P,
                                  tuple(level_budget or self.DEFAULT_BUDGET))

@@ -281,10 +281,8 @@ class HybridBlock:
         ckks, D = self.ckks, self.D
         cts = []
         for j in js:
-            rep = np.asarray(inputs[j], dtype=np.complex128)
-            rep = np.concatenate([np.tile(rep, ckks.slots // D), rep[:ckks.slots % D]])
-            cts.append(ckks.sk.encrypt_symmetric(ckks.ctx, ckks.encoder.encode_complex_vector(ckks.ctx, rep, ckks.scale),
-                                                 enc_id=base + j))
+            cts.append(ckks.sk.encrypt_vector(ckks.ctx, np.asarray(inputs[j], dtype=np.complex128), ckks.scale,
+                                              replicate=True, enc_id=base + j))
         return cts
 
     def _serve(self, phase, inputs):

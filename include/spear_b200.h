@@ -123,6 +123,17 @@ int spear_encrypt_asymmetric(spear_context* ctx, const spear_public_key* pk, con
 /* [ref: phantom_binding.cu:108-110 decrypt] */
 int spear_decrypt(spear_context* ctx, const spear_secret_key* sk, const spear_obj* ct, spear_obj** out);
 
+/* The client legs of a projection round trip, three kernel launches each [ref: CKKSBootstrapContext.encrypt /
+ * encrypt_replicated / encrypt_replicated_complex and decrypt_vec / decrypt_vec_complex / decrypt_slot0,
+ * scripts/bootstrap_generation.py:119-147 -- encode_*_vector + sk.encrypt_symmetric, sk.decrypt + decode_*_vector].
+ * values: `count` complex slot values (interleaved re, im) on the host; replicate != 0 tiles them over all slots
+ * (replicate_vector, :53-58), else the remaining slots are zero.  Fresh ciphertext (chain_index 1), bit-identical to
+ * spear_encode + spear_encrypt_symmetric with the same enc_id.  out of spear_decrypt_decode: the first `want` slots
+ * (interleaved re, im), bit-identical to spear_decrypt + spear_decode. */
+int spear_encrypt_vector(spear_context* ctx, const spear_secret_key* sk, const double* values, int count, int replicate,
+                         double scale, uint64_t enc_id, spear_obj** out);
+int spear_decrypt_decode(spear_context* ctx, const spear_secret_key* sk, const spear_obj* ct, double* out, int want);
+
 /* ---- evaluator  [ref: phantom_binding.cu:165-205] ----------------------------------------------------- */
 int spear_negate(spear_context* ctx, const spear_obj* a, spear_obj** out);
 int spear_add(spear_context* ctx, const spear_obj* a, const spear_obj* b, spear_obj** out);
@@ -173,6 +184,13 @@ int spear_diagset_encode_shard(spear_context* ctx, const double* diags, int n_di
 int spear_diagset_encode_matrix(spear_context* ctx, const double* m_re, const double* m_im, int D, int G, int B,
                                 int g_first, int g_stride, double scale, int chain_index, int compress,
                                 spear_diagset** out);
+/* the same from a VIEW of host memory, so that chunks of a larger weight matrix need no host-side copy
+ * [ref: the chunk extraction of fhe_projection_bsgs :575-591, :630-642 and test_fully_enc_bsgs.py:41-79]:
+ * M[i][j] = m[i * pitch + j] (transposed = 0) or m[j * pitch + i] (transposed != 0) for i < rows_valid, j < cols_valid,
+ * zero elsewhere in the D x D matrix; pitch in doubles. */
+int spear_diagset_encode_matrix_view(spear_context* ctx, const double* m_re, const double* m_im, int D, int rows_valid,
+                                     int cols_valid, size_t pitch, int transposed, int G, int B, int g_first, int g_stride,
+                                     double scale, int chain_index, int compress, spear_diagset** out);
 void spear_diagset_destroy(spear_diagset* d);
 int spear_diagset_info(const spear_diagset* d, int* D, int* G, int* B, int* limbs, int* ring_n, double* scale,
                        uint64_t* bytes);

@@ -8,6 +8,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# the reference's own scripts staged as a test asset (tools/stage_reference.py) are run as programs, never collected
+collect_ignore_glob = ["_ref/*"]
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

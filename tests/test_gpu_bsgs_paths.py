@@ -307,6 +307,40 @@ def test_hybrid_block_single_rank_and_encryption_ids():
             assert all(plan.mine(r) for r in range(world))
 
 
+def test_diagonal_sets_from_matrix_views():
+    """diagonal_set.from_matrix reads row-pitched, transposed and short views in place (chunks of a larger weight
+    matrix, reference fhe_projection_bsgs :575-591 / :630-642): same limbs as from the zero-padded compact copy, and
+    the same as the host-side diagonal extraction (both encoders: one-kernel sub-ring and staged)."""
+    from fhe_spear_b200 import bsgs as hb
+    from fhe_spear_b200 import pyPhantom as ph
+    D, F = 32, 80                                                    # ragged: the last chunk has 16 columns
+    ckks = hb.CKKSBootstrapContext(poly_degree=2048, L0=4, prime_bits=59, special_mod_size=2, max_rot_dim=1,
+                                   bsgs_dim=[D], skip_bootstrap=True, seed=SEED, verbose=False)
+    G, B = hb.compute_bsgs_params(D)
+    rng = np.random.default_rng(5)
+    Wk, Wv = rng.standard_normal((D, F)), rng.standard_normal((F, D))
+    views = [Wk[:, 0:32].T, Wk[:, 64:80].T, Wv[32:64, :].T, Wv[64:80, :].T, Wk[:, 32:64], Wv[10:42, :], Wk[:20, 5:30]]
+    for V in views:
+        compact = hb._padded(np.ascontiguousarray(V), D)
+        a = ph.diagonal_set.from_matrix(ckks.ctx, V, G, B, ckks.diag_scale, D=D).to_numpy()
+        b = ph.diagonal_set.from_matrix(ckks.ctx, compact, G, B, ckks.diag_scale).to_numpy()
+        c = ph.diagonal_set(ckks.ctx, hb._pre_rotate(hb._extract_diagonals(compact, D), D, G), G, B, ckks.diag_scale).to_numpy()
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+    # complex pair with different shapes (last chunk pair of a ragged F) and a full-ring (uncompressed) set
+    a = ph.diagonal_set.from_matrix(ckks.ctx, views[0], G, B, ckks.diag_scale, M_imag=views[1], D=D).to_numpy()
+    b = ph.diagonal_set.from_matrix(ckks.ctx, hb._padded(views[0], D), G, B, ckks.diag_scale, M_imag=hb._padded(views[1], D)).to_numpy()
+    assert np.array_equal(a, b)
+    full = ph.diagonal_set.from_matrix(ckks.ctx, views[2], G, B, ckks.diag_scale, compress=False, D=D)
+    assert full.info()["ring_n"] == 2048
+    x = rng.standard_normal(D)
+    y = ph.bsgs_hoisted(ckks.ctx, ckks.encrypt_replicated(x), full, ckks.gk)
+    assert np.abs(ckks.decrypt_vec(y, D) - hb._padded(views[2], D) @ x).max() < 1e-8
+    # the whole D -> F and F -> D projections over views (ragged F) still match float64
+    assert np.abs(hb.fhe_projection_bsgs(ckks, x, Wk, D, F) - x @ Wk).max() < 1e-8
+    xf = rng.standard_normal(F)
+    assert np.abs(hb.fhe_projection_bsgs(ckks, xf, Wv, F, D) - xf @ Wv).max() < 1e-8
+
+
 def test_retrieval_wrapper_flow():
     """The call sequence of the reference's PhantomFHE retrieval wrapper (fhe_common.py:83-194; BASELINE config 1
     uses the same primitives): N=8192, primes [60, 40, 40, 60], P=1, asymmetric encryption, complex-packed

@@ -394,3 +394,44 @@ def test_reference_inference_primitives_golden_limbs():
     assert np.array_equal(sq.to_numpy(), g["sq"]) and np.array_equal(pr.to_numpy(), g["pr"])
     got = [enc.decode_double_vector(ctx, sk.decrypt(ctx, c))[0] for c in (d1, d2, ws, sq, pr)]
     assert np.abs(np.array(got) - g["slot0"]).max() < 1e-9 and np.abs(np.array(got) - g["slot0_float64"]).max() < 1e-4
+
+
+@pytest.mark.parametrize("N,bits,P", [(2048, (59,) * 4, 1), (4096, (60, 40, 40, 40, 60), 1), (8192, (59,) * 6, 2),
+                                      (32768, (59,) * 5, 2), (65536, (59,) * 4, 1)])
+def test_fused_client_legs_match_the_staged_path_bit_for_bit(N, bits, P):
+    """csrc/client.cu: encode + encrypt and decrypt + decode in three launches each give the
+    same limbs / the same doubles as encode -> encrypt_symmetric and decrypt -> decode (which the tests above pin to
+    the oracle), for every pass-A split (N = 2^11 .. 2^16), real and complex, replicated and zero-padded inputs,
+    mixed prime sizes, and size-3 ciphertexts."""
+    S = Setup(N=N, bits=bits, P=P)
+    ph, ctx, sk = S.gpu([1])
+    enc = ph.ckks_encoder(ctx)
+    slots = N // 2
+    rng = np.random.default_rng(N)
+    for D, cplx, rep in [(16, False, True), (20, True, True), (slots, True, True), (33, False, False), (1, False, True)]:
+        v = rng.standard_normal(D) + (1j * rng.standard_normal(D) if cplx else 0)
+        full = np.zeros(slots, dtype=np.complex128)
+        if rep:
+            full[:] = np.concatenate([np.tile(v, slots // D), v[:slots % D]])
+        else:
+            full[:D] = v
+        two_step = sk.encrypt_symmetric(ctx, enc.encode_complex_vector(ctx, full, S.scale), enc_id=77)
+        fused = sk.encrypt_vector(ctx, v, S.scale, replicate=rep, enc_id=77)
+        assert fused.chain_index() == 1 and fused.scale() == two_step.scale()
+        assert np.array_equal(fused.to_numpy(), two_step.to_numpy()), (N, D, cplx, rep)
+        ref = np.array(enc.decode_complex_vector(ctx, sk.decrypt(ctx, two_step)))
+        got = sk.decrypt_decode(ctx, fused)
+        assert np.array_equal(got, ref) and np.abs(got - full).max() < 1e-6
+        assert np.array_equal(sk.decrypt_decode(ctx, fused, 7), ref[:7])
+    # deeper levels and a size-3 ciphertext (the decoder reads the first min(l, 3) limbs)
+    a = sk.encrypt_vector(ctx, rng.standard_normal(8), S.scale, enc_id=5)
+    sq = ph.multiply(ctx, a, a)
+    assert np.array_equal(sk.decrypt_decode(ctx, sq), np.array(enc.decode_complex_vector(ctx, sk.decrypt(ctx, sq))))
+    low = ph.rescale_to_next(ctx, ph.relinearize(ctx, sq, sk.gen_relinkey(ctx)))
+    while low.coeff_modulus_size() > 1:
+        assert np.array_equal(sk.decrypt_decode(ctx, low), np.array(enc.decode_complex_vector(ctx, sk.decrypt(ctx, low))))
+        low = ph.mod_switch_to_next(ctx, low)
+    assert np.array_equal(sk.decrypt_decode(ctx, low), np.array(enc.decode_complex_vector(ctx, sk.decrypt(ctx, low))))
+    # the auto counter: two encryptions of the same vector never share randomness
+    c1, c2 = sk.encrypt_vector(ctx, [1.0], S.scale), sk.encrypt_vector(ctx, [1.0], S.scale)
+    assert not np.array_equal(c1.to_numpy()[1], c2.to_numpy()[1])

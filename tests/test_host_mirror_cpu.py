@@ -44,26 +44,27 @@ def test_chunk_packing_reproduces_projection():
     Wk, Wv = rng.standard_normal((D, F)), rng.standard_normal((F, D))
     x, xf = rng.standard_normal(D), rng.standard_normal(F)
     up = np.zeros(F)
+    pad = lambda M: hb._padded(M, D)                 # chunk helpers return views; the device zero-pads them to D x D
     for c, c2 in hb._chunk_pairs(F, D):
         lo, hi = c * D, min((c + 1) * D, F)
-        up[lo:hi] = (hb._key_chunk(Wk, c, D, F) @ x)[:hi - lo]
+        up[lo:hi] = (pad(hb._key_chunk(Wk, c, D, F)) @ x)[:hi - lo]
         if c2 is not None:
             lo2, hi2 = c2 * D, min((c2 + 1) * D, F)
-            up[lo2:hi2] = (hb._key_chunk(Wk, c2, D, F) @ x)[:hi2 - lo2]
+            up[lo2:hi2] = (pad(hb._key_chunk(Wk, c2, D, F)) @ x)[:hi2 - lo2]
     assert np.allclose(up, x @ Wk)
     down = np.zeros(D)
     for c, c2 in hb._chunk_pairs(F, D):
         x0 = np.zeros(D)
         lo, hi = c * D, min((c + 1) * D, F)
         x0[:hi - lo] = xf[lo:hi]
-        M0 = hb._val_chunk(Wv, c, D, F)
+        M0 = pad(hb._val_chunk(Wv, c, D, F))
         if c2 is None:
             down += M0 @ x0
         else:
             x1 = np.zeros(D)
             lo1, hi1 = c2 * D, min((c2 + 1) * D, F)
             x1[:hi1 - lo1] = xf[lo1:hi1]
-            M1n = hb._val_chunk(Wv, c2, D, F, -1.0)
+            M1n = pad(hb._val_chunk(Wv, c2, D, F, -1.0))
             down += ((M0 + 1j * M1n) @ (x0 + 1j * x1)).real     # diagonals d0 + i*(-d1): Enc(x0 + i x1) * (d0 - i d1)
     assert np.allclose(down, xf @ Wv)
 

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--no-bootstrap", action="store_true")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--weight", type=float, default=1.0, help="BSGS split G = ceil(sqrt(weight * D)); 1 = the reference's")
+    ap.add_argument("--phases", action="store_true", help="host-clock seconds per phase (adds synchronisations)")
     a = ap.parse_args()
     rank, world, local = 0, 1, int(os.environ.get("LOCAL_RANK", "0"))
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:      # torchrun: every mat-vec giant-step sharded over the ranks
@@ -37,6 +38,9 @@ def main():
     from fhe_spear_b200 import pyPhantom as ph
     from fhe_spear_b200.ffn_block import fully_encrypted_ffn_block, plaintext_ffn_block
     D, F, L0 = a.D, a.F, a.L0
+    if a.phases:
+        from fhe_spear_b200 import ffn_block as fb
+        fb.PHASES = {}
     np.random.seed(a.seed)                                          # [ref: test_fully_enc_bsgs.py:153, 171-201]
     W_keys = [np.random.randn(D, F) * 0.02 for _ in range(a.num_blocks)]
     W_raw = [np.random.randn(F, D) * 0.02 for _ in range(a.num_blocks)]
@@ -98,7 +102,8 @@ def main():
                       "s_per_block": float(np.mean([r["seconds"] for r in rows])) if rows else None,
                       "s_per_bootstrap": float(np.mean([r["seconds"] for r in boots])) if boots else None,
                       "final_corr": rows[-1]["corr"] if rows else None, "final_max_abs_err": rows[-1]["max_abs_err"] if rows else None,
-                      "match": bool(rows and rows[-1]["corr"] > 0.999), "setup_s": setup_s, "blocks": rows, "boot": boots}))
+                      "match": bool(rows and rows[-1]["corr"] > 0.999), "setup_s": setup_s,
+                      "phase_seconds_total": (fb.PHASES if a.phases else None), "blocks": rows, "boot": boots}))
 
 
 if __name__ == "__main__":
