@@ -40,6 +40,7 @@ _SIG = {
     "spear_pinned_alloc": (C.c_int, [C.c_size_t, vpp]),
     "spear_pinned_free": (None, [vp]),
     "spear_mem_info": (C.c_int, [vp, u64p, u64p]),
+    "spear_mem_reserve": (C.c_int, [vp, C.c_uint64]),
     "spear_secret_key_create": (C.c_int, [vp, C.c_char_p, vpp]),
     "spear_secret_key_destroy": (None, [vp]),
     "spear_gen_public_key": (C.c_int, [vp, vp, vpp]),

@@ -188,6 +188,10 @@ class context:
         _check(_lib.spear_profile_read(self._h, ms, cnt, n))
         return {k: {"ms": ms[i], "launches": int(cnt[i])} for i, k in enumerate(self.PROFILE_CLASSES)}
 
+    def reserve(self, nbytes):
+        """grow the device memory pool to at least `nbytes` now (kept by the pool; see spear_mem_reserve)"""
+        _check(_lib.spear_mem_reserve(self._h, int(nbytes)))
+
     def mem_info(self):
         u, r = C.c_uint64(), C.c_uint64()
         _check(_lib.spear_mem_info(self._h, C.byref(u), C.byref(r)))

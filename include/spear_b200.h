@@ -69,6 +69,9 @@ int spear_pinned_alloc(size_t bytes, void** out);
 void spear_pinned_free(void* p);
 /* device memory currently held by the stream-ordered pool (bytes) */
 int spear_mem_info(spear_context* ctx, uint64_t* used, uint64_t* reserved);
+/* grow the pool to at least `bytes` now (one allocation, freed at once: the pool keeps it), so that a computation
+ * that creates large temporaries on the fly never waits for the pool to grow in the middle */
+int spear_mem_reserve(spear_context* ctx, uint64_t bytes);
 
 /* ---- keys ------------------------------------------------------------------------------------- */
 /* [ref: phantom_binding.cu:100-101 secret_key(ctx)] ternary secret from a 32-byte seed (ChaCha20 streams) */
