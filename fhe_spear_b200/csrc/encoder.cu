@@ -4,7 +4,10 @@
 // root table comes from the same libm calls, so coefficients are bit-identical to the oracle's.
 // Replaces PhantomCKKSEncoder::{encode,decode} (reference gpu/phantom_binding.cu:138-156) and the
 // fork-only encode_*_vector_batch (reference scripts/bootstrap_generation.py:382,423).
+#include <cstdlib>
+
 #include "engine.h"
+#include "ntt_core.cuh"
 #include "ops.h"
 
 namespace {
@@ -226,6 +229,93 @@ __global__ void __launch_bounds__(256) k_encode_ring_fused(const double2* __rest
     }
 }
 
+// The same with the per-limb NTT done by the register-tiled passes of ntt_core.cuh inside shared memory (n = 2^(SA+8):
+// 2048 or 4096 points, n / 8 threads): pass A on [2^SA][16] column tiles of the residue buffer, pass B one 256-point
+// chunk per warp, written straight to global memory -- four block barriers per limb instead of thirteen and the lazy
+// butterflies instead of the exact ones.  The embedding itself (one transform of the l + P + 1) keeps the simple loop.
+template <int SA>
+__global__ void __launch_bounds__(32 << SA) k_encode_ring_tiled(const double2* __restrict__ vals, u64* __restrict__ out,
+                                                                 int rows, RowMap rm, double fix, ModTab mt, NttTab tb, int N,
+                                                                 const double2* __restrict__ zeta, int split,
+                                                                 int* __restrict__ overflow) {
+    using namespace nttc;
+    constexpr int logn = SA + 8, n = 1 << logn, half = n >> 1, T = 32 << SA, S = n >> SA, TILE_T = 2 << SA;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    double2* W = reinterpret_cast<double2*>(smraw);                 // [n]  embedding values, then (lo, hi | sign) integers
+    u64* buf = reinterpret_cast<u64*>(W + n);                       // [n]  one limb's residues / pass-A output
+    u64* xt = buf + n;                                              // [n]  exchange tiles of pass A, chunk buffers of pass B
+    const int tid = threadIdx.x;
+    const size_t v = blockIdx.x;
+    const u32 m2 = 2u * n;
+    for (int j = tid; j < half; j += T) {
+        const u32 pos = pow5_mod((u32)j, m2 - 1);
+        const double2 z = vals[v * half + j];
+        W[brev_n((pos - 1) >> 1, logn)] = z;
+        W[brev_n((m2 - pos - 1) >> 1, logn)] = make_double2(z.x, -z.y);
+    }
+    __syncthreads();
+    for (int m = n, t = 1; m > 1; m >>= 1, t <<= 1) {
+        const int h = m >> 1;
+        for (int b = tid; b < half; b += T) {
+            const int i = b / t, kk = b - i * t;
+            double2* a = W + 2 * i * t + kk;
+            const double2 w = zeta[h + i], U = a[0], V = a[t];
+            const double wr = w.x, wi = -w.y;
+            a[0] = make_double2(__dadd_rn(U.x, V.x), __dadd_rn(U.y, V.y));
+            const double dr = __dsub_rn(U.x, V.x), di = __dsub_rn(U.y, V.y);
+            a[t] = make_double2(__dsub_rn(__dmul_rn(dr, wr), __dmul_rn(di, wi)), __dadd_rn(__dmul_rn(dr, wi), __dmul_rn(di, wr)));
+        }
+        __syncthreads();
+    }
+    u64* I = reinterpret_cast<u64*>(W);
+    for (int j = tid; j < n; j += T) {
+        const double x = rint(__dmul_rn(W[j].x, fix));
+        const bool neg = x < 0.0;
+        double ax = fabs(x);
+        if (!(ax < 0x1p126)) {
+            *overflow = 1;
+            ax = 0.0;
+        }
+        u64 lo = 0, hi = 0;
+        if (ax >= 1.0) {
+            const long long bits = __double_as_longlong(ax);
+            const int ex = (int)(bits >> 52) - 1075;
+            const u64 mant = ((u64)bits & 0xFFFFFFFFFFFFFull) | (1ull << 52);
+            if (ex <= 0) lo = mant >> (-ex);
+            else if (ex < 64) lo = mant << ex, hi = mant >> (64 - ex);
+            else hi = mant << (ex - 64);
+        }
+        I[2 * j] = lo, I[2 * j + 1] = hi | ((u64)neg << 63);
+    }
+    __syncthreads();
+    const int tile = tid / TILE_T, lt = tid % TILE_T, c = lt & (COLS - 1), g = lt >> 4;   // pass A: (tile, column, row group)
+    const int warp = tid >> 5, lane = tid & 31;                                           // pass B: chunk = warp
+    for (int r = 0; r < rows; r++) {
+        const int lt_id = rm.limb(r);
+        const u64 q = mt.q[lt_id], r0 = mt.ratio0[lt_id], r1 = mt.ratio1[lt_id];
+        const ulonglong2* __restrict__ tw = tb.psi + (size_t)lt_id * N;
+        const bool lazy = q < (1ull << 59) && q > (1ull << 33);
+        for (int j = tid; j < n; j += T) {
+            const u64 hi = I[2 * j + 1];
+            const u64 res = barrett128(I[2 * j], hi & ~(1ull << 63), q, r0, r1);
+            buf[j] = (hi >> 63) ? neg_mod(res, q) : res;
+        }
+        __syncthreads();
+        u64 x8[8];
+        if (lazy) fwd_a2_body<SA, true>(buf + tile * COLS + c, xt + tile * (COLS << SA), tw, q, S, c, g, x8);
+        else fwd_a2_body<SA, false>(buf + tile * COLS + c, xt + tile * (COLS << SA), tw, q, S, c, g, x8);
+        __syncthreads();
+        u64* sw = xt + warp * 256;
+        if (lazy) fwd_b2_body<true, false, const u64*>(buf + warp * 256, sw, tw, q, SA, warp, lane, split != 0);
+        else fwd_b2_body<false, false, const u64*>(buf + warp * 256, sw, tw, q, SA, warp, lane, split != 0);
+        __syncwarp();
+        u64* o = out + (v * rows + r) * n + warp * 256;
+#pragma unroll
+        for (int k = 0; k < 8; k++) o[lane + 32 * k] = sw[swz(lane + 32 * k)];
+        __syncthreads();
+    }
+}
+
 int grid_for(const Ctx* c, size_t total) {
     size_t blocks = (total + TPB - 1) / TPB, cap = (size_t)c->sm_count * 16;
     return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
@@ -269,6 +359,22 @@ bool encode_ring_fused(const Ctx* c, const double2* vals, int count, int n, doub
     const size_t smem = (size_t)n * (sizeof(double2) + sizeof(u64));
     if ((1 << logn) != n || n < 4 || n > c->N || smem > 200 * 1024 || count < 1) return false;
     const int rows = l + (ext ? c->P : 0);
+    static const bool tiled = [] {
+        const char* e = getenv("SPEAR_ENCODE_TILED");
+        return !(e && e[0] == '0');
+    }();
+    if (tiled && (logn == 11 || logn == 12) && count <= 65535 * 16) {   // 2048 / 4096 points: register-tiled NTT passes in shared memory
+        const size_t smem_t = (size_t)n * 32;
+        auto go = [&](auto kern, int threads) {
+            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            LAUNCH(kern, count, threads, smem_t, s)(vals, out, rows, RowMap{rows, l, c->L, 0}, scale / (double)n, c->modtab(),
+                                                    c->ntttab(), c->N, c->d_zeta, split30_out ? 1 : 0, overflow);
+        };
+        if (logn == 11) go(k_encode_ring_tiled<3>, 32 << 3);
+        else go(k_encode_ring_tiled<4>, 32 << 4);
+        CUDA_CHECK(cudaGetLastError());
+        return true;
+    }
     CUDA_CHECK(cudaFuncSetAttribute(k_encode_ring_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     for (int v0 = 0; v0 < count; v0 += 65535 * 16) {   // grid.x is wide enough; kept as a loop for clarity of the bound
         const int nv = std::min(count - v0, 65535 * 16);
