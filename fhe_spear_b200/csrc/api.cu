@@ -998,16 +998,31 @@ int spear_diagset_encode_matrix_view(spear_context* ctx, const double* m_re, con
         // pageable caller memory: the lines are packed into the context's page-locked staging buffer (plain memcpy, one
         // line at a time) and cross the bus in one asynchronous copy
         const int parts = m_im ? 2 : 1;
-        double* st = (double*)c->staging(sizeof(double) * mw * parts);
-        for (int part = 0; part < parts; part++) {
-            const double* src = part ? m_im : m_re;
-            double* dst = st + (size_t)part * mw;
-            if (pitch == (size_t)run) memcpy(dst, src, sizeof(double) * mw);
-            else
-                for (int i = 0; i < lines; i++) memcpy(dst + (size_t)i * run, src + (size_t)i * pitch, sizeof(double) * run);
+        auto page_locked = [](const void* p) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+                cudaGetLastError();
+                return false;
+            }
+            return at.type == cudaMemoryTypeHost;
+        };
+        if (page_locked(m_re) && (!m_im || page_locked(m_im))) {
+            // weights already in page-locked memory (spear_pinned_alloc / cudaHostRegister): straight DMA of the view
+            for (int part = 0; part < parts; part++)
+                CUDA_CHECK(cudaMemcpy2DAsync(dm + (size_t)part * mw, sizeof(double) * run, part ? m_im : m_re,
+                                             sizeof(double) * pitch, sizeof(double) * run, lines, cudaMemcpyHostToDevice, c->stream));
+        } else {
+            double* st = (double*)c->staging(sizeof(double) * mw * parts);
+            for (int part = 0; part < parts; part++) {
+                const double* src = part ? m_im : m_re;
+                double* dst = st + (size_t)part * mw;
+                if (pitch == (size_t)run) memcpy(dst, src, sizeof(double) * mw);
+                else
+                    for (int i = 0; i < lines; i++) memcpy(dst + (size_t)i * run, src + (size_t)i * pitch, sizeof(double) * run);
+            }
+            CUDA_CHECK(cudaMemcpyAsync(dm, st, sizeof(double) * mw * parts, cudaMemcpyHostToDevice, c->stream));
+            CUDA_CHECK(cudaEventRecord(c->staged, c->stream));
         }
-        CUDA_CHECK(cudaMemcpyAsync(dm, st, sizeof(double) * mw * parts, cudaMemcpyHostToDevice, c->stream));
-        CUDA_CHECK(cudaEventRecord(c->staged, c->stream));
     }
     double2* dv = (double2*)c->alloc((size_t)std::max(n_diags, 1) * D * 2);
     if (n_diags > 0)
