@@ -241,7 +241,7 @@ def run_reference(args):
 
 
 # ---- op counts of one mat-vec (integer roofline) -------------------------------------------------------------------
-def integer_work(N, l, P, D, G, B, n_giant=None, n_baby=None):
+def integer_work(N, l, P, D, G, B, n_giant=None, n_baby=None, row_share=None):
     """Multiplier-pipe work of one hoisted mat-vec: NTT butterflies and modular multiply-accumulate terms, from the
     algorithm, in SM-sub-partition cycles at the measured issue cost of the instructions that
     carry them.  n_giant / n_baby: rotations done by this rank (sharded runs)."""
@@ -252,6 +252,8 @@ def integer_work(N, l, P, D, G, B, n_giant=None, n_baby=None):
     row_ntts = (l + dig) + n_giant * (P + l + l + dig) + (2 * (P + l) + 2 + 2 * (l - 1))
     butterflies = row_ntts * (N // 2) * logn
     d_share = (n_giant + 1) / B                             # share of the diagonals this rank multiplies
+    if row_share is not None:                               # two-phase mat-vec: this rank's rows of every baby step and diagonal
+        d_share, n_baby = row_share, n_baby * row_share
     mac_terms = ((n_baby + n_giant) * rows * N * beta * 2   # key inner products
                  + D * d_share * 2 * rows * N               # diagonal MAC
                  + (1 + n_giant) * beta * (rows - P) * N * P   # ModUp
@@ -329,9 +331,34 @@ def run_ours(args):
             return ph.bsgs_hoisted_batch(ctx, cts, dsets, ckks.gk)
         parallelism = "1 GPU: three mat-vecs on three streams"
         n_giant_rank = B - 1
+    elif sh.HybridBlock.two_phase_default(world):
+        # strong scaling, two-phase mat-vecs: EVERY mat-vec is served by all N ranks -- baby steps and diagonal MAC split
+        # by rows of the RNS basis, the MAC's epilogue scattering the giant groups' accumulators to their owners over NVLink
+        # peer memory, giant steps split by group, accumulators summed by the fused peer all-reduce
+        pg = {}
+        all_ranks = tuple(range(world))
+        mine = [(all_ranks, list(range(nb)))]
+        dsets = {}
+        for j in range(nb):
+            full = hb.pre_encode_real_diags(ckks, Ws[j], D, G, B, level=1, compress=compress)
+            if j == 0:
+                info = full.info()
+            dsets[j] = full.slice_rows(rank, world)
+            del full
+        sh.PeerExchange.get(ctx, None)
+        sh.PeerExchange.get(ctx, None, tag="split", slot_bytes=sh.split_slot_bytes(ctx, B, world))
+
+        def step():
+            return dict(enumerate(sh.split_matvec_batch(ckks, cts, [dsets[j] for j in range(nb)])))
+        r0_, r1_ = ph.diagonal_set.row_range(L0, P, rank, world)
+        parallelism = (f"{world} GPUs, strong scaling, two-phase mat-vecs: every mat-vec on all ranks -- hoisted baby steps + diagonal "
+                       f"MAC split by rows of the {L0 + P}-limb basis (k_pmac_tma's epilogue stores scatter the giant groups' "
+                       f"accumulators to their owners over NVLink peer memory), giant steps split by group, accumulators summed by "
+                       f"spear_peer_allreduce; all inside the timed region")
+        n_giant_rank = max(len(sh.giant_groups(B, r, world)) - (1 if r == 0 else 0) for r in range(world))
     else:
-        # strong scaling: the same nb mat-vecs dealt to rank groups, giant steps sharded inside a group; every rank
-        # creates every process group in the same order
+        # strong scaling (round-1 plan, SPEAR_TWO_PHASE=0): the same nb mat-vecs dealt to rank groups, giant steps sharded
+        # inside a group; every rank creates every process group in the same order
         plan = sh.PhasePlan(nb, world)
         pg = {ranks: (dist.group.WORLD if len(ranks) == world else dist.new_group(list(ranks))) for ranks in plan.groups}
         mine = plan.mine(rank)
@@ -414,9 +441,13 @@ def run_ours(args):
 
     # latency and per-kernel times of ONE mat-vec alone on the engine stream (rank-local: the unsharded mat-vec at N = 1,
     # this rank's shard accumulator + finish at N > 1), event pair around each launch, for the roofline line
+    two_phase = sh.HybridBlock.two_phase_default(world)
     if world == 1:
         def single():
             return ph.bsgs_hoisted(ctx, cts[j0], full0, ckks.gk)
+    elif two_phase:
+        def single():          # collective: every rank runs it the same number of times
+            return sh.split_matvec_batch(ckks, [cts[j0]], [dsets[j0]])[0]
     else:
         def single():
             return ph.bsgs_finish(ctx, ph.bsgs_hoisted_partial(ctx, cts[j0], dsets[j0], ckks.gk))
@@ -457,6 +488,8 @@ def run_ours(args):
         ins = {j: ph.ciphertext.from_numpy(ctx, h_in[j], scale) for j in my_js}          # wire -> server (H2D)
         if world == 1:
             res = dict(enumerate(ph.bsgs_hoisted_batch(ctx, [ins[j] for j in range(nb)], dsets, ckks.gk)))
+        elif two_phase:
+            res = dict(enumerate(sh.split_matvec_batch(ckks, [ins[j] for j in range(nb)], [dsets[j] for j in range(nb)])))
         else:
             res = {}
             for ranks, js in mine:
@@ -533,9 +566,12 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     n_baby = G - 1
+    row_share = 1.0
+    if world > 1 and two_phase:      # this rank's rows of the baby-step keys and of the diagonals
+        row_share = (r1_ - r0_) / float(l + P)
     alg_bytes = {   # algorithmic bytes per MAT-VEC of each kernel: SURVEY.md section 8(d) -- keys and diagonals read once
-        "ks_baby_fused": n_baby * key_bytes, "ntt_ks_fused": n_giant_rank * key_bytes, "ks_inner": n_giant_rank * key_bytes,
-        "pmac": info["bytes"],
+        "ks_baby_fused": n_baby * key_bytes * row_share, "ntt_ks_fused": n_giant_rank * key_bytes,
+        "ks_inner": n_giant_rank * key_bytes, "pmac": info["bytes"] * row_share,
     }
     traffic_tab = {}
     tpath = os.path.join(ROOT, "profiles", "r2_kernel_traffic.json")
@@ -555,9 +591,9 @@ def run_ours(args):
         kernels[k]["frac"] = kernels[k]["achieved"] / peak
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_matvec"])
     dk = kernels[dom]
-    iw = integer_work(N, l, P, D, G, B, n_giant=n_giant_rank)
+    iw = integer_work(N, l, P, D, G, B, n_giant=n_giant_rank, row_share=row_share if (world > 1 and two_phase) else None)
     avail = single_ms * 1e-3 * (clk["sm_mhz"] or 1965.0) * 1e6 * SMSP_PER_GPU
-    mv_bytes = (n_baby + n_giant_rank) * key_bytes + info["bytes"] + (4 * l - 2) * N * 8
+    mv_bytes = (n_baby * row_share + n_giant_rank) * key_bytes + info["bytes"] * row_share + (4 * l - 2) * N * 8
     roofline = {
         "bound": "hbm", "kernel": dk["kernel"], "class": dom, "achieved": dk["achieved"], "peak": peak, "unit": "GB/s",
         "frac": dk["frac"], "traffic": (traffic_tab.get(dom) or {}).get("dram_bytes_per_launch"),
@@ -570,7 +606,7 @@ def run_ours(args):
         "kernels": kernels,
         "matvec": {"algorithmic_bytes": mv_bytes, "achieved_gbs": mv_bytes / (single_ms * 1e-3) / 1e9,
                    "frac": mv_bytes / (single_ms * 1e-3) / 1e9 / peak, "diagonal_bytes": info["bytes"],
-                   "key_bytes": (n_baby + n_giant_rank) * key_bytes},
+                   "key_bytes": (n_baby * row_share + n_giant_rank) * key_bytes},
         "integer": {"bound": "integer multiplier pipe", "unit": "SM-sub-partition cycles per mat-vec",
                     "achieved": iw["multiplier_warp_cycles"], "peak": avail, "frac": iw["multiplier_warp_cycles"] / avail,
                     "butterflies": iw["butterflies"], "mac_terms": iw["mac_terms"], "row_transforms": iw["row_ntts"],
@@ -624,7 +660,10 @@ def measure_token(ckks, hb, rb, sh, D, F, rank, world, n_tokens):
     base = rb.RWKVBlockWeights.random(D, F, H, S, block_idx=0, seed=0)
     if world > 1:
         pe = sh.HybridBlock(ckks, base, D, F, rank, world)
-        split = "per rank group: G = ceil(sqrt(8 / size * D))"
+        if pe.two_phase:
+            split = (f"G={pe.split_GB[0]} B={pe.split_GB[1]} (hoisting-aware), every mat-vec two-phase over all {world} ranks: rows | giant groups")
+        else:
+            split = "per rank group: G = ceil(sqrt(8 / size * D))"
     else:
         w = hb.hoisting_weight(1)
         Gt, Bt = hb.compute_bsgs_params(D, w)

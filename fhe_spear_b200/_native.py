@@ -106,6 +106,10 @@ _SIG = {
     "spear_peer_window_status": (C.c_int, [vp]),
     "spear_peer_window_destroy": (None, [vp]),
     "spear_peer_selftest": (C.c_int, [vp, vpp, C.c_int]),
+    "spear_diagset_slice_rows": (C.c_int, [vp, vp, C.c_int, C.c_int, vpp]),
+    "spear_bsgs_split": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, vpp]),
+    "spear_bsgs_split_batch": (C.c_int, [vp, vpp, vpp, C.c_int, vp, vp, C.c_int, vpp]),
+    "spear_bsgs_split_selftest": (C.c_int, [vp, vp, vpp, C.c_int, vp, vpp]),
     "spear_ntt_host": (C.c_int, [vp, vp, C.c_int, ip, C.c_int, C.c_int]),
 }
 

@@ -27,6 +27,10 @@ void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, i
                           int n_diags, int g_first, int g_stride, const u32* belt, const u64* const* bkey,
                           const u32* gelt, const u64* const* gkey, u64* R, cudaStream_t s);
 void bsgs_finish(const Ctx* c, u64* R, int l, u64* out, cudaStream_t s);
+void bsgs_split_phase1(const Ctx* c, const u64* ct, int l, const u64* diag, int rshift, int G, int B, int n_diags, int row0,
+                       int nrows, const u32* belt, const u64* const* bkey, const PmacDst& dst, cudaStream_t s);
+void bsgs_split_phase2(const Ctx* c, u64* A, int l, int G, int B, int n_groups, const u32* gelt, const u64* const* gkey,
+                       int world, u64* R, cudaStream_t s);
 }  // namespace eng
 
 namespace {
@@ -1055,7 +1059,7 @@ int spear_diagset_info(const spear_diagset* d_, int* D, int* G, int* B, int* lim
     if (limbs) *limbs = d->l;
     if (ring_n) *ring_n = d->n;
     if (scale) *scale = d->scale;
-    if (bytes) *bytes = sizeof(u64) * (size_t)d->n_diags * (d->l + d->ctx->P) * d->n;
+    if (bytes) *bytes = sizeof(u64) * (size_t)d->n_diags * d->stored_rows() * d->n;
     API_END
 }
 int spear_diagset_export(const spear_diagset* d_, uint64_t* host, size_t words) {
@@ -1063,7 +1067,7 @@ int spear_diagset_export(const spear_diagset* d_, uint64_t* host, size_t words) 
     const DiagSet* d = reinterpret_cast<const DiagSet*>(d_);
     Ctx* c = d->ctx;
     use(c);
-    const size_t have = (size_t)d->n_diags * (d->l + c->P) * d->n;
+    const size_t have = (size_t)d->n_diags * d->stored_rows() * d->n;
     REQUIRE(words == have, "export: buffer holds %zu words, diagonal set has %zu", words, have);
     u64* tmp = c->alloc(have);   // canonical residues for the caller; the resident copy stays split-30
     CUDA_CHECK(cudaMemcpyAsync(tmp, d->d, sizeof(u64) * have, cudaMemcpyDeviceToDevice, c->stream));
@@ -1074,9 +1078,31 @@ int spear_diagset_export(const spear_diagset* d_, uint64_t* host, size_t words) 
     API_END
 }
 
+// rows [row0, row0 + nrows) of a full set, as a set of its own: the diagonals a rank holds in a two-phase mat-vec
+int spear_diagset_slice_rows(spear_context* ctx, const spear_diagset* full_, int row0, int nrows, spear_diagset** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const DiagSet* f = reinterpret_cast<const DiagSet*>(full_);
+    REQUIRE(f && f->nrows < 0 && f->g_first == 0 && f->g_stride == 1, "slice_rows: expected a full diagonal set");
+    const int rows = f->l + c->P;
+    REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= rows, "slice_rows: rows [%d, %d) of %d", row0, row0 + nrows, rows);
+    std::unique_ptr<DiagSet> ds(new DiagSet);
+    ds->bind(c), ds->D = f->D, ds->G = f->G, ds->B = f->B, ds->l = f->l, ds->n = f->n, ds->scale = f->scale;
+    ds->n_diags = f->n_diags, ds->g_first = 0, ds->g_stride = 1, ds->rshift = f->rshift;
+    ds->row0 = row0, ds->nrows = nrows;
+    ds->d = c->alloc((size_t)std::max(f->n_diags, 1) * std::max(nrows, 1) * f->n);
+    if (f->n_diags > 0 && nrows > 0)
+        CUDA_CHECK(cudaMemcpy2DAsync(ds->d, sizeof(u64) * nrows * f->n, f->d + (size_t)row0 * f->n, sizeof(u64) * rows * f->n,
+                                     sizeof(u64) * nrows * f->n, f->n_diags, cudaMemcpyDeviceToDevice, c->stream));
+    *out = reinterpret_cast<spear_diagset*>(ds.release());
+    API_END
+}
+
 static Obj* bsgs_partial(Ctx* c, const Obj* ct, const DiagSet* ds, const GaloisKeys* gk, cudaStream_t s = nullptr) {
     if (!s) s = c->stream;
     check_ct(ct, "bsgs_hoisted");
+    REQUIRE(ds->nrows < 0, "bsgs_hoisted: row-sliced diagonal set (use bsgs_split)");
     REQUIRE(ct->size == 2, "bsgs_hoisted: relinearize first");
     REQUIRE(ds->l == ct->l, "bsgs_hoisted: diagonals encoded for %d limbs, ciphertext has %d", ds->l, ct->l);
     const int G = std::min(ds->G, ds->D), B = ds->B, D = ds->D, l = ct->l;
@@ -1186,6 +1212,140 @@ int spear_bsgs_hoisted_partial_batch(spear_context* ctx, spear_obj* const* cts, 
     for (int i = 0; i < count; i++) outs[i] = H_(acc[i].release());
     API_END
 }
+// ---- two-phase mat-vec over a rank group ---------------------------------------------------------------------------
+// Phase 1 (baby steps + diagonal MAC) split by ROWS, phase 2 (giant steps) split by GIANT GROUP; in between every rank's
+// MAC epilogue scatters the accumulators of group g into the window of rank g % world (csrc/peer.cu, bsgs.cu).
+struct SplitPlan {
+    int G, nB, l;
+    std::vector<u32> belt;
+    std::vector<const u64*> bkey;
+    size_t slot_words(const Ctx* c, int world) const { return (size_t)((nB + world - 1) / world) * 2 * (l + c->P) * c->N; }
+};
+static SplitPlan split_plan(Ctx* c, const Obj* ct, const DiagSet* ds, const GaloisKeys* gk) {
+    check_ct(ct, "bsgs_split");
+    REQUIRE(ct->size == 2, "bsgs_split: relinearize first");
+    REQUIRE(ds->l == ct->l, "bsgs_split: diagonals encoded for %d limbs, ciphertext has %d", ds->l, ct->l);
+    REQUIRE(ds->g_first == 0 && ds->g_stride == 1, "bsgs_split: the set must hold every giant group (rows are sliced instead)");
+    SplitPlan p;
+    p.G = std::min(ds->G, ds->D), p.l = ct->l;
+    p.nB = (ds->D + ds->G - 1) / ds->G;
+    p.belt.assign(p.G, 0), p.bkey.assign(p.G, nullptr);
+    for (int b = 1; b < p.G; b++) {
+        p.belt[b] = (u32)elt_from_step(b, c->N);
+        p.bkey[b] = find_key(gk, p.belt[b])->d;
+    }
+    return p;
+}
+// the giant groups rank serves: g = rank, rank + world, ... (Galois elements / keys; group 0: none)
+static void split_groups(Ctx* c, const DiagSet* ds, const GaloisKeys* gk, int nB, int rank, int world, std::vector<u32>& gelt,
+                         std::vector<const u64*>& gkey) {
+    for (int g = rank; g < nB; g += world) {
+        gelt.push_back(g ? (u32)elt_from_step(g * ds->G, c->N) : 0);
+        gkey.push_back(g ? find_key(gk, gelt.back())->d : nullptr);
+    }
+}
+static void split_check_rows(const Ctx* c, const DiagSet* ds, int l, int rank, int world) {
+    const int rows = l + c->P, r0 = rank * rows / world, r1 = (rank + 1) * rows / world;
+    REQUIRE(ds->row0 == r0 && ds->stored_rows() == r1 - r0, "bsgs_split: rank %d of %d serves rows [%d, %d), the set holds [%d, %d)",
+            rank, world, r0, r1, ds->row0, ds->row0 + ds->stored_rows());
+}
+static Obj* bsgs_split(Ctx* c, const Obj* ct, const DiagSet* ds, const GaloisKeys* gk, spear_peer_window* win, int slot,
+                       cudaStream_t s) {
+    SplitPlan p = split_plan(c, ct, ds, gk);
+    int rank = 0, world = 1;
+    peer::window_geometry(win, &rank, &world);
+    split_check_rows(c, ds, p.l, rank, world);
+    std::vector<u32> gelt;
+    std::vector<const u64*> gkey;
+    split_groups(c, ds, gk, p.nB, rank, world, gelt, gkey);
+    // everything that can throw comes before the first kernel a peer will wait for
+    std::unique_ptr<Obj> R(new_obj(c, 2, p.l, true, c->N, ct->scale * ds->scale, s));
+    const peer::SplitView v = peer::split_begin(c, win, slot, p.slot_words(c, world), s);
+    PmacDst dst = {};
+    for (int r = 0; r < 8; r++) dst.base[r] = v.base[r];
+    dst.world = world;
+    eng::bsgs_split_phase1(c, ct->d, p.l, ds->d, ds->rshift, p.G, p.nB, ds->n_diags, ds->row0, ds->stored_rows(), p.belt.data(),
+                           p.bkey.data(), dst, s);
+    peer::split_exchange(win, slot, s);
+    eng::bsgs_split_phase2(c, v.base[rank], p.l, p.G, p.nB, (int)gelt.size(), gelt.data(), gkey.data(), world, R->d, s);
+    peer::split_release(win, slot, R->d, R->words(), s);
+    return R.release();
+}
+int spear_bsgs_split(spear_context* ctx, const spear_obj* ct_, const spear_diagset* ds_, const spear_galois_keys* gk_,
+                     spear_peer_window* win, int slot, spear_obj** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    *out = H_(bsgs_split(c, O_(ct_), reinterpret_cast<const DiagSet*>(ds_), reinterpret_cast<const GaloisKeys*>(gk_), win, slot,
+                         c->stream));
+    API_END
+}
+// item i runs on auxiliary stream i % 3 and exchanges through window slot slot0 + i
+int spear_bsgs_split_batch(spear_context* ctx, spear_obj* const* cts, spear_diagset* const* dss, int count,
+                           const spear_galois_keys* gk_, spear_peer_window* win, int slot0, spear_obj** outs) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    REQUIRE(count >= 1, "bsgs_split_batch: empty batch");
+    const GaloisKeys* gk = reinterpret_cast<const GaloisKeys*>(gk_);
+    for (int i = 0; i < count; i++) {   // validate everything before anything is queued
+        REQUIRE(dss[i] && cts[i], "bsgs_split_batch: null item %d", i);
+        split_plan(c, O_(cts[i]), reinterpret_cast<const DiagSet*>(dss[i]), gk);
+    }
+    std::vector<std::unique_ptr<Obj>> acc(count);
+    CUDA_CHECK(cudaEventRecord(c->ev_main, c->stream));
+    {
+        AuxJoin join{c, count > 1 ? std::min(count, 3) : 0};
+        for (int i = 0; i < count; i++) {
+            cudaStream_t s = count == 1 ? c->stream : c->aux[i % 3];
+            if (count > 1 && i < 3) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_main, 0));
+            acc[i].reset(bsgs_split(c, O_(cts[i]), reinterpret_cast<const DiagSet*>(dss[i]), gk, win, slot0 + i, s));
+        }
+    }
+    for (int i = 0; i < count; i++) outs[i] = H_(acc[i].release());
+    API_END
+}
+// Test hook (one GPU, one process): the two phases of all `world` ranks run one after the other over local stand-ins
+// for the exchange windows; dss[r] = the row slice of rank r.  *out = the summed accumulator (bsgs_finish completes it).
+int spear_bsgs_split_selftest(spear_context* ctx, const spear_obj* ct_, spear_diagset* const* dss, int world,
+                              const spear_galois_keys* gk_, spear_obj** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    REQUIRE(world >= 1 && world <= 8, "bsgs_split_selftest: 1..8 ranks");
+    const Obj* ct = O_(ct_);
+    const GaloisKeys* gk = reinterpret_cast<const GaloisKeys*>(gk_);
+    cudaStream_t s = c->stream;
+    SplitPlan p = split_plan(c, ct, reinterpret_cast<const DiagSet*>(dss[0]), gk);
+    const size_t words = std::max<size_t>(p.slot_words(c, world), 32);
+    PmacDst dst = {};
+    dst.world = world;
+    std::vector<u64*> win(world);
+    for (int r = 0; r < world; r++) win[r] = c->alloc(words, s);
+    for (int r = 0; r < 8; r++) dst.base[r] = win[r < world ? r : 0];
+    for (int r = 0; r < world; r++) {
+        const DiagSet* ds = reinterpret_cast<const DiagSet*>(dss[r]);
+        split_plan(c, ct, ds, gk);
+        split_check_rows(c, ds, p.l, r, world);
+        eng::bsgs_split_phase1(c, ct->d, p.l, ds->d, ds->rshift, p.G, p.nB, ds->n_diags, ds->row0, ds->stored_rows(),
+                               p.belt.data(), p.bkey.data(), dst, s);
+    }
+    std::unique_ptr<Obj> sum;
+    for (int r = 0; r < world; r++) {
+        const DiagSet* ds = reinterpret_cast<const DiagSet*>(dss[r]);
+        std::vector<u32> gelt;
+        std::vector<const u64*> gkey;
+        split_groups(c, ds, gk, p.nB, r, world, gelt, gkey);
+        std::unique_ptr<Obj> R(new_obj(c, 2, p.l, true, c->N, ct->scale * ds->scale, s));
+        eng::bsgs_split_phase2(c, win[r], p.l, p.G, p.nB, (int)gelt.size(), gelt.data(), gkey.data(), world, R->d, s);
+        if (!sum) sum = std::move(R);
+        else ops::add(c, sum->d, R->d, sum->d, 2, sum->rows(), c->N, RowMap{sum->rows(), sum->l, c->L, 0}, 2, s);
+    }
+    for (int r = 0; r < world; r++) c->free(win[r], s);
+    *out = H_(sum.release());
+    API_END
+}
+
 int spear_bsgs_finish(spear_context* ctx, spear_obj* acc, spear_obj** out) {
     API_BEGIN
     Ctx* c = C_(ctx);

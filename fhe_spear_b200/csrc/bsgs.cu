@@ -154,56 +154,75 @@ void bsgs_exact_from_host(const Ctx* c, const u64* const* baby, const u64* host_
     rescale(c, res, 2, l, out, s);
 }
 
-// ct [2][l][N]; diag [n_diags][l+P][N >> rshift] holds the giant groups g_first + k*g_stride (k < n_groups);
-// bkey[b] (1 <= b < G); gelt/gkey indexed by LOCAL group k (unused where the global group is 0).
-// R [2][l+P][N]: this shard's accumulator in basis Q_l*P (sum over shards, mod q, = the full accumulator).
-void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, int rshift, int G, int n_groups,
-                          int n_diags, int g_first, int g_stride, const u32* belt, const u64* const* bkey,
-                          const u32* gelt, const u64* const* gkey, u64* R, cudaStream_t s) {
-    const size_t N = c->N, rows = l + c->P, pw = rows * N;
-    const int beta = c->digits(l);
-    const int k0 = (g_first == 0) ? 1 : 0;          // group 0 (if owned) needs no rotation
-    const int nrot = n_groups > k0 ? n_groups - k0 : 0;
-    // Giant-step launches.  A mat-vec running alone on the engine stream takes everything in single launches over all
-    // giant groups (mode 1: ModUp, first transform pass, fused pass + key product; each small launch pays ~10 us of ramp-up
-    // and tail: 11.6 -> 10.8 ms at C3).  Mat-vecs sharing the GPU on the auxiliary streams (spear_bsgs_hoisted_batch) keep
-    // one launch per group and stage (mode 0): the streams fill each other's gaps anyway (94.7 / 94.9 / 94.1 mat-vecs/s
-    // for modes 0 / 2 / 1 on one box), so they keep the small workspace (mode 1 adds 3.7 GB per stream at C3).
-    // Mode 2 = ModUp and first pass batched, product per group.  SPEAR_BATCH_GIANT / SPEAR_BATCH_GIANT_MULTI override.
+// Giant-step launch mode.  A mat-vec running alone on the engine stream takes everything in single launches over all
+// giant groups (mode 1: ModUp, first transform pass, fused pass + key product; each small launch pays ~10 us of ramp-up
+// and tail: 11.6 -> 10.8 ms at C3).  Mode 0 = one launch per group and stage, mode 2 = ModUp and first pass batched,
+// product per group.  SPEAR_BATCH_GIANT / SPEAR_BATCH_GIANT_MULTI (mat-vecs on the auxiliary streams) override.
+static int giant_mode(const Ctx* c, cudaStream_t s) {
     static const int mode_single = getenv("SPEAR_BATCH_GIANT") ? atoi(getenv("SPEAR_BATCH_GIANT")) : 1;
     static const int mode_multi = getenv("SPEAR_BATCH_GIANT_MULTI") ? atoi(getenv("SPEAR_BATCH_GIANT_MULTI")) : 1;
-    const int mode = s == c->stream ? mode_single : mode_multi;
-    const bool batch_e = mode != 0 && nrot >= 2 && ntt_ks_fused_applies(c, l) && (size_t)nrot * beta * rows <= 65535 &&
-                         (size_t)nrot * beta * pw * sizeof(u64) <= ((size_t)6 << 30);
-    Arena sc(c, s, l * N + beta * pw + (size_t)G * 2 * pw + (size_t)n_groups * 2 * pw + 3 * (size_t)nrot * l * N + 32 * 8 +
-                       (batch_e ? (size_t)nrot * (beta + 2) * pw + 64 : 0));
-    u64* x = sc.get(l * N);
-    u64* E = sc.get(beta * pw);
-    u64* Y = sc.get((size_t)G * 2 * pw);
-    u64* A = sc.get((size_t)n_groups * 2 * pw);
-    const u64 *c0 = ct, *c1 = ct + l * N;
+    return s == c->stream ? mode_single : mode_multi;
+}
+static bool giant_batched(const Ctx* c, int l, int nrot, cudaStream_t s) {
+    const size_t pw = (size_t)(l + c->P) * c->N;
+    const int beta = c->digits(l);
+    return giant_mode(c, s) != 0 && nrot >= 2 && ntt_ks_fused_applies(c, l) && (size_t)nrot * beta * (l + c->P) <= 65535 &&
+           (size_t)nrot * beta * pw * sizeof(u64) <= ((size_t)6 << 30);
+}
+static size_t phase1_words(const Ctx* c, int l, int G, int n_groups, bool local_a) {
+    const size_t N = c->N, pw = (size_t)(l + c->P) * N;
+    return l * N + c->digits(l) * pw + (size_t)G * 2 * pw + (local_a ? (size_t)n_groups * 2 * pw : 0) + 32 * 4;
+}
+static size_t phase2_words(const Ctx* c, int l, int nrot, cudaStream_t s) {
+    const size_t N = c->N, pw = (size_t)(l + c->P) * N;
+    const int beta = c->digits(l);
+    return l * N + beta * pw + 3 * (size_t)nrot * l * N + 32 * 8 + (giant_batched(c, l, nrot, s) ? (size_t)nrot * (beta + 2) * pw + 64 : 0);
+}
 
-    // 1-2. hoisted baby steps, kept in basis Q_l * P
+// Phase 1 of the hoisted mat-vec on the rows [row0, row0 + nrows) of the l + P: one decomposition of c1 shared by all
+// baby steps, the baby rotations kept in basis Q_l*P, and the diagonal MAC of every giant group of the set, whose
+// accumulators A_g go to `dst` (ops.h PmacDst: one local array, or the exchange windows of a rank group).
+// diag [n_diags][nrows][N >> rshift]; x, E, Y: scratch ([l][N], [beta][l+P][N], [G][2][l+P][N]); tmp: [n_groups][2][l+P][N]
+// when the set is walked in several baby-step chunks (G > 64), else unused.
+static void bsgs_phase1(const Ctx* c, const u64* ct, int l, const u64* diag, int rshift, int G, int n_groups, int n_diags,
+                        const u32* belt, const u64* const* bkey, u64* x, u64* E, u64* Y, const PmacDst& dst, u64* tmp,
+                        int row0, int nrows, cudaStream_t s) {
+    const size_t N = c->N, rows = l + c->P, pw = rows * N;
+    const u64 *c0 = ct, *c1 = ct + l * N;
     ops::decompose(c, c1, l, x, E, s);
     ops::pscale(c, ct, Y, l, s);
-    if (G > 1 && !ops::ks_baby_fused(c, E, bkey + 1, belt + 1, G - 1, Y + 2 * pw, l, c0, s))
+    if (G > 1 && !ops::ks_baby_fused(c, E, bkey + 1, belt + 1, G - 1, Y + 2 * pw, l, c0, s, row0, nrows)) {
+        REQUIRE(row0 == 0 && nrows == (int)rows, "two-phase mat-vec: the fused baby-step kernel does not apply to this shape");
         for (int b = 1; b < G; b++)
             ops::ks_inner(c, E, bkey[b], Y + (size_t)b * 2 * pw, l, belt[b], c0, l, 1, 0, s);
-    // 3. diagonal multiply-accumulate for every local giant group
-    ops::pmac_hoisted(c, Y, diag, A, G, n_groups, n_diags, l, rshift, s);
-    // 4. giant steps: R = sum_k (pi_g(A_k.0) + <pi_g(F), k0>, <pi_g(F), k1>)   (g = g_first + k*g_stride; g = 0: R = A_k)
-    //    The ModDown of every A_k.1 and the INTT that starts its decomposition are batched over all groups
-    //    (few large launches instead of ~10 small ones per giant step); ModUp + NTT + key product stay per group
-    //    so that the 57 MB of digits never leave L2.
+    }
+    ops::pmac_hoisted_rows(c, Y, diag, dst, tmp, G, n_groups, n_diags, l, rshift, row0, nrows, s);
+}
+
+// Phase 2: the giant steps of the n_groups accumulators A [n_groups][2][l+P][N] (destroyed: the ModDown transforms their
+// special rows in place):  R = sum_k (pi_g(A_k.0) + <pi_g(F_k), k0_g>, <pi_g(F_k), k1_g>),  F_k = decompose(ModDown(A_k.1));
+// a group with gelt[k] == 0 and gkey[k] == nullptr is giant group 0 (no rotation; it must come first).
+// The ModDown of every A_k.1 and the INTT that starts its decomposition are batched over all groups.
+static void bsgs_phase2(const Ctx* c, u64* A, int l, int n_groups, const u32* gelt, const u64* const* gkey, u64* R,
+                        Arena& sc, cudaStream_t s) {
+    const size_t N = c->N, rows = l + c->P, pw = rows * N;
+    const int beta = c->digits(l);
+    const int k0 = (n_groups > 0 && gkey[0] == nullptr) ? 1 : 0;   // group 0 (if owned) needs no rotation
+    const int nrot = n_groups > k0 ? n_groups - k0 : 0;
+    const int mode = giant_mode(c, s);
+    const bool batch_e = giant_batched(c, l, nrot, s);
     bool have = false;
-    if (g_first == 0 && n_groups > 0) {
+    if (k0) {
         CUDA_CHECK(cudaMemcpyAsync(R, A, sizeof(u64) * 2 * pw, cudaMemcpyDeviceToDevice, s));
         have = true;
     }
     if (nrot > 0) {
+        u64* x = sc.get(l * N);
+        u64* E = sc.get(beta * pw);
         u64* t_all = sc.get((size_t)nrot * l * N);      // ModDown(A_k.1), NTT form
         u64* x_all = sc.get((size_t)nrot * l * N);      // scratch: the same on its way to coefficient form
         u64* tmp = sc.get((size_t)nrot * l * N);
+        (void)x;
         ops::moddown(c, A + (size_t)k0 * 2 * pw + pw, 2 * pw, nrot, l, tmp, nullptr, t_all, s);
         if (batch_e) {
             // The decomposition front end of ALL giant groups in one launch (inverse pass A + ModUp + forward pass A
@@ -238,6 +257,51 @@ void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, i
         }
     }
     if (!have) CUDA_CHECK(cudaMemsetAsync(R, 0, sizeof(u64) * 2 * pw, s));
+}
+
+// ct [2][l][N]; diag [n_diags][l+P][N >> rshift] holds the giant groups g_first + k*g_stride (k < n_groups);
+// bkey[b] (1 <= b < G); gelt/gkey indexed by LOCAL group k (0 / nullptr where the global group is 0).
+// R [2][l+P][N]: this shard's accumulator in basis Q_l*P (sum over shards, mod q, = the full accumulator).
+void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, int rshift, int G, int n_groups,
+                          int n_diags, int g_first, int g_stride, const u32* belt, const u64* const* bkey,
+                          const u32* gelt, const u64* const* gkey, u64* R, cudaStream_t s) {
+    const size_t N = c->N, rows = l + c->P, pw = rows * N;
+    const int k0 = (g_first == 0) ? 1 : 0;
+    const int nrot = n_groups > k0 ? n_groups - k0 : 0;
+    (void)g_stride;
+    Arena sc(c, s, phase1_words(c, l, G, n_groups, true) + phase2_words(c, l, nrot, s));
+    u64* x = sc.get(l * N);
+    u64* E = sc.get(c->digits(l) * pw);
+    u64* Y = sc.get((size_t)G * 2 * pw);
+    u64* A = sc.get((size_t)n_groups * 2 * pw);
+    PmacDst dst = {};
+    dst.base[0] = A, dst.world = 1;
+    bsgs_phase1(c, ct, l, diag, rshift, G, n_groups, n_diags, belt, bkey, x, E, Y, dst, A, 0, (int)rows, s);
+    bsgs_phase2(c, A, l, n_groups, gelt, gkey, R, sc, s);
+}
+
+// ---- two-phase mat-vec over a rank group (peer.cu drives the exchange between the phases) -----------------------------
+// Phase 1 on this rank's ROWS for every giant group of the matrix; the accumulators of group g land in dst.base[g % world]
+// (slot (g / world)): the all-to-all that turns the row split into the giant-group split is the diagonal MAC's own
+// epilogue.  diag [n_diags][nrows][N >> rshift] holds all B groups.
+void bsgs_split_phase1(const Ctx* c, const u64* ct, int l, const u64* diag, int rshift, int G, int B, int n_diags, int row0,
+                       int nrows, const u32* belt, const u64* const* bkey, const PmacDst& dst, cudaStream_t s) {
+    const size_t N = c->N, pw = (size_t)(l + c->P) * N;
+    const bool chunks = G > 64;
+    Arena sc(c, s, std::max(phase1_words(c, l, G, B, chunks), phase2_words(c, l, (B + dst.world - 1) / dst.world, s)));
+    u64* x = sc.get(l * N);
+    u64* E = sc.get(c->digits(l) * pw);
+    u64* Y = sc.get((size_t)G * 2 * pw);
+    u64* tmp = chunks ? sc.get((size_t)B * 2 * pw) : nullptr;
+    bsgs_phase1(c, ct, l, diag, rshift, G, B, n_diags, belt, bkey, x, E, Y, dst, tmp, row0, nrows, s);
+}
+// Phase 2 on this rank's giant groups, whose accumulators A [n_groups][2][l+P][N] every rank of the group has written.
+void bsgs_split_phase2(const Ctx* c, u64* A, int l, int G, int B, int n_groups, const u32* gelt, const u64* const* gkey,
+                       int world, u64* R, cudaStream_t s) {
+    const int k0 = (n_groups > 0 && gkey[0] == nullptr) ? 1 : 0;
+    Arena sc(c, s, std::max(phase1_words(c, l, G, B, G > 64), phase2_words(c, l, (B + world - 1) / world, s)));
+    (void)k0;
+    bsgs_phase2(c, A, l, n_groups, gelt, gkey, R, sc, s);
 }
 
 // R [2][l+P][N] (destroyed) -> out [2][l-1][N]: one ModDown, one rescale

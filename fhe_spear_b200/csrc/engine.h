@@ -140,8 +140,10 @@ struct DiagSet : CtxRef {
     int l = 0;       // data limbs
     int n = 0;       // coefficients stored per row (N >> rshift)
     int rshift = 0;
+    int row0 = 0, nrows = -1;  // row slice of a two-phase mat-vec: rows [row0, row0 + nrows) of the l + P (nrows < 0: all rows)
     double scale = 1.0;
-    u64* d = nullptr;  // [D][l+P][n]
+    u64* d = nullptr;  // [n_diags][stored_rows()][n]
+    int stored_rows() const { return nrows >= 0 ? nrows : l + ctx->P; }
     ~DiagSet() {
         if (d && ctx) ctx->free(d);
     }
@@ -185,6 +187,23 @@ bool ntt_ks_fused(const Ctx* c, u64* E, const u64* key, u64* out, int l, u32 elt
 bool ntt_ks_fused_all(const Ctx* c, const u64* E, const u64* const* keys, const u32* elts, int groups, u64* out, int l,
                       const u64* addp, size_t add_stride, int add_rows, cudaStream_t s);
 void ntt_inverse(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s, bool pass_b_only = false);
+
+// ---- two-phase mat-vec over a rank group: exchange hooks (peer.cu), phases (bsgs.cu) -----------------------------
+struct PmacDst;
+struct spear_peer_window;
+namespace peer {
+struct SplitView {
+    int rank, world;
+    u64* base[8];   // the slot of every rank of the group (base[rank]: this rank's own, the others peer-mapped)
+};
+void window_geometry(const spear_peer_window* win, int* rank, int* world);
+// waits (on s) until every peer has consumed the slot's previous contents, opens a new epoch
+SplitView split_begin(const Ctx* c, spear_peer_window* win, int slot, size_t need_words, cudaStream_t s);
+// posts "my phase-1 stores are out" to every peer and waits for theirs
+void split_exchange(spear_peer_window* win, int slot, cudaStream_t s);
+// posts "slot consumed" to every peer; R (words) is overwritten with all-ones words if a peer never arrived
+void split_release(spear_peer_window* win, int slot, u64* R, size_t words, cudaStream_t s);
+}  // namespace peer
 
 // ---- stream ids shared with the oracle ------------------------------------------------------
 enum { DOM_SK = 1, DOM_PK_A = 2, DOM_PK_E = 3, DOM_KSK_A = 4, DOM_KSK_E = 5,

@@ -324,7 +324,7 @@ template <int FOLD, int BETA>
 __global__ void __launch_bounds__(KS_TILE, 6) k_ks_baby_fused(const __grid_constant__ BabyTab tab, KsArgs a, ModTab mt,
                                                                const ulonglong2* __restrict__ pmod) {
     const int b = blockIdx.y;
-    ks_tile_body<FOLD, BETA>(&tab.map[b], a, mt, pmod, blockIdx.z, blockIdx.x * KS_TPC, tab.elt[b],
+    ks_tile_body<FOLD, BETA>(&tab.map[b], a, mt, pmod, blockIdx.z + a.row0, blockIdx.x * KS_TPC, tab.elt[b],
                              a.out + (size_t)b * 2 * a.rows * a.N);
 }
 
@@ -469,11 +469,14 @@ __global__ void __launch_bounds__(TPB) k_pmac_list(PmacPtrs ptrs, int nb, u64* _
 // shared memory and reused for all B giant groups, so Y is read from L2/HBM once and every diagonal
 // element is read once.
 constexpr int PM_TILE = 128;
+__device__ __forceinline__ u64* pmac_dst(const PmacDst& d, int g, int p, size_t pw) {
+    return d.base[g % d.world] + (size_t)((g / d.world) * 2 + p) * pw;
+}
 __global__ void __launch_bounds__(PM_TILE) k_pmac_hoisted(const u64* __restrict__ Y, const u64* __restrict__ diag,
-                                                           u64* __restrict__ A, int G, int B, int D, int l, int rows,
-                                                           int N, int L, int rshift, ModTab mt) {
+                                                           PmacDst dst, int G, int B, int D, int l, int rows,
+                                                           int N, int L, int rshift, int row0, int nrows, ModTab mt) {
     extern __shared__ u64 sm[];   // [G][2][PM_TILE]
-    const int r = blockIdx.y, n = blockIdx.x * PM_TILE + threadIdx.x;
+    const int r = blockIdx.y + row0, n = blockIdx.x * PM_TILE + threadIdx.x;
     const int t = r < l ? r : L + (r - l);
     const size_t pw = (size_t)rows * N, off = (size_t)r * N + n;
     for (int b = 0; b < G; b++) {
@@ -483,8 +486,8 @@ __global__ void __launch_bounds__(PM_TILE) k_pmac_hoisted(const u64* __restrict_
     // each thread only re-reads its own column: no barrier needed
     const u64 q = mt.q[t], r0 = mt.ratio0[t], r1 = mt.ratio1[t];
     const int dn = N >> rshift;
-    const u64* dg = diag + (size_t)r * dn + (n >> rshift);
-    const size_t dstride = (size_t)rows * dn;
+    const u64* dg = diag + (size_t)blockIdx.y * dn + (n >> rshift);   // the set stores its nrows rows only
+    const size_t dstride = (size_t)nrows * dn;
     const u64 pol = evict_first_policy();
     for (int g = 0; g < B; g++) {
         int nb = min(G, D - g * G);
@@ -497,9 +500,10 @@ __global__ void __launch_bounds__(PM_TILE) k_pmac_hoisted(const u64* __restrict_
             mac128(lo0, hi0, sm[(b * 2 + 0) * PM_TILE + threadIdx.x], d);
             mac128(lo1, hi1, sm[(b * 2 + 1) * PM_TILE + threadIdx.x], d);
         }
-        A[(size_t)g * 2 * pw + off] = barrett128(lo0, hi0, q, r0, r1);
-        A[(size_t)g * 2 * pw + pw + off] = barrett128(lo1, hi1, q, r0, r1);
+        pmac_dst(dst, g, 0, pw)[off] = barrett128(lo0, hi0, q, r0, r1);
+        pmac_dst(dst, g, 1, pw)[off] = barrett128(lo1, hi1, q, r0, r1);
     }
+    if (dst.world > 1) __threadfence_system();   // the stores crossed NVLink: visible before the next kernel posts its flag
 }
 
 
@@ -523,8 +527,8 @@ constexpr int PM_T2 = 64;       // coefficients per CTA
 // NG giant groups of one pipeline stage: A[g0 + k] (+)= sum_b y_b * d_{k,b}
 template <int FOLD, int W, int NG>
 __device__ __forceinline__ void pmac_groups(const u64* __restrict__ ycol, const u64* __restrict__ dg, size_t group_words,
-                                            int Gc, u64* __restrict__ Aout, size_t a_stride, u64 q, u64 r0, u64 r1,
-                                            bool accumulate) {
+                                            int Gc, const PmacDst& dst, const u64* Ain, int g0, int p, size_t pw,
+                                            size_t off, u64 q, u64 r0, u64 r1) {
     Acc3 acc[NG];
     u64 lo[NG], hi[NG];
 #pragma unroll
@@ -543,8 +547,8 @@ __device__ __forceinline__ void pmac_groups(const u64* __restrict__ ycol, const 
 #pragma unroll
     for (int k = 0; k < NG; k++) {
         u64 v = barrett128(lo[k], hi[k], q, r0, r1);
-        if (accumulate) v = add_mod(v, Aout[k * a_stride], q);
-        Aout[k * a_stride] = v;
+        if (Ain) v = add_mod(v, Ain[(size_t)((g0 + k) * 2 + p) * pw + off], q);   // earlier baby-step chunks (local)
+        pmac_dst(dst, g0 + k, p, pw)[off] = v;
     }
 }
 
@@ -555,16 +559,17 @@ constexpr int PM_HS = 2;
 constexpr int PM_NG = PM_GT / PM_HS;   // groups per thread and stage
 template <int FOLD, int RSH>
 __global__ void __launch_bounds__(2 * PM_T2 * PM_HS) k_pmac_tma(const __grid_constant__ CUtensorMap tmap,
-                                                                 const u64* __restrict__ Y, u64* __restrict__ A, int G,
-                                                                 int Gc, int b0, int nbc, int accumulate, int Beff, int l,
-                                                                 int rows, int N, int L, ModTab mt) {
+                                                                 const u64* __restrict__ Y, PmacDst dst,
+                                                                 const u64* Ain, int G, int Gc, int b0, int nbc,
+                                                                 int Beff, int l, int rows, int N, int L, int row0,
+                                                                 ModTab mt) {
     extern __shared__ __align__(128) unsigned char smraw[];
     constexpr int W = PM_T2 >> RSH;
     u64* dsm = reinterpret_cast<u64*>(smraw);                         // [PM_STAGES][PM_GT][Gc][W]
     u64* ysm = dsm + (size_t)PM_STAGES * PM_GT * Gc * W;              // [Gc][2][PM_T2]
     uint64_t* full = reinterpret_cast<uint64_t*>(ysm + (size_t)Gc * 2 * PM_T2);
     const int tid = threadIdx.x, h = tid / (2 * PM_T2), p = (tid / PM_T2) & 1, i = tid % PM_T2;
-    const int r = blockIdx.y, n0 = blockIdx.x * PM_T2;
+    const int r = blockIdx.y + row0, n0 = blockIdx.x * PM_T2;   // the diagonal set stores rows row0 .. only (TMA row = blockIdx.y)
     const int t = r < l ? r : L + (r - l);
     const int iters = (Beff + PM_GT - 1) / PM_GT;
     const size_t group_words = (size_t)Gc * W, stage_words = PM_GT * group_words;
@@ -580,23 +585,23 @@ __global__ void __launch_bounds__(2 * PM_T2 * PM_HS) k_pmac_tma(const __grid_con
         const int s = it % PM_STAGES, ng = min(PM_GT, Beff - it * PM_GT);
         mbar_expect_tx(&full[s], (u32)(ng * Gc * W * sizeof(u64)));
         for (int k = 0; k < ng; k++)
-            tma_load_3d(dsm + s * stage_words + k * group_words, &tmap, n0 >> RSH, r, (it * PM_GT + k) * G + b0, &full[s]);
+            tma_load_3d(dsm + s * stage_words + k * group_words, &tmap, n0 >> RSH, blockIdx.y, (it * PM_GT + k) * G + b0, &full[s]);
     };
     if (tid == 0)
         for (int it = 0; it < PM_STAGES && it < iters; it++) issue(it);
     const u64 q = mt.q[t], r0 = mt.ratio0[t], r1 = mt.ratio1[t];
     const u64* ycol = ysm + p * PM_T2 + i;
-    const bool acc = accumulate != 0;
     for (int it = 0; it < iters; it++) {
         const int s = it % PM_STAGES, ng = min(PM_NG, Beff - it * PM_GT - h * PM_NG);   // this thread's groups
         mbar_wait(&full[s], (it / PM_STAGES) & 1);
         const u64* dg = dsm + s * stage_words + (size_t)h * PM_NG * group_words + (i >> RSH);
-        u64* Aout = A + (size_t)((it * PM_GT + h * PM_NG) * 2 + p) * pw + off;
-        if (ng >= PM_NG) pmac_groups<FOLD, W, PM_NG>(ycol, dg, group_words, Gc, Aout, 2 * pw, q, r0, r1, acc);
-        else if (ng == 1) pmac_groups<FOLD, W, 1>(ycol, dg, group_words, Gc, Aout, 2 * pw, q, r0, r1, acc);
+        const int g0 = it * PM_GT + h * PM_NG;
+        if (ng >= PM_NG) pmac_groups<FOLD, W, PM_NG>(ycol, dg, group_words, Gc, dst, Ain, g0, p, pw, off, q, r0, r1);
+        else if (ng == 1) pmac_groups<FOLD, W, 1>(ycol, dg, group_words, Gc, dst, Ain, g0, p, pw, off, q, r0, r1);
         __syncthreads();   // every thread is done with stage s
         if (tid == 0 && it + PM_STAGES < iters) issue(it + PM_STAGES);
     }
+    if (dst.world > 1) __threadfence_system();   // the stores crossed NVLink: visible before the next kernel posts its flag
 }
 
 // in-place conversion between canonical residues and the split-30 storage form
@@ -783,8 +788,11 @@ void ks_inner(const Ctx* c, const u64* E, const u64* key, u64* out, int l, u32 e
 // Y[b] for b = 1..nb (out points at Y[1]): all hoisted baby steps against their keys in one launch.
 // Returns false when the fused path does not apply (caller falls back to one launch per baby step).
 bool ks_baby_fused(const Ctx* c, const u64* E, const u64* const* keys, const u32* elts, int nb, u64* out, int l,
-                   const u64* c0, cudaStream_t s) {
+                   const u64* c0, cudaStream_t s, int row0, int nrows) {
     const int beta = c->digits(l), rows = l + c->P;
+    if (nrows < 0) nrows = rows - row0;
+    REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= rows, "baby steps: bad row range");
+    if (nrows == 0) return true;
     if (nb < 1 || nb > KS_MAX_BABY || beta > 8 || c->N % KS_TILE != 0) return false;
     static thread_local BabyTab tab;   // 12.6 KB by-value kernel parameter
     cuuint64_t dims[3] = {(cuuint64_t)c->N, (cuuint64_t)c->K, (cuuint64_t)(2 * c->beta)};
@@ -801,6 +809,7 @@ bool ks_baby_fused(const Ctx* c, const u64* E, const u64* const* keys, const u32
     KsArgs a;
     a.E = E, a.key = nullptr, a.out = out, a.addp = c0, a.add_rows = l, a.add_pscale = 1, a.accumulate = 0;
     a.beta = beta, a.l = l, a.rows = rows, a.N = c->N, a.logn = c->logn, a.L = c->L, a.K = c->K, a.elt = 0;
+    a.row0 = row0;
     bool small = true;
     for (u64 qq : c->q) small = small && qq < (1ull << 59);
     const size_t smem = (size_t)4 * beta * KS_TILE * sizeof(u64) + 64;
@@ -808,7 +817,7 @@ bool ks_baby_fused(const Ctx* c, const u64* E, const u64* const* keys, const u32
     ProfScope ps(c, PROF_KS_BABY, s);
     auto go = [&](auto kern) {
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        LAUNCH(kern, dim3(gx, nb, rows), KS_TILE, smem, s)(tab, a, c->modtab(), c->d_pmod);
+        LAUNCH(kern, dim3(gx, nb, nrows), KS_TILE, smem, s)(tab, a, c->modtab(), c->d_pmod);
     };
 #define KB_CASE(B)                                  \
     case B:                                         \
@@ -886,7 +895,16 @@ void pmac_list(const Ctx* c, const u64* const* baby, const u64* const* pt, int n
 
 void pmac_hoisted(const Ctx* c, const u64* Y, const u64* diag, u64* A, int G, int B, int D, int l, int rshift,
                   cudaStream_t s) {
+    PmacDst dst = {};
+    dst.base[0] = A, dst.world = 1;
+    pmac_hoisted_rows(c, Y, diag, dst, A, G, B, D, l, rshift, 0, l + c->P, s);
+}
+
+void pmac_hoisted_rows(const Ctx* c, const u64* Y, const u64* diag, const PmacDst& dst, u64* tmp, int G, int B, int D, int l,
+                       int rshift, int row0, int nrows, cudaStream_t s) {
     const int rows = l + c->P, dn = c->N >> rshift, W = PM_T2 >> rshift;
+    REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= rows && dst.world >= 1 && dst.world <= 8, "diagonal MAC: bad row range");
+    if (nrows == 0) return;
     // baby steps are walked in chunks of Gc <= 64 rows (a multiple of 16) so that 2-3 CTAs fit per SM
     const int nchunks = (G + 63) / 64, Gc = ((G + nchunks - 1) / nchunks + 15) / 16 * 16;
     REQUIRE(c->N % PM_TILE == 0, "N must be a multiple of %d", PM_TILE);
@@ -896,8 +914,8 @@ void pmac_hoisted(const Ctx* c, const u64* Y, const u64* diag, u64* A, int G, in
     if (rshift >= 1 && rshift <= 5 && W * sizeof(u64) >= 16 && ((size_t)Gc * W * sizeof(u64)) % 128 == 0 &&
         Gc <= D && tma_smem <= 227 * 1024) {
         CUtensorMap tmap;
-        cuuint64_t dims[3] = {(cuuint64_t)dn, (cuuint64_t)rows, (cuuint64_t)D};
-        cuuint64_t strides[2] = {(cuuint64_t)dn * sizeof(u64), (cuuint64_t)rows * dn * sizeof(u64)};
+        cuuint64_t dims[3] = {(cuuint64_t)dn, (cuuint64_t)nrows, (cuuint64_t)D};
+        cuuint64_t strides[2] = {(cuuint64_t)dn * sizeof(u64), (cuuint64_t)nrows * dn * sizeof(u64)};
         cuuint32_t box[3] = {(cuuint32_t)W, 1, (cuuint32_t)Gc};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult rc = encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, (void*)diag, dims, strides, box, estr,
@@ -907,13 +925,19 @@ void pmac_hoisted(const Ctx* c, const u64* Y, const u64* diag, u64* A, int G, in
         // partial sums of 30x30-bit products: 16 terms fit 64 bits when every q < 2^59, else 8
         bool small = true;
         for (u64 qq : c->q) small = small && qq < (1ull << 59);
-        dim3 grid(c->N / PM_T2, rows);
+        dim3 grid(c->N / PM_T2, nrows);
         const ModTab mt = c->modtab();
+        // several chunks: the earlier ones accumulate in the local array `tmp`, only the last one writes the destination
+        // (which may be peer memory: no read-modify-write across NVLink)
+        PmacDst local = {};
+        local.base[0] = tmp, local.world = 1;
         auto go = [&](auto kern) {
             CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            for (int b0 = 0; b0 < G; b0 += Gc)
-                LAUNCH(kern, grid, 2 * PM_T2 * PM_HS, tma_smem, s)(tmap, Y, A, G, Gc, b0, std::min(Gc, G - b0), b0 > 0 ? 1 : 0, B, l,
-                                                           rows, c->N, c->L, mt);
+            for (int b0 = 0; b0 < G; b0 += Gc) {
+                const bool last = b0 + Gc >= G;
+                LAUNCH(kern, grid, 2 * PM_T2 * PM_HS, tma_smem, s)(tmap, Y, last ? dst : local, b0 > 0 ? tmp : nullptr, G, Gc, b0,
+                                                                   std::min(Gc, G - b0), B, l, rows, c->N, c->L, row0, mt);
+            }
         };
         switch (rshift * 2 + (small ? 1 : 0)) {
             case 2: go(k_pmac_tma<8, 1>); break;
@@ -933,8 +957,8 @@ void pmac_hoisted(const Ctx* c, const u64* Y, const u64* diag, u64* A, int G, in
     size_t smem = sizeof(u64) * (size_t)G * 2 * PM_TILE;
     REQUIRE(smem <= 227 * 1024, "too many baby steps (%d) for the shared-memory tile", G);
     CUDA_CHECK(cudaFuncSetAttribute(k_pmac_hoisted, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per device
-    LAUNCH(k_pmac_hoisted, dim3(c->N / PM_TILE, rows), PM_TILE, smem, s)(Y, diag, A, G, B, D, l, rows, c->N, c->L, rshift,
-                                                                     c->modtab());
+    LAUNCH(k_pmac_hoisted, dim3(c->N / PM_TILE, nrows), PM_TILE, smem, s)(Y, diag, dst, G, B, D, l, rows, c->N, c->L, rshift,
+                                                                      row0, nrows, c->modtab());
     CUDA_CHECK(cudaGetLastError());
 }
 

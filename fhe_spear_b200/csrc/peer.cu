@@ -39,6 +39,7 @@ struct PeerWindow : CtxRef {
     u64* base = nullptr;               // [DATA_OFFSET_WORDS flags][slots][slot_words]
     u64* peer[MAX_PEERS] = {};         // mapped windows of the group (peer[rank] == base)
     bool connected = false;
+    int mode = 0;                      // 0: unused yet, 1: accumulator all-reduce, 2: two-phase mat-vec exchange (never mixed)
     u64 epoch[MAX_SLOTS] = {};
     int* status = nullptr;             // pinned host word, written by the waiting kernels on time-out
     int* d_status = nullptr;           // its device address (zero-copy: only the one-warp sync kernels touch it)
@@ -86,12 +87,17 @@ __host__ __device__ __forceinline__ size_t flag_index(int slot, int kind, int wr
     return (size_t)slot * SLOT_FLAG_WORDS + (size_t)kind * MAX_PEERS + writer;
 }
 
-// lane r < world:  (post != 0) tell peer r that `me` reached `epoch` of `kind`;  then wait until peer r told us the same
+// lane r < world:  (post != 0) tell peer r that `me` reached `epoch` of `kind`;  then (wait != 0) wait until peer r told
+// us the same
 __global__ void k_peer_sync(PeerPtrs pp, int world, int me, int slot, int kind, int post, u64 epoch, int* status,
-                            int* failed) {
+                            int* failed, int wait = 1) {
     const int r = threadIdx.x;
     if (r >= world) return;
-    if (post) st_release_sys(pp.w[r] + flag_index(slot, kind, me), epoch);
+    if (post) {
+        __threadfence_system();
+        st_release_sys(pp.w[r] + flag_index(slot, kind, me), epoch);
+    }
+    if (!wait) return;
     const u64* mine = pp.w[me] + flag_index(slot, kind, r);
     const unsigned long long deadline = globaltimer_ns() + SPIN_TIMEOUT_NS;
     while (ld_acquire_sys(mine) < epoch) {
@@ -151,7 +157,60 @@ __global__ void k_peer_collect(const u64* __restrict__ win, u64* __restrict__ ac
 
 inline PeerWindow* W_(spear_peer_window* w) { return reinterpret_cast<PeerWindow*>(w); }
 
+// R <- all-ones words when a wait of this window timed out (no valid residue: q < 2^61)
+__global__ void k_peer_poison(u64* __restrict__ R, size_t words, const int* failed_flag) {
+    if (*(volatile const int*)failed_flag == 0) return;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < words; e += (size_t)gridDim.x * blockDim.x) R[e] = ~0ull;
+}
+
 }  // namespace
+
+// ---- two-phase mat-vec: the exchange between the row-split phase and the giant-group-split phase -----------------------
+// Flags of a slot: kind 0 = "my phase-1 stores into your slot are complete" (epoch e), kind 1 = "I have consumed my slot
+// of epoch e".  A rank may write into a peer's slot for epoch e only after that peer consumed epoch e - 1.
+namespace peer {
+static PeerPtrs ptrs_of(const PeerWindow* w) {
+    PeerPtrs pp;
+    for (int r = 0; r < MAX_PEERS; r++) pp.w[r] = w->peer[r < w->world ? r : w->rank];
+    return pp;
+}
+void window_geometry(const spear_peer_window* win, int* rank, int* world) {
+    const PeerWindow* w = reinterpret_cast<const PeerWindow*>(win);
+    REQUIRE(w, "two-phase mat-vec: null window");
+    *rank = w->rank, *world = w->world;
+}
+SplitView split_begin(const Ctx* c, spear_peer_window* win, int slot, size_t need_words, cudaStream_t s) {
+    PeerWindow* w = W_(win);
+    REQUIRE(w && w->connected && w->ctx == c, "two-phase mat-vec: window not connected");
+    REQUIRE(w->mode == 0 || w->mode == 2, "two-phase mat-vec: this window serves accumulator all-reduces");
+    REQUIRE(slot >= 0 && slot < w->slots, "two-phase mat-vec: slot %d of %d", slot, w->slots);
+    REQUIRE(need_words <= w->slot_words, "two-phase mat-vec: the window slot holds %zu words, %zu needed", w->slot_words, need_words);
+    REQUIRE(*(volatile int*)w->status == 0, "two-phase mat-vec: peer %d never arrived (CUDA peer exchange timed out)",
+            *(volatile int*)w->status - 1);
+    w->mode = 2;
+    const u64 epoch = ++w->epoch[slot];
+    if (w->world > 1)
+        LAUNCH(k_peer_sync, 1, 32, 0, s)(ptrs_of(w), w->world, w->rank, slot, 1, 0, epoch - 1, w->d_status, w->d_failed, 1);
+    SplitView v;
+    v.rank = w->rank, v.world = w->world;
+    const size_t data_off = DATA_OFFSET_WORDS + (size_t)slot * w->slot_words;
+    for (int r = 0; r < MAX_PEERS; r++) v.base[r] = w->peer[r < w->world ? r : w->rank] + data_off;
+    return v;
+}
+void split_exchange(spear_peer_window* win, int slot, cudaStream_t s) {
+    PeerWindow* w = W_(win);
+    if (w->world > 1)
+        LAUNCH(k_peer_sync, 1, 32, 0, s)(ptrs_of(w), w->world, w->rank, slot, 0, 1, w->epoch[slot], w->d_status, w->d_failed, 1);
+}
+void split_release(spear_peer_window* win, int slot, u64* R, size_t words, cudaStream_t s) {
+    PeerWindow* w = W_(win);
+    if (w->world > 1) {
+        LAUNCH(k_peer_sync, 1, 32, 0, s)(ptrs_of(w), w->world, w->rank, slot, 1, 1, w->epoch[slot], w->d_status, w->d_failed, 0);
+        LAUNCH(k_peer_poison, (int)std::min<size_t>((words + 255) / 256, (size_t)w->ctx->sm_count * 4), 256, 0, s)(R, words, w->d_failed);
+    }
+    CUDA_CHECK(cudaGetLastError());
+}
+}  // namespace peer
 
 void spear_set_last_error(const char* msg);   // api.cu
 
@@ -224,6 +283,8 @@ int spear_peer_allreduce(spear_context* ctx, spear_peer_window* win, int slot, s
     PeerWindow* w = W_(win);
     Obj* acc = reinterpret_cast<Obj*>(acc_);
     REQUIRE(w && w->connected, "peer all-reduce: window not connected");
+    REQUIRE(w->mode == 0 || w->mode == 1, "peer all-reduce: this window serves the two-phase mat-vec exchange");
+    w->mode = 1;
     REQUIRE(slot >= 0 && slot < w->slots, "peer all-reduce: slot %d of %d", slot, w->slots);
     REQUIRE(acc && acc->n == c->N && acc->words() % 2 == 0, "peer all-reduce: bad operand");
     REQUIRE(acc->words() <= w->slot_words, "peer all-reduce: operand larger than the window slot");
@@ -240,7 +301,7 @@ int spear_peer_allreduce(spear_context* ctx, spear_peer_window* win, int slot, s
     PeerPtrs pp;
     for (int r = 0; r < MAX_PEERS; r++) pp.w[r] = w->peer[r < w->world ? r : w->rank];
     CUDA_CHECK(cudaMemcpyAsync(w->base + data_off, acc->d, bytes, cudaMemcpyDeviceToDevice, s));
-    LAUNCH(k_peer_sync, 1, 32, 0, s)(pp, w->world, w->rank, slot, 0, 1, epoch, w->d_status, w->d_failed);
+    LAUNCH(k_peer_sync, 1, 32, 0, s)(pp, w->world, w->rank, slot, 0, 1, epoch, w->d_status, w->d_failed, 1);
     const size_t pairs = acc->words() / 2, per = (pairs + w->world - 1) / w->world;
     const size_t lo = std::min(pairs, per * w->rank), hi = std::min(pairs, lo + per);
     const int grid = (int)std::max<size_t>(1, std::min<size_t>((hi - lo + 255) / 256, (size_t)c->sm_count * 8));
@@ -258,7 +319,7 @@ int spear_peer_allreduce(spear_context* ctx, spear_peer_window* win, int slot, s
         case 7: go(k_peer_reduce<7>); break;
         default: go(k_peer_reduce<8>); break;
     }
-    LAUNCH(k_peer_sync, 1, 32, 0, s)(pp, w->world, w->rank, slot, 1, 0, epoch, w->d_status, w->d_failed);
+    LAUNCH(k_peer_sync, 1, 32, 0, s)(pp, w->world, w->rank, slot, 1, 0, epoch, w->d_status, w->d_failed, 1);
     LAUNCH(k_peer_collect, (int)std::min<size_t>((acc->words() + 255) / 256, (size_t)c->sm_count * 8), 256, 0, s)(
         w->base + data_off, acc->d, acc->words(), w->d_failed);
     CUDA_CHECK(cudaGetLastError());

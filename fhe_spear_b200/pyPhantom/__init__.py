@@ -752,9 +752,34 @@ class diagonal_set:
         return dict(D=D.value, G=G.value, B=B.value, limbs=limbs.value, ring_n=ring.value, scale=scale.value,
                     bytes=nbytes.value)
 
+    @staticmethod
+    def row_range(limbs, P, rank, world):
+        """rows [r0, r1) of the limbs + P served by `rank` in the row-split phase of a two-phase mat-vec"""
+        rows = int(limbs) + int(P)
+        return rank * rows // world, (rank + 1) * rows // world
+
+    def slice_rows(self, rank, world):
+        """The rows rank `rank` of `world` holds in a two-phase mat-vec (bsgs_split): every giant group, rows
+        row_range(...) only -- 1/world of the set's bytes."""
+        if self.shard != (0, 1):
+            raise RuntimeError("slice_rows: expected a set holding every giant group")
+        r0, r1 = self.row_range(self.info()["limbs"], self._ctx.P, rank, world)
+        h = C.c_void_p()
+        _check(_lib.spear_diagset_slice_rows(self._ctx._h, self._h, r0, r1 - r0, C.byref(h)))
+        out = type(self).__new__(type(self))
+        out._ctx, out._h = self._ctx, h
+        out.D, out.G, out.B, out.shard, out.rows = self.D, self.G, self.B, self.shard, self.rows
+        out.row_slice = (r0, r1)
+        return out
+
     def to_numpy(self):
         i = self.info()
-        out = np.empty((len(self.rows), i["limbs"] + self._ctx.P, i["ring_n"]), dtype=np.uint64)
+        nrows = i["limbs"] + self._ctx.P
+        if getattr(self, "row_slice", None):
+            nrows = self.row_slice[1] - self.row_slice[0]
+        out = np.empty((len(self.rows), nrows, i["ring_n"]), dtype=np.uint64)
+        if out.size == 0:
+            return out
         _check(_lib.spear_diagset_export(self._h, out.ctypes.data_as(C.c_void_p), out.size))
         return out
 
@@ -780,6 +805,27 @@ def bsgs_hoisted_partial_batch(ctx, cts, shards, gk):
     _check(_lib.spear_bsgs_hoisted_partial_batch(ctx._h, (C.c_void_p * n)(*[c._h for c in cts]),
                                                  (C.c_void_p * n)(*[d._h for d in shards]), n, gk._h, outs))
     return [ciphertext(ctx, C.c_void_p(h)) for h in outs]
+
+
+def bsgs_split(ctx, ct, rows, gk, window, slot=0):
+    """Two-phase mat-vec over the rank group of `window` (include/spear_b200.h): baby steps + diagonal MAC on this rank's
+    rows, accumulators scattered to the owners of the giant groups over NVLink, giant steps of this rank's groups.
+    Returns this rank's accumulator in basis Q_l*P (sum over the ranks = the full accumulator)."""
+    return _new(ciphertext, ctx, _lib.spear_bsgs_split, ct._h, rows._h, gk._h, window._h, int(slot))
+
+
+def bsgs_split_batch(ctx, cts, rows, gk, window, slot0=0):
+    n = len(cts)
+    outs = (C.c_void_p * n)()
+    _check(_lib.spear_bsgs_split_batch(ctx._h, (C.c_void_p * n)(*[c._h for c in cts]),
+                                       (C.c_void_p * n)(*[d._h for d in rows]), n, gk._h, window._h, int(slot0), outs))
+    return [ciphertext(ctx, C.c_void_p(h)) for h in outs]
+
+
+def bsgs_split_selftest(ctx, ct, row_sets, gk):
+    """One-GPU emulation of bsgs_split over len(row_sets) ranks (test hook): the summed accumulator."""
+    n = len(row_sets)
+    return _new(ciphertext, ctx, _lib.spear_bsgs_split_selftest, ct._h, (C.c_void_p * n)(*[d._h for d in row_sets]), n, gk._h)
 
 
 def bsgs_finish(ctx, acc):

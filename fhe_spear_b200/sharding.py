@@ -68,8 +68,9 @@ class PeerExchange:
     swapped with one all_gather_object over the group -- host plumbing only; the data path is csrc/peer.cu."""
 
     _cache = {}
+    _retired = []      # replaced windows stay mapped: peers may hold their IPC mappings for the life of the process
 
-    def __init__(self, ctx, group=None, slots=3):
+    def __init__(self, ctx, group=None, slots=3, slot_bytes=None):
         """Every rank runs the SAME collective sequence whether or not a local step fails (handle all-gather, outcome
         all-gather after mapping), so a failure on one rank degrades the whole group to the NCCL path instead of
         leaving the others in a mismatched collective.  `self.ok` is the agreed outcome."""
@@ -77,7 +78,9 @@ class PeerExchange:
         from . import pyPhantom as ph
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.slots, self.window, err = slots, None, None
-        slot_bytes = 2 * (ctx.L + ctx.P) * ctx.N * 8            # an accumulator at the top level
+        if slot_bytes is None:
+            slot_bytes = 2 * (ctx.L + ctx.P) * ctx.N * 8        # an accumulator at the top level
+        self.slot_bytes = int(slot_bytes)
         try:
             self.window = ph.peer_window(ctx, self.rank, self.world, slot_bytes, slots)
         except RuntimeError as e:
@@ -99,17 +102,24 @@ class PeerExchange:
             self.window = None
 
     @classmethod
-    def get(cls, ctx, group=None):
-        """The exchange of (ctx, group), or None when peer windows are switched off (SPEAR_PEER=0), not on CUDA
-        ranks, or cannot be mapped (then the callers use the integer all-reduce)."""
+    def get(cls, ctx, group=None, tag="acc", slot_bytes=None):
+        """The exchange `tag` of (ctx, group) -- "acc": accumulator all-reduces, "split": the two-phase mat-vec's scatter
+        windows (slot_bytes = what a slot must hold; a cached window that is too small is replaced, on every rank alike)
+        -- or None when peer windows are switched off (SPEAR_PEER=0), not on CUDA ranks, or cannot be mapped (then the
+        callers use the integer all-reduce)."""
         import torch.distributed as dist
         if os.environ.get("SPEAR_PEER", "1") == "0" or not dist.is_initialized() or dist.get_world_size(group) < 2:
             return None
         import weakref
-        key = (id(ctx), id(group) if group is not None else 0)
+        key = (id(ctx), id(group) if group is not None else 0, tag)
         hit = cls._cache.get(key)
-        if hit is None or hit[0]() is not ctx:   # ids are recycled: the entry must belong to this very context
-            ex = cls(ctx, group)
+        stale = hit is not None and hit[1] is not None and slot_bytes is not None and hit[1].slot_bytes < slot_bytes
+        if hit is None or hit[0]() is not ctx or stale:   # ids are recycled: the entry must belong to this very context
+            if stale:
+                ctx.synchronize()
+                dist.barrier(group)                        # nobody is still writing into the window that is replaced
+                cls._retired.append(hit[1])
+            ex = cls(ctx, group, slot_bytes=slot_bytes)
             hit = cls._cache[key] = (weakref.ref(ctx), ex if ex.ok else None)
         return hit[1]
 
@@ -183,6 +193,41 @@ def sharded_matvec_batch(ckks, cts, shard_sets, group=None):
     return outs
 
 
+def split_slot_bytes(ctx, groups, world):
+    """bytes a scatter-window slot must hold: the accumulators of ceil(groups / world) giant groups at the top level"""
+    return -(-int(groups) // world) * 2 * (ctx.L + ctx.P) * ctx.N * 8
+
+
+def split_matvec_batch(ckks, cts, row_sets, group=None):
+    """Independent mat-vecs served by ALL ranks of `group` in two phases each (include/spear_b200.h, "two-phase mat-vec"):
+    the hoisted baby steps and the diagonal MAC split by rows of the RNS basis, the MAC's epilogue scattering the giant
+    groups' accumulators to their owners over NVLink peer memory, the giant steps split by group, the ranks' accumulators
+    summed by the fused peer all-reduce, one ModDown + rescale.  row_sets[i] = diagonal_set.slice_rows(rank, world) of
+    mat-vec i.  Every rank ends with the same ciphertexts, bit-identical to the unsharded ones.  The data path needs
+    peer-mapped windows: there is no NCCL stand-in for a scatter fused into a kernel's stores."""
+    import torch.distributed as dist
+    from . import pyPhantom as ph
+    ctx = ckks.ctx
+    if not dist.is_initialized() or dist.get_world_size(group) < 2:
+        raise RuntimeError("split_matvec_batch needs a rank group of two or more (use bsgs_hoisted_batch on one GPU)")
+    world = dist.get_world_size(group)
+    exr = PeerExchange.get(ctx, group)
+    outs = []
+    for i0 in range(0, len(cts), 3):                      # three window slots, three auxiliary streams
+        part = list(range(i0, min(i0 + 3, len(cts))))
+        need = max(split_slot_bytes(ctx, -(-row_sets[i].D // row_sets[i].G), world) for i in part)
+        exa = PeerExchange.get(ctx, group, tag="split", slot_bytes=need)
+        if exa is None or exr is None:
+            raise RuntimeError("two-phase mat-vec: the ranks' peer windows could not be mapped (CUDA IPC / peer access)")
+        accs = ph.bsgs_split_batch(ctx, [cts[i] for i in part], [row_sets[i] for i in part], ckks.gk, exa.window, 0)
+        for k, acc in enumerate(accs):
+            exr.allreduce(acc, k)
+        outs += [ph.bsgs_finish(ctx, acc) for acc in accs]
+    exr.check(ctx)
+    PeerExchange.get(ctx, group, tag="split").check(ctx)
+    return outs
+
+
 class ShardedMatvec:
     """Giant-step-sharded hoisted BSGS mat-vec  Enc(x) -> Enc(W @ x)  over the ranks of `group`.
 
@@ -243,15 +288,26 @@ class HybridBlock:
                 "ffn_val": PhasePlan(npairs, world)}
 
     @staticmethod
-    def required_weights(world, D, F):
+    def two_phase_default(world):
+        """two-phase mat-vecs (rows | giant groups, split_matvec_batch) unless SPEAR_TWO_PHASE=0 asks for the round-1 plan
+        (mat-vecs dealt to rank groups, giant steps sharded inside a group, baby steps replicated)"""
+        return world > 1 and os.environ.get("SPEAR_TWO_PHASE", "1") != "0"
+
+    @staticmethod
+    def required_weights(world, D, F, two_phase=None):
         """baby weights (BSGS splits) whose rotation keys the context must hold"""
         from . import bsgs as hb
+        if two_phase is None:
+            two_phase = HybridBlock.two_phase_default(world)
+        if two_phase:      # both phases are divided by the ranks: the single-GPU optimum holds for every world size
+            return (hb.hoisting_weight(1),)
         return tuple(sorted({hb.hoisting_weight(len(g)) for p in HybridBlock.plans(world, D, F).values() for g in p.groups}))
 
-    def __init__(self, ckks, block, D, F, rank=0, world=1):
+    def __init__(self, ckks, block, D, F, rank=0, world=1, two_phase=None):
         import torch.distributed as dist
         from . import bsgs as hb
         self.ckks, self.D, self.F, self.rank, self.world = ckks, D, F, rank, world
+        self.two_phase = self.two_phase_default(world) if two_phase is None else bool(two_phase)
         self.plan = self.plans(world, D, F)
         self.pairs = hb._chunk_pairs(F, D)
         level = ckks.encrypt_replicated(np.zeros(1)).chain_index()
@@ -268,6 +324,19 @@ class HybridBlock:
             M0 = hb._val_chunk(block.W_val_ffn, c, D, F)
             mats["ffn_val"].append(("real", M0) if c2 is None else ("complex", M0, hb._val_chunk(block.W_val_ffn, c2, D, F, -1.0)))
         self.sets = {}
+        if self.two_phase:
+            G, B = hb.compute_bsgs_params(D, hb.hoisting_weight(1))
+            self.split_GB = (G, B)
+            for phase in self.PHASES:
+                for j, m in enumerate(mats[phase]):
+                    enc = hb.pre_encode_real_diags if m[0] == "real" else hb.pre_encode_complex_diags
+                    full = enc(ckks, *m[1:], D, G, B, level)
+                    self.sets[(phase, j)] = full.slice_rows(rank, world)
+                    del full
+            ctx = ckks.ctx
+            PeerExchange.get(ctx, None)                     # windows come up outside any timed region
+            PeerExchange.get(ctx, None, tag="split", slot_bytes=split_slot_bytes(ctx, B, world))
+            return
         for phase in self.PHASES:
             for ranks, js in self.plan[phase].mine(rank):
                 G, B = hb.compute_bsgs_params(D, hb.hoisting_weight(len(ranks)))
@@ -290,6 +359,13 @@ class HybridBlock:
         import torch
         import torch.distributed as dist
         ckks, D, plan = self.ckks, self.D, self.plan[phase]
+        if self.two_phase:
+            # every rank runs the same client code (identical ciphertexts: same key seed, same encryption ids), serves its
+            # rows and its giant groups of EVERY mat-vec of the phase, and ends with every result ciphertext
+            js = list(range(plan.k))
+            cts = self._encrypt_inputs(inputs, js, ckks.sk.reserve_enc_ids(plan.k))
+            outs = split_matvec_batch(ckks, cts, [self.sets[(phase, j)] for j in js])
+            return np.stack([ckks.decrypt_vec_complex(ct_y, D) for ct_y in outs])
         # Encryption ids come from the secret key's one monotonic counter: every rank runs the same client code in the
         # same order, so all ranks reserve the same range (the ranks of a group form identical ciphertexts) and no
         # (seed, nonce) pair is ever used twice -- neither across blocks, tokens, nor against plain encrypt calls.

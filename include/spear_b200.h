@@ -244,6 +244,26 @@ int spear_peer_window_status(const spear_peer_window* w);   /* 0 = healthy; 1 + 
 int spear_peer_selftest(spear_context* ctx, spear_obj* const* accs, int world);
 void spear_peer_window_destroy(spear_peer_window* w);
 
+/* ---- two-phase mat-vec over a rank group ("baby steps sharded, partial ciphertexts combined over
+ *      NVLink"; reference loop scripts/bootstrap_generation.py:435-485) -------------------------------------------
+ * Phase 1 -- the hoisted baby steps and the diagonal multiply-accumulate -- is split by ROWS of the l + P RNS limbs:
+ * rank r of w serves rows [r*(l+P)/w, (r+1)*(l+P)/w) for EVERY giant group and holds just those rows of the diagonals
+ * (spear_diagset_slice_rows).  Phase 2 -- the giant steps -- is split by giant group g = r, r + w, ...  In between, the
+ * MAC kernel's own epilogue stores scatter the accumulators of group g into the window of rank g % w over NVLink peer
+ * memory (the all-to-all is fused into the compute kernel), epoch flags order the phases, and the call returns this
+ * rank's accumulator in basis Q_l*P: spear_peer_allreduce (on a SECOND window) sums them, spear_bsgs_finish completes.
+ * `w` must have slots of at least ceil(B/world) * 2 * (l+P) * N * 8 bytes and must not be used for all-reduces. */
+int spear_diagset_slice_rows(spear_context* ctx, const spear_diagset* full, int row0, int nrows, spear_diagset** out);
+int spear_bsgs_split(spear_context* ctx, const spear_obj* ct, const spear_diagset* rows, const spear_galois_keys* gk,
+                     spear_peer_window* w, int slot, spear_obj** out);
+/* item i on auxiliary stream i % 3, exchanging through slot slot0 + i */
+int spear_bsgs_split_batch(spear_context* ctx, spear_obj* const* cts, spear_diagset* const* rows, int count,
+                           const spear_galois_keys* gk, spear_peer_window* w, int slot0, spear_obj** outs);
+/* Test hook for one-GPU boxes: both phases of all `world` ranks, one after the other, over local stand-ins for the
+ * windows; rows[r] = the slice of rank r.  *out = the summed accumulator (spear_bsgs_finish completes it). */
+int spear_bsgs_split_selftest(spear_context* ctx, const spear_obj* ct, spear_diagset* const* rows, int world,
+                              const spear_galois_keys* gk, spear_obj** out);
+
 /* ---- raw transforms (tests / profiling) ------------------------------------------------------------- */
 /* in-place on a host buffer of `rows` x ring_n residues whose row r uses modulus limb_ids[r] */
 int spear_ntt_host(spear_context* ctx, uint64_t* data, int rows, const int* limb_ids, int ring_n, int inverse);

@@ -102,6 +102,46 @@ def test_giant_sharding_on_one_gpu(D, world):
     assert np.abs(dec - W @ x).max() < 1e-9
 
 
+@pytest.mark.parametrize("D,world,weight", [(64, 2, 1.0), (64, 3, 1.0), (20, 2, 1.0), (16, 4, 1.0), (64, 8, 1.0), (512, 2, 32.0),
+                                             (512, 3, 32.0)])
+def test_two_phase_split_on_one_gpu(D, world, weight):
+    """Two-phase mat-vec (rows split for the baby steps and the diagonal MAC, giant groups split for the giant steps;
+    include/spear_b200.h) emulated on one GPU: the summed accumulator equals the unsharded accumulator limb for limb,
+    hence (the unsharded path is pinned to the oracle) the oracle's.  Covers the TMA-staged MAC (rshift 1..5), its
+    fall-back (D = 16: rshift 6; D = 20: full ring) and sets walked in two baby-step chunks (G = 128)."""
+    S = Setup(N=2048, bits=(59,) * 6, P=2)
+    G = int(np.ceil(np.sqrt(weight * D)))
+    B = -(-D // G)
+    steps = list(range(1, G)) + [g * G for g in range(1, B)]
+    ph, ctx, sk = S.gpu(steps)
+    gk = sk.create_galois_keys(ctx)
+    enc = ph.ckks_encoder(ctx)
+    rng = np.random.default_rng(7 * D + world)
+    W, x = rng.standard_normal((D, D)) * 0.1, rng.standard_normal(D)
+    rolled = rolled_diagonals(W, D, G, B)
+    ct = sk.encrypt_symmetric(ctx, enc.encode_double_vector(ctx, tile(x, S.N // 2), S.scale), enc_id=5)
+    full = ph.diagonal_set(ctx, rolled, G, B, S.scale)
+    ref_acc = ph.bsgs_hoisted_partial(ctx, ct, full, gk)
+    slices = [full.slice_rows(r, world) for r in range(world)]
+    rows_total = full.info()["limbs"] + ctx.P
+    whole = full.to_numpy()
+    at = 0
+    for r, sl in enumerate(slices):                       # the slices partition the rows of the set
+        r0, r1 = ph.diagonal_set.row_range(full.info()["limbs"], ctx.P, r, world)
+        assert r0 == at and sl.row_slice == (r0, r1)
+        assert np.array_equal(sl.to_numpy(), whole[:, r0:r1, :])
+        at = r1
+    assert at == rows_total
+    acc = ph.bsgs_split_selftest(ctx, ct, slices, gk)
+    assert np.array_equal(acc.to_numpy(), ref_acc.to_numpy())
+    y = ph.bsgs_finish(ctx, acc)
+    assert np.array_equal(y.to_numpy(), ph.bsgs_hoisted(ctx, ct, full, gk).to_numpy())
+    dec = np.array(enc.decode_double_vector(ctx, sk.decrypt(ctx, y)))[:D]
+    assert np.abs(dec - W @ x).max() < 1e-9
+    with pytest.raises(RuntimeError):                     # a row slice is not a giant-group shard
+        ph.bsgs_hoisted(ctx, ct, slices[0], gk)
+
+
 def test_host_mirror_projections():
     """fhe_projection_bsgs for D->D, D->F (complex-packed, ragged last chunk) and F->D (conjugate-packed),
     hoisted path and reference-order path, against float64 x @ W (tolerance 1e-8 at scale 2^59)."""

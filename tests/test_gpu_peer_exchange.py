@@ -67,6 +67,47 @@ def _worker(rank, world, port, D, out):
         raise
 
 
+def _split_worker(rank, world, port, D, weight, out):
+    """two-phase mat-vecs through the real windows: slots reused over several epochs, batches on the auxiliary streams"""
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SPEAR_DEVICE=str(rank))
+        os.environ.pop("LOCAL_RANK", None)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from fhe_spear_b200 import sharding as sh
+
+        class K:
+            pass
+        S = Setup(N=2048, bits=(59,) * 6, P=2)
+        G = int(np.ceil(np.sqrt(weight * D)))
+        B = -(-D // G)
+        steps = list(range(1, G)) + [g * G for g in range(1, B)]
+        ph, ctx, sk = S.gpu(steps)
+        ckks = K()
+        ckks.ctx, ckks.gk = ctx, sk.create_galois_keys(ctx)
+        enc = ph.ckks_encoder(ctx)
+        rng = np.random.default_rng(D)
+        Ws = [rng.standard_normal((D, D)) * 0.1 for _ in range(2)]
+        x = rng.standard_normal(D)
+        ct = sk.encrypt_symmetric(ctx, enc.encode_double_vector(ctx, tile(x, S.N // 2), S.scale), enc_id=3)
+        fulls = [ph.diagonal_set(ctx, rolled_diagonals(W, D, G, B), G, B, S.scale) for W in Ws]
+        refs = [ph.bsgs_hoisted(ctx, ct, f, ckks.gk).to_numpy() for f in fulls]
+        rows = [f.slice_rows(rank, world) for f in fulls]
+        same = True
+        for it in range(4):                               # epochs advance, slots are reused
+            ys = sh.split_matvec_batch(ckks, [ct, ct], rows)
+            same &= all(np.array_equal(y.to_numpy(), r) for y, r in zip(ys, refs))
+        ys = sh.split_matvec_batch(ckks, [ct] * 5, [rows[0], rows[1], rows[0], rows[1], rows[0]])   # two rounds of slots
+        same &= all(np.array_equal(y.to_numpy(), refs[i % 2]) for i, y in enumerate(ys))
+        dec = np.array(enc.decode_double_vector(ctx, sk.decrypt(ctx, ys[1])))[:D]
+        status = max(sh.PeerExchange.get(ctx).window.status(), sh.PeerExchange.get(ctx, tag="split").window.status())
+        out.put((rank, same, float(np.abs(dec - Ws[1] @ x).max()), status))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:   # noqa: BLE001 -- reported to the parent, which fails the test
+        out.put((rank, False, repr(e), -1))
+        raise
+
+
 def _gpu_count():
     try:
         import torch
@@ -135,6 +176,34 @@ def test_two_process_peer_exchange_matches_unsharded(D):
     for rank, same, err, status in res:
         assert status == 0, f"rank {rank}: window status {status} ({err})"
         assert same, f"rank {rank}: peer-exchanged result differs from the unsharded one"
+        assert err < 1e-9
+    assert all(p.exitcode == 0 for p in procs)
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs (kernels that wait on one another must not share one)")
+@pytest.mark.parametrize("D,weight", [(64, 1.0), (512, 32.0)])
+def test_two_process_two_phase_matvec_matches_unsharded(D, weight):
+    """the two-phase mat-vec over real peer windows (rows | giant groups, scatter fused into the MAC's stores)"""
+    world = min(_gpu_count(), 4)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mpc = mp.get_context("spawn")
+    out = mpc.Queue()
+    procs = [mpc.Process(target=_split_worker, args=(r, world, port, D, weight, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    try:
+        res = [out.get(timeout=240) for _ in procs]
+        for p in procs:
+            p.join(timeout=60)
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+    for rank, same, err, status in res:
+        assert status == 0, f"rank {rank}: window status {status} ({err})"
+        assert same, f"rank {rank}: two-phase result differs from the unsharded one ({err})"
         assert err < 1e-9
     assert all(p.exitcode == 0 for p in procs)
 

@@ -33,6 +33,30 @@ def test_shard_plan_partitions_the_matrix():
     assert sh.lazy_sum_is_safe(q59, 8) and not sh.lazy_sum_is_safe([(1 << 60) - 1], 16)
 
 
+def test_two_phase_plan_partitions_rows_and_groups():
+    """host side of the two-phase mat-vec: the row ranges of the ranks partition the l + P rows of the RNS basis (some may be
+    empty when there are more ranks than rows), the giant groups are dealt round-robin, a window slot holds a rank's share"""
+    from fhe_spear_b200 import pyPhantom as ph
+    from fhe_spear_b200 import sharding as sh
+    for limbs, P in ((24, 3), (36, 3), (4, 2), (1, 1)):
+        for world in (1, 2, 3, 4, 8):
+            at = 0
+            for r in range(world):
+                r0, r1 = ph.diagonal_set.row_range(limbs, P, r, world)
+                assert r0 == at and r1 >= r0
+                at = r1
+            assert at == limbs + P
+            sizes = [b - a for a, b in (ph.diagonal_set.row_range(limbs, P, r, world) for r in range(world))]
+            assert max(sizes) - min(sizes) <= 1
+
+    class Ctx:
+        L, P, N = 24, 3, 32768
+    assert sh.split_slot_bytes(Ctx, 45, 8) == 6 * 2 * 27 * 32768 * 8      # ceil(45 / 8) groups of [2][L+P][N] words
+    assert sh.split_slot_bytes(Ctx, 16, 8) == 2 * 2 * 27 * 32768 * 8
+    assert sh.HybridBlock.required_weights(8, 2048, 8192, two_phase=True) == (8.0,)
+    assert not sh.HybridBlock.two_phase_default(1)
+
+
 def _worker(rank, world, port, D, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -90,7 +114,7 @@ def test_phase_plans_cover_every_matvec_once_and_balance_the_ranks():
                 assert sum(len(js) for _, js in mine) == sum(1 for _, g in plan.assign if rank in g)
     p = sh.PhasePlan(3, 2)      # r -> rank 0, k -> rank 1, v sharded over both: 1.5 mat-vecs each
     assert p.assign == [(0, (0,)), (1, (1,)), (2, (0, 1))]
-    assert sh.HybridBlock.required_weights(8, 2048, 8192) == (1.0, 2.0, 8.0 / 3.0, 4.0)
+    assert sh.HybridBlock.required_weights(8, 2048, 8192, two_phase=False) == (1.0, 2.0, 8.0 / 3.0, 4.0)
 
 
 @pytest.mark.parametrize("D", [16, 20])
