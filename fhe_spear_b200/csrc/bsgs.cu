@@ -189,8 +189,32 @@ static void bsgs_phase1(const Ctx* c, const u64* ct, int l, const u64* diag, int
                         int row0, int nrows, cudaStream_t s) {
     const size_t N = c->N, rows = l + c->P, pw = rows * N;
     const u64 *c0 = ct, *c1 = ct + l * N;
-    ops::decompose(c, c1, l, x, E, s);
+    if (nrows == 0) return;   // more ranks than rows: this one only serves giant groups
+    ops::decompose(c, c1, l, x, E, s, row0, nrows);   // only the rows this launch set serves
     ops::pscale(c, ct, Y, l, s);
+    // A/B switch for the north-star item "diagonal MAC fused into the key-switch epilogue": SPEAR_PIPE_ROWS=k walks the rows
+    // in k chunks, the MAC of chunk i on an auxiliary stream under the key stream of chunk i+1 -- the overlap of the HBM-bound
+    // baby steps with the integer-bound MAC that a fused kernel could buy at best (profiles/r2_ns1_overlap.md)
+    static const int pipe = getenv("SPEAR_PIPE_ROWS") ? atoi(getenv("SPEAR_PIPE_ROWS")) : 0;
+    if (pipe > 1 && s == c->stream && G > 1 && nrows >= pipe) {
+        cudaStream_t h = c->aux[0];
+        std::vector<cudaEvent_t> ev(pipe + 1);
+        for (auto& e : ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        bool ok = true;
+        for (int ch = 0; ch < pipe && ok; ch++) {
+            const int a = row0 + nrows * ch / pipe, b = row0 + nrows * (ch + 1) / pipe;
+            ok = ops::ks_baby_fused(c, E, bkey + 1, belt + 1, G - 1, Y + 2 * pw, l, c0, s, a, b - a);
+            CUDA_CHECK(cudaEventRecord(ev[ch], s));
+            CUDA_CHECK(cudaStreamWaitEvent(h, ev[ch], 0));
+            ops::pmac_hoisted_rows(c, Y, diag + (size_t)(a - row0) * (c->N >> rshift), dst, tmp, G, n_groups, n_diags, l, rshift, a,
+                                   b - a, h, nrows);
+        }
+        REQUIRE(ok, "SPEAR_PIPE_ROWS: the fused baby-step kernel does not apply to this shape");
+        CUDA_CHECK(cudaEventRecord(ev[pipe], h));
+        CUDA_CHECK(cudaStreamWaitEvent(s, ev[pipe], 0));
+        for (auto& e : ev) cudaEventDestroy(e);
+        return;
+    }
     if (G > 1 && !ops::ks_baby_fused(c, E, bkey + 1, belt + 1, G - 1, Y + 2 * pw, l, c0, s, row0, nrows)) {
         REQUIRE(row0 == 0 && nrows == (int)rows, "two-phase mat-vec: the fused baby-step kernel does not apply to this shape");
         for (int b = 1; b < G; b++)
@@ -307,6 +331,7 @@ void bsgs_split_phase2(const Ctx* c, u64* A, int l, int G, int B, int n_groups, 
 // R [2][l+P][N] (destroyed) -> out [2][l-1][N]: one ModDown, one rescale
 void bsgs_finish(const Ctx* c, u64* R, int l, u64* out, cudaStream_t s) {
     const size_t N = c->N, pw = (l + c->P) * N;
+    if (ops::finish_fused(c, R, 2, l, out, s)) return;
     Scratch sc(c, s);
     u64* tmp = sc.get(2 * l * N);
     u64* full = sc.get(2 * l * N);

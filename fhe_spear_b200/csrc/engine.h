@@ -172,11 +172,15 @@ struct ProfScope {   // brackets the launches of one kernel class with an event 
 
 // ---- launchers (ntt.cu) --------------------------------------------------------------------
 // rows x n in-place transforms; `n` may be a power-of-two prefix size (sub-ring) <= N
+// row_lo / row_hi: only the rows [row_lo, row_hi) of every polynomial (second pass of the register-tiled path only)
 void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s, int skip_digit_alpha = 0,
-                 bool split30_out = false, bool pass_a_only = false, bool pass_b_only = false);
+                 bool split30_out = false, bool pass_a_only = false, bool pass_b_only = false, int row_lo = 0,
+                 int row_hi = 1 << 30);
 // decomposition front end in one kernel (inverse pass A + n^-1 * hatinv + ModUp + forward pass A); false: not applicable
 bool ntt_decompose_a_applies(const Ctx* c, int l);
-bool ntt_decompose_a(const Ctx* c, const u64* cin, int l, u64* x, u64* E, int count, cudaStream_t s);
+// row_lo / row_hi: produce the rows [row_lo, row_hi) of every digit only (row_hi < 0: all l + P rows)
+bool ntt_decompose_a(const Ctx* c, const u64* cin, int l, u64* x, u64* E, int count, cudaStream_t s, int row_lo = 0,
+                     int row_hi = -1);
 // forward transform of freshly ModUp'd digits fused with the key inner product (ntt.cu); false: not applicable.
 // pass_a_done: the first pass already ran (ntt_pass_a_batch over several decompositions at once)
 bool ntt_ks_fused_applies(const Ctx* c, int l);

@@ -179,11 +179,13 @@ __global__ void __launch_bounds__(TPB) ntt_inv_a(u64* __restrict__ data, RowMap 
 //           shared/global access is a contiguous 128-byte row segment.
 // =============================================================================================
 __global__ void __launch_bounds__(WB * 32) ntt_fwd_b2(u64* __restrict__ data, RowMap rm, NttTab tb, int N, int n,
-                                                       int sA, int skip_alpha, int split) {
+                                                       int sA, int skip_alpha, int split, int row_lo, int row_hi) {
     __shared__ u64 smem[WB][256];
     const int row = blockIdx.y;
     const int limb = rm.limb(row);
     if (own_digit_row(skip_alpha, limb, row, rm)) return;
+    const int rr = row % rm.rpp;                 // row within its polynomial: launches restricted to a row range skip the rest
+    if (rr < row_lo || rr >= row_hi) return;
     const u64 q = tb.q[limb];
     const ulonglong2* __restrict__ tw = tb.psi + (size_t)limb * N;
     const int warp = threadIdx.x >> 5, j = threadIdx.x & 31;
@@ -272,7 +274,8 @@ __global__ void __launch_bounds__(2 << SA) k_intt_modup_fwd_a(const u64* __restr
                                                                u64* __restrict__ E, int l, int N, int L, int P, int K,
                                                                NttTab tb, ModTab mt,
                                                                const ulonglong2* __restrict__ hatinv_n,
-                                                               const u64* __restrict__ hat, int sbits, int rsplit) {
+                                                               const u64* __restrict__ hat, int sbits, int rsplit, int row_lo,
+                                                               int row_hi) {
     constexpr int R = 1 << SA, T = 2 << SA;
     extern __shared__ __align__(16) u64 dyn[];
     u64* sm = dyn;                                   // [R][COLS]      exchange tile of the transforms
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(2 << SA) k_intt_modup_fwd_a(const u64* __restr
     __syncthreads();                                 // tab complete (also when the digit is empty of work above)
     // 2. every target row of this CTA: ModUp in registers, then forward pass A
     int idx = 0;
-    for (int r = 0; r < rows; r++) {
+    for (int r = row_lo; r < row_hi; r++) {          // (all l + P rows unless the caller serves a row range only)
         const int t = r < l ? r : L + (r - l);
         if (t >= lo && t < hi) continue;             // own-digit rows: step 3
         if (idx++ % rsplit != part) continue;
@@ -340,6 +343,7 @@ __global__ void __launch_bounds__(2 << SA) k_intt_modup_fwd_a(const u64* __restr
     // 3. own-digit rows arrive in NTT form already: the consumers want them split-30
     if (part == 0)
         for (int i = 0; i < a; i++) {
+            if (lo + i < row_lo || lo + i >= row_hi) continue;
             const size_t off = (size_t)(lo + i) * N + col;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
@@ -499,7 +503,7 @@ inline void split(int logn, int& sA, int& sB) {
 static int max_rows_per_launch(const RowMap& rm) { return 65535 / rm.rpp * rm.rpp; }
 
 void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s, int skip_alpha, bool split30_out,
-                 bool pass_a_only, bool pass_b_only) {
+                 bool pass_a_only, bool pass_b_only, int row_lo, int row_hi) {
     int logn = 0;
     while ((1 << logn) < n) logn++;
     REQUIRE((1 << logn) == n && n <= c->N && logn <= 16 && n >= 2, "ntt: bad size %d", n);
@@ -509,13 +513,14 @@ void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream
         REQUIRE(step > 0 && !skip_alpha, "ntt: %d rows per polynomial do not fit one launch", rm.rpp);   // callers keep skip batches below 65536 rows
         for (int r0 = 0; r0 < rows; r0 += step)
             ntt_forward(c, data + rm.offset(r0, n), std::min(step, rows - r0), rm, n, s, skip_alpha, split30_out,
-                        pass_a_only, pass_b_only);
+                        pass_a_only, pass_b_only, row_lo, row_hi);
         return;
     }
     int sA, sB;
     split(logn, sA, sB);
     NttTab tb = c->ntttab();
     REQUIRE(!(pass_a_only || pass_b_only) || sA >= 3, "ntt: a single pass needs n >= 2048");
+    REQUIRE((row_lo == 0 && row_hi >= rm.rpp) || (pass_b_only && sA >= 3), "ntt: a row range needs the register-tiled second pass");
     if (sA >= 3) {   // n >= 2048: register-tiled kernels
         if (!pass_b_only) {
             ProfScope ps(c, PROF_NTT_FWD_A, s);
@@ -530,7 +535,8 @@ void ntt_forward(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream
         }
         if (!pass_a_only) {
             ProfScope ps(c, PROF_NTT_FWD_B, s);
-            LAUNCH(ntt_fwd_b2, dim3(n / (256 * WB), rows), WB * 32, 0, s)(data, rm, tb, c->N, n, sA, skip_alpha, split30_out ? 1 : 0);
+            LAUNCH(ntt_fwd_b2, dim3(n / (256 * WB), rows), WB * 32, 0, s)(data, rm, tb, c->N, n, sA, skip_alpha, split30_out ? 1 : 0,
+                                                                          row_lo, row_hi);
         }
         CUDA_CHECK(cudaGetLastError());
         return;
@@ -561,9 +567,11 @@ bool ntt_decompose_a_applies(const Ctx* c, int l) {
     split(c->logn, sA, sB);
     return enabled && sA >= 3 && c->P <= 4 && decompose_a_smem(c, l, sA, c->P) <= 200 * 1024;
 }
-bool ntt_decompose_a(const Ctx* c, const u64* cin, int l, u64* x, u64* E, int count, cudaStream_t s) {
+bool ntt_decompose_a(const Ctx* c, const u64* cin, int l, u64* x, u64* E, int count, cudaStream_t s, int row_lo, int row_hi) {
     if (!ntt_decompose_a_applies(c, l)) return false;
     const int N = c->N, P = c->P, rows = l + P, beta = c->digits(l);
+    if (row_hi < 0 || row_hi > rows) row_hi = rows;
+    REQUIRE(row_lo >= 0 && row_lo <= row_hi, "decompose: bad row range");
     int sA, sB;
     split(c->logn, sA, sB);
     REQUIRE(count >= 1 && count <= 65535, "decompose: bad batch");
@@ -571,7 +579,7 @@ bool ntt_decompose_a(const Ctx* c, const u64* cin, int l, u64* x, u64* E, int co
     ntt_inverse(c, x, count * l, RowMap{l, l, c->L, 0}, N, s, /*pass_b_only=*/true);
     // target rows of a digit are dealt to `rsplit` CTAs so that small batches still fill the GPU (the inverse part is
     // repeated by each of them: alpha of l + P - alpha row transforms)
-    const int tiles = (N >> sA) / COLS, targets = rows - std::min(P, l);
+    const int tiles = (N >> sA) / COLS, targets = std::max(1, std::min(rows - std::min(P, l), row_hi - row_lo));
     int rsplit = 1;
     while (rsplit < targets && (size_t)tiles * beta * count * rsplit < (size_t)c->sm_count * 6) rsplit++;
     const size_t smem = decompose_a_smem(c, l, sA, P);
@@ -580,7 +588,7 @@ bool ntt_decompose_a(const Ctx* c, const u64* cin, int l, u64* x, u64* E, int co
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         LAUNCH(kern, dim3(tiles, beta * rsplit, count), 2 << sA, smem, s)(
             x, cin, E, l, N, c->L, P, c->K, c->ntttab(), c->modtab(), c->d_up_hatinv_n + (size_t)l * c->beta * P,
-            c->d_up_hat + (size_t)l * c->beta * P * c->K, c->sbits, rsplit);
+            c->d_up_hat + (size_t)l * c->beta * P * c->K, c->sbits, rsplit, row_lo, row_hi);
     };
 #define DA_CASE(SA_)                                              \
     case SA_:                                                     \

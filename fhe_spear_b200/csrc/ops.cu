@@ -395,6 +395,55 @@ __global__ void k_moddown_final(const u64* __restrict__ in, const u64* __restric
     }
 }
 
+// ---- ModDown + rescale of a finished accumulator, in the coefficient domain ---------------------------------------
+// R: [polys][l+P][N] with EVERY row in coefficient form.  Per coefficient: t_i = (R_i - conv_i) * P^-1 exactly as
+// k_moddown_conv / k_moddown_final (linear, so the coefficient-domain result is the inverse transform of theirs), then the
+// rescale by q_{l-1} exactly as k_rescale_conv / k_rescale_final:  out_i = (t_i - ([x]_{q_i} - [half]_{q_i})) * q_{l-1}^-1
+// with x = t_{l-1} + half.  out: [polys][l-1][N], coefficient form.  One launch instead of two conversions, two
+// finals and the forward transform of the l ModDown correction rows in between.
+template <int A>
+__global__ void __launch_bounds__(TPB) k_finish_conv(const u64* __restrict__ R, u64* __restrict__ out, int l, int N, int L,
+                                                      int P, int K, ModTab mt, const ulonglong2* __restrict__ hatinv,
+                                                      const u64* __restrict__ half, const u64* __restrict__ hat,
+                                                      const ulonglong2* __restrict__ pinv,
+                                                      const ulonglong2* __restrict__ rsinv) {
+    const int p = blockIdx.y, n = blockIdx.x * TPB + threadIdx.x;
+    const u64* in = R + (size_t)p * (l + P) * N + n;
+    const u64* sp = in + (size_t)l * N;
+    u64 y[A];
+    u32 ys[A];
+#pragma unroll
+    for (int k = 0; k < A; k++) {
+        y[k] = 0, ys[k] = 0;
+        if (k < P) {
+            u64 pk = mt.q[L + k];
+            ulonglong2 h = hatinv[k];
+            y[k] = split30(mul_shoup(add_mod(sp[(size_t)k * N], half[L + k], pk), h.x, h.y, pk));
+            ys[k] = (u32)y[k] + (u32)(y[k] >> 32);
+        }
+    }
+    auto moddown = [&](int i) {
+        Acc3 acc = {0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < A; k++) mac_split(acc, y[k], ys[k], hat[(size_t)k * K + i]);
+        u64 alo = 0, ahi = 0;
+        fold_split(alo, ahi, acc);
+        const u64 q = mt.q[i];
+        const u64 conv = sub_mod(reduce_wide(alo, ahi, q, mt.rwide[i]), half[i], q);
+        const ulonglong2 pi = pinv[i];
+        return mul_shoup(sub_mod(in[(size_t)i * N], conv, q), pi.x, pi.y, q);
+    };
+    const u64 ql = mt.q[l - 1], hl = ql >> 1;
+    const u64 x = add_mod(moddown(l - 1), hl, ql);
+    u64* o = out + (size_t)p * (l - 1) * N + n;
+    for (int i = 0; i < l - 1; i++) {
+        const u64 q = mt.q[i], r1 = mt.ratio1[i];
+        const u64 corr = sub_mod(barrett64(x, q, r1), barrett64(hl, q, r1), q);
+        const ulonglong2 w = rsinv[i];
+        o[(size_t)i * N] = mul_shoup(sub_mod(moddown(i), corr, q), w.x, w.y, q);
+    }
+}
+
 // ---- ModRaise (bootstrapping) ---------------------------------------------------------------------
 // x: [polys][N] coefficient form modulo q_0; out[p][i][n] = centred representative of x modulo q_i (coefficient form)
 __global__ void __launch_bounds__(TPB) k_modraise(const u64* __restrict__ x, u64* __restrict__ out, int l, int N,
@@ -474,7 +523,7 @@ __device__ __forceinline__ u64* pmac_dst(const PmacDst& d, int g, int p, size_t 
 }
 __global__ void __launch_bounds__(PM_TILE) k_pmac_hoisted(const u64* __restrict__ Y, const u64* __restrict__ diag,
                                                            PmacDst dst, int G, int B, int D, int l, int rows,
-                                                           int N, int L, int rshift, int row0, int nrows, ModTab mt) {
+                                                           int N, int L, int rshift, int row0, int diag_rows, ModTab mt) {
     extern __shared__ u64 sm[];   // [G][2][PM_TILE]
     const int r = blockIdx.y + row0, n = blockIdx.x * PM_TILE + threadIdx.x;
     const int t = r < l ? r : L + (r - l);
@@ -486,8 +535,8 @@ __global__ void __launch_bounds__(PM_TILE) k_pmac_hoisted(const u64* __restrict_
     // each thread only re-reads its own column: no barrier needed
     const u64 q = mt.q[t], r0 = mt.ratio0[t], r1 = mt.ratio1[t];
     const int dn = N >> rshift;
-    const u64* dg = diag + (size_t)blockIdx.y * dn + (n >> rshift);   // the set stores its nrows rows only
-    const size_t dstride = (size_t)nrows * dn;
+    const u64* dg = diag + (size_t)blockIdx.y * dn + (n >> rshift);   // diag points at the first row served
+    const size_t dstride = (size_t)diag_rows * dn;
     const u64 pol = evict_first_policy();
     for (int g = 0; g < B; g++) {
         int nb = min(G, D - g * G);
@@ -686,12 +735,14 @@ void galois(const Ctx* c, const u64* in, u64* out, int rows, u32 elt, cudaStream
 }
 
 // cin [l][N] NTT form -> E [digits(l)][l+P][N] NTT form (scratch x: [l][N])
-void decompose(const Ctx* c, const u64* cin, int l, u64* x, u64* E, cudaStream_t s) {
-    if (ntt_decompose_a(c, cin, l, x, E, 1, s)) {   // fused front end; the second forward pass completes the digits
+void decompose(const Ctx* c, const u64* cin, int l, u64* x, u64* E, cudaStream_t s, int row0, int nrows) {
+    const int row1 = nrows < 0 ? l + c->P : row0 + nrows;
+    if (ntt_decompose_a(c, cin, l, x, E, 1, s, row0, row1)) {   // fused front end; the second forward pass completes the digits
         ntt_forward(c, E, c->digits(l) * (l + c->P), RowMap{l + c->P, l, c->L, 0}, c->N, s, c->P, /*split30_out=*/true,
-                    /*pass_a_only=*/false, /*pass_b_only=*/true);
+                    /*pass_a_only=*/false, /*pass_b_only=*/true, row0, row1);
         return;
     }
+    // (the staged path below produces every row)
     CUDA_CHECK(cudaMemcpyAsync(x, cin, sizeof(u64) * l * c->N, cudaMemcpyDeviceToDevice, s));
     ntt_inverse(c, x, l, RowMap{l, l, c->L, 0}, c->N, s);
     decompose_from(c, cin, x, l, E, s);
@@ -860,6 +911,31 @@ void moddown(const Ctx* c, u64* in, size_t in_pstride, int polys, int l, u64* tm
     CUDA_CHECK(cudaGetLastError());
 }
 
+// R [polys][l+P][N] (NTT form, destroyed) -> out [polys][l-1][N] = rescale(ModDown(R)); false: not applicable
+bool finish_fused(const Ctx* c, u64* R, int polys, int l, u64* out, cudaStream_t s) {
+    static const bool enabled = [] {
+        const char* e = getenv("SPEAR_FUSED_FINISH");
+        return !(e && e[0] == '0');
+    }();
+    const int N = c->N, P = c->P, rows = l + P;
+    if (!enabled || P > 4 || l < 2 || N % TPB != 0) return false;
+    ntt_inverse(c, R, polys * rows, RowMap{rows, l, c->L, 0}, N, s);
+    {
+        ProfScope ps(c, PROF_MODDOWN, s);
+        auto go = [&](auto kern) {
+            LAUNCH(kern, dim3(N / TPB, polys), TPB, 0, s)(R, out, l, N, c->L, P, c->K, c->modtab(), c->d_dn_hatinv, c->d_dn_half,
+                                                          c->d_dn_hat, c->d_pinv, c->d_rs_inv + (size_t)(l - 1) * c->K);
+        };
+        if (P == 1) go(k_finish_conv<1>);
+        else if (P == 2) go(k_finish_conv<2>);
+        else if (P == 3) go(k_finish_conv<3>);
+        else go(k_finish_conv<4>);
+    }
+    ntt_forward(c, out, polys * (l - 1), RowMap{l - 1, l - 1, c->L, 0}, N, s);
+    CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
 // in [polys][l][N] -> out [polys][l-1][N]; scratch last [polys][N], tmp [polys][l-1][N]
 void rescale(const Ctx* c, const u64* in, int polys, int l, u64* last, u64* tmp, u64* out, cudaStream_t s) {
     const int N = c->N;
@@ -901,8 +977,9 @@ void pmac_hoisted(const Ctx* c, const u64* Y, const u64* diag, u64* A, int G, in
 }
 
 void pmac_hoisted_rows(const Ctx* c, const u64* Y, const u64* diag, const PmacDst& dst, u64* tmp, int G, int B, int D, int l,
-                       int rshift, int row0, int nrows, cudaStream_t s) {
+                       int rshift, int row0, int nrows, cudaStream_t s, int diag_rows) {
     const int rows = l + c->P, dn = c->N >> rshift, W = PM_T2 >> rshift;
+    if (diag_rows < 0) diag_rows = nrows;
     REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= rows && dst.world >= 1 && dst.world <= 8, "diagonal MAC: bad row range");
     if (nrows == 0) return;
     // baby steps are walked in chunks of Gc <= 64 rows (a multiple of 16) so that 2-3 CTAs fit per SM
@@ -915,7 +992,7 @@ void pmac_hoisted_rows(const Ctx* c, const u64* Y, const u64* diag, const PmacDs
         Gc <= D && tma_smem <= 227 * 1024) {
         CUtensorMap tmap;
         cuuint64_t dims[3] = {(cuuint64_t)dn, (cuuint64_t)nrows, (cuuint64_t)D};
-        cuuint64_t strides[2] = {(cuuint64_t)dn * sizeof(u64), (cuuint64_t)nrows * dn * sizeof(u64)};
+        cuuint64_t strides[2] = {(cuuint64_t)dn * sizeof(u64), (cuuint64_t)diag_rows * dn * sizeof(u64)};
         cuuint32_t box[3] = {(cuuint32_t)W, 1, (cuuint32_t)Gc};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult rc = encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, (void*)diag, dims, strides, box, estr,
@@ -958,7 +1035,7 @@ void pmac_hoisted_rows(const Ctx* c, const u64* Y, const u64* diag, const PmacDs
     REQUIRE(smem <= 227 * 1024, "too many baby steps (%d) for the shared-memory tile", G);
     CUDA_CHECK(cudaFuncSetAttribute(k_pmac_hoisted, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per device
     LAUNCH(k_pmac_hoisted, dim3(c->N / PM_TILE, nrows), PM_TILE, smem, s)(Y, diag, dst, G, B, D, l, rows, c->N, c->L, rshift,
-                                                                      row0, nrows, c->modtab());
+                                                                      row0, diag_rows, c->modtab());
     CUDA_CHECK(cudaGetLastError());
 }
 

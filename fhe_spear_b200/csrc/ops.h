@@ -37,7 +37,8 @@ void reduce_inplace(const Ctx* c, u64* x, int polys, int rows, RowMap rm, cudaSt
 void sum_groups(const Ctx* c, const u64* parts, int nparts, const u64* first, u64* out, int l, cudaStream_t s);
 void tensor(const Ctx* c, const u64* a, const u64* b, u64* out, int l, cudaStream_t s);
 void galois(const Ctx* c, const u64* in, u64* out, int rows, u32 elt, cudaStream_t s);
-void decompose(const Ctx* c, const u64* cin, int l, u64* x, u64* E, cudaStream_t s);
+// row0 / nrows: only the rows [row0, row0 + nrows) of every digit are produced (nrows < 0: all)
+void decompose(const Ctx* c, const u64* cin, int l, u64* x, u64* E, cudaStream_t s, int row0 = 0, int nrows = -1);
 // count > 1: `count` polynomials back to back (cin, x: [count][l][N]) -> E [count][beta][l+P][N], ModUp only (transform = false)
 void decompose_from(const Ctx* c, const u64* cin, const u64* x, int l, u64* E, cudaStream_t s, bool transform = true,
                     int count = 1);
@@ -52,15 +53,19 @@ bool ks_baby_fused(const Ctx* c, const u64* E, const u64* const* keys, const u32
 void encode_key_map(const Ctx* c, const u64* key, int box_n, int beta, CUtensorMap* out);
 void pscale(const Ctx* c, const u64* x, u64* y, int l, cudaStream_t s);
 void moddown(const Ctx* c, u64* in, size_t in_pstride, int polys, int l, u64* tmp, const u64* add, u64* out, cudaStream_t s);
+// R [polys][l+P][N] (NTT form, destroyed) -> out [polys][l-1][N] = rescale(ModDown(R)) in one conversion kernel between an
+// inverse and a forward transform (bit-identical to moddown + rescale); false: not applicable, nothing done
+bool finish_fused(const Ctx* c, u64* R, int polys, int l, u64* out, cudaStream_t s);
 void mod_raise(const Ctx* c, const u64* in, int polys, int l, u64* x, u64* out, cudaStream_t s);
 void rescale(const Ctx* c, const u64* in, int polys, int l, u64* last, u64* tmp, u64* out, cudaStream_t s);
 void pmac_list(const Ctx* c, const u64* const* baby, const u64* const* pt, int nb, u64* out, int l, cudaStream_t s);
 void split30_inplace(const Ctx* c, u64* x, size_t n, bool unsplit, cudaStream_t s);
 void pmac_hoisted(const Ctx* c, const u64* Y, const u64* diag, u64* A, int G, int B, int D, int l, int rshift, cudaStream_t s);
-// the same for the rows [row0, row0 + nrows) only -- diag holds exactly those rows: [D][nrows][N >> rshift] -- with the
+// the same for the rows [row0, row0 + nrows) only -- diag points at the first of them, inside a set that stores diag_rows
+// rows per diagonal ([D][diag_rows][N >> rshift]; default: exactly the rows served) -- with the
 // accumulators scattered to `dst`; tmp: local scratch [B][2][l+P][N] for sets walked in several baby-step chunks
 void pmac_hoisted_rows(const Ctx* c, const u64* Y, const u64* diag, const PmacDst& dst, u64* tmp, int G, int B, int D, int l,
-                       int rshift, int row0, int nrows, cudaStream_t s);
+                       int rshift, int row0, int nrows, cudaStream_t s, int diag_rows = -1);
 }  // namespace ops
 
 namespace sampler {
