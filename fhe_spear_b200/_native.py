@@ -95,6 +95,7 @@ _SIG = {
     "spear_diagset_export": (C.c_int, [vp, vp, C.c_size_t]),
     "spear_bsgs_hoisted": (C.c_int, [vp, vp, vp, vp, vpp]),
     "spear_bsgs_hoisted_batch": (C.c_int, [vp, vpp, vpp, C.c_int, vp, vpp]),
+    "spear_bsgs_hoisted_batch_host": (C.c_int, [vp, vpp, C.c_int, C.c_double, vpp, C.c_int, vp, vpp, f64p]),
     "spear_bsgs_hoisted_partial": (C.c_int, [vp, vp, vp, vp, vpp]),
     "spear_bsgs_hoisted_partial_batch": (C.c_int, [vp, vpp, vpp, C.c_int, vp, vpp]),
     "spear_bsgs_finish": (C.c_int, [vp, vp, vpp]),

@@ -1183,6 +1183,41 @@ int spear_bsgs_hoisted_batch(spear_context* ctx, spear_obj* const* cts, spear_di
     for (int i = 0; i < count; i++) outs[i] = H_(res[i].release());
     API_END
 }
+// Serving form of the batch: ciphertexts arrive in and leave to HOST memory.  Item i is uploaded, multiplied and
+// downloaded on auxiliary stream i % 3, so the PCIe legs of one item run under the arithmetic of the others.
+int spear_bsgs_hoisted_batch_host(spear_context* ctx, const uint64_t* const* in, int limbs, double scale,
+                                  spear_diagset* const* dss, int count, const spear_galois_keys* gk_, uint64_t* const* out,
+                                  double* out_scale) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    REQUIRE(count >= 1 && limbs >= 2 && limbs <= c->L, "bsgs_hoisted_batch_host: bad batch");
+    const GaloisKeys* gk = reinterpret_cast<const GaloisKeys*>(gk_);
+    for (int i = 0; i < count; i++) {   // validate everything before anything is queued
+        const DiagSet* ds = reinterpret_cast<const DiagSet*>(dss[i]);
+        REQUIRE(ds && in[i] && out[i], "bsgs_hoisted_batch_host: null item %d", i);
+        REQUIRE(ds->g_first == 0 && ds->g_stride == 1 && ds->nrows < 0, "bsgs_hoisted_batch_host: sharded diagonal set");
+        REQUIRE(ds->l == limbs, "bsgs_hoisted_batch_host: diagonals encoded for %d limbs, ciphertexts have %d", ds->l, limbs);
+    }
+    std::vector<std::unique_ptr<Obj>> ct(count), acc(count), res(count);
+    const int used = std::min(count, 3);
+    CUDA_CHECK(cudaEventRecord(c->ev_main, c->stream));
+    {
+        AuxJoin join{c, used};
+        for (int i = 0; i < count; i++) {
+            cudaStream_t s = c->aux[i % 3];
+            if (i < 3) CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_main, 0));
+            ct[i].reset(new_obj(c, 2, limbs, false, c->N, scale, s));
+            CUDA_CHECK(cudaMemcpyAsync(ct[i]->d, in[i], sizeof(u64) * ct[i]->words(), cudaMemcpyHostToDevice, s));
+            acc[i].reset(bsgs_partial(c, ct[i].get(), reinterpret_cast<const DiagSet*>(dss[i]), gk, s));
+            res[i].reset(bsgs_finish(c, acc[i].get(), s));
+            CUDA_CHECK(cudaMemcpyAsync(out[i], res[i]->d, sizeof(u64) * res[i]->words(), cudaMemcpyDeviceToHost, s));
+            if (out_scale) out_scale[i] = res[i]->scale;
+        }
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));   // the auxiliary streams were joined into it: every result has landed
+    API_END
+}
 int spear_bsgs_hoisted_partial(spear_context* ctx, const spear_obj* ct_, const spear_diagset* ds_,
                                const spear_galois_keys* gk_, spear_obj** out) {
     API_BEGIN

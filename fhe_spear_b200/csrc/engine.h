@@ -152,7 +152,7 @@ struct DiagSet : CtxRef {
 // one class per kernel of the mat-vec path (bench.py picks the dominant one for its roofline line live)
 enum { PROF_KS_INNER = 0, PROF_PMAC = 1, PROF_NTT_FWD_A = 2, PROF_MODUP = 3, PROF_MODDOWN = 4, PROF_RESCALE = 5,
        PROF_KS_BABY = 6, PROF_NTT_KS = 7, PROF_NTT_FWD_B = 8, PROF_NTT_INV_A = 9, PROF_NTT_INV_B = 10,
-       PROF_SUM_GROUPS = 11, PROF_CLASSES = 12 };
+       PROF_SUM_GROUPS = 11, PROF_PEER_WAIT = 12, PROF_PEER_REDUCE = 13, PROF_CLASSES = 14 };
 struct ProfScope {   // brackets the launches of one kernel class with an event pair when profiling is on
     const Ctx* c;
     cudaStream_t s;

@@ -189,6 +189,7 @@ SplitView split_begin(const Ctx* c, spear_peer_window* win, int slot, size_t nee
             *(volatile int*)w->status - 1);
     w->mode = 2;
     const u64 epoch = ++w->epoch[slot];
+    ProfScope ps(c, PROF_PEER_WAIT, s);
     if (w->world > 1)
         LAUNCH(k_peer_sync, 1, 32, 0, s)(ptrs_of(w), w->world, w->rank, slot, 1, 0, epoch - 1, w->d_status, w->d_failed, 1);
     SplitView v;
@@ -199,6 +200,7 @@ SplitView split_begin(const Ctx* c, spear_peer_window* win, int slot, size_t nee
 }
 void split_exchange(spear_peer_window* win, int slot, cudaStream_t s) {
     PeerWindow* w = W_(win);
+    ProfScope ps(w->ctx, PROF_PEER_WAIT, s);
     if (w->world > 1)
         LAUNCH(k_peer_sync, 1, 32, 0, s)(ptrs_of(w), w->world, w->rank, slot, 0, 1, w->epoch[slot], w->d_status, w->d_failed, 1);
 }
@@ -300,8 +302,14 @@ int spear_peer_allreduce(spear_context* ctx, spear_peer_window* win, int slot, s
     const size_t data_off = DATA_OFFSET_WORDS + (size_t)slot * w->slot_words, bytes = acc->words() * sizeof(u64);
     PeerPtrs pp;
     for (int r = 0; r < MAX_PEERS; r++) pp.w[r] = w->peer[r < w->world ? r : w->rank];
-    CUDA_CHECK(cudaMemcpyAsync(w->base + data_off, acc->d, bytes, cudaMemcpyDeviceToDevice, s));
-    LAUNCH(k_peer_sync, 1, 32, 0, s)(pp, w->world, w->rank, slot, 0, 1, epoch, w->d_status, w->d_failed, 1);
+    {
+        ProfScope ps(c, PROF_PEER_REDUCE, s);
+        CUDA_CHECK(cudaMemcpyAsync(w->base + data_off, acc->d, bytes, cudaMemcpyDeviceToDevice, s));
+    }
+    {
+        ProfScope ps(c, PROF_PEER_WAIT, s);
+        LAUNCH(k_peer_sync, 1, 32, 0, s)(pp, w->world, w->rank, slot, 0, 1, epoch, w->d_status, w->d_failed, 1);
+    }
     const size_t pairs = acc->words() / 2, per = (pairs + w->world - 1) / w->world;
     const size_t lo = std::min(pairs, per * w->rank), hi = std::min(pairs, lo + per);
     const int grid = (int)std::max<size_t>(1, std::min<size_t>((hi - lo + 255) / 256, (size_t)c->sm_count * 8));
@@ -310,16 +318,23 @@ int spear_peer_allreduce(spear_context* ctx, spear_peer_window* win, int slot, s
         LAUNCH(kern, grid, 256, 0, s)(pp, data_off, lo, hi, acc->rows(), c->logn, rm, c->modtab(), w->rank, slot, epoch,
                                       w->d_failed);
     };
-    switch (w->world) {
-        case 2: go(k_peer_reduce<2>); break;
-        case 3: go(k_peer_reduce<3>); break;
-        case 4: go(k_peer_reduce<4>); break;
-        case 5: go(k_peer_reduce<5>); break;
-        case 6: go(k_peer_reduce<6>); break;
-        case 7: go(k_peer_reduce<7>); break;
-        default: go(k_peer_reduce<8>); break;
+    {
+        ProfScope ps(c, PROF_PEER_REDUCE, s);
+        switch (w->world) {
+            case 2: go(k_peer_reduce<2>); break;
+            case 3: go(k_peer_reduce<3>); break;
+            case 4: go(k_peer_reduce<4>); break;
+            case 5: go(k_peer_reduce<5>); break;
+            case 6: go(k_peer_reduce<6>); break;
+            case 7: go(k_peer_reduce<7>); break;
+            default: go(k_peer_reduce<8>); break;
+        }
     }
-    LAUNCH(k_peer_sync, 1, 32, 0, s)(pp, w->world, w->rank, slot, 1, 0, epoch, w->d_status, w->d_failed, 1);
+    {
+        ProfScope ps(c, PROF_PEER_WAIT, s);
+        LAUNCH(k_peer_sync, 1, 32, 0, s)(pp, w->world, w->rank, slot, 1, 0, epoch, w->d_status, w->d_failed, 1);
+    }
+    ProfScope ps(c, PROF_PEER_REDUCE, s);
     LAUNCH(k_peer_collect, (int)std::min<size_t>((acc->words() + 255) / 256, (size_t)c->sm_count * 8), 256, 0, s)(
         w->base + data_off, acc->d, acc->words(), w->d_failed);
     CUDA_CHECK(cudaGetLastError());

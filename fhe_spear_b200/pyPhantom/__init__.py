@@ -176,7 +176,7 @@ class context:
         return ms.value
 
     PROFILE_CLASSES = ("ks_inner", "pmac", "ntt_fwd_a", "modup", "moddown", "rescale", "ks_baby_fused", "ntt_ks_fused",
-                       "ntt_fwd_b", "ntt_inv_a", "ntt_inv_b", "sum_groups")
+                       "ntt_fwd_b", "ntt_inv_a", "ntt_inv_b", "sum_groups", "peer_wait", "peer_reduce")
 
     def profile(self, on=True):
         """Bracket every launch of each kernel class with a CUDA event pair (bench.py roofline line)."""
@@ -791,6 +791,24 @@ def bsgs_hoisted_batch(ctx, cts, diag_sets, gk):
     _check(_lib.spear_bsgs_hoisted_batch(ctx._h, (C.c_void_p * n)(*[c._h for c in cts]),
                                          (C.c_void_p * n)(*[d._h for d in diag_sets]), n, gk._h, outs))
     return [ciphertext(ctx, C.c_void_p(h)) for h in outs]
+
+
+def bsgs_hoisted_batch_host(ctx, host_in, scale, diag_sets, gk, host_out):
+    """Serving form of bsgs_hoisted_batch: host_in[i] = (2, l, N) uint64 ciphertext limbs in host memory (pinned_empty for
+    asynchronous copies), host_out[i] = (2, l - 1, N) receives result i; uploads, mat-vecs and downloads of the items are
+    pipelined over the engine's streams.  Returns the scales of the results."""
+    n = len(host_in)
+    l = int(host_in[0].shape[1])
+    for a, b in zip(host_in, host_out):
+        if a.dtype != np.uint64 or b.dtype != np.uint64 or not a.flags.c_contiguous or not b.flags.c_contiguous:
+            raise RuntimeError("bsgs_hoisted_batch_host: contiguous uint64 arrays expected")
+        if a.shape != (2, l, ctx.N) or b.shape != (2, l - 1, ctx.N):
+            raise RuntimeError("bsgs_hoisted_batch_host: in (2, l, N), out (2, l - 1, N) expected")
+    scales = (C.c_double * n)()
+    _check(_lib.spear_bsgs_hoisted_batch_host(ctx._h, (C.c_void_p * n)(*[a.ctypes.data for a in host_in]), l, float(scale),
+                                              (C.c_void_p * n)(*[d._h for d in diag_sets]), n, gk._h,
+                                              (C.c_void_p * n)(*[b.ctypes.data for b in host_out]), scales))
+    return list(scales)
 
 
 def bsgs_hoisted_partial(ctx, ct, shard, gk):

@@ -61,7 +61,8 @@ int spear_timer_stop(spear_context* ctx, float* elapsed_ms);
  * classes 0 key inner product (one rotation per launch), 1 diagonal MAC, 2 forward NTT pass A, 3 ModUp (stand-alone, or
  * the fused inverse pass A + ModUp + forward pass A front end), 4 ModDown, 5 rescale, 6 fused hoisted baby-step key inner
  * product (G-1 rotations per launch), 7 forward pass B fused with the key product (giant steps), 8 forward pass B,
- * 9 inverse pass A, 10 inverse pass B, 11 sum of the giant groups' partial results */
+ * 9 inverse pass A, 10 inverse pass B, 11 sum of the giant groups' partial results, 12 peer-exchange flag kernels (post +
+ * wait: the time this rank waits for its peers), 13 peer reduce-scatter + Barrett + all-gather kernel and its copies */
 int spear_profile_enable(spear_context* ctx, int on);
 int spear_profile_read(spear_context* ctx, double* ms, uint64_t* launches, int classes);
 /* pinned host buffers for the host<->device legs of the end-to-end path */
@@ -208,6 +209,14 @@ int spear_bsgs_hoisted(spear_context* ctx, const spear_obj* ct, const spear_diag
  * one overlaps the transforms of the others.  outs receives `count` ciphertexts. */
 int spear_bsgs_hoisted_batch(spear_context* ctx, spear_obj* const* cts, spear_diagset* const* diags, int count,
                              const spear_galois_keys* gk, spear_obj** outs);
+/* Serving form of the batch (the reference keeps client and server in one process and hands ciphertexts over in host
+ * memory when it offloads them, scripts/bootstrap_generation.py:336-358, 545-556): in[i] = [2][limbs][N] ciphertext limbs
+ * in host memory (page-locked for asynchronous copies), out[i] = [2][limbs-1][N].  Item i is uploaded, multiplied and
+ * downloaded on auxiliary stream i % 3: the PCIe legs of one item run under the arithmetic of the others.  Returns when
+ * every result has landed; out_scale[i] (optional) = scale of result i. */
+int spear_bsgs_hoisted_batch_host(spear_context* ctx, const uint64_t* const* in, int limbs, double scale,
+                                  spear_diagset* const* diags, int count, const spear_galois_keys* gk, uint64_t* const* out,
+                                  double* out_scale);
 /* Sharded form: the shard's accumulator in basis Q_l*P (size 2, ext).  Accumulators of all shards are summed
  * (spear_add, or an integer all-reduce over spear_obj_device_ptr followed by spear_obj_reduce) and finished once. */
 int spear_bsgs_hoisted_partial(spear_context* ctx, const spear_obj* ct, const spear_diagset* shard,

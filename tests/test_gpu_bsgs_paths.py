@@ -142,6 +142,37 @@ def test_two_phase_split_on_one_gpu(D, world, weight):
         ph.bsgs_hoisted(ctx, ct, slices[0], gk)
 
 
+def test_host_buffer_serving_batch_matches_device_batch():
+    """spear_bsgs_hoisted_batch_host (ciphertexts in and out of page-locked host memory, transfers pipelined with the
+    mat-vecs over the engine's streams) returns exactly the limbs of the device-resident batch call, for more items than
+    streams"""
+    D = 64
+    S = Setup(N=2048, bits=(59,) * 6, P=2)
+    G, B = bsgs_params(D)
+    steps = list(range(1, G)) + [g * G for g in range(1, B)]
+    ph, ctx, sk = S.gpu(steps)
+    gk = sk.create_galois_keys(ctx)
+    enc = ph.ckks_encoder(ctx)
+    rng = np.random.default_rng(21)
+    Ws = [rng.standard_normal((D, D)) * 0.1 for _ in range(5)]
+    xs = [rng.standard_normal(D) for _ in range(5)]
+    cts = [sk.encrypt_symmetric(ctx, enc.encode_double_vector(ctx, tile(x, S.N // 2), S.scale), enc_id=40 + i)
+           for i, x in enumerate(xs)]
+    sets = [ph.diagonal_set(ctx, rolled_diagonals(W, D, G, B), G, B, S.scale) for W in Ws]
+    ref = ph.bsgs_hoisted_batch(ctx, cts, sets, gk)
+    l = cts[0].coeff_modulus_size()
+    h_in = [ph.pinned_empty((2, l, S.N)) for _ in cts]
+    h_out = [ph.pinned_empty((2, l - 1, S.N)) for _ in cts]
+    for ct, h in zip(cts, h_in):
+        ct.to_numpy(out=h)
+    for _ in range(2):                                     # buffers and streams are reused
+        scales = ph.bsgs_hoisted_batch_host(ctx, h_in, cts[0].scale(), sets, gk, h_out)
+        for y, h, sc in zip(ref, h_out, scales):
+            assert np.array_equal(y.to_numpy(), h) and sc == y.scale()
+    with pytest.raises(RuntimeError):
+        ph.bsgs_hoisted_batch_host(ctx, h_in, cts[0].scale(), sets, gk, h_in)   # wrong output shape
+
+
 def test_host_mirror_projections():
     """fhe_projection_bsgs for D->D, D->F (complex-packed, ragged last chunk) and F->D (conjugate-packed),
     hoisted path and reference-order path, against float64 x @ W (tolerance 1e-8 at scale 2^59)."""
