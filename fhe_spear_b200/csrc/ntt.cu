@@ -364,11 +364,14 @@ __global__ void __launch_bounds__(2 << SA) k_intt_modup_fwd_a(const u64* __restr
 // =============================================================================================
 constexpr int FK_CHUNK = 256, FK_MAXW = 8;
 
-template <int FOLD>
+// FIX8: exactly 8 digits on 8 warps (C3, C2): every loop over digits / output coefficients is a single trip, known at
+// compile time (no trip-count division by blockDim.x, no loop control in the prologue and epilogue of these small CTAs)
+template <int FOLD, bool FIX8>
 __device__ __forceinline__ void fk_body(const CUtensorMap* kmap_p, const KsArgs& a, const ModTab& mt, const NttTab& tb,
                                         const ulonglong2* __restrict__ pmod, int sA, int alpha, int wide_ok) {
     extern __shared__ __align__(128) unsigned char smraw[];
-    const int beta = a.beta;
+    const int beta = FIX8 ? 8 : a.beta;
+    const int nthreads = FIX8 ? 256 : (int)blockDim.x;
     u64* ksm = reinterpret_cast<u64*>(smraw);                     // [2*beta][256]  key box (TMA destination)
     u64* esm = ksm + (size_t)2 * beta * FK_CHUNK;                 // [beta][256]    transformed digits, swizzled per chunk
     uint64_t* full = reinterpret_cast<uint64_t*>(esm + (size_t)beta * FK_CHUNK);
@@ -383,7 +386,7 @@ __device__ __forceinline__ void fk_body(const CUtensorMap* kmap_p, const KsArgs&
     const u32 csrc = (a.elt ? galois_src(n0, a.elt, a.logn) : n0) / FK_CHUNK;   // chunk the output chunk is gathered from
     const bool has_add = a.addp && r < a.add_rows;
     // the epilogue's read-modify-write operands are pulled into L2 now, a whole transform ahead of their use
-    for (int o = threadIdx.x; o < FK_CHUNK; o += blockDim.x) {
+    for (int o = threadIdx.x; o < FK_CHUNK; o += nthreads) {
         if (a.accumulate) {
             const u64* o0 = a.out + (size_t)r * a.N + n0 + o;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(o0));
@@ -394,7 +397,7 @@ __device__ __forceinline__ void fk_body(const CUtensorMap* kmap_p, const KsArgs&
     const int own = r < a.l ? r / alpha : -1;   // the digit this row belongs to (ModUp wrote its NTT form already)
     const u64 q = tb.q[t];
     const ulonglong2* __restrict__ tw = tb.psi + (size_t)t * a.N;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = nthreads >> 5;
     const bool lazy = q < (1ull << 59) && q > (1ull << 33);
     for (int j = warp; j < beta; j += nwarps) {
         u64* s = esm + (size_t)j * FK_CHUNK;
@@ -414,7 +417,7 @@ __device__ __forceinline__ void fk_body(const CUtensorMap* kmap_p, const KsArgs&
     ulonglong2 pm = make_ulonglong2(0, 0);
     if (has_add && a.add_pscale) pm = pmod[t];
     mbar_wait(full, 0);
-    for (int o = threadIdx.x; o < FK_CHUNK; o += blockDim.x) {
+    for (int o = threadIdx.x; o < FK_CHUNK; o += nthreads) {
         const u32 n = n0 + o;
         const u32 src = a.elt ? galois_src(n, a.elt, a.logn) : n;
         const int sl = swz((int)(src & (FK_CHUNK - 1)));
@@ -422,7 +425,7 @@ __device__ __forceinline__ void fk_body(const CUtensorMap* kmap_p, const KsArgs&
         u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
         Acc3 acc0 = {0, 0, 0}, acc1 = {0, 0, 0};
         const u64* kcol = ksm + o;
-#pragma unroll 4
+#pragma unroll(FIX8 ? 8 : 4)
         for (int j = 0; j < beta; j++) {
             const u64 dj = esm[(size_t)j * FK_CHUNK + sl];
             const u32 dsum = (u32)dj + (u32)(dj >> 32);
@@ -456,11 +459,11 @@ __device__ __forceinline__ void fk_body(const CUtensorMap* kmap_p, const KsArgs&
     }
 }
 
-template <int FOLD>
+template <int FOLD, bool FIX8>
 __global__ void __launch_bounds__(FK_MAXW * 32, 4) k_ntt_b_ks(const __grid_constant__ CUtensorMap kmap, KsArgs a, ModTab mt,
                                                             NttTab tb, const ulonglong2* __restrict__ pmod, int sA,
                                                             int alpha, int wide_ok) {
-    fk_body<FOLD>(&kmap, a, mt, tb, pmod, sA, alpha, wide_ok);
+    fk_body<FOLD, FIX8>(&kmap, a, mt, tb, pmod, sA, alpha, wide_ok);
 }
 
 // All giant steps of a mat-vec in ONE launch (blockIdx.z = giant group): group z reads its own digits and rotation key,
@@ -470,7 +473,7 @@ struct GiantTab {
     CUtensorMap map[FK_MAX_GROUPS];
     u32 elt[FK_MAX_GROUPS];
 };
-template <int FOLD>
+template <int FOLD, bool FIX8>
 __global__ void __launch_bounds__(FK_MAXW * 32, 4) k_ntt_b_ks_all(const __grid_constant__ GiantTab tab, KsArgs a, ModTab mt,
                                                                 NttTab tb, const ulonglong2* __restrict__ pmod, int sA,
                                                                 int alpha, int wide_ok, size_t e_stride, size_t out_stride,
@@ -478,7 +481,7 @@ __global__ void __launch_bounds__(FK_MAXW * 32, 4) k_ntt_b_ks_all(const __grid_c
     const int z = blockIdx.z;
     a.E += (size_t)z * e_stride, a.out += (size_t)z * out_stride, a.elt = tab.elt[z];
     if (a.addp) a.addp += (size_t)z * add_stride;
-    fk_body<FOLD>(&tab.map[z], a, mt, tb, pmod, sA, alpha, wide_ok);
+    fk_body<FOLD, FIX8>(&tab.map[z], a, mt, tb, pmod, sA, alpha, wide_ok);
 }
 
 template <int SA>
@@ -639,8 +642,9 @@ bool ntt_ks_fused(const Ctx* c, u64* E, const u64* key, u64* out, int l, u32 elt
         LAUNCH(kern, dim3(c->N / FK_CHUNK, rows), threads, smem, s)(kmap, a, c->modtab(), c->ntttab(), c->d_pmod, sA, c->P,
                                                                     small && beta <= 8 ? 1 : 0);
     };
-    if (small) go(k_ntt_b_ks<16>);
-    else go(k_ntt_b_ks<8>);
+    if (small && beta == 8) go(k_ntt_b_ks<16, true>);
+    else if (small) go(k_ntt_b_ks<16, false>);
+    else go(k_ntt_b_ks<8, false>);
     CUDA_CHECK(cudaGetLastError());
     return true;
 }
@@ -673,8 +677,9 @@ bool ntt_ks_fused_all(const Ctx* c, const u64* E, const u64* const* keys, const 
                                                                            small && beta <= 8 ? 1 : 0, (size_t)beta * pw, 2 * pw,
                                                                            add_stride);
     };
-    if (small) go(k_ntt_b_ks_all<16>);
-    else go(k_ntt_b_ks_all<8>);
+    if (small && beta == 8) go(k_ntt_b_ks_all<16, true>);
+    else if (small) go(k_ntt_b_ks_all<16, false>);
+    else go(k_ntt_b_ks_all<8, false>);
     CUDA_CHECK(cudaGetLastError());
     return true;
 }
