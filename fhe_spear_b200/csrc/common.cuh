@@ -159,6 +159,13 @@ __device__ __forceinline__ u64 reduce_wide_s(u64 lo, u64 hi, u64 q, u64 R, int s
     r = r >= q2 ? r - q2 : r;
     return r >= q ? r - q : r;
 }
+// the same without the two conditional subtractions: a representative in [0, 3q) -- for consumers that take lazy inputs
+// (the forward butterflies accept [0, 4q); the fully lazy passes of ntt_core.cuh have the head-room up to seven stages)
+__device__ __forceinline__ u64 reduce_wide_lazy(u64 lo, u64 hi, u64 q, u64 R, int s) {
+    const u64 top = (hi << (64 - s)) | (lo >> s);
+    const u64 Q = __umul64hi(top, R);
+    return lo - Q * q;
+}
 __device__ __forceinline__ u64 mul_mod(u64 a, u64 b, u64 q, u64 r0, u64 r1) {
     return barrett128(a * b, __umul64hi(a, b), q, r0, r1);
 }
