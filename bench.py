@@ -352,9 +352,9 @@ def run_ours(args):
 
         def step():
             return dict(enumerate(sh.split_matvec_batch(ckks, cts, [dsets[j] for j in range(nb)])))
-        r0_, r1_ = ph.diagonal_set.row_range(L0, P, rank, world)
+        r0_, r1_, c0_, c1_ = ph.diagonal_set.share(L0, P, N, rank, world)
         parallelism = (f"{world} GPUs, strong scaling, two-phase mat-vecs: every mat-vec on all ranks -- hoisted baby steps + diagonal "
-                       f"MAC split by rows of the {L0 + P}-limb basis (k_pmac_tma's epilogue stores scatter the giant groups' "
+                       f"MAC split by rows of the {L0 + P}-limb basis{' and column halves' if world >= 5 else ''} (k_pmac_tma's epilogue stores scatter the giant groups' "
                        f"accumulators to their owners over NVLink peer memory), giant steps split by group, accumulators summed by "
                        f"spear_peer_allreduce; all inside the timed region")
         n_giant_rank = max(len(sh.giant_groups(B, r, world)) - (1 if r == 0 else 0) for r in range(world))
@@ -575,7 +575,7 @@ def run_ours(args):
     n_baby = G - 1
     row_share = 1.0
     if world > 1 and two_phase:      # this rank's rows of the baby-step keys and of the diagonals
-        row_share = (r1_ - r0_) / float(l + P)
+        row_share = (r1_ - r0_) * (c1_ - c0_) / float((l + P) * N)
     alg_bytes = {   # algorithmic bytes per MAT-VEC of each kernel: SURVEY.md section 8(d) -- keys and diagonals read once
         "ks_baby_fused": n_baby * key_bytes * row_share, "ntt_ks_fused": n_giant_rank * key_bytes,
         "ks_inner": n_giant_rank * key_bytes, "pmac": info["bytes"] * row_share,

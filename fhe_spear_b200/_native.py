@@ -108,6 +108,8 @@ _SIG = {
     "spear_peer_window_destroy": (None, [vp]),
     "spear_peer_selftest": (C.c_int, [vp, vpp, C.c_int]),
     "spear_diagset_slice_rows": (C.c_int, [vp, vp, C.c_int, C.c_int, vpp]),
+    "spear_diagset_slice_share": (C.c_int, [vp, vp, C.c_int, C.c_int, vpp]),
+    "spear_split_share": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, ip, ip]),
     "spear_bsgs_split": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, vpp]),
     "spear_bsgs_split_batch": (C.c_int, [vp, vpp, vpp, C.c_int, vp, vp, C.c_int, vpp]),
     "spear_bsgs_split_selftest": (C.c_int, [vp, vp, vpp, C.c_int, vp, vpp]),

@@ -28,7 +28,8 @@ void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, i
                           const u32* gelt, const u64* const* gkey, u64* R, cudaStream_t s);
 void bsgs_finish(const Ctx* c, u64* R, int l, u64* out, cudaStream_t s);
 void bsgs_split_phase1(const Ctx* c, const u64* ct, int l, const u64* diag, int rshift, int G, int B, int n_diags, int row0,
-                       int nrows, const u32* belt, const u64* const* bkey, const PmacDst& dst, cudaStream_t s);
+                       int nrows, int col0, int ncols, const u32* belt, const u64* const* bkey, const PmacDst& dst,
+                       cudaStream_t s);
 void bsgs_split_phase2(const Ctx* c, u64* A, int l, int G, int B, int n_groups, const u32* gelt, const u64* const* gkey,
                        int world, u64* R, cudaStream_t s);
 }  // namespace eng
@@ -1059,7 +1060,7 @@ int spear_diagset_info(const spear_diagset* d_, int* D, int* G, int* B, int* lim
     if (limbs) *limbs = d->l;
     if (ring_n) *ring_n = d->n;
     if (scale) *scale = d->scale;
-    if (bytes) *bytes = sizeof(u64) * (size_t)d->n_diags * d->stored_rows() * d->n;
+    if (bytes) *bytes = sizeof(u64) * (size_t)d->n_diags * d->stored_rows() * d->stored_cols();
     API_END
 }
 int spear_diagset_export(const spear_diagset* d_, uint64_t* host, size_t words) {
@@ -1067,7 +1068,7 @@ int spear_diagset_export(const spear_diagset* d_, uint64_t* host, size_t words) 
     const DiagSet* d = reinterpret_cast<const DiagSet*>(d_);
     Ctx* c = d->ctx;
     use(c);
-    const size_t have = (size_t)d->n_diags * d->stored_rows() * d->n;
+    const size_t have = (size_t)d->n_diags * d->stored_rows() * d->stored_cols();
     REQUIRE(words == have, "export: buffer holds %zu words, diagonal set has %zu", words, have);
     u64* tmp = c->alloc(have);   // canonical residues for the caller; the resident copy stays split-30
     CUDA_CHECK(cudaMemcpyAsync(tmp, d->d, sizeof(u64) * have, cudaMemcpyDeviceToDevice, c->stream));
@@ -1078,31 +1079,69 @@ int spear_diagset_export(const spear_diagset* d_, uint64_t* host, size_t words) 
     API_END
 }
 
-// rows [row0, row0 + nrows) of a full set, as a set of its own: the diagonals a rank holds in a two-phase mat-vec
+// out[d][r][c] = in[d][row0 + r][col0 + c]
+__global__ void k_diag_slice(const u64* __restrict__ in, u64* __restrict__ out, int n_diags, int rows, int n, int row0,
+                             int nrows, int col0, int ncols) {
+    const size_t total = (size_t)n_diags * nrows * ncols;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int cc = (int)(e % ncols);
+        const size_t dr = e / ncols;
+        const int r = (int)(dr % nrows);
+        const size_t d = dr / nrows;
+        out[e] = in[(d * rows + row0 + r) * n + col0 + cc];
+    }
+}
+// rows [row0, row0 + nrows) x stored columns [col0, col0 + ncols) of a full set, as a set of its own: the diagonals a
+// rank holds in a two-phase mat-vec
+static DiagSet* diagset_slice(Ctx* c, const DiagSet* f, int row0, int nrows, int col0, int ncols) {
+    REQUIRE(f && f->nrows < 0 && f->ncols < 0 && f->g_first == 0 && f->g_stride == 1, "slice: expected a full diagonal set");
+    const int rows = f->l + c->P;
+    REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= rows, "slice: rows [%d, %d) of %d", row0, row0 + nrows, rows);
+    REQUIRE(col0 >= 0 && ncols >= 0 && col0 + ncols <= f->n, "slice: columns [%d, %d) of %d", col0, col0 + ncols, f->n);
+    std::unique_ptr<DiagSet> ds(new DiagSet);
+    ds->bind(c), ds->D = f->D, ds->G = f->G, ds->B = f->B, ds->l = f->l, ds->n = f->n, ds->scale = f->scale;
+    ds->n_diags = f->n_diags, ds->g_first = 0, ds->g_stride = 1, ds->rshift = f->rshift;
+    ds->row0 = row0, ds->nrows = nrows, ds->col0 = col0, ds->ncols = ncols;
+    const size_t words = (size_t)std::max(f->n_diags, 1) * std::max(nrows, 1) * std::max(ncols, 1);
+    ds->d = c->alloc(words);
+    if (f->n_diags > 0 && nrows > 0 && ncols > 0)
+        LAUNCH(k_diag_slice, c->sm_count * 8, 256, 0, c->stream)(f->d, ds->d, f->n_diags, rows, f->n, row0, nrows, col0, ncols);
+    CUDA_CHECK(cudaGetLastError());
+    return ds.release();
+}
 int spear_diagset_slice_rows(spear_context* ctx, const spear_diagset* full_, int row0, int nrows, spear_diagset** out) {
     API_BEGIN
     Ctx* c = C_(ctx);
     use(c);
     const DiagSet* f = reinterpret_cast<const DiagSet*>(full_);
-    REQUIRE(f && f->nrows < 0 && f->g_first == 0 && f->g_stride == 1, "slice_rows: expected a full diagonal set");
-    const int rows = f->l + c->P;
-    REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= rows, "slice_rows: rows [%d, %d) of %d", row0, row0 + nrows, rows);
-    std::unique_ptr<DiagSet> ds(new DiagSet);
-    ds->bind(c), ds->D = f->D, ds->G = f->G, ds->B = f->B, ds->l = f->l, ds->n = f->n, ds->scale = f->scale;
-    ds->n_diags = f->n_diags, ds->g_first = 0, ds->g_stride = 1, ds->rshift = f->rshift;
-    ds->row0 = row0, ds->nrows = nrows;
-    ds->d = c->alloc((size_t)std::max(f->n_diags, 1) * std::max(nrows, 1) * f->n);
-    if (f->n_diags > 0 && nrows > 0)
-        CUDA_CHECK(cudaMemcpy2DAsync(ds->d, sizeof(u64) * nrows * f->n, f->d + (size_t)row0 * f->n, sizeof(u64) * rows * f->n,
-                                     sizeof(u64) * nrows * f->n, f->n_diags, cudaMemcpyDeviceToDevice, c->stream));
-    *out = reinterpret_cast<spear_diagset*>(ds.release());
+    REQUIRE(f, "slice_rows: null set");
+    *out = reinterpret_cast<spear_diagset*>(diagset_slice(c, f, row0, nrows, 0, f->n));
+    API_END
+}
+// the phase-1 share of `rank` in a group of `world` (engine.h split_share): rows, and for groups of more than four ranks
+// one half of the columns
+int spear_diagset_slice_share(spear_context* ctx, const spear_diagset* full_, int rank, int world, spear_diagset** out) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    const DiagSet* f = reinterpret_cast<const DiagSet*>(full_);
+    REQUIRE(f && world >= 1 && world <= 8 && rank >= 0 && rank < world, "slice_share: rank %d of %d", rank, world);
+    const SplitShare sh = split_share(rank, world, f->l + c->P, c->N);
+    *out = reinterpret_cast<spear_diagset*>(diagset_slice(c, f, sh.row0, sh.nrows, sh.col0 >> f->rshift, sh.ncols >> f->rshift));
+    API_END
+}
+int spear_split_share(int rank, int world, int rows, int N, int* row0, int* nrows, int* col0, int* ncols) {
+    API_BEGIN
+    REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world && rows >= 1 && N >= 2, "split_share: bad arguments");
+    const SplitShare sh = split_share(rank, world, rows, N);
+    *row0 = sh.row0, *nrows = sh.nrows, *col0 = sh.col0, *ncols = sh.ncols;
     API_END
 }
 
 static Obj* bsgs_partial(Ctx* c, const Obj* ct, const DiagSet* ds, const GaloisKeys* gk, cudaStream_t s = nullptr) {
     if (!s) s = c->stream;
     check_ct(ct, "bsgs_hoisted");
-    REQUIRE(ds->nrows < 0, "bsgs_hoisted: row-sliced diagonal set (use bsgs_split)");
+    REQUIRE(ds->nrows < 0 && ds->ncols < 0, "bsgs_hoisted: sliced diagonal set (use bsgs_split)");
     REQUIRE(ct->size == 2, "bsgs_hoisted: relinearize first");
     REQUIRE(ds->l == ct->l, "bsgs_hoisted: diagonals encoded for %d limbs, ciphertext has %d", ds->l, ct->l);
     const int G = std::min(ds->G, ds->D), B = ds->B, D = ds->D, l = ct->l;
@@ -1196,7 +1235,7 @@ int spear_bsgs_hoisted_batch_host(spear_context* ctx, const uint64_t* const* in,
     for (int i = 0; i < count; i++) {   // validate everything before anything is queued
         const DiagSet* ds = reinterpret_cast<const DiagSet*>(dss[i]);
         REQUIRE(ds && in[i] && out[i], "bsgs_hoisted_batch_host: null item %d", i);
-        REQUIRE(ds->g_first == 0 && ds->g_stride == 1 && ds->nrows < 0, "bsgs_hoisted_batch_host: sharded diagonal set");
+        REQUIRE(ds->g_first == 0 && ds->g_stride == 1 && ds->nrows < 0 && ds->ncols < 0, "bsgs_hoisted_batch_host: sharded diagonal set");
         REQUIRE(ds->l == limbs, "bsgs_hoisted_batch_host: diagonals encoded for %d limbs, ciphertexts have %d", ds->l, limbs);
     }
     std::vector<std::unique_ptr<Obj>> ct(count), acc(count), res(count);
@@ -1279,17 +1318,21 @@ static void split_groups(Ctx* c, const DiagSet* ds, const GaloisKeys* gk, int nB
         gkey.push_back(g ? find_key(gk, gelt.back())->d : nullptr);
     }
 }
-static void split_check_rows(const Ctx* c, const DiagSet* ds, int l, int rank, int world) {
-    const int rows = l + c->P, r0 = rank * rows / world, r1 = (rank + 1) * rows / world;
-    REQUIRE(ds->row0 == r0 && ds->stored_rows() == r1 - r0, "bsgs_split: rank %d of %d serves rows [%d, %d), the set holds [%d, %d)",
-            rank, world, r0, r1, ds->row0, ds->row0 + ds->stored_rows());
+static SplitShare split_check_rows(const Ctx* c, const DiagSet* ds, int l, int rank, int world) {
+    const SplitShare sh = split_share(rank, world, l + c->P, c->N);
+    REQUIRE(ds->row0 == sh.row0 && ds->stored_rows() == sh.nrows && ds->col0 == (sh.col0 >> ds->rshift) &&
+                ds->stored_cols() == (sh.ncols >> ds->rshift),
+            "bsgs_split: rank %d of %d serves rows [%d, %d) x columns [%d, %d); the set holds rows [%d, %d) x stored columns [%d, %d)",
+            rank, world, sh.row0, sh.row0 + sh.nrows, sh.col0, sh.col0 + sh.ncols, ds->row0, ds->row0 + ds->stored_rows(), ds->col0,
+            ds->col0 + ds->stored_cols());
+    return sh;
 }
 static Obj* bsgs_split(Ctx* c, const Obj* ct, const DiagSet* ds, const GaloisKeys* gk, spear_peer_window* win, int slot,
                        cudaStream_t s) {
     SplitPlan p = split_plan(c, ct, ds, gk);
     int rank = 0, world = 1;
     peer::window_geometry(win, &rank, &world);
-    split_check_rows(c, ds, p.l, rank, world);
+    const SplitShare sh = split_check_rows(c, ds, p.l, rank, world);
     std::vector<u32> gelt;
     std::vector<const u64*> gkey;
     split_groups(c, ds, gk, p.nB, rank, world, gelt, gkey);
@@ -1299,8 +1342,8 @@ static Obj* bsgs_split(Ctx* c, const Obj* ct, const DiagSet* ds, const GaloisKey
     PmacDst dst = {};
     for (int r = 0; r < 8; r++) dst.base[r] = v.base[r];
     dst.world = world;
-    eng::bsgs_split_phase1(c, ct->d, p.l, ds->d, ds->rshift, p.G, p.nB, ds->n_diags, ds->row0, ds->stored_rows(), p.belt.data(),
-                           p.bkey.data(), dst, s);
+    eng::bsgs_split_phase1(c, ct->d, p.l, ds->d, ds->rshift, p.G, p.nB, ds->n_diags, sh.row0, sh.nrows, sh.col0, sh.ncols,
+                           p.belt.data(), p.bkey.data(), dst, s);
     peer::split_exchange(win, slot, s);
     eng::bsgs_split_phase2(c, v.base[rank], p.l, p.G, p.nB, (int)gelt.size(), gelt.data(), gkey.data(), world, R->d, s);
     peer::split_release(win, slot, R->d, R->words(), s);
@@ -1361,8 +1404,8 @@ int spear_bsgs_split_selftest(spear_context* ctx, const spear_obj* ct_, spear_di
     for (int r = 0; r < world; r++) {
         const DiagSet* ds = reinterpret_cast<const DiagSet*>(dss[r]);
         split_plan(c, ct, ds, gk);
-        split_check_rows(c, ds, p.l, r, world);
-        eng::bsgs_split_phase1(c, ct->d, p.l, ds->d, ds->rshift, p.G, p.nB, ds->n_diags, ds->row0, ds->stored_rows(),
+        const SplitShare sh = split_check_rows(c, ds, p.l, r, world);
+        eng::bsgs_split_phase1(c, ct->d, p.l, ds->d, ds->rshift, p.G, p.nB, ds->n_diags, sh.row0, sh.nrows, sh.col0, sh.ncols,
                                p.belt.data(), p.bkey.data(), dst, s);
     }
     std::unique_ptr<Obj> sum;

@@ -186,17 +186,19 @@ static size_t phase2_words(const Ctx* c, int l, int nrot, cudaStream_t s) {
 // when the set is walked in several baby-step chunks (G > 64), else unused.
 static void bsgs_phase1(const Ctx* c, const u64* ct, int l, const u64* diag, int rshift, int G, int n_groups, int n_diags,
                         const u32* belt, const u64* const* bkey, u64* x, u64* E, u64* Y, const PmacDst& dst, u64* tmp,
-                        int row0, int nrows, cudaStream_t s) {
+                        int row0, int nrows, cudaStream_t s, int col0 = 0, int ncols = -1) {
     const size_t N = c->N, rows = l + c->P, pw = rows * N;
     const u64 *c0 = ct, *c1 = ct + l * N;
-    if (nrows == 0) return;   // more ranks than rows: this one only serves giant groups
+    if (ncols < 0) ncols = (int)N - col0;
+    const int dcols = ncols >> rshift;   // a column-sliced set stores exactly its columns
+    if (nrows == 0 || ncols == 0) return;   // more ranks than rows: this one only serves giant groups
     ops::decompose(c, c1, l, x, E, s, row0, nrows);   // only the rows this launch set serves
     ops::pscale(c, ct, Y, l, s);
     // A/B switch for the north-star item "diagonal MAC fused into the key-switch epilogue": SPEAR_PIPE_ROWS=k walks the rows
     // in k chunks, the MAC of chunk i on an auxiliary stream under the key stream of chunk i+1 -- the overlap of the HBM-bound
     // baby steps with the integer-bound MAC that a fused kernel could buy at best (profiles/r2_ns1_overlap.md)
     static const int pipe = getenv("SPEAR_PIPE_ROWS") ? atoi(getenv("SPEAR_PIPE_ROWS")) : 0;
-    if (pipe > 1 && s == c->stream && G > 1 && nrows >= pipe) {
+    if (pipe > 1 && s == c->stream && G > 1 && nrows >= pipe && ncols == (int)N) {
         cudaStream_t h = c->aux[0];
         std::vector<cudaEvent_t> ev(pipe + 1);
         for (auto& e : ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -215,12 +217,13 @@ static void bsgs_phase1(const Ctx* c, const u64* ct, int l, const u64* diag, int
         for (auto& e : ev) cudaEventDestroy(e);
         return;
     }
-    if (G > 1 && !ops::ks_baby_fused(c, E, bkey + 1, belt + 1, G - 1, Y + 2 * pw, l, c0, s, row0, nrows)) {
-        REQUIRE(row0 == 0 && nrows == (int)rows, "two-phase mat-vec: the fused baby-step kernel does not apply to this shape");
+    if (G > 1 && !ops::ks_baby_fused(c, E, bkey + 1, belt + 1, G - 1, Y + 2 * pw, l, c0, s, row0, nrows, col0, ncols)) {
+        REQUIRE(row0 == 0 && nrows == (int)rows && ncols == (int)N,
+                "two-phase mat-vec: the fused baby-step kernel does not apply to this shape");
         for (int b = 1; b < G; b++)
             ops::ks_inner(c, E, bkey[b], Y + (size_t)b * 2 * pw, l, belt[b], c0, l, 1, 0, s);
     }
-    ops::pmac_hoisted_rows(c, Y, diag, dst, tmp, G, n_groups, n_diags, l, rshift, row0, nrows, s);
+    ops::pmac_hoisted_rows(c, Y, diag, dst, tmp, G, n_groups, n_diags, l, rshift, row0, nrows, s, nrows, col0, ncols, dcols);
 }
 
 // Phase 2: the giant steps of the n_groups accumulators A [n_groups][2][l+P][N] (destroyed: the ModDown transforms their
@@ -305,11 +308,12 @@ void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, i
 }
 
 // ---- two-phase mat-vec over a rank group (peer.cu drives the exchange between the phases) -----------------------------
-// Phase 1 on this rank's ROWS for every giant group of the matrix; the accumulators of group g land in dst.base[g % world]
+// Phase 1 on this rank's ROWS (and, in groups of more than four ranks, its half of the COLUMNS) for every giant group; the accumulators of group g land in dst.base[g % world]
 // (slot (g / world)): the all-to-all that turns the row split into the giant-group split is the diagonal MAC's own
 // epilogue.  diag [n_diags][nrows][N >> rshift] holds all B groups.
 void bsgs_split_phase1(const Ctx* c, const u64* ct, int l, const u64* diag, int rshift, int G, int B, int n_diags, int row0,
-                       int nrows, const u32* belt, const u64* const* bkey, const PmacDst& dst, cudaStream_t s) {
+                       int nrows, int col0, int ncols, const u32* belt, const u64* const* bkey, const PmacDst& dst,
+                       cudaStream_t s) {
     const size_t N = c->N, pw = (size_t)(l + c->P) * N;
     const bool chunks = G > 64;
     Arena sc(c, s, std::max(phase1_words(c, l, G, B, chunks), phase2_words(c, l, (B + dst.world - 1) / dst.world, s)));
@@ -317,7 +321,7 @@ void bsgs_split_phase1(const Ctx* c, const u64* ct, int l, const u64* diag, int 
     u64* E = sc.get(c->digits(l) * pw);
     u64* Y = sc.get((size_t)G * 2 * pw);
     u64* tmp = chunks ? sc.get((size_t)B * 2 * pw) : nullptr;
-    bsgs_phase1(c, ct, l, diag, rshift, G, B, n_diags, belt, bkey, x, E, Y, dst, tmp, row0, nrows, s);
+    bsgs_phase1(c, ct, l, diag, rshift, G, B, n_diags, belt, bkey, x, E, Y, dst, tmp, row0, nrows, s, col0, ncols);
 }
 // Phase 2 on this rank's giant groups, whose accumulators A [n_groups][2][l+P][N] every rank of the group has written.
 void bsgs_split_phase2(const Ctx* c, u64* A, int l, int G, int B, int n_groups, const u32* gelt, const u64* const* gkey,

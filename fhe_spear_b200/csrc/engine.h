@@ -141,6 +141,8 @@ struct DiagSet : CtxRef {
     int n = 0;       // coefficients stored per row (N >> rshift)
     int rshift = 0;
     int row0 = 0, nrows = -1;  // row slice of a two-phase mat-vec: rows [row0, row0 + nrows) of the l + P (nrows < 0: all rows)
+    int col0 = 0, ncols = -1;  // ... and its column slice, in STORED values (n = N >> rshift per row; ncols < 0: all)
+    int stored_cols() const { return ncols >= 0 ? ncols : n; }
     double scale = 1.0;
     u64* d = nullptr;  // [n_diags][stored_rows()][n]
     int stored_rows() const { return nrows >= 0 ? nrows : l + ctx->P; }
@@ -193,6 +195,19 @@ bool ntt_ks_fused_all(const Ctx* c, const u64* E, const u64* const* keys, const 
 void ntt_inverse(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s, bool pass_b_only = false);
 
 // ---- two-phase mat-vec over a rank group: exchange hooks (peer.cu), phases (bsgs.cu) -----------------------------
+// Phase-1 share of `rank`: up to four ranks split the rows of the RNS basis; larger even groups form world/2 row groups
+// of two ranks that take one half of the columns each (27 rows over 8 ranks: 3.5 row-equivalents instead of 4).
+struct SplitShare {
+    int row0, nrows, col0, ncols;   // columns in coefficients of the full ring
+};
+inline SplitShare split_share(int rank, int world, int rows, int N) {
+    const int halves = (world >= 5 && world % 2 == 0 && N % 256 == 0) ? 2 : 1, groups = world / halves;
+    const int rg = rank / halves, h = rank % halves;
+    SplitShare s;
+    s.row0 = rg * rows / groups, s.nrows = (rg + 1) * rows / groups - s.row0;
+    s.col0 = h * (N / halves), s.ncols = N / halves;
+    return s;
+}
 struct PmacDst;
 struct spear_peer_window;
 namespace peer {

@@ -203,7 +203,7 @@ __device__ __forceinline__ void ks_tile_body(const CUtensorMap* kmap, const KsAr
     u64* ksm = reinterpret_cast<u64*>(smraw);                       // [2 stages][2*beta][KS_TILE]
     uint64_t* full = reinterpret_cast<uint64_t*>(ksm + 2 * stage_words);
     const int t = r < a.l ? r : a.L + (r - a.l);
-    const int ntiles = min(KS_TPC, a.N / KS_TILE - tile0);
+    const int ntiles = min(KS_TPC, min(a.N / KS_TILE, a.tile1) - tile0);
     const u32 stage_bytes = (u32)(stage_words * sizeof(u64));
     u64 pol_first = 0;
     if (threadIdx.x == 0) {
@@ -324,7 +324,7 @@ template <int FOLD, int BETA>
 __global__ void __launch_bounds__(KS_TILE, 6) k_ks_baby_fused(const __grid_constant__ BabyTab tab, KsArgs a, ModTab mt,
                                                                const ulonglong2* __restrict__ pmod) {
     const int b = blockIdx.y;
-    ks_tile_body<FOLD, BETA>(&tab.map[b], a, mt, pmod, blockIdx.z + a.row0, blockIdx.x * KS_TPC, tab.elt[b],
+    ks_tile_body<FOLD, BETA>(&tab.map[b], a, mt, pmod, blockIdx.z + a.row0, a.tile0 + blockIdx.x * KS_TPC, tab.elt[b],
                              a.out + (size_t)b * 2 * a.rows * a.N);
 }
 
@@ -523,9 +523,10 @@ __device__ __forceinline__ u64* pmac_dst(const PmacDst& d, int g, int p, size_t 
 }
 __global__ void __launch_bounds__(PM_TILE) k_pmac_hoisted(const u64* __restrict__ Y, const u64* __restrict__ diag,
                                                            PmacDst dst, int G, int B, int D, int l, int rows,
-                                                           int N, int L, int rshift, int row0, int diag_rows, ModTab mt) {
+                                                           int N, int L, int rshift, int row0, int diag_rows, int col0,
+                                                           int diag_cols, ModTab mt) {
     extern __shared__ u64 sm[];   // [G][2][PM_TILE]
-    const int r = blockIdx.y + row0, n = blockIdx.x * PM_TILE + threadIdx.x;
+    const int r = blockIdx.y + row0, n = col0 + blockIdx.x * PM_TILE + threadIdx.x;
     const int t = r < l ? r : L + (r - l);
     const size_t pw = (size_t)rows * N, off = (size_t)r * N + n;
     for (int b = 0; b < G; b++) {
@@ -534,8 +535,8 @@ __global__ void __launch_bounds__(PM_TILE) k_pmac_hoisted(const u64* __restrict_
     }
     // each thread only re-reads its own column: no barrier needed
     const u64 q = mt.q[t], r0 = mt.ratio0[t], r1 = mt.ratio1[t];
-    const int dn = N >> rshift;
-    const u64* dg = diag + (size_t)blockIdx.y * dn + (n >> rshift);   // diag points at the first row served
+    const int dn = diag_cols;
+    const u64* dg = diag + (size_t)blockIdx.y * dn + ((n >> rshift) - (col0 >> rshift));   // diag: first row / column served
     const size_t dstride = (size_t)diag_rows * dn;
     const u64 pol = evict_first_policy();
     for (int g = 0; g < B; g++) {
@@ -611,14 +612,14 @@ __global__ void __launch_bounds__(2 * PM_T2 * PM_HS) k_pmac_tma(const __grid_con
                                                                  const u64* __restrict__ Y, PmacDst dst,
                                                                  const u64* Ain, int G, int Gc, int b0, int nbc,
                                                                  int Beff, int l, int rows, int N, int L, int row0,
-                                                                 ModTab mt) {
+                                                                 int col0, ModTab mt) {
     extern __shared__ __align__(128) unsigned char smraw[];
     constexpr int W = PM_T2 >> RSH;
     u64* dsm = reinterpret_cast<u64*>(smraw);                         // [PM_STAGES][PM_GT][Gc][W]
     u64* ysm = dsm + (size_t)PM_STAGES * PM_GT * Gc * W;              // [Gc][2][PM_T2]
     uint64_t* full = reinterpret_cast<uint64_t*>(ysm + (size_t)Gc * 2 * PM_T2);
     const int tid = threadIdx.x, h = tid / (2 * PM_T2), p = (tid / PM_T2) & 1, i = tid % PM_T2;
-    const int r = blockIdx.y + row0, n0 = blockIdx.x * PM_T2;   // the diagonal set stores rows row0 .. only (TMA row = blockIdx.y)
+    const int r = blockIdx.y + row0, n0 = col0 + blockIdx.x * PM_T2;   // the tensor map starts at (row0, col0): TMA row = blockIdx.y
     const int t = r < l ? r : L + (r - l);
     const int iters = (Beff + PM_GT - 1) / PM_GT;
     const size_t group_words = (size_t)Gc * W, stage_words = PM_GT * group_words;
@@ -634,7 +635,8 @@ __global__ void __launch_bounds__(2 * PM_T2 * PM_HS) k_pmac_tma(const __grid_con
         const int s = it % PM_STAGES, ng = min(PM_GT, Beff - it * PM_GT);
         mbar_expect_tx(&full[s], (u32)(ng * Gc * W * sizeof(u64)));
         for (int k = 0; k < ng; k++)
-            tma_load_3d(dsm + s * stage_words + k * group_words, &tmap, n0 >> RSH, blockIdx.y, (it * PM_GT + k) * G + b0, &full[s]);
+            tma_load_3d(dsm + s * stage_words + k * group_words, &tmap, (int)(blockIdx.x * PM_T2) >> RSH, blockIdx.y,
+                        (it * PM_GT + k) * G + b0, &full[s]);
     };
     if (tid == 0)
         for (int it = 0; it < PM_STAGES && it < iters; it++) issue(it);
@@ -839,11 +841,14 @@ void ks_inner(const Ctx* c, const u64* E, const u64* key, u64* out, int l, u32 e
 // Y[b] for b = 1..nb (out points at Y[1]): all hoisted baby steps against their keys in one launch.
 // Returns false when the fused path does not apply (caller falls back to one launch per baby step).
 bool ks_baby_fused(const Ctx* c, const u64* E, const u64* const* keys, const u32* elts, int nb, u64* out, int l,
-                   const u64* c0, cudaStream_t s, int row0, int nrows) {
+                   const u64* c0, cudaStream_t s, int row0, int nrows, int col0, int ncols) {
     const int beta = c->digits(l), rows = l + c->P;
     if (nrows < 0) nrows = rows - row0;
+    if (ncols < 0) ncols = c->N - col0;
     REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= rows, "baby steps: bad row range");
-    if (nrows == 0) return true;
+    REQUIRE(col0 >= 0 && ncols >= 0 && col0 + ncols <= c->N && col0 % KS_TILE == 0 && ncols % KS_TILE == 0,
+            "baby steps: bad column range");
+    if (nrows == 0 || ncols == 0) return true;
     if (nb < 1 || nb > KS_MAX_BABY || beta > 8 || c->N % KS_TILE != 0) return false;
     static thread_local BabyTab tab;   // 12.6 KB by-value kernel parameter
     cuuint64_t dims[3] = {(cuuint64_t)c->N, (cuuint64_t)c->K, (cuuint64_t)(2 * c->beta)};
@@ -860,11 +865,11 @@ bool ks_baby_fused(const Ctx* c, const u64* E, const u64* const* keys, const u32
     KsArgs a;
     a.E = E, a.key = nullptr, a.out = out, a.addp = c0, a.add_rows = l, a.add_pscale = 1, a.accumulate = 0;
     a.beta = beta, a.l = l, a.rows = rows, a.N = c->N, a.logn = c->logn, a.L = c->L, a.K = c->K, a.elt = 0;
-    a.row0 = row0;
+    a.row0 = row0, a.tile0 = col0 / KS_TILE, a.tile1 = (col0 + ncols) / KS_TILE;
     bool small = true;
     for (u64 qq : c->q) small = small && qq < (1ull << 59);
     const size_t smem = (size_t)4 * beta * KS_TILE * sizeof(u64) + 64;
-    const int gx = (c->N / KS_TILE + KS_TPC - 1) / KS_TPC;
+    const int gx = (ncols / KS_TILE + KS_TPC - 1) / KS_TPC;
     ProfScope ps(c, PROF_KS_BABY, s);
     auto go = [&](auto kern) {
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -977,11 +982,16 @@ void pmac_hoisted(const Ctx* c, const u64* Y, const u64* diag, u64* A, int G, in
 }
 
 void pmac_hoisted_rows(const Ctx* c, const u64* Y, const u64* diag, const PmacDst& dst, u64* tmp, int G, int B, int D, int l,
-                       int rshift, int row0, int nrows, cudaStream_t s, int diag_rows) {
-    const int rows = l + c->P, dn = c->N >> rshift, W = PM_T2 >> rshift;
+                       int rshift, int row0, int nrows, cudaStream_t s, int diag_rows, int col0, int ncols, int diag_cols) {
+    const int rows = l + c->P, W = PM_T2 >> rshift;
     if (diag_rows < 0) diag_rows = nrows;
+    if (ncols < 0) ncols = c->N - col0;
+    if (diag_cols < 0) diag_cols = c->N >> rshift;
+    const int dn = diag_cols;                     // stored values per (diagonal, row)
     REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= rows && dst.world >= 1 && dst.world <= 8, "diagonal MAC: bad row range");
-    if (nrows == 0) return;
+    REQUIRE(col0 >= 0 && ncols >= 0 && col0 + ncols <= c->N && col0 % PM_TILE == 0 && ncols % PM_TILE == 0 &&
+                (ncols >> rshift) <= diag_cols, "diagonal MAC: bad column range");
+    if (nrows == 0 || ncols == 0) return;
     // baby steps are walked in chunks of Gc <= 64 rows (a multiple of 16) so that 2-3 CTAs fit per SM
     const int nchunks = (G + 63) / 64, Gc = ((G + nchunks - 1) / nchunks + 15) / 16 * 16;
     REQUIRE(c->N % PM_TILE == 0, "N must be a multiple of %d", PM_TILE);
@@ -991,7 +1001,7 @@ void pmac_hoisted_rows(const Ctx* c, const u64* Y, const u64* diag, const PmacDs
     if (rshift >= 1 && rshift <= 5 && W * sizeof(u64) >= 16 && ((size_t)Gc * W * sizeof(u64)) % 128 == 0 &&
         Gc <= D && tma_smem <= 227 * 1024) {
         CUtensorMap tmap;
-        cuuint64_t dims[3] = {(cuuint64_t)dn, (cuuint64_t)nrows, (cuuint64_t)D};
+        cuuint64_t dims[3] = {(cuuint64_t)(ncols >> rshift), (cuuint64_t)nrows, (cuuint64_t)D};
         cuuint64_t strides[2] = {(cuuint64_t)dn * sizeof(u64), (cuuint64_t)diag_rows * dn * sizeof(u64)};
         cuuint32_t box[3] = {(cuuint32_t)W, 1, (cuuint32_t)Gc};
         cuuint32_t estr[3] = {1, 1, 1};
@@ -1002,7 +1012,7 @@ void pmac_hoisted_rows(const Ctx* c, const u64* Y, const u64* diag, const PmacDs
         // partial sums of 30x30-bit products: 16 terms fit 64 bits when every q < 2^59, else 8
         bool small = true;
         for (u64 qq : c->q) small = small && qq < (1ull << 59);
-        dim3 grid(c->N / PM_T2, nrows);
+        dim3 grid(ncols / PM_T2, nrows);
         const ModTab mt = c->modtab();
         // several chunks: the earlier ones accumulate in the local array `tmp`, only the last one writes the destination
         // (which may be peer memory: no read-modify-write across NVLink)
@@ -1013,7 +1023,7 @@ void pmac_hoisted_rows(const Ctx* c, const u64* Y, const u64* diag, const PmacDs
             for (int b0 = 0; b0 < G; b0 += Gc) {
                 const bool last = b0 + Gc >= G;
                 LAUNCH(kern, grid, 2 * PM_T2 * PM_HS, tma_smem, s)(tmap, Y, last ? dst : local, b0 > 0 ? tmp : nullptr, G, Gc, b0,
-                                                                   std::min(Gc, G - b0), B, l, rows, c->N, c->L, row0, mt);
+                                                                   std::min(Gc, G - b0), B, l, rows, c->N, c->L, row0, col0, mt);
             }
         };
         switch (rshift * 2 + (small ? 1 : 0)) {
@@ -1034,8 +1044,8 @@ void pmac_hoisted_rows(const Ctx* c, const u64* Y, const u64* diag, const PmacDs
     size_t smem = sizeof(u64) * (size_t)G * 2 * PM_TILE;
     REQUIRE(smem <= 227 * 1024, "too many baby steps (%d) for the shared-memory tile", G);
     CUDA_CHECK(cudaFuncSetAttribute(k_pmac_hoisted, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per device
-    LAUNCH(k_pmac_hoisted, dim3(c->N / PM_TILE, nrows), PM_TILE, smem, s)(Y, diag, dst, G, B, D, l, rows, c->N, c->L, rshift,
-                                                                      row0, diag_rows, c->modtab());
+    LAUNCH(k_pmac_hoisted, dim3(ncols / PM_TILE, nrows), PM_TILE, smem, s)(Y, diag, dst, G, B, D, l, rows, c->N, c->L, rshift,
+                                                                       row0, diag_rows, col0, diag_cols, c->modtab());
     CUDA_CHECK(cudaGetLastError());
 }
 

@@ -16,6 +16,7 @@ struct KsArgs {
     int beta, l, rows, N, logn, L, K;
     u32 elt;           // 0: identity
     int row0 = 0;      // first row served by a row-restricted launch (k_ks_baby_fused: grid.z rows from row0)
+    int tile0 = 0, tile1 = 1 << 30;   // column range of such a launch, in tiles of 128 coefficients (k_ks_baby_fused)
 };
 
 // Destination of the diagonal MAC's giant-group accumulators.  Group g goes to  base[g % world] + (g / world) * 2 * pw :
@@ -48,8 +49,9 @@ void decompose_ks(const Ctx* c, const u64* cin, u64* x, int l, u64* E, const u64
 void ks_inner(const Ctx* c, const u64* E, const u64* key, u64* out, int l, u32 elt, const u64* addp, int add_rows,
               int add_pscale, int accumulate, cudaStream_t s);
 // row0 / nrows: rows (of the l + P) this launch serves -- all of them by default
+// col0 / ncols: columns (coefficients) served, multiples of 128 -- all of them by default
 bool ks_baby_fused(const Ctx* c, const u64* E, const u64* const* keys, const u32* elts, int nb, u64* out, int l,
-                   const u64* c0, cudaStream_t s, int row0 = 0, int nrows = -1);
+                   const u64* c0, cudaStream_t s, int row0 = 0, int nrows = -1, int col0 = 0, int ncols = -1);
 void encode_key_map(const Ctx* c, const u64* key, int box_n, int beta, CUtensorMap* out);
 void pscale(const Ctx* c, const u64* x, u64* y, int l, cudaStream_t s);
 void moddown(const Ctx* c, u64* in, size_t in_pstride, int polys, int l, u64* tmp, const u64* add, u64* out, cudaStream_t s);
@@ -62,10 +64,12 @@ void pmac_list(const Ctx* c, const u64* const* baby, const u64* const* pt, int n
 void split30_inplace(const Ctx* c, u64* x, size_t n, bool unsplit, cudaStream_t s);
 void pmac_hoisted(const Ctx* c, const u64* Y, const u64* diag, u64* A, int G, int B, int D, int l, int rshift, cudaStream_t s);
 // the same for the rows [row0, row0 + nrows) only -- diag points at the first of them, inside a set that stores diag_rows
-// rows per diagonal ([D][diag_rows][N >> rshift]; default: exactly the rows served) -- with the
+// rows per diagonal ([D][diag_rows][diag_cols]; default: exactly the rows served, all N >> rshift columns) -- and for the
+// columns [col0, col0 + ncols) only (multiples of 64; diag then points at the value of column col0) -- with the
 // accumulators scattered to `dst`; tmp: local scratch [B][2][l+P][N] for sets walked in several baby-step chunks
 void pmac_hoisted_rows(const Ctx* c, const u64* Y, const u64* diag, const PmacDst& dst, u64* tmp, int G, int B, int D, int l,
-                       int rshift, int row0, int nrows, cudaStream_t s, int diag_rows = -1);
+                       int rshift, int row0, int nrows, cudaStream_t s, int diag_rows = -1, int col0 = 0, int ncols = -1,
+                       int diag_cols = -1);
 }  // namespace ops
 
 namespace sampler {

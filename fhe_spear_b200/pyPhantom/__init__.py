@@ -753,31 +753,38 @@ class diagonal_set:
                     bytes=nbytes.value)
 
     @staticmethod
-    def row_range(limbs, P, rank, world):
-        """rows [r0, r1) of the limbs + P served by `rank` in the row-split phase of a two-phase mat-vec"""
-        rows = int(limbs) + int(P)
-        return rank * rows // world, (rank + 1) * rows // world
+    def share(limbs, P, N, rank, world):
+        """(row0, row1, col0, col1): the rows of the limbs + P and the coefficient columns served by `rank` in the first
+        phase of a two-phase mat-vec (spear_split_share: rows; beyond four ranks, row groups of two ranks x column halves)"""
+        r0, nr, c0, nc = (C.c_int() for _ in range(4))
+        _check(_lib.spear_split_share(int(rank), int(world), int(limbs) + int(P), int(N), C.byref(r0), C.byref(nr),
+                                      C.byref(c0), C.byref(nc)))
+        return r0.value, r0.value + nr.value, c0.value, c0.value + nc.value
 
     def slice_rows(self, rank, world):
-        """The rows rank `rank` of `world` holds in a two-phase mat-vec (bsgs_split): every giant group, rows
-        row_range(...) only -- 1/world of the set's bytes."""
+        """The share of the set rank `rank` of `world` holds in a two-phase mat-vec (bsgs_split): every giant group, its
+        rows (and column half) only -- 1/world of the set's bytes."""
         if self.shard != (0, 1):
             raise RuntimeError("slice_rows: expected a set holding every giant group")
-        r0, r1 = self.row_range(self.info()["limbs"], self._ctx.P, rank, world)
+        i = self.info()
+        r0, r1, c0, c1 = self.share(i["limbs"], self._ctx.P, self._ctx.N, rank, world)
         h = C.c_void_p()
-        _check(_lib.spear_diagset_slice_rows(self._ctx._h, self._h, r0, r1 - r0, C.byref(h)))
+        _check(_lib.spear_diagset_slice_share(self._ctx._h, self._h, int(rank), int(world), C.byref(h)))
         out = type(self).__new__(type(self))
         out._ctx, out._h = self._ctx, h
         out.D, out.G, out.B, out.shard, out.rows = self.D, self.G, self.B, self.shard, self.rows
-        out.row_slice = (r0, r1)
+        shift = (self._ctx.N // i["ring_n"]).bit_length() - 1
+        out.row_slice, out.col_slice = (r0, r1), (c0 >> shift, c1 >> shift)      # columns in stored values
         return out
 
     def to_numpy(self):
         i = self.info()
         nrows = i["limbs"] + self._ctx.P
+        ncols = i["ring_n"]
         if getattr(self, "row_slice", None):
             nrows = self.row_slice[1] - self.row_slice[0]
-        out = np.empty((len(self.rows), nrows, i["ring_n"]), dtype=np.uint64)
+            ncols = self.col_slice[1] - self.col_slice[0]
+        out = np.empty((len(self.rows), nrows, ncols), dtype=np.uint64)
         if out.size == 0:
             return out
         _check(_lib.spear_diagset_export(self._h, out.ctypes.data_as(C.c_void_p), out.size))

@@ -256,12 +256,16 @@ void spear_peer_window_destroy(spear_peer_window* w);
 /* ---- two-phase mat-vec over a rank group ("baby steps sharded, partial ciphertexts combined over
  *      NVLink"; reference loop scripts/bootstrap_generation.py:435-485) -------------------------------------------
  * Phase 1 -- the hoisted baby steps and the diagonal multiply-accumulate -- is split by ROWS of the l + P RNS limbs:
- * rank r of w serves rows [r*(l+P)/w, (r+1)*(l+P)/w) for EVERY giant group and holds just those rows of the diagonals
- * (spear_diagset_slice_rows).  Phase 2 -- the giant steps -- is split by giant group g = r, r + w, ...  In between, the
+ * up to four ranks take rows [r*(l+P)/w, (r+1)*(l+P)/w) each; larger even groups form w/2 row groups of two ranks that
+ * take one half of the coefficient columns each (27 rows over 8 ranks: 3.5 row-equivalents per rank instead of 4).  A rank
+ * serves its share for EVERY giant group and holds just that share of the diagonals (spear_split_share,
+ * spear_diagset_slice_share).  Phase 2 -- the giant steps -- is split by giant group g = r, r + w, ...  In between, the
  * MAC kernel's own epilogue stores scatter the accumulators of group g into the window of rank g % w over NVLink peer
  * memory (the all-to-all is fused into the compute kernel), epoch flags order the phases, and the call returns this
  * rank's accumulator in basis Q_l*P: spear_peer_allreduce (on a SECOND window) sums them, spear_bsgs_finish completes.
  * `w` must have slots of at least ceil(B/world) * 2 * (l+P) * N * 8 bytes and must not be used for all-reduces. */
+int spear_split_share(int rank, int world, int rows, int N, int* row0, int* nrows, int* col0, int* ncols);
+int spear_diagset_slice_share(spear_context* ctx, const spear_diagset* full, int rank, int world, spear_diagset** out);
 int spear_diagset_slice_rows(spear_context* ctx, const spear_diagset* full, int row0, int nrows, spear_diagset** out);
 int spear_bsgs_split(spear_context* ctx, const spear_obj* ct, const spear_diagset* rows, const spear_galois_keys* gk,
                      spear_peer_window* w, int slot, spear_obj** out);

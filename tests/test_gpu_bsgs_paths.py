@@ -102,7 +102,7 @@ def test_giant_sharding_on_one_gpu(D, world):
     assert np.abs(dec - W @ x).max() < 1e-9
 
 
-@pytest.mark.parametrize("D,world,weight", [(64, 2, 1.0), (64, 3, 1.0), (20, 2, 1.0), (16, 4, 1.0), (64, 8, 1.0), (512, 2, 32.0),
+@pytest.mark.parametrize("D,world,weight", [(64, 2, 1.0), (64, 3, 1.0), (20, 2, 1.0), (16, 4, 1.0), (64, 8, 1.0), (64, 6, 1.0), (20, 8, 1.0), (512, 2, 32.0), (512, 8, 32.0),
                                              (512, 3, 32.0)])
 def test_two_phase_split_on_one_gpu(D, world, weight):
     """Two-phase mat-vec (rows split for the baby steps and the diagonal MAC, giant groups split for the giant steps;
@@ -125,13 +125,14 @@ def test_two_phase_split_on_one_gpu(D, world, weight):
     slices = [full.slice_rows(r, world) for r in range(world)]
     rows_total = full.info()["limbs"] + ctx.P
     whole = full.to_numpy()
-    at = 0
-    for r, sl in enumerate(slices):                       # the slices partition the rows of the set
-        r0, r1 = ph.diagonal_set.row_range(full.info()["limbs"], ctx.P, r, world)
-        assert r0 == at and sl.row_slice == (r0, r1)
-        assert np.array_equal(sl.to_numpy(), whole[:, r0:r1, :])
-        at = r1
-    assert at == rows_total
+    cover = np.zeros(whole.shape[1:], dtype=np.int64)
+    shift = (S.N // full.info()["ring_n"]).bit_length() - 1
+    for r, sl in enumerate(slices):                       # the shares partition the (rows x columns) of the set
+        r0, r1, c0, c1 = ph.diagonal_set.share(full.info()["limbs"], ctx.P, S.N, r, world)
+        assert sl.row_slice == (r0, r1) and sl.col_slice == (c0 >> shift, c1 >> shift)
+        assert np.array_equal(sl.to_numpy(), whole[:, r0:r1, c0 >> shift:c1 >> shift])
+        cover[r0:r1, c0 >> shift:c1 >> shift] += 1
+    assert cover.shape[0] == rows_total and (cover == 1).all()
     acc = ph.bsgs_split_selftest(ctx, ct, slices, gk)
     assert np.array_equal(acc.to_numpy(), ref_acc.to_numpy())
     y = ph.bsgs_finish(ctx, acc)

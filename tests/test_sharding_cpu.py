@@ -39,15 +39,19 @@ def test_two_phase_plan_partitions_rows_and_groups():
     from fhe_spear_b200 import pyPhantom as ph
     from fhe_spear_b200 import sharding as sh
     for limbs, P in ((24, 3), (36, 3), (4, 2), (1, 1)):
-        for world in (1, 2, 3, 4, 8):
-            at = 0
+        for world in (1, 2, 3, 4, 5, 6, 8):
+            N = 2048
+            cover = np.zeros((limbs + P, N // 128), dtype=np.int64)
+            area = []
             for r in range(world):
-                r0, r1 = ph.diagonal_set.row_range(limbs, P, r, world)
-                assert r0 == at and r1 >= r0
-                at = r1
-            assert at == limbs + P
-            sizes = [b - a for a, b in (ph.diagonal_set.row_range(limbs, P, r, world) for r in range(world))]
-            assert max(sizes) - min(sizes) <= 1
+                r0, r1, c0, c1 = ph.diagonal_set.share(limbs, P, N, r, world)
+                assert 0 <= r0 <= r1 <= limbs + P and 0 <= c0 < c1 <= N and c0 % 128 == 0 and c1 % 128 == 0
+                cover[r0:r1, c0 // 128:c1 // 128] += 1
+                area.append((r1 - r0) * (c1 - c0))
+            assert (cover == 1).all()                       # the shares partition rows x columns
+            assert max(area) - min(area) <= N               # at most one row (or one half row) apart
+            if world == 8 and limbs + P == 27:
+                assert max(area) == 7 * N // 2              # 3.5 row-equivalents instead of 4
 
     class Ctx:
         L, P, N = 24, 3, 32768
