@@ -16,5 +16,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s $S -c 200 --csv --l
 FLAGS="--steps 2 --warmup 3 --no-cpu-baseline --no-tuned --no-token"
 S2=$(python bench.py $FLAGS --count-only) &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s $S2 -c 260 --csv --log-file $O/r2_final_bench_launches.csv python bench.py $FLAGS > $O/r2_final_ncu_b.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'k_intt_modup_fwd_a|k_ntt_b_ks_all|k_pmac_tma|k_ks_baby_fused' -s 5 -c 4 -o $O/r2_final_full python tools/profile_step.py > $O/r2_final_ncu_c.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_intt_modup_fwd_a|k_ntt_b_ks_all|k_pmac_tma|k_ks_baby_fused' -s 5 -c 5 -o $O/r2_final_full python tools/profile_step.py > $O/r2_final_ncu_c.log 2>&1
 tail -n 3 $O/r2_final_smoke.log $O/r2_final_gputest.log $O/r2_final_bench_n1.err
