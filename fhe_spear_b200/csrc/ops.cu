@@ -519,7 +519,9 @@ __global__ void __launch_bounds__(TPB) k_pmac_list(PmacPtrs ptrs, int nb, u64* _
 // element is read once.
 constexpr int PM_TILE = 128;
 __device__ __forceinline__ u64* pmac_dst(const PmacDst& d, int g, int p, size_t pw) {
-    return d.base[g % d.world] + (size_t)((g / d.world) * 2 + p) * pw;
+    if (d.world == 1) return d.base[0] + (size_t)(g * 2 + p) * pw;   // (uniform branch: the one-GPU path pays no division)
+    const int slot = (int)(((u32)g * ((65536u + d.world - 1) / d.world)) >> 16);   // g / world, exact for g < 8192
+    return d.base[g - slot * d.world] + (size_t)(slot * 2 + p) * pw;
 }
 __global__ void __launch_bounds__(PM_TILE) k_pmac_hoisted(const u64* __restrict__ Y, const u64* __restrict__ diag,
                                                            PmacDst dst, int G, int B, int D, int l, int rows,
