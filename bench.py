@@ -303,8 +303,9 @@ def run_ours(args):
     weights = {1.0}
     if do_tuned:
         weights.add(args.tuned_weight)
-    if do_token:
-        weights |= set(sh.HybridBlock.required_weights(world, D, F)) if world > 1 else {hb.hoisting_weight(1)}
+    if do_token:   # (both multi-GPU plans' splits: the two-phase path falls back to the round-1 plan without peer windows)
+        weights |= (set(sh.HybridBlock.required_weights(world, D, F, two_phase=True)) |
+                    set(sh.HybridBlock.required_weights(world, D, F, two_phase=False))) if world > 1 else {hb.hoisting_weight(1)}
     ckks = hb.CKKSBootstrapContext(poly_degree=N, L0=L0, prime_bits=59, special_mod_size=P, max_rot_dim=1,
                                    bsgs_dim=[D], skip_bootstrap=True, seed=bytes(range(32)), device=local,
                                    verbose=(rank == 0 and args.verbose), baby_weights=tuple(sorted(weights)))
@@ -328,16 +329,18 @@ def run_ours(args):
         info = dsets[0].info()
         mine = [((0,), list(range(nb)))]
         pg = {}
+        two_phase = False
 
         def step():
             return ph.bsgs_hoisted_batch(ctx, cts, dsets, ckks.gk)
         parallelism = "1 GPU: three mat-vecs on three streams"
         n_giant_rank = B - 1
-    elif sh.HybridBlock.two_phase_default(world):
+    elif sh.HybridBlock.two_phase_default(world) and sh.two_phase_ready(ctx, max(B, hb.compute_bsgs_params(D, hb.hoisting_weight(1))[1]), world):
         # strong scaling, two-phase mat-vecs: EVERY mat-vec is served by all N ranks -- baby steps and diagonal MAC split
         # by rows of the RNS basis, the MAC's epilogue scattering the giant groups' accumulators to their owners over NVLink
         # peer memory, giant steps split by group, accumulators summed by the fused peer all-reduce
         pg = {}
+        two_phase = True
         all_ranks = tuple(range(world))
         mine = [(all_ranks, list(range(nb)))]
         dsets = {}
@@ -347,8 +350,6 @@ def run_ours(args):
                 info = full.info()
             dsets[j] = full.slice_rows(rank, world)
             del full
-        sh.PeerExchange.get(ctx, None)
-        sh.PeerExchange.get(ctx, None, tag="split", slot_bytes=sh.split_slot_bytes(ctx, B, world))
 
         def step():
             return dict(enumerate(sh.split_matvec_batch(ckks, cts, [dsets[j] for j in range(nb)])))
@@ -361,6 +362,7 @@ def run_ours(args):
     else:
         # strong scaling (round-1 plan, SPEAR_TWO_PHASE=0): the same nb mat-vecs dealt to rank groups, giant steps sharded
         # inside a group; every rank creates every process group in the same order
+        two_phase = False
         plan = sh.PhasePlan(nb, world)
         pg = {ranks: (dist.group.WORLD if len(ranks) == world else dist.new_group(list(ranks))) for ranks in plan.groups}
         mine = plan.mine(rank)
@@ -443,7 +445,6 @@ def run_ours(args):
 
     # latency and per-kernel times of ONE mat-vec alone on the engine stream (rank-local: the unsharded mat-vec at N = 1,
     # this rank's shard accumulator + finish at N > 1), event pair around each launch, for the roofline line
-    two_phase = sh.HybridBlock.two_phase_default(world)
     if world == 1:
         def single():
             return ph.bsgs_hoisted(ctx, cts[j0], full0, ckks.gk)

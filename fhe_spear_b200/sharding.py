@@ -193,6 +193,17 @@ def sharded_matvec_batch(ckks, cts, shard_sets, group=None):
     return outs
 
 
+def two_phase_ready(ctx, groups, world, group=None):
+    """Bring up the two windows of the two-phase mat-vec (accumulator all-reduce + scatter) for mat-vecs of up to `groups`
+    giant groups; False -- on every rank alike -- when they cannot be mapped (no CUDA IPC / peer access between the GPUs,
+    SPEAR_PEER=0): the callers then use the giant-step sharding of round 1, whose exchange has an NCCL stand-in."""
+    if world < 2:
+        return False
+    acc = PeerExchange.get(ctx, group)
+    sc = PeerExchange.get(ctx, group, tag="split", slot_bytes=split_slot_bytes(ctx, groups, world)) if acc is not None else None
+    return acc is not None and sc is not None
+
+
 def split_slot_bytes(ctx, groups, world):
     """bytes a scatter-window slot must hold: the accumulators of ceil(groups / world) giant groups at the top level"""
     return -(-int(groups) // world) * 2 * (ctx.L + ctx.P) * ctx.N * 8
@@ -308,6 +319,12 @@ class HybridBlock:
         from . import bsgs as hb
         self.ckks, self.D, self.F, self.rank, self.world = ckks, D, F, rank, world
         self.two_phase = self.two_phase_default(world) if two_phase is None else bool(two_phase)
+        if self.two_phase:   # the windows come up here, outside any timed region; without them: the round-1 plan
+            Gs, Bs = hb.compute_bsgs_params(D, hb.hoisting_weight(1))
+            self.two_phase = two_phase_ready(ckks.ctx, Bs, world)
+            if not self.two_phase and rank == 0:
+                print("[spear] peer windows unavailable: two-phase mat-vecs off, giant-step sharding with the NCCL exchange "
+                      "(the context must hold the rotation keys of HybridBlock.required_weights(..., two_phase=False))")
         self.plan = self.plans(world, D, F)
         self.pairs = hb._chunk_pairs(F, D)
         level = ckks.encrypt_replicated(np.zeros(1)).chain_index()
@@ -333,9 +350,6 @@ class HybridBlock:
                     full = enc(ckks, *m[1:], D, G, B, level)
                     self.sets[(phase, j)] = full.slice_rows(rank, world)
                     del full
-            ctx = ckks.ctx
-            PeerExchange.get(ctx, None)                     # windows come up outside any timed region
-            PeerExchange.get(ctx, None, tag="split", slot_bytes=split_slot_bytes(ctx, B, world))
             return
         for phase in self.PHASES:
             for ranks, js in self.plan[phase].mine(rank):
