@@ -108,6 +108,45 @@ def _split_worker(rank, world, port, D, weight, out):
         raise
 
 
+def _block_worker(rank, world, port, out):
+    """a whole client-aided RWKV-7 block served by sharding.HybridBlock in two-phase mode over real windows"""
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SPEAR_DEVICE=str(rank))
+        os.environ.pop("LOCAL_RANK", None)
+        os.environ.pop("SPEAR_TWO_PHASE", None)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from helpers import SEED
+        from fhe_spear_b200 import bsgs as hb
+        from fhe_spear_b200.rwkv_block import RWKVBlockWeights, client_aided_block, plaintext_block
+        from fhe_spear_b200.sharding import HybridBlock
+        D, F, H, S = 32, 128, 2, 16
+        ckks = hb.CKKSBootstrapContext(poly_degree=2048, L0=3, prime_bits=59, special_mod_size=1, max_rot_dim=1,
+                                       bsgs_dim=[D], skip_bootstrap=True, seed=SEED, verbose=False, device=rank,
+                                       baby_weights=HybridBlock.required_weights(world, D, F, two_phase=True))
+        blocks = [RWKVBlockWeights.random(D, F, H, S, block_idx=i, seed=30 + i) for i in range(2)]
+        servers = [HybridBlock(ckks, b, D, F, rank, world) for b in blocks]
+        rng = np.random.default_rng(2)
+        x = rng.standard_normal(D)
+        xf, xp = x.copy(), x.copy()
+        st_f = st_p = np.zeros((H, S, S))
+        pa_f = pa_p = pf_f = pf_p = np.zeros(D)
+        vf_f = vf_p = None
+        err = 0.0
+        for blk, srv in zip(blocks, servers):
+            xf, pa_f, pf_f, st_f, vf_f, tm = client_aided_block(ckks, blk, xf, pa_f, pf_f, st_f, vf_f, preencoded_block=srv)
+            xp, pa_p, pf_p, st_p, vf_p = plaintext_block(blk, xp, pa_p, pf_p, st_p, vf_p)
+            err = max(err, float(np.abs(xf - xp).max()), float(np.abs(st_f - st_p).max()))
+        outs = [None] * world
+        dist.all_gather_object(outs, xf)                       # every rank ends with the same activations
+        same = all(np.array_equal(o, outs[0]) for o in outs)
+        out.put((rank, same and all(s.two_phase for s in servers), err, 0))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:   # noqa: BLE001 -- reported to the parent, which fails the test
+        out.put((rank, False, repr(e), -1))
+        raise
+
+
 def _gpu_count():
     try:
         import torch
@@ -205,6 +244,34 @@ def test_two_process_two_phase_matvec_matches_unsharded(D, weight):
         assert status == 0, f"rank {rank}: window status {status} ({err})"
         assert same, f"rank {rank}: two-phase result differs from the unsharded one ({err})"
         assert err < 1e-9
+    assert all(p.exitcode == 0 for p in procs)
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs (kernels that wait on one another must not share one)")
+def test_two_process_hybrid_block_two_phase_matches_plaintext_block():
+    """sharding.HybridBlock over 2 GPUs (two-phase mat-vecs, real windows) drives client_aided_block
+    (reference scripts/bootstrap_generation.py:756-899) to the float64 block within 1e-7, identically on every rank"""
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mpc = mp.get_context("spawn")
+    out = mpc.Queue()
+    procs = [mpc.Process(target=_block_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    try:
+        res = [out.get(timeout=240) for _ in procs]
+        for p in procs:
+            p.join(timeout=60)
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+    for rank, same, err, status in res:
+        assert status == 0, f"rank {rank}: {err}"
+        assert same, f"rank {rank}: ranks disagree or the two-phase path was not taken"
+        assert err < 1e-7
     assert all(p.exitcode == 0 for p in procs)
 
 
