@@ -870,7 +870,10 @@ bool ks_baby_fused(const Ctx* c, const u64* E, const u64* const* keys, const u32
     a.row0 = row0, a.tile0 = col0 / KS_TILE, a.tile1 = (col0 + ncols) / KS_TILE;
     bool small = true;
     for (u64 qq : c->q) small = small && qq < (1ull << 59);
-    const size_t smem = (size_t)4 * beta * KS_TILE * sizeof(u64) + 64;
+    // SPEAR_BABY_SMEM_PAD (bytes, A/B switch): extra dynamic shared memory per CTA = fewer resident CTAs of this HBM-bound
+    // kernel per SM, which leaves room for the CTAs of an issue-bound kernel running next to it on another stream
+    static const size_t pad = getenv("SPEAR_BABY_SMEM_PAD") ? (size_t)atol(getenv("SPEAR_BABY_SMEM_PAD")) : 0;
+    const size_t smem = std::min<size_t>((size_t)4 * beta * KS_TILE * sizeof(u64) + 64 + pad, 200 * 1024);
     const int gx = (ncols / KS_TILE + KS_TPC - 1) / KS_TPC;
     ProfScope ps(c, PROF_KS_BABY, s);
     auto go = [&](auto kern) {
