@@ -95,6 +95,7 @@ _SIG = {
     "spear_diagset_export": (C.c_int, [vp, vp, C.c_size_t]),
     "spear_bsgs_hoisted": (C.c_int, [vp, vp, vp, vp, vpp]),
     "spear_bsgs_hoisted_batch": (C.c_int, [vp, vpp, vpp, C.c_int, vp, vpp]),
+    "spear_bsgs_hoisted_shared": (C.c_int, [vp, vp, vpp, C.c_int, vp, vpp]),
     "spear_bsgs_hoisted_batch_host": (C.c_int, [vp, vpp, C.c_int, C.c_double, vpp, C.c_int, vp, vpp, f64p]),
     "spear_bsgs_hoisted_partial": (C.c_int, [vp, vp, vp, vp, vpp]),
     "spear_bsgs_hoisted_partial_batch": (C.c_int, [vp, vpp, vpp, C.c_int, vp, vpp]),
@@ -112,6 +113,7 @@ _SIG = {
     "spear_split_share": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, ip, ip]),
     "spear_bsgs_split": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, vpp]),
     "spear_bsgs_split_batch": (C.c_int, [vp, vpp, vpp, C.c_int, vp, vp, C.c_int, vpp]),
+    "spear_bsgs_split_shared": (C.c_int, [vp, vp, vpp, C.c_int, vp, vp, C.c_int, vpp]),
     "spear_bsgs_split_selftest": (C.c_int, [vp, vp, vpp, C.c_int, vp, vpp]),
     "spear_ntt_host": (C.c_int, [vp, vp, C.c_int, ip, C.c_int, C.c_int]),
 }

@@ -338,7 +338,10 @@ def fhe_projection_bsgs(ckks, x, W, D_in, D_out, label="", preencoded_diags=None
         from .sharding import sharded_matvec_batch
         run_batch = lambda cts, sets: sharded_matvec_batch(ckks, cts, sets)      # giant-step shards on every rank
     else:
-        run_batch = lambda cts, sets: ph.bsgs_hoisted_batch(ckks.ctx, cts, sets, ckks.gk)
+        def run_batch(cts, sets):
+            if len(cts) > 1 and all(c is cts[0] for c in cts) and len({(d.D, d.G, d.B) for d in sets}) == 1:
+                return ph.bsgs_hoisted_shared(ckks.ctx, cts[0], sets, ckks.gk)   # one input: the baby steps once [ref: :575-600]
+            return ph.bsgs_hoisted_batch(ckks.ctx, cts, sets, ckks.gk)
     if D_out > D_in and all_sets:
         # every chunk pair is an independent mat-vec on the same input: one batched call, then unpack (re, im)
         D, F = D_in, D_out

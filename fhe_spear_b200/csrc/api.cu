@@ -32,6 +32,12 @@ void bsgs_split_phase1(const Ctx* c, const u64* ct, int l, const u64* diag, int 
                        cudaStream_t s);
 void bsgs_split_phase2(const Ctx* c, u64* A, int l, int G, int B, int n_groups, const u32* gelt, const u64* const* gkey,
                        int world, u64* R, cudaStream_t s);
+void bsgs_hoisted_shared(const Ctx* c, const u64* ct, int l, int G, const u32* belt, const u64* const* bkey,
+                         const SharedSet* sets, int count, cudaStream_t s);
+void bsgs_split_baby(const Ctx* c, const u64* ct, int l, int G, int B, int row0, int nrows, int col0, int ncols,
+                     const u32* belt, const u64* const* bkey, int world, cudaStream_t s);
+void bsgs_split_mac(const Ctx* c, int l, const u64* diag, int rshift, int G, int B, int n_diags, int row0, int nrows, int col0,
+                    int ncols, const PmacDst& dst, cudaStream_t s);
 }  // namespace eng
 
 namespace {
@@ -1222,6 +1228,49 @@ int spear_bsgs_hoisted_batch(spear_context* ctx, spear_obj* const* cts, spear_di
     for (int i = 0; i < count; i++) outs[i] = H_(res[i].release());
     API_END
 }
+// `count` diagonal sets (same D, G, level) multiplying ONE ciphertext -- the chunk pairs of a D -> F projection
+// [ref: scripts/bootstrap_generation.py:575-600, where the baby rotations are computed once for all chunks]: one
+// decomposition and one set of hoisted baby steps, then the diagonal MAC, the giant steps and the finish per set.
+int spear_bsgs_hoisted_shared(spear_context* ctx, const spear_obj* ct_, spear_diagset* const* dss, int count,
+                              const spear_galois_keys* gk_, spear_obj** outs) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    REQUIRE(count >= 1, "bsgs_hoisted_shared: empty batch");
+    const Obj* ct = O_(ct_);
+    const GaloisKeys* gk = reinterpret_cast<const GaloisKeys*>(gk_);
+    check_ct(ct, "bsgs_hoisted_shared");
+    REQUIRE(ct->size == 2 && ct->l >= 2, "bsgs_hoisted_shared: a fresh size-2 ciphertext with a level to spare expected");
+    const DiagSet* d0 = reinterpret_cast<const DiagSet*>(dss[0]);
+    REQUIRE(d0, "bsgs_hoisted_shared: null set");
+    const int G = std::min(d0->G, d0->D), l = ct->l;
+    std::vector<u32> belt(G, 0);
+    std::vector<const u64*> bkey(G, nullptr);
+    for (int b = 1; b < G; b++) {
+        belt[b] = (u32)elt_from_step(b, c->N);
+        bkey[b] = find_key(gk, belt[b])->d;
+    }
+    std::vector<std::vector<u32>> gelt(count);
+    std::vector<std::vector<const u64*>> gkey(count);
+    std::vector<SharedSet> sets(count);
+    std::vector<std::unique_ptr<Obj>> acc(count), res(count);
+    cudaStream_t s = c->stream;
+    for (int i = 0; i < count; i++) {
+        const DiagSet* ds = reinterpret_cast<const DiagSet*>(dss[i]);
+        REQUIRE(ds && ds->g_first == 0 && ds->g_stride == 1 && ds->nrows < 0 && ds->ncols < 0, "bsgs_hoisted_shared: full sets expected");
+        REQUIRE(ds->l == l && ds->G == d0->G && ds->D == d0->D, "bsgs_hoisted_shared: the sets must share D, G and the level");
+        for (int g = 0; g < ds->B && g * ds->G < ds->D; g++) {
+            gelt[i].push_back(g ? (u32)elt_from_step(g * ds->G, c->N) : 0);
+            gkey[i].push_back(g ? find_key(gk, gelt[i].back())->d : nullptr);
+        }
+        acc[i].reset(new_obj(c, 2, l, true, c->N, ct->scale * ds->scale, s));
+        sets[i] = SharedSet{ds->d, ds->rshift, (int)gelt[i].size(), ds->n_diags, gelt[i].data(), gkey[i].data(), acc[i]->d};
+    }
+    eng::bsgs_hoisted_shared(c, ct->d, l, G, belt.data(), bkey.data(), sets.data(), count, s);
+    for (int i = 0; i < count; i++) res[i].reset(bsgs_finish(c, acc[i].get(), s));
+    for (int i = 0; i < count; i++) outs[i] = H_(res[i].release());
+    API_END
+}
 // Serving form of the batch: ciphertexts arrive in and leave to HOST memory.  Item i is uploaded, multiplied and
 // downloaded on auxiliary stream i % 3, so the PCIe legs of one item run under the arithmetic of the others.
 int spear_bsgs_hoisted_batch_host(spear_context* ctx, const uint64_t* const* in, int limbs, double scale,
@@ -1356,6 +1405,61 @@ int spear_bsgs_split(spear_context* ctx, const spear_obj* ct_, const spear_diags
     use(c);
     *out = H_(bsgs_split(c, O_(ct_), reinterpret_cast<const DiagSet*>(ds_), reinterpret_cast<const GaloisKeys*>(gk_), win, slot,
                          c->stream));
+    API_END
+}
+// `count` row-sliced sets multiplying ONE ciphertext over a rank group: this rank's share of the baby steps once, the
+// diagonal MAC of set i scattered into window slot slot0 + i, then -- after every set's stores are posted -- the giant
+// steps of this rank's groups per set.  outs[i]: this rank's accumulator of set i.
+int spear_bsgs_split_shared(spear_context* ctx, const spear_obj* ct_, spear_diagset* const* dss, int count,
+                            const spear_galois_keys* gk_, spear_peer_window* win, int slot0, spear_obj** outs) {
+    API_BEGIN
+    Ctx* c = C_(ctx);
+    use(c);
+    REQUIRE(count >= 1, "bsgs_split_shared: empty batch");
+    const Obj* ct = O_(ct_);
+    const GaloisKeys* gk = reinterpret_cast<const GaloisKeys*>(gk_);
+    int rank = 0, world = 1;
+    peer::window_geometry(win, &rank, &world);
+    std::vector<SplitPlan> plans;
+    std::vector<std::vector<u32>> gelt(count);
+    std::vector<std::vector<const u64*>> gkey(count);
+    for (int i = 0; i < count; i++) {   // validate everything before anything is queued
+        const DiagSet* ds = reinterpret_cast<const DiagSet*>(dss[i]);
+        REQUIRE(ds, "bsgs_split_shared: null set %d", i);
+        plans.push_back(split_plan(c, ct, ds, gk));
+        REQUIRE(plans[i].G == plans[0].G && ds->D == reinterpret_cast<const DiagSet*>(dss[0])->D,
+                "bsgs_split_shared: the sets must share D and G");
+        split_check_rows(c, ds, plans[i].l, rank, world);
+        split_groups(c, ds, gk, plans[i].nB, rank, world, gelt[i], gkey[i]);
+    }
+    const SplitPlan& p0 = plans[0];
+    const SplitShare sh = split_share(rank, world, p0.l + c->P, c->N);
+    cudaStream_t s = c->stream;
+    std::vector<std::unique_ptr<Obj>> R(count);
+    for (int i = 0; i < count; i++)
+        R[i].reset(new_obj(c, 2, p0.l, true, c->N, ct->scale * reinterpret_cast<const DiagSet*>(dss[i])->scale, s));
+    std::vector<peer::SplitView> v(count);
+    int maxB = 0;
+    for (int i = 0; i < count; i++) {
+        v[i] = peer::split_begin(c, win, slot0 + i, plans[i].slot_words(c, world), s);
+        maxB = std::max(maxB, plans[i].nB);
+    }
+    eng::bsgs_split_baby(c, ct->d, p0.l, p0.G, maxB, sh.row0, sh.nrows, sh.col0, sh.ncols, p0.belt.data(), p0.bkey.data(), world, s);
+    for (int i = 0; i < count; i++) {
+        const DiagSet* ds = reinterpret_cast<const DiagSet*>(dss[i]);
+        PmacDst dst = {};
+        for (int r = 0; r < 8; r++) dst.base[r] = v[i].base[r];
+        dst.world = world;
+        eng::bsgs_split_mac(c, p0.l, ds->d, ds->rshift, p0.G, plans[i].nB, ds->n_diags, sh.row0, sh.nrows, sh.col0, sh.ncols, dst, s);
+        peer::split_post(win, slot0 + i, s);
+    }
+    for (int i = 0; i < count; i++) {
+        peer::split_wait(win, slot0 + i, s);
+        eng::bsgs_split_phase2(c, v[i].base[rank], p0.l, p0.G, plans[i].nB, (int)gelt[i].size(), gelt[i].data(), gkey[i].data(), world,
+                               R[i]->d, s);
+        peer::split_release(win, slot0 + i, R[i]->d, R[i]->words(), s);
+    }
+    for (int i = 0; i < count; i++) outs[i] = H_(R[i].release());
     API_END
 }
 // item i runs on auxiliary stream i % 3 and exchanges through window slot slot0 + i

@@ -198,7 +198,7 @@ static void bsgs_phase1(const Ctx* c, const u64* ct, int l, const u64* diag, int
     // in k chunks, the MAC of chunk i on an auxiliary stream under the key stream of chunk i+1 -- the overlap of the HBM-bound
     // baby steps with the integer-bound MAC that a fused kernel could buy at best (profiles/r2_ns1_overlap.md)
     static const int pipe = getenv("SPEAR_PIPE_ROWS") ? atoi(getenv("SPEAR_PIPE_ROWS")) : 0;
-    if (pipe > 1 && s == c->stream && G > 1 && nrows >= pipe && ncols == (int)N) {
+    if (pipe > 1 && diag && s == c->stream && G > 1 && nrows >= pipe && ncols == (int)N) {
         cudaStream_t h = c->aux[0];
         std::vector<cudaEvent_t> ev(pipe + 1);
         for (auto& e : ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -223,7 +223,14 @@ static void bsgs_phase1(const Ctx* c, const u64* ct, int l, const u64* diag, int
         for (int b = 1; b < G; b++)
             ops::ks_inner(c, E, bkey[b], Y + (size_t)b * 2 * pw, l, belt[b], c0, l, 1, 0, s);
     }
-    ops::pmac_hoisted_rows(c, Y, diag, dst, tmp, G, n_groups, n_diags, l, rshift, row0, nrows, s, nrows, col0, ncols, dcols);
+    if (diag) ops::pmac_hoisted_rows(c, Y, diag, dst, tmp, G, n_groups, n_diags, l, rshift, row0, nrows, s, nrows, col0, ncols, dcols);
+}
+// the baby steps alone (shared by several diagonal sets multiplying the same ciphertext): Y for the rows / columns served
+static void bsgs_baby(const Ctx* c, const u64* ct, int l, int G, const u32* belt, const u64* const* bkey, u64* x, u64* E, u64* Y,
+                      int row0, int nrows, cudaStream_t s, int col0 = 0, int ncols = -1) {
+    PmacDst none = {};
+    none.world = 1;
+    bsgs_phase1(c, ct, l, nullptr, 0, G, 0, 0, belt, bkey, x, E, Y, none, nullptr, row0, nrows, s, col0, ncols);
 }
 
 // Phase 2: the giant steps of the n_groups accumulators A [n_groups][2][l+P][N] (destroyed: the ModDown transforms their
@@ -307,6 +314,33 @@ void bsgs_hoisted_partial(const Ctx* c, const u64* ct, int l, const u64* diag, i
     bsgs_phase2(c, A, l, n_groups, gelt, gkey, R, sc, s);
 }
 
+// Several diagonal sets multiplying the SAME ciphertext (the chunk pairs of a D -> F projection: the reference computes
+// the baby rotations once for all of them, scripts/bootstrap_generation.py:575-600): one decomposition and one set of baby
+// steps, then per set the diagonal MAC and the giant steps.  Same limbs as `count` separate calls.
+void bsgs_hoisted_shared(const Ctx* c, const u64* ct, int l, int G, const u32* belt, const u64* const* bkey,
+                         const SharedSet* sets, int count, cudaStream_t s) {
+    const size_t N = c->N, rows = l + c->P, pw = rows * N;
+    int max_groups = 0, max_rot = 0;
+    for (int i = 0; i < count; i++) {
+        max_groups = std::max(max_groups, sets[i].n_groups);
+        max_rot = std::max(max_rot, sets[i].n_groups);
+    }
+    Arena sc(c, s, phase1_words(c, l, G, max_groups, true) + phase2_words(c, l, max_rot, s));
+    u64* x = sc.get(l * N);
+    u64* E = sc.get(c->digits(l) * pw);
+    u64* Y = sc.get((size_t)G * 2 * pw);
+    u64* A = sc.get((size_t)max_groups * 2 * pw);
+    bsgs_baby(c, ct, l, G, belt, bkey, x, E, Y, 0, (int)rows, s);
+    const Arena mark = sc;
+    for (int i = 0; i < count; i++) {
+        PmacDst dst = {};
+        dst.base[0] = A, dst.world = 1;
+        ops::pmac_hoisted_rows(c, Y, sets[i].diag, dst, A, G, sets[i].n_groups, sets[i].n_diags, l, sets[i].rshift, 0, (int)rows, s);
+        sc = mark;   // the giant-step scratch of the previous set is free again (stream order)
+        bsgs_phase2(c, A, l, sets[i].n_groups, sets[i].gelt, sets[i].gkey, sets[i].R, sc, s);
+    }
+}
+
 // ---- two-phase mat-vec over a rank group (peer.cu drives the exchange between the phases) -----------------------------
 // Phase 1 on this rank's ROWS (and, in groups of more than four ranks, its half of the COLUMNS) for every giant group; the accumulators of group g land in dst.base[g % world]
 // (slot (g / world)): the all-to-all that turns the row split into the giant-group split is the diagonal MAC's own
@@ -322,6 +356,30 @@ void bsgs_split_phase1(const Ctx* c, const u64* ct, int l, const u64* diag, int 
     u64* Y = sc.get((size_t)G * 2 * pw);
     u64* tmp = chunks ? sc.get((size_t)B * 2 * pw) : nullptr;
     bsgs_phase1(c, ct, l, diag, rshift, G, B, n_diags, belt, bkey, x, E, Y, dst, tmp, row0, nrows, s, col0, ncols);
+}
+// The same in two steps for several sets multiplying one ciphertext: the baby steps once ...
+void bsgs_split_baby(const Ctx* c, const u64* ct, int l, int G, int B, int row0, int nrows, int col0, int ncols,
+                     const u32* belt, const u64* const* bkey, int world, cudaStream_t s) {
+    const size_t N = c->N, pw = (size_t)(l + c->P) * N;
+    Arena sc(c, s, std::max(phase1_words(c, l, G, B, G > 64), phase2_words(c, l, (B + world - 1) / world, s)));
+    u64* x = sc.get(l * N);
+    u64* E = sc.get(c->digits(l) * pw);
+    u64* Y = sc.get((size_t)G * 2 * pw);
+    bsgs_baby(c, ct, l, G, belt, bkey, x, E, Y, row0, nrows, s, col0, ncols);
+}
+// ... then the diagonal MAC of one set over the baby ciphertexts bsgs_split_baby left in the stream's workspace (every MAC
+// of the sets comes before the first bsgs_split_phase2, which reuses that workspace)
+void bsgs_split_mac(const Ctx* c, int l, const u64* diag, int rshift, int G, int B, int n_diags, int row0, int nrows, int col0,
+                    int ncols, const PmacDst& dst, cudaStream_t s) {
+    const size_t N = c->N, pw = (size_t)(l + c->P) * N;
+    if (nrows == 0 || ncols == 0) return;
+    const bool chunks = G > 64;
+    Arena sc(c, s, std::max(phase1_words(c, l, G, B, chunks), phase2_words(c, l, (B + dst.world - 1) / dst.world, s)));
+    sc.get(l * N);
+    sc.get(c->digits(l) * pw);
+    u64* Y = sc.get((size_t)G * 2 * pw);
+    u64* tmp = chunks ? sc.get((size_t)B * 2 * pw) : nullptr;
+    ops::pmac_hoisted_rows(c, Y, diag, dst, tmp, G, B, n_diags, l, rshift, row0, nrows, s, nrows, col0, ncols, ncols >> rshift);
 }
 // Phase 2 on this rank's giant groups, whose accumulators A [n_groups][2][l+P][N] every rank of the group has written.
 void bsgs_split_phase2(const Ctx* c, u64* A, int l, int G, int B, int n_groups, const u32* gelt, const u64* const* gkey,

@@ -194,6 +194,15 @@ bool ntt_ks_fused_all(const Ctx* c, const u64* E, const u64* const* keys, const 
                       const u64* addp, size_t add_stride, int add_rows, cudaStream_t s);
 void ntt_inverse(const Ctx* c, u64* data, int rows, RowMap rm, int n, cudaStream_t s, bool pass_b_only = false);
 
+// one diagonal set of a shared-baby-step call (bsgs.cu bsgs_hoisted_shared)
+struct SharedSet {
+    const u64* diag;
+    int rshift, n_groups, n_diags;
+    const u32* gelt;
+    const u64* const* gkey;
+    u64* R;   // [2][l+P][N] accumulator of this set
+};
+
 // ---- two-phase mat-vec over a rank group: exchange hooks (peer.cu), phases (bsgs.cu) -----------------------------
 // Phase-1 share of `rank`: up to four ranks split the rows of the RNS basis; larger even groups form world/2 row groups
 // of two ranks that take one half of the columns each (27 rows over 8 ranks: 3.5 row-equivalents instead of 4).
@@ -218,8 +227,11 @@ struct SplitView {
 void window_geometry(const spear_peer_window* win, int* rank, int* world);
 // waits (on s) until every peer has consumed the slot's previous contents, opens a new epoch
 SplitView split_begin(const Ctx* c, spear_peer_window* win, int slot, size_t need_words, cudaStream_t s);
-// posts "my phase-1 stores are out" to every peer and waits for theirs
+// posts "my phase-1 stores are out" to every peer and waits for theirs (split_post / split_wait: the two halves, for
+// callers that queue more work between them)
 void split_exchange(spear_peer_window* win, int slot, cudaStream_t s);
+void split_post(spear_peer_window* win, int slot, cudaStream_t s);
+void split_wait(spear_peer_window* win, int slot, cudaStream_t s);
 // posts "slot consumed" to every peer; R (words) is overwritten with all-ones words if a peer never arrived
 void split_release(spear_peer_window* win, int slot, u64* R, size_t words, cudaStream_t s);
 }  // namespace peer

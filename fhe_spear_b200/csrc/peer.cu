@@ -204,6 +204,17 @@ void split_exchange(spear_peer_window* win, int slot, cudaStream_t s) {
     if (w->world > 1)
         LAUNCH(k_peer_sync, 1, 32, 0, s)(ptrs_of(w), w->world, w->rank, slot, 0, 1, w->epoch[slot], w->d_status, w->d_failed, 1);
 }
+void split_post(spear_peer_window* win, int slot, cudaStream_t s) {
+    PeerWindow* w = W_(win);
+    if (w->world > 1)
+        LAUNCH(k_peer_sync, 1, 32, 0, s)(ptrs_of(w), w->world, w->rank, slot, 0, 1, w->epoch[slot], w->d_status, w->d_failed, 0);
+}
+void split_wait(spear_peer_window* win, int slot, cudaStream_t s) {
+    PeerWindow* w = W_(win);
+    ProfScope ps(w->ctx, PROF_PEER_WAIT, s);
+    if (w->world > 1)
+        LAUNCH(k_peer_sync, 1, 32, 0, s)(ptrs_of(w), w->world, w->rank, slot, 0, 0, w->epoch[slot], w->d_status, w->d_failed, 1);
+}
 void split_release(spear_peer_window* win, int slot, u64* R, size_t words, cudaStream_t s) {
     PeerWindow* w = W_(win);
     if (w->world > 1) {

@@ -800,6 +800,16 @@ def bsgs_hoisted_batch(ctx, cts, diag_sets, gk):
     return [ciphertext(ctx, C.c_void_p(h)) for h in outs]
 
 
+def bsgs_hoisted_shared(ctx, ct, diag_sets, gk):
+    """Several diagonal sets (same D, G, level) times ONE ciphertext -- the chunk pairs of a D -> F projection: the baby
+    steps are computed once, as the reference does (scripts/bootstrap_generation.py:575-600).  Same limbs as
+    [bsgs_hoisted(ctx, ct, d, gk) for d in diag_sets]."""
+    n = len(diag_sets)
+    outs = (C.c_void_p * n)()
+    _check(_lib.spear_bsgs_hoisted_shared(ctx._h, ct._h, (C.c_void_p * n)(*[d._h for d in diag_sets]), n, gk._h, outs))
+    return [ciphertext(ctx, C.c_void_p(h)) for h in outs]
+
+
 def bsgs_hoisted_batch_host(ctx, host_in, scale, diag_sets, gk, host_out):
     """Serving form of bsgs_hoisted_batch: host_in[i] = (2, l, N) uint64 ciphertext limbs in host memory (pinned_empty for
     asynchronous copies), host_out[i] = (2, l - 1, N) receives result i; uploads, mat-vecs and downloads of the items are
@@ -844,6 +854,16 @@ def bsgs_split_batch(ctx, cts, rows, gk, window, slot0=0):
     outs = (C.c_void_p * n)()
     _check(_lib.spear_bsgs_split_batch(ctx._h, (C.c_void_p * n)(*[c._h for c in cts]),
                                        (C.c_void_p * n)(*[d._h for d in rows]), n, gk._h, window._h, int(slot0), outs))
+    return [ciphertext(ctx, C.c_void_p(h)) for h in outs]
+
+
+def bsgs_split_shared(ctx, ct, rows, gk, window, slot0=0):
+    """bsgs_split for several row-sliced sets multiplying ONE ciphertext: this rank's baby steps once; set i exchanges
+    through window slot slot0 + i.  Returns this rank's accumulators."""
+    n = len(rows)
+    outs = (C.c_void_p * n)()
+    _check(_lib.spear_bsgs_split_shared(ctx._h, ct._h, (C.c_void_p * n)(*[d._h for d in rows]), n, gk._h, window._h,
+                                        int(slot0), outs))
     return [ciphertext(ctx, C.c_void_p(h)) for h in outs]
 
 

@@ -230,7 +230,11 @@ def split_matvec_batch(ckks, cts, row_sets, group=None):
         exa = PeerExchange.get(ctx, group, tag="split", slot_bytes=need)
         if exa is None or exr is None:
             raise RuntimeError("two-phase mat-vec: the ranks' peer windows could not be mapped (CUDA IPC / peer access)")
-        accs = ph.bsgs_split_batch(ctx, [cts[i] for i in part], [row_sets[i] for i in part], ckks.gk, exa.window, 0)
+        if len(part) > 1 and all(cts[i] is cts[part[0]] for i in part) and len({(row_sets[i].D, row_sets[i].G) for i in part}) == 1:
+            # one input for all of them (the chunk pairs of a D -> F projection): this rank's baby steps once
+            accs = ph.bsgs_split_shared(ctx, cts[part[0]], [row_sets[i] for i in part], ckks.gk, exa.window, 0)
+        else:
+            accs = ph.bsgs_split_batch(ctx, [cts[i] for i in part], [row_sets[i] for i in part], ckks.gk, exa.window, 0)
         for k, acc in enumerate(accs):
             exr.allreduce(acc, k)
         outs += [ph.bsgs_finish(ctx, acc) for acc in accs]
@@ -377,7 +381,10 @@ class HybridBlock:
             # every rank runs the same client code (identical ciphertexts: same key seed, same encryption ids), serves its
             # rows and its giant groups of EVERY mat-vec of the phase, and ends with every result ciphertext
             js = list(range(plan.k))
-            cts = self._encrypt_inputs(inputs, js, ckks.sk.reserve_enc_ids(plan.k))
+            if plan.k > 1 and all(v is inputs[0] for v in inputs):     # one vector for every mat-vec of the phase (ffn_key):
+                cts = self._encrypt_inputs(inputs, [0], ckks.sk.reserve_enc_ids(1)) * plan.k   # one ciphertext, shared baby steps
+            else:
+                cts = self._encrypt_inputs(inputs, js, ckks.sk.reserve_enc_ids(plan.k))
             outs = split_matvec_batch(ckks, cts, [self.sets[(phase, j)] for j in js])
             return np.stack([ckks.decrypt_vec_complex(ct_y, D) for ct_y in outs])
         # Encryption ids come from the secret key's one monotonic counter: every rank runs the same client code in the

@@ -209,6 +209,12 @@ int spear_bsgs_hoisted(spear_context* ctx, const spear_obj* ct, const spear_diag
  * one overlaps the transforms of the others.  outs receives `count` ciphertexts. */
 int spear_bsgs_hoisted_batch(spear_context* ctx, spear_obj* const* cts, spear_diagset* const* diags, int count,
                              const spear_galois_keys* gk, spear_obj** outs);
+/* `count` diagonal sets (same D, G and level) multiplying ONE ciphertext -- the chunk pairs of a D -> F projection, for
+ * which the reference computes the baby rotations once [ref: scripts/bootstrap_generation.py:575-600]: one decomposition
+ * and one set of hoisted baby steps, then diagonal MAC, giant steps, ModDown + rescale per set.  outs[i] has the limbs of
+ * spear_bsgs_hoisted(ct, diags[i]). */
+int spear_bsgs_hoisted_shared(spear_context* ctx, const spear_obj* ct, spear_diagset* const* diags, int count,
+                              const spear_galois_keys* gk, spear_obj** outs);
 /* Serving form of the batch (the reference keeps client and server in one process and hands ciphertexts over in host
  * memory when it offloads them, scripts/bootstrap_generation.py:336-358, 545-556): in[i] = [2][limbs][N] ciphertext limbs
  * in host memory (page-locked for asynchronous copies), out[i] = [2][limbs-1][N].  Item i is uploaded, multiplied and
@@ -272,6 +278,10 @@ int spear_bsgs_split(spear_context* ctx, const spear_obj* ct, const spear_diagse
 /* item i on auxiliary stream i % 3, exchanging through slot slot0 + i */
 int spear_bsgs_split_batch(spear_context* ctx, spear_obj* const* cts, spear_diagset* const* rows, int count,
                            const spear_galois_keys* gk, spear_peer_window* w, int slot0, spear_obj** outs);
+/* the same for `count` sets multiplying ONE ciphertext (shared baby steps, see spear_bsgs_hoisted_shared); set i goes
+ * through slot slot0 + i; outs[i] = this rank's accumulator of set i */
+int spear_bsgs_split_shared(spear_context* ctx, const spear_obj* ct, spear_diagset* const* rows, int count,
+                            const spear_galois_keys* gk, spear_peer_window* w, int slot0, spear_obj** outs);
 /* Test hook for one-GPU boxes: both phases of all `world` ranks, one after the other, over local stand-ins for the
  * windows; rows[r] = the slice of rank r.  *out = the summed accumulator (spear_bsgs_finish completes it). */
 int spear_bsgs_split_selftest(spear_context* ctx, const spear_obj* ct, spear_diagset* const* rows, int world,

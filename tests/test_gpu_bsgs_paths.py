@@ -143,6 +143,42 @@ def test_two_phase_split_on_one_gpu(D, world, weight):
         ph.bsgs_hoisted(ctx, ct, slices[0], gk)
 
 
+@pytest.mark.parametrize("D,weight", [(64, 1.0), (512, 32.0)])
+def test_shared_baby_steps_match_separate_calls(D, weight):
+    """Several diagonal sets times one ciphertext (the chunk pairs of a D -> F projection, for which the reference computes
+    the baby rotations once, scripts/bootstrap_generation.py:575-600): spear_bsgs_hoisted_shared and -- through a one-rank
+    window -- spear_bsgs_split_shared return the limbs of separate bsgs_hoisted calls."""
+    S = Setup(N=2048, bits=(59,) * 6, P=2)
+    G = int(np.ceil(np.sqrt(weight * D)))
+    B = -(-D // G)
+    steps = list(range(1, G)) + [g * G for g in range(1, B)]
+    ph, ctx, sk = S.gpu(steps)
+    gk = sk.create_galois_keys(ctx)
+    enc = ph.ckks_encoder(ctx)
+    rng = np.random.default_rng(3 * D)
+    Ws = [rng.standard_normal((D, D)) * 0.1 for _ in range(3)]
+    x = rng.standard_normal(D)
+    ct = sk.encrypt_symmetric(ctx, enc.encode_double_vector(ctx, tile(x, S.N // 2), S.scale), enc_id=9)
+    sets = [ph.diagonal_set(ctx, rolled_diagonals(W, D, G, B), G, B, S.scale) for W in Ws]
+    refs = [ph.bsgs_hoisted(ctx, ct, d, gk).to_numpy() for d in sets]
+    for _ in range(2):
+        outs = ph.bsgs_hoisted_shared(ctx, ct, sets, gk)
+        assert all(np.array_equal(y.to_numpy(), r) for y, r in zip(outs, refs))
+    dec = np.array(enc.decode_double_vector(ctx, sk.decrypt(ctx, outs[2])))[:D]
+    assert np.abs(dec - Ws[2] @ x).max() < 1e-9
+    # the two-phase form over a group of one rank: same code path as on several GPUs, minus the waits
+    rows = [d.slice_rows(0, 1) for d in sets]
+    win = ph.peer_window(ctx, 0, 1, B * 2 * (S.L + S.P) * S.N * 8, slots=3)
+    for _ in range(2):
+        accs = ph.bsgs_split_shared(ctx, ct, rows, gk, win, 0)
+        assert all(np.array_equal(ph.bsgs_finish(ctx, a).to_numpy(), r) for a, r in zip(accs, refs))
+    accs = ph.bsgs_split_batch(ctx, [ct] * 3, rows, gk, win, 0)
+    assert all(np.array_equal(ph.bsgs_finish(ctx, a).to_numpy(), r) for a, r in zip(accs, refs))
+    with pytest.raises(RuntimeError):                     # sets of different splits cannot share baby steps
+        other = ph.diagonal_set(ctx, rolled_diagonals(Ws[0], D, 2 * G, -(-D // (2 * G))), 2 * G, -(-D // (2 * G)), S.scale)
+        ph.bsgs_hoisted_shared(ctx, ct, [sets[0], other], gk)
+
+
 def test_host_buffer_serving_batch_matches_device_batch():
     """spear_bsgs_hoisted_batch_host (ciphertexts in and out of page-locked host memory, transfers pipelined with the
     mat-vecs over the engine's streams) returns exactly the limbs of the device-resident batch call, for more items than
