@@ -61,6 +61,17 @@ def test_two_phase_plan_partitions_rows_and_groups():
     assert not sh.HybridBlock.two_phase_default(1)
 
 
+def test_two_phase_entry_points_refuse_a_single_rank_loudly():
+    """no silent fallback: the two-phase batch needs a rank group (and peer windows); alone it raises before touching a device"""
+    from fhe_spear_b200 import sharding as sh
+
+    class K:
+        ctx = gk = None
+    with pytest.raises(RuntimeError, match="rank group of two or more"):
+        sh.split_matvec_batch(K, [object()], [object()])
+    assert sh.two_phase_ready(None, 45, 1) is False
+
+
 def _worker(rank, world, port, D, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
